@@ -1,0 +1,299 @@
+#!/usr/bin/env python
+"""bench.py — matches/sec of the search tick (BASELINE.json metric).
+
+A step = one pass of the hot path (one search tick) over one synthetic player pool.
+  value  whole-job lobbies/sec with the pool already resident in HBM; the timed region
+         of a step is the tick itself (all its kernels), timed with CUDA events on the
+         engine's own stream (mm_tick_stats.device_us); max over ranks.  Between steps
+         (untimed) the pool is restored from a device snapshot and L2 is flushed by
+         writing a buffer larger than L2.
+  e2e    same metric through the C-ABI with HOST buffers: mm_enqueue (pinned host
+         columns, H2D inside) + mm_tick (lobbies + member ids D2H inside), wall clock.
+  roofline / cpu_baseline: see DESIGN.md §Measurement.
+Launch: `python bench.py --gpus 1 --steps K --warmup W`, or under torchrun for N>1
+(one rank per GPU; ranks own disjoint rating groups — no data-path collective).
+`--impl reference` times the CPU restatement of the reference loop (oracle/).
+"""
+import argparse
+import importlib
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+PKG = "microservice-matchmaking_b200"
+
+B_ALG_TICK = 22  # SURVEY §8(d) strict-parity mode: read id 8 + rating 4 + mode 1 + team_size 1, write id 8
+B_ALG_PLACE = 21  # the placement kernel: read rating 4 + mode 1 + id 8, write id 8
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.rows, self.proc, self.idx = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.idx}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); smax.append(float(r[2]))
+                for nm, v in zip(names, r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+            except Exception:
+                pass
+        hi = [x for x in sm if x >= 0.5 * max(sm)] if sm else []
+        return {"sm_mhz": statistics.median(hi) if hi else None, "sm_max_mhz": max(smax) if smax else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def workload_cfg(pkg, name, order, rank, world, capacity):
+    w = pkg.synth.WORKLOADS[name]
+    # weak scaling: every rank owns its own w["n_groups"] rating groups (a contiguous
+    # slice of a world*G-group ladder) and a full-size pool routed to them
+    cfg = pkg.synth.make_config(n_groups=w["n_groups"], order=order, capacity=capacity, device=0)
+    return w, cfg
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the CPU restatement of the reference loop on the host cores."""
+    if rank != 0:
+        return
+    pkg = importlib.import_module(PKG)
+    orc = importlib.import_module("oracle.oracle")
+    orc.build()
+    order = pkg.abi.MM_ORDER_RATING if args.order == "rating" else pkg.abi.MM_ORDER_ARRIVAL
+    w, cfg = workload_cfg(pkg, args.workload, order, 0, 1, 1)
+    n = min(w["n"], args.ref_sample)
+    ids, rating, mode, _ = pkg.synth.gen_pool(1, n, mode=w["mode"])
+    threads = max(1, min(os.cpu_count() or 1, cfg.n_groups))
+    for _ in range(args.warmup):
+        orc.time_literal(cfg, ids, rating, mode, threads)
+    secs, lobbies = 0.0, 0
+    for _ in range(args.steps):
+        s, nl = orc.time_literal(cfg, ids, rating, mode, threads)
+        secs += s; lobbies += nl
+    value = lobbies / secs
+    sample = f"{n} of {w['n']} players of {args.workload}, literal consume/5 loop, one worker per rating group"
+    line = {
+        "impl": "reference", "metric": "matches/sec", "value": value, "unit": "lobbies/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * secs / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32/u64", "data": "synthetic",
+        "config": {"workload": args.workload, "order": args.order, "players_per_step": n,
+                   "note": "reference BEAM pipeline cannot run here (no Elixir/RabbitMQ, strategist absent): "
+                           "CPU restatement oracle/mm_oracle.c, policy S0"},
+        "cpu_baseline": {"value": value, "unit": "lobbies/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "lobbies/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="config3_10m_g32_5v5")
+    ap.add_argument("--order", default="rating", choices=["rating", "arrival"])
+    ap.add_argument("--rank-impl", type=int, default=1)
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--ref-sample", type=int, default=10_000_000)
+    ap.add_argument("--cpu-sample", type=int, default=10_000_000)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        return run_reference(args, rank, world)
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the search tick has no CPU path "
+                         "(use --impl reference for the CPU restatement)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    import __graft_entry__ as ge
+    pkg = ge.build()
+    abi = pkg.abi
+    order = abi.MM_ORDER_RATING if args.order == "rating" else abi.MM_ORDER_ARRIVAL
+    w, _ = workload_cfg(pkg, args.workload, order, rank, world, 1)
+    n, L = w["n"], (2 if w["mode"] == 0 else 10)
+    cfg = pkg.synth.make_config(n_groups=w["n_groups"], order=order, capacity=n, device=local)
+    # rank r's shard of the N x n pool: its own seed stream (weak scaling, disjoint ids)
+    ids, rating, mode, ts = pkg.synth.gen_pool(1, n, first=rank * n, mode=w["mode"])
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    eng = pkg.Engine(cfg)
+    eng.set_option("rank_impl", args.rank_impl)
+    acc = eng.enqueue(ids, rating, mode, ts)
+    assert acc.all()
+    eng.snapshot()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
+
+    def one_step():
+        eng.restore()
+        flush.fill_(1)  # evict the pool from L2
+        torch.cuda.synchronize()
+        return eng.tick_device()
+
+    for _ in range(args.warmup):
+        st = one_step()
+    sampler = ClockSampler(local)
+    barrier()
+    sampler.start()
+    t_wall = time.perf_counter()
+    dev_us, place_us = [], []
+    for _ in range(args.steps):
+        st = one_step()
+        dev_us.append(st.device_us); place_us.append(st.place_us)
+    barrier()
+    wall_s = time.perf_counter() - t_wall
+    clocks = sampler.stop()
+    lobbies_per_step = st.n_lobbies
+    tick_s = sum(dev_us) * 1e-6  # device time of the K timed ticks on this rank
+    if world > 1:
+        t = torch.tensor([tick_s, float(sum(place_us)) * 1e-6], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        tick_s, place_s = t.tolist()
+        tl = torch.tensor([lobbies_per_step], device="cuda", dtype=torch.int64)
+        dist.all_reduce(tl)
+        total_lobbies_per_step = int(tl.item())
+    else:
+        place_s = sum(place_us) * 1e-6
+        total_lobbies_per_step = lobbies_per_step
+    value = total_lobbies_per_step * args.steps / tick_s
+
+    # ---- e2e through the C ABI with host buffers ------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        eng.close()
+        eng = pkg.Engine(cfg)
+        eng.set_option("rank_impl", args.rank_impl)
+        pin = lambda a: torch.from_numpy(a).pin_memory()
+        h_ids, h_rating, h_mode, h_ts = pin(ids), pin(rating), pin(mode), pin(ts)
+        h_acc = torch.empty(n, dtype=torch.uint8).pin_memory()
+        h_lob = torch.empty(n // L + 1, dtype=torch.int64).pin_memory()  # 8-byte mm_lobby_hdr
+        h_mem = torch.empty(n, dtype=torch.int64).pin_memory()
+        times = []
+        for it in range(args.e2e_steps + 1):
+            barrier()
+            t0 = time.perf_counter()
+            eng.enqueue_raw(n, h_ids.data_ptr(), h_rating.data_ptr(), h_mode.data_ptr(), h_ts.data_ptr(),
+                            h_acc.data_ptr())
+            st2 = eng.tick_raw(h_lob.data_ptr(), n // L + 1, h_mem.data_ptr(), n)
+            dt = time.perf_counter() - t0
+            if it:  # first iteration = warm-up
+                times.append(dt)
+            eng.remove(ids)  # what the lobby stage does later (game-lobby/worker.ex:80); untimed
+        assert st2.n_lobbies == lobbies_per_step
+        e2e_s = max(times) if False else sum(times) / len(times)
+        if world > 1:
+            t = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            e2e_s = float(t.item())
+        e2e = {"value": total_lobbies_per_step / e2e_s, "unit": "lobbies/s",
+               "h2d_bytes_per_step": n * (8 + 4 + 1 + 4), "d2h_bytes_per_step": n + st2.n_matched * 8 + st2.n_lobbies * 8,
+               "ms_per_step": 1e3 * e2e_s, "steps": len(times),
+               "call": "mm_enqueue(host columns) + mm_tick(host lobbies/member_ids)"}
+    eng.close()
+
+    # ---- CPU baseline (rank 0, N=1 only): the oracle's literal loop on a bounded sample ----
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        orc = importlib.import_module("oracle.oracle")
+        ns = min(n, args.cpu_sample)
+        s1, nl1 = orc.time_literal(cfg, ids[:ns], rating[:ns], mode[:ns], 1)
+        cpu = {"value": nl1 / s1, "unit": "lobbies/s", "cores": 1, "kind": "port",
+               "sample": f"first {ns} of {n} players of {args.workload}; oracle/mm_oracle.c literal consume/5 loop, "
+                         f"1 thread, {s1:.2f} s", "players_per_s": ns / s1}
+
+    if rank == 0:
+        peak, peak_src = peaks()
+        place_avg_s = place_s / args.steps
+        ach = B_ALG_PLACE * n / place_avg_s / 1e9
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "place_traffic.json")
+        if os.path.exists(tp):
+            try:
+                traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+            except Exception:
+                pass
+        line = {
+            "metric": "matches/sec", "value": value, "unit": "lobbies/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * tick_s / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "int32/u64", "data": "synthetic",
+            "config": {"workload": args.workload, "players_per_gpu": n, "rating_groups_per_gpu": w["n_groups"],
+                       "lobby_size": L, "order": args.order, "ratings": "uniform 0..5000, seed 1",
+                       "parallelism": f"rating-group shards x{world}, no collective",
+                       "l2": "flushed between steps (256 MiB write); pool 180 MB > L2",
+                       "timed_region": "mm_tick_device: k_hist+k_colscan+k_place+k_finish+k_headers, CUDA events "
+                                       "on the engine stream; snapshot restore + L2 flush between steps untimed"},
+            "players_per_s": n * world * args.steps / tick_s,
+            "wall_ms_per_step_incl_restore": 1e3 * wall_s / args.steps,
+            "roofline": {"bound": "hbm", "kernel": "k_place", "achieved": ach, "peak": peak, "unit": "GB/s",
+                         "frac": ach / peak, "traffic": traffic, "peak_source": peak_src,
+                         "bytes_per_player": B_ALG_PLACE, "us_per_launch": 1e6 * place_avg_s},
+            "tick_roofline": {"bytes_per_player": B_ALG_TICK, "achieved": B_ALG_TICK * n * args.steps / tick_s / 1e9,
+                              "frac": B_ALG_TICK * n * args.steps / tick_s / 1e9 / peak, "unit": "GB/s",
+                              "frac_of_8000": B_ALG_TICK * n * args.steps / tick_s / 1e9 / 8000.0},
+            "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": 5 * args.steps, "clocks": clocks,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

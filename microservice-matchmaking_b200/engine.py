@@ -96,6 +96,18 @@ class Engine:
         self._check(self.lib.mm_enqueue(self.h, n, _p(ids), _p(rating), _p(mode), _p(enq_ts), _p(acc)), "mm_enqueue")
         return acc
 
+    def enqueue_raw(self, n, p_ids, p_rating, p_mode, p_ts=0, p_accepted=0):
+        """mm_enqueue on raw HOST addresses (e.g. pinned torch tensors' data_ptr())."""
+        self._check(self.lib.mm_enqueue(self.h, n, p_ids, p_rating, p_mode, p_ts or None, p_accepted or None),
+                    "mm_enqueue")
+
+    def tick_raw(self, p_lobbies, lobby_cap, p_members, member_cap, p_emit_seq=0, now=0):
+        """mm_tick on raw HOST addresses. -> TickStats"""
+        st = abi.TickStats()
+        self._check(self.lib.mm_tick(self.h, now, p_lobbies, lobby_cap, p_members, member_cap, p_emit_seq or None,
+                                     C.byref(st)), "mm_tick")
+        return st
+
     def enqueue_device(self, n, d_ids, d_rating, d_mode, d_ts=0, d_accepted=0):
         """Device-pointer ingest (ints = raw device addresses). -> n_accepted"""
         na = C.c_uint32(0)

@@ -13,6 +13,7 @@
 #include "mm_oracle.h"
 
 #include <pthread.h>
+#include <stddef.h>
 #include <stdlib.h>
 #include <string.h>
 #include <time.h>
@@ -90,6 +91,12 @@ typedef struct {
   uint64_t member[ORC_MAX_LOBBY]; /* team t at [t*S, t*S + count[t]) */
 } orc_teams;
 
+/* copy a teams document: header + the L = T*S member slots actually in use (the
+ * reference re-encodes the whole O(L) document per request, lobby_state.ex:97,122) */
+static inline void orc_teams_copy(orc_teams* dst, const orc_teams* src, uint32_t L) {
+  memcpy(dst, src, offsetof(orc_teams, member) + (size_t)L * sizeof(uint64_t));
+}
+
 /* search/worker.ex:263-265 — get_players_count/1 */
 static uint32_t orc_players_count(const orc_teams* t) { return orc_required_slots(t->count, t->n_teams); }
 
@@ -103,23 +110,28 @@ typedef struct {
 typedef struct {
   orc_row* rows;
   uint32_t n, cap;
+  char pad[48]; /* one cache line per table: workers of different groups never share one */
 } orc_lobby_table;
 
 /* lobby_state.ex:61-104 — get_state/4: select (limit 1) a row with this game_mode,
  * delete it, return its decoded dump; {:ok, %{}} when none.                       */
-static void orc_get_state(orc_lobby_table* tb, uint8_t mode, orc_teams* out) {
+static void orc_get_state(orc_lobby_table* tb, uint8_t mode, uint32_t L, orc_teams* out) {
   for (uint32_t i = 0; i < tb->n; ++i) {
     if (tb->rows[i].mode == mode) {
-      *out = tb->rows[i].teams;
-      tb->rows[i] = tb->rows[tb->n - 1]; /* Mnesia.delete(table, id) */
+      orc_teams_copy(out, &tb->rows[i].teams, L);
+      if (i != tb->n - 1) { /* Mnesia.delete(table, id) */
+        tb->rows[i].mode = tb->rows[tb->n - 1].mode;
+        orc_teams_copy(&tb->rows[i].teams, &tb->rows[tb->n - 1].teams, ORC_MAX_LOBBY);
+      }
       tb->n--;
       return;
     }
   }
-  memset(out, 0, sizeof(*out)); /* get_an_empty_state/0 */
+  out->n_teams = 0; /* get_an_empty_state/0 */
+  memset(out->count, 0, sizeof(out->count));
 }
 /* lobby_state.ex:109-131 — update_state/5: write a row under a fresh UUID        */
-static int orc_update_state(orc_lobby_table* tb, uint8_t mode, const orc_teams* st) {
+static int orc_update_state(orc_lobby_table* tb, uint8_t mode, uint32_t L, const orc_teams* st) {
   if (tb->n == tb->cap) {
     uint32_t nc = tb->cap ? tb->cap * 2 : 4;
     orc_row* nr = (orc_row*)realloc(tb->rows, nc * sizeof(orc_row));
@@ -127,7 +139,7 @@ static int orc_update_state(orc_lobby_table* tb, uint8_t mode, const orc_teams* 
     tb->rows = nr; tb->cap = nc;
   }
   tb->rows[tb->n].mode = mode;
-  tb->rows[tb->n].teams = *st;
+  orc_teams_copy(&tb->rows[tb->n].teams, st, L);
   tb->n++;
   return 0;
 }
@@ -220,15 +232,16 @@ static int orc_emit_lobby(orc_world* w, uint8_t mode, uint8_t group, const orc_t
 /* search/worker.ex:291-324 — consume/5, one request.  Returns 1 when the player must
  * be requeued (:308-310), 0 otherwise, <0 on allocation failure.                   */
 static int orc_consume(orc_world* w, uint8_t group, uint64_t player_id, uint8_t game_mode, uint32_t seq) {
+  const uint32_t L = (uint32_t)w->cfg->modes[game_mode].teams * w->cfg->modes[game_mode].team_size;
   orc_teams grouped;                                             /* :295 */
-  orc_get_state(&w->tables[group], game_mode, &grouped);
+  orc_get_state(&w->tables[group], game_mode, L, &grouped);
   orc_reply data = orc_strategist_s0(w->cfg, game_mode, player_id, &grouped); /* :296-306 */
   int requeue = orc_in_queue(&w->active, player_id) && !data.added;           /* :308 */
   int is_changed = orc_remove_inactive(&w->active, w->cfg->modes[game_mode].team_size, &grouped); /* :312 */
   if (data.is_filled && !is_changed) {                                          /* :313 */
     if (orc_emit_lobby(w, game_mode, group, &grouped, seq) < 0) return -1;      /* :314-319 */
   } else {
-    if (orc_update_state(&w->tables[group], game_mode, &grouped) < 0) return -1; /* :320 */
+    if (orc_update_state(&w->tables[group], game_mode, L, &grouped) < 0) return -1; /* :320 */
   }
   return requeue;                                                                /* :323 ack */
 }

@@ -1,0 +1,314 @@
+"""GPU parity tests: the CUDA search tick, called through the C ABI, against the CPU
+oracle on the same seeded inputs — bit-exact (integer / index work, no tolerance)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+ARRIVAL, RATING = 0, 1
+
+
+def lobby_lists(lob, mem):
+    return [tuple(mem[h["first_member"]:h["first_member"] + h["n_members"]]) for h in lob]
+
+
+def assert_tick_matches(eng, ref, lob, mem, seq, st):
+    assert st.n_lobbies == ref.n_lobbies
+    assert st.n_matched == ref.n_matched
+    assert st.n_residual == ref.n_residual
+    assert st.n_dead == ref.n_dead
+    assert np.array_equal(lob, ref.lobbies)
+    assert np.array_equal(mem, ref.member_ids)
+    if seq is not None:
+        assert np.array_equal(seq, ref.emit_seq)
+    assert np.array_equal(eng.pool_read()["id"], ref.residual_ids)
+
+
+def make_pool(pkg, seed, n, n_modes=2, bell=False, oor=0.01):
+    rng = np.random.default_rng(seed)
+    ids, rating, _, ts = pkg.synth.gen_pool(seed, n, bell=bell)
+    rating = rating.copy()
+    k = int(n * oor)
+    if k:
+        rating[rng.integers(0, n, k)] = rng.integers(-100, 5200, k)
+    mode = rng.integers(0, n_modes, n).astype(np.uint8)
+    return ids, rating, mode, ts
+
+
+@pytest.mark.parametrize("impl", [1, 0])
+@pytest.mark.parametrize("order", [ARRIVAL, RATING])
+@pytest.mark.parametrize("n", [0, 1, 2, 9, 31, 33, 1000, 4095, 4096, 4097, 70001])
+def test_random_pool_matches_literal_oracle(pkg, oracle, n, order, impl):
+    cfg = pkg.synth.make_config(groups=pkg.synth.REFERENCE_GROUPS, order=order, capacity=max(n, 1))
+    ids, rating, mode, ts = make_pool(pkg, 11 + n, n)
+    with pkg.Engine(cfg) as eng:
+        eng.set_option("rank_impl", impl)
+        acc = eng.enqueue(ids, rating, mode, ts)
+        assert (acc == 1).all()
+        assert eng.pool_size() == n
+        lob, mem, seq, st = eng.tick()
+        ref = oracle.run_literal(cfg, ids, rating, mode)
+        assert_tick_matches(eng, ref, lob, mem, seq, st)
+        if order == ARRIVAL and n:
+            # sorting by emit_seq reproduces the serialized reference's emission order
+            assert np.array_equal(np.argsort(seq, kind="stable"), np.argsort(ref.emission_rank, kind="stable"))
+
+
+@pytest.mark.parametrize("order", [ARRIVAL, RATING])
+@pytest.mark.parametrize("bell", [False, True])
+def test_one_million_mixed(pkg, oracle, order, bell):
+    n = 1_000_003
+    cfg = pkg.synth.make_config(n_groups=8, order=order, capacity=n)
+    ids, rating, mode, ts = make_pool(pkg, 5, n, bell=bell, oor=0.0)
+    with pkg.Engine(cfg) as eng:
+        assert eng.enqueue(ids, rating, mode, ts).all()
+        lob, mem, seq, st = eng.tick()
+        ref = oracle.run_closed_form(cfg, ids, rating, mode)
+        assert_tick_matches(eng, ref, lob, mem, seq, st)
+
+
+def test_config2_and_both_rank_impls_agree(pkg, oracle):
+    # BASELINE.json configs[1]: 1M players, 8 rating groups, 1v1
+    w = pkg.synth.WORKLOADS["config2_1m_g8_1v1"]
+    cfg = pkg.synth.make_config(n_groups=w["n_groups"], order=RATING, capacity=w["n"])
+    ids, rating, mode, ts = pkg.synth.gen_pool(1, w["n"], mode=w["mode"])
+    out = []
+    for impl in (1, 0):
+        with pkg.Engine(cfg) as eng:
+            eng.set_option("rank_impl", impl)
+            assert eng.enqueue(ids, rating, mode, ts).all()
+            lob, mem, seq, st = eng.tick()
+            out.append((lob, mem, seq))
+    assert all(np.array_equal(a, b) for a, b in zip(out[0], out[1]))
+    ref = oracle.run_closed_form(cfg, ids, rating, mode)
+    assert np.array_equal(out[0][1], ref.member_ids) and np.array_equal(out[0][0], ref.lobbies)
+
+
+def test_degenerate_everyone_same_rating(pkg, oracle):
+    n = 200_000
+    cfg = pkg.synth.make_config(groups=pkg.synth.REFERENCE_GROUPS, order=RATING, capacity=n)
+    ids, _, _, ts = pkg.synth.gen_pool(3, n)
+    rating = np.full(n, 1500, np.int32)
+    mode = np.ones(n, np.uint8)
+    with pkg.Engine(cfg) as eng:
+        assert eng.enqueue(ids, rating, mode, ts).all()
+        lob, mem, seq, st = eng.tick()
+        ref = oracle.run_closed_form(cfg, ids, rating, mode)
+        assert_tick_matches(eng, ref, lob, mem, seq, st)
+        assert np.array_equal(mem, ids[: (n // 10) * 10])  # pure enqueue order
+
+
+def test_few_distinct_ratings(pkg, oracle):
+    # ratings rounded to 10: every bin is shared by several warps in every round
+    n = 300_000
+    cfg = pkg.synth.make_config(groups=pkg.synth.REFERENCE_GROUPS, order=RATING, capacity=n)
+    ids, rating, mode, ts = make_pool(pkg, 9, n, oor=0.0)
+    rating = (rating // 10 * 10).astype(np.int32)
+    with pkg.Engine(cfg) as eng:
+        assert eng.enqueue(ids, rating, mode, ts).all()
+        lob, mem, seq, st = eng.tick()
+        assert_tick_matches(eng, oracle.run_closed_form(cfg, ids, rating, mode), lob, mem, seq, st)
+
+
+def test_overlapping_unsorted_groups(pkg, oracle):
+    groups = [(3000, 5000), (0, 1200), (1000, 3500)]  # first match in list order; default = none
+    n = 50_000
+    for order in (ARRIVAL, RATING):
+        cfg = pkg.synth.make_config(groups=groups, order=order, capacity=n, default_group=1)
+        ids, rating, mode, ts = make_pool(pkg, 21, n, oor=0.02)
+        with pkg.Engine(cfg) as eng:
+            assert eng.enqueue(ids, rating, mode, ts).all()
+            lob, mem, seq, st = eng.tick()
+            assert_tick_matches(eng, oracle.run_literal(cfg, ids, rating, mode), lob, mem, seq, st)
+
+
+def test_many_modes_and_team_shapes(pkg, oracle):
+    modes = (("1v1", 2, 1), ("2v2", 2, 2), ("3v3v3", 3, 3), ("5v5", 2, 5), ("solo7", 7, 1))
+    n = 120_000
+    for order in (ARRIVAL, RATING):
+        cfg = pkg.synth.make_config(n_groups=16, modes=modes, order=order, capacity=n)
+        ids, rating, mode, ts = make_pool(pkg, 33, n, n_modes=len(modes), oor=0.0)
+        with pkg.Engine(cfg) as eng:
+            assert eng.enqueue(ids, rating, mode, ts).all()
+            lob, mem, seq, st = eng.tick()
+            assert_tick_matches(eng, oracle.run_literal(cfg, ids, rating, mode), lob, mem, seq, st)
+            assert set(np.unique(lob["n_members"])) <= {2, 4, 9, 10, 7}
+
+
+# ---- active set: dedupe / remove / in_queue (models/active_user.ex, middleware/worker.ex:65-70) ----
+def test_dedupe_within_and_across_batches(pkg):
+    cfg = pkg.synth.make_config(groups=pkg.synth.REFERENCE_GROUPS, order=ARRIVAL, capacity=100)
+    with pkg.Engine(cfg) as eng:
+        acc = eng.enqueue([5, 6, 5, 7, 6, 5], [100] * 6, [0] * 6)
+        assert list(acc) == [1, 1, 0, 1, 0, 0]  # first occurrence wins
+        assert list(eng.pool_read()["id"]) == [5, 6, 7]
+        acc = eng.enqueue([8, 5, 9], [100, 100, 100], [0, 0, 0])
+        assert list(acc) == [1, 0, 1]  # "You are already in the queue."
+        assert list(eng.pool_read()["id"]) == [5, 6, 7, 8, 9]
+        assert list(eng.in_queue([5, 9, 10])) == [True, True, False]
+        assert eng.active_size() == 5
+
+
+def test_invalid_players_rejected(pkg):
+    cfg = pkg.synth.make_config(n_groups=2, order=ARRIVAL, capacity=100)  # G=2: no default group
+    assert cfg.default_group == -1
+    with pkg.Engine(cfg) as eng:
+        acc = eng.enqueue([1, 2, 3, 4, 2 ** 64 - 1], [100, 6000, -5, 100, 100], [0, 0, 0, 7, 0])
+        assert list(acc) == [1, 2, 2, 2, 2]
+        assert list(eng.pool_read()["id"]) == [1]
+
+
+def test_pool_capacity(pkg):
+    cfg = pkg.synth.make_config(groups=pkg.synth.REFERENCE_GROUPS, order=ARRIVAL, capacity=5)
+    with pkg.Engine(cfg) as eng:
+        acc = eng.enqueue(np.arange(1, 9), [100] * 8, [1] * 8)
+        assert list(acc) == [1, 1, 1, 1, 1, 3, 3, 3]
+        assert eng.pool_size() == 5 and eng.active_size() == 5
+        assert not eng.in_queue([6])[0]
+
+
+def test_matched_players_stay_active_until_removed(pkg):
+    # the lobby stage removes them later (game-lobby/worker.ex:80); search only emits
+    cfg = pkg.synth.make_config(groups=pkg.synth.REFERENCE_GROUPS, order=ARRIVAL, capacity=16)
+    with pkg.Engine(cfg) as eng:
+        eng.enqueue([1, 2, 3], [100, 100, 100], [0, 0, 0])
+        lob, mem, _, st = eng.tick()
+        assert lobby_lists(lob, mem) == [(1, 2)] and eng.pool_size() == 1
+        assert list(eng.in_queue([1, 2, 3])) == [True, True, True]
+        assert list(eng.enqueue([1], [100], [0])) == [0]  # still "in the queue"
+        assert eng.remove([1, 2, 99]) == 2
+        assert list(eng.in_queue([1, 2, 3])) == [False, False, True]
+        assert list(eng.enqueue([1], [100], [0])) == [1]
+        lob, mem, _, st = eng.tick()
+        assert lobby_lists(lob, mem) == [(3, 1)]
+
+
+@pytest.mark.parametrize("order", [ARRIVAL, RATING])
+def test_leavers_are_filtered(pkg, oracle, order):
+    # search/worker.ex:267-280: players removed while queued never reach a lobby
+    n = 60_000
+    cfg = pkg.synth.make_config(groups=pkg.synth.REFERENCE_GROUPS, order=order, capacity=n)
+    ids, rating, mode, ts = make_pool(pkg, 41, n)
+    rng = np.random.default_rng(4)
+    alive = (rng.random(n) > 0.1).astype(np.uint8)
+    with pkg.Engine(cfg) as eng:
+        assert eng.enqueue(ids, rating, mode, ts).all()
+        gone = ids[alive == 0]
+        assert eng.remove(np.concatenate([gone, gone[:10]])) == len(gone)  # twins in a batch count once
+        assert not eng.in_queue(gone).any()
+        lob, mem, seq, st = eng.tick()
+        ref = oracle.run_literal(cfg, ids, rating, mode, alive)
+        assert_tick_matches(eng, ref, lob, mem, seq, st)
+        assert not np.isin(gone, mem).any()
+
+
+def test_kat_leaver(pkg):
+    cfg = pkg.synth.make_config(groups=pkg.synth.REFERENCE_GROUPS, order=ARRIVAL, capacity=16)
+    with pkg.Engine(cfg) as eng:
+        eng.enqueue([1, 2, 3, 4, 5], [100] * 5, [0] * 5)
+        eng.remove([2])
+        lob, mem, seq, st = eng.tick()
+        assert lobby_lists(lob, mem) == [(1, 3), (4, 5)] and st.n_dead == 1 and list(seq) == [2, 4]
+
+
+# ---- residual players stay queued, in order, across ticks (save_new_state analogue) ----
+@pytest.mark.parametrize("order", [ARRIVAL, RATING])
+def test_multi_tick_stream(pkg, oracle, order):
+    cfg = pkg.synth.make_config(n_groups=8, order=order, capacity=40_000)
+    rng = np.random.default_rng(8)
+    queued = [np.zeros(0, np.uint64), np.zeros(0, np.int32), np.zeros(0, np.uint8)]
+    alive = np.zeros(0, np.uint8)
+    with pkg.Engine(cfg) as eng:
+        first = 0
+        for step in range(6):
+            n = int(rng.integers(1, 9000))
+            ids, rating, _, ts = pkg.synth.gen_pool(77, n, first=first)
+            first += n
+            mode = rng.integers(0, 2, n).astype(np.uint8)
+            assert eng.enqueue(ids, rating, mode, ts).all()
+            queued = [np.concatenate([q, x]) for q, x in zip(queued, (ids, rating, mode))]
+            alive = np.concatenate([alive, np.ones(n, np.uint8)])
+            lob, mem, seq, st = eng.tick()
+            ref = oracle.run_literal(cfg, *queued, alive=alive)
+            assert_tick_matches(eng, ref, lob, mem, seq, st)
+            keep = np.isin(queued[0], ref.residual_ids)
+            queued = [q[keep] for q in queued]
+            alive = np.ones(len(queued[0]), np.uint8)
+            pr = eng.pool_read()
+            assert np.array_equal(pr["id"], queued[0]) and np.array_equal(pr["rating"], queued[1])
+            assert np.array_equal(pr["mode"], queued[2])
+            assert np.array_equal(pr["team_size"], np.where(queued[2] == 0, 1, 5))
+            # a residual player can still be removed after the pool was compacted
+            if len(queued[0]):
+                assert eng.remove(queued[0][:1]) == 1
+                alive[0] = 0
+
+
+def test_lobby_cap_too_small_consumes_nothing(pkg):
+    cfg = pkg.synth.make_config(groups=pkg.synth.REFERENCE_GROUPS, order=ARRIVAL, capacity=64)
+    with pkg.Engine(cfg) as eng:
+        eng.enqueue(np.arange(1, 21), [100] * 20, [0] * 20)
+        import ctypes as C
+        lob = np.empty(3, pkg.engine.LOBBY_DTYPE)
+        mem = np.empty(64, np.uint64)
+        st = pkg.abi.TickStats()
+        rc = eng.lib.mm_tick(eng.h, 0, lob.ctypes.data_as(C.c_void_p), 3, mem.ctypes.data_as(C.c_void_p), 64, None,
+                             C.byref(st))
+        assert rc == pkg.abi.MM_E_CAP and eng.pool_size() == 20
+        lob, mem, _, st = eng.tick()
+        assert st.n_lobbies == 10 and eng.pool_size() == 0
+
+
+def test_snapshot_restore_replays_identically(pkg):
+    n = 100_000
+    cfg = pkg.synth.make_config(n_groups=32, order=RATING, capacity=n)
+    ids, rating, mode, ts = make_pool(pkg, 17, n)
+    with pkg.Engine(cfg) as eng:
+        assert eng.enqueue(ids, rating, mode, ts).all()
+        eng.snapshot()
+        a = eng.tick()
+        eng.restore()
+        assert eng.pool_size() == n
+        b = eng.tick()
+        assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2])
+        # device-resident variant gives the same member list
+        eng.restore()
+        st = eng.tick_device()
+        assert st.n_lobbies == a[3].n_lobbies and st.n_matched == a[3].n_matched
+
+
+# ---- BASELINE.json full size (configs[2]): size-independent properties + numpy closed form ----
+def test_config3_ten_million_5v5(pkg, oracle):
+    w = pkg.synth.WORKLOADS["config3_10m_g32_5v5"]
+    n, G = w["n"], w["n_groups"]
+    for order in (RATING, ARRIVAL):
+        cfg = pkg.synth.make_config(n_groups=G, order=order, capacity=n)
+        ids, rating, mode, ts = pkg.synth.gen_pool(1, n, mode=w["mode"])
+        with pkg.Engine(cfg) as eng:
+            assert eng.enqueue(ids, rating, mode, ts).all()
+            lob, mem, seq, st = eng.tick()
+            resid = eng.pool_read()["id"]
+        L = 10
+        assert st.n_matched == st.n_lobbies * L and st.n_matched + st.n_residual == n
+        assert st.n_residual <= (L - 1) * G
+        # permutation: every queued player is in exactly one lobby or still queued
+        allout = np.concatenate([mem, resid])
+        assert len(allout) == n and np.array_equal(np.sort(allout), np.sort(ids))
+        # every lobby is inside one rating group; rating order: sorted by (rating, enqueue)
+        pos = np.argsort(ids, kind="stable")
+        idx = pos[np.searchsorted(ids[pos], mem)]  # pool index of each member
+        r = rating[idx].reshape(-1, L)
+        los, his = pkg.synth.equal_width_groups(G)
+        g = np.searchsorted(np.array(his), r[:, 0])
+        assert np.array_equal(g, lob["group"])
+        assert (r >= np.array(los)[g][:, None]).all() and (r <= np.array(his)[g][:, None]).all()
+        # inside a group: non-decreasing rating (RATING) and, on ties, increasing enqueue index
+        full = (g.repeat(L).astype(np.int64) << 50) + \
+               ((rating[idx].astype(np.int64) << 25) if order == RATING else 0)
+        assert (np.diff(full) >= 0).all()
+        tie = np.diff(full) == 0
+        assert (np.diff(idx)[tie] > 0).all()
+        # exact: numpy closed form of the oracle
+        lm, lg, members, res = oracle.closed_form_numpy(cfg, ids, rating, mode)
+        assert np.array_equal(members, mem) and np.array_equal(res, resid)
+        assert np.array_equal(lg, lob["group"]) and np.array_equal(lm, lob["mode"])
