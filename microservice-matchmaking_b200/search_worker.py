@@ -1,0 +1,227 @@
+"""Host-side mirror of the reference search stage's worker interface.
+
+Reference: matchmaking/lib/search/worker.ex (`Matchmaking.Search.Worker`), a GenServer
+per (rating group, worker id).  The BEAM toolchain is absent in this environment
+(SURVEY F5), so the host side above the C ABI is mirrored in Python with the same
+names, argument meaning and error behaviour:
+
+    start_link(opts)                 worker.ex:68-71     opts: group_name (required), channel_name
+    configure(channel_name, opts)    worker.ex:73-76     declares/consumes the group queue
+    consume(channel_name, group_name, tag, headers, payload)   worker.ex:291-324
+    ack / nack(channel_name, tag)    worker.ex:81-90
+    status()                         worker.ex:115-117,326-334
+    handle_info(msg)                 worker.ex:337-368
+
+What changed behind the interface: consume/5 no longer pops a partial lobby from Mnesia
+and asks the strategist per request (worker.ex:295-321).  It stages the player in the
+shared `SearchPool` (the GPU-resident pool, `Matchmaking.Search.Engine` in
+INTEGRATION.md); `SearchPool.flush()` ingests a batch through mm_enqueue and acks the
+deliveries once the players are resident (manual ack after processing, worker.ex:323);
+`SearchPool.tick()` runs one search tick and publishes every emitted lobby as the same
+JSON document, to the same exchange/routing key, with the same publish options as
+prepare_game_lobby/4 (worker.ex:250-261, 315-319).  A player that is not matched is not
+re-published to the requeue exchange (worker.ex:239-248): it simply stays resident.
+
+The AMQP connection is duck-typed (declare_exchange / declare_queue / bind / qos /
+basic_consume / basic_publish / basic_ack / basic_nack / queue_status) so the same code
+drives a real client or the in-memory broker used by the tests.
+"""
+import hashlib
+import json
+
+import numpy as np
+
+# module attributes of the reference (worker.ex:23-40)
+DEFAULT_EXCHANGE_PATH = "open-matchmaking.matchmaking"
+DEFAULT_EXCHANGE_TYPE = "direct"
+DEFAULT_QUEUE_PATH = "matchmaking.queues"
+QUEUE_OPTIONS = {"durable": True}
+EXCHANGE_OPTIONS = {"type": "direct", "durable": True}
+QOS_OPTIONS = {"prefetch_count": 10}
+EXCHANGE_FORWARD = "open-matchmaking.matchmaking.game-lobby.direct"
+QUEUE_FORWARD = "matchmaking.queues.lobbies"
+EXCHANGE_REQUEUE = "open-matchmaking.matchmaking.requeue.direct"
+QUEUE_REQUEUE = "matchmaking.games.requeue"
+
+
+def generate_queue_name(suffix):  # worker.ex:46-48
+    return f"{DEFAULT_QUEUE_PATH}.{suffix}"
+
+
+def generate_exchange_name(suffix):  # worker.ex:50-52
+    return f"{DEFAULT_EXCHANGE_PATH}.{suffix}.{DEFAULT_EXCHANGE_TYPE}"
+
+
+def prepare_config(opts):  # worker.ex:54-66
+    if not opts.get("group_name"):
+        raise RuntimeError("You need to configure group_name in options.")
+    queue_name = generate_queue_name(opts["group_name"])
+    return {
+        "queue": dict(name=queue_name, routing_key=queue_name, **QUEUE_OPTIONS),
+        "exchange": dict(name=generate_exchange_name(opts["group_name"]), **EXCHANGE_OPTIONS),
+        "qos": dict(QOS_OPTIONS),
+    }
+
+
+def player_handle(player_id):
+    """u64 device handle of a player id (reference ids are UUID strings, active_user.ex:7).
+    The two top values are reserved by the engine's hash table."""
+    h = int.from_bytes(hashlib.blake2b(str(player_id).encode(), digest_size=8).digest(), "little")
+    return h if h < 0xFFFFFFFFFFFFFFFE else h - 2
+
+
+class SearchPool:
+    """Owner of the GPU pool shared by every search worker of this node.
+
+    engine: an object with the `Engine` API (enqueue / tick / remove / in_queue /
+    pool_size); mode_names: index -> "1v1", ...; group_names: index -> "bronze", ...
+    """
+
+    def __init__(self, engine, mode_names, group_names, max_batch=65536):
+        self.engine = engine
+        self.mode_names = list(mode_names)
+        self.mode_index = {m: i for i, m in enumerate(self.mode_names)}
+        self.group_names = list(group_names)
+        self.max_batch = max_batch
+        self.players = {}   # handle -> decoded player document (without "game-mode")
+        self.workers = {}   # group name -> worker that publishes the group's lobbies
+        self._staged = []   # (handle, rating, mode, player, worker, tag)
+        self.stats = {"enqueued": 0, "duplicates": 0, "invalid": 0, "lobbies": 0}
+
+    # -- models/active_user.ex mirrors ---------------------------------------------------
+    def in_queue(self, player_id):  # ActiveUser.in_queue?/1
+        return bool(self.engine.in_queue([player_handle(player_id)])[0])
+
+    def remove_user(self, player_id):  # ActiveUser.remove_user/1 -> {:ok, :removed}
+        self.flush()
+        h = player_handle(player_id)
+        self.engine.remove([h])
+        self.players.pop(h, None)
+        return ("ok", "removed")
+
+    # -- ingest -----------------------------------------------------------------------------
+    def stage(self, worker, tag, player, game_mode, rating):
+        self._staged.append((player_handle(player["id"]), int(rating), game_mode, player, worker, tag))
+        if len(self._staged) >= self.max_batch:
+            self.flush()
+
+    def flush(self):
+        """mm_enqueue the staged deliveries; ack each one once its player is resident."""
+        staged, self._staged = self._staged, []
+        if not staged:
+            return 0
+        ids = np.array([s[0] for s in staged], np.uint64)
+        rating = np.clip(np.array([s[1] for s in staged], np.int64), -(2 ** 31), 2 ** 31 - 1).astype(np.int32)
+        mode = np.array([self.mode_index.get(s[2], 255) for s in staged], np.uint8)
+        acc = self.engine.enqueue(ids, rating, mode, None)
+        for code, (h, _r, _m, player, worker, tag) in zip(acc, staged):
+            if code == 1:
+                self.players[h] = player
+                self.stats["enqueued"] += 1
+                worker.ack(worker.channel_name, tag)       # worker.ex:323
+            elif code == 0:                                 # "You are already in the queue."
+                self.stats["duplicates"] += 1
+                worker.ack(worker.channel_name, tag)
+            else:                                           # unknown mode / unroutable rating / full
+                self.stats["invalid"] += 1
+                worker.nack(worker.channel_name, tag)
+        return len(staged)
+
+    # -- the tick ---------------------------------------------------------------------------
+    def tick(self, now=0):
+        """One search tick; publishes each lobby like prepare_game_lobby/4. -> lobbies emitted"""
+        self.flush()
+        lob, mem, _seq, _st = self.engine.tick(now)
+        for h in lob:
+            mode_name = self.mode_names[h["mode"]]
+            group_name = self.group_names[h["group"]]
+            first, n = int(h["first_member"]), int(h["n_members"])
+            members = [self.players.pop(int(x)) for x in mem[first:first + n]]
+            size = n // self._teams_of(h["mode"])
+            teams = {f"team {t + 1}": members[t * size:(t + 1) * size] for t in range(n // size)}
+            payload = json.dumps({"teams": teams, "game-mode": mode_name})      # worker.ex:315-318
+            worker = self.workers.get(group_name) or next(iter(self.workers.values()))
+            worker.prepare_game_lobby(worker.channel_name, EXCHANGE_FORWARD, QUEUE_FORWARD, payload)
+        self.stats["lobbies"] += len(lob)
+        return len(lob)
+
+    def _teams_of(self, mode):
+        return self.engine.cfg.modes[int(mode)].teams
+
+
+class SearchWorker:
+    """Matchmaking.Search.Worker — one consumer of `matchmaking.queues.<group>`."""
+
+    CHANNEL_NAME = "Matchmaking.Search.Worker.Channel"  # worker.ex:20
+
+    def __init__(self, connection, pool, config, opts):
+        self.connection, self.pool = connection, pool
+        self.config = config
+        self.channel_name = opts.get("channel_name", self.CHANNEL_NAME)
+        self.group_name = opts["group_name"]
+        self.channel = None
+        self.meta = None
+
+    # worker.ex:68-71 + init/1 :220-237
+    @classmethod
+    def start_link(cls, connection, pool, opts):
+        config = prepare_config(opts)
+        if connection is None:
+            return ("error", "noconn")  # worker.ex:225-228
+        w = cls(connection, pool, config, opts)
+        w.channel = connection.spawn_channel(w.channel_name)
+        connection.configure_channel(w.channel, config)  # exchange + queue + bind + qos (worker.ex:27-29)
+        ok, w.meta = w.configure(w.channel_name, config)
+        pool.workers[w.group_name] = w
+        return ("ok", w)
+
+    def configure(self, channel_name, opts):  # worker.ex:73-76
+        consumer = self.create_consumer(channel_name, opts["queue"]["name"])
+        return ("ok", {"consumer": consumer})
+
+    def create_consumer(self, channel_name, queue_name):  # worker.ex:95-103
+        return self.channel.basic_consume(queue_name, self)
+
+    def ack(self, channel_name, tag):  # worker.ex:81-83
+        return self.channel.basic_ack(tag)
+
+    def nack(self, channel_name, tag):  # worker.ex:88-90
+        return self.channel.basic_nack(tag)
+
+    def status(self):  # worker.ex:115-117, 326-334
+        st = dict(self.channel.queue_status(self.config["queue"]["name"]))
+        st["pool"] = self.pool.engine.status() if hasattr(self.pool.engine, "status") else {}
+        return ("ok", st)
+
+    def prepare_game_lobby(self, channel_name, exchange_forward, queue_forward, payload):  # worker.ex:250-261
+        return self.channel.basic_publish(exchange_forward, queue_forward, payload, persistent=True,
+                                          content_type="application/json")
+
+    # worker.ex:291-324 — one delivery
+    def consume(self, channel_name, group_name, tag, headers, payload):
+        player_data = json.loads(payload)                         # :292
+        game_mode = player_data.pop("game-mode", None)           # :294
+        rating = player_data.get("rating")                        # generic/worker.ex:57 reads it top-level
+        if rating is None and isinstance(player_data.get("detail"), dict):
+            rating = player_data["detail"].get("rating")
+        if "id" not in player_data or game_mode is None or not isinstance(rating, (int, float)):
+            return self.nack(channel_name, tag)
+        if isinstance(rating, float) and rating != int(rating):
+            rating = 2 ** 31 - 1  # falls between the integer ranges -> default group (generic/worker.ex:46-53)
+        self.pool.stage(self, tag, player_data, game_mode, rating)
+
+    # worker.ex:337-368
+    def handle_info(self, msg):
+        kind = msg[0]
+        if kind in ("basic_consume_ok", "basic_cancel_ok"):
+            return ("noreply", self)
+        if kind == "basic_cancel":
+            return ("stop", "normal", self)
+        if kind == "basic_deliver":
+            _, payload, headers = msg
+            self.consume(self.channel_name, self.group_name, headers.get("delivery_tag"), headers, payload)
+            return ("noreply", self)
+        if kind == "DOWN":  # re-register the consumer (worker.ex:361-368)
+            self.meta = {"consumer": self.create_consumer(self.channel_name, self.config["queue"]["name"])}
+            return ("noreply", self)
+        return ("noreply", self)

@@ -1,0 +1,119 @@
+"""Host mirror of Matchmaking.Search.Worker (search_worker.py): queue/exchange names,
+ack-after-resident semantics, lobby JSON shape, duplicates, leavers.  The same scenario
+runs on the CPU (OracleEngine test double) and on the GPU (real Engine via the C ABI)."""
+import importlib
+import json
+
+import numpy as np
+import pytest
+
+from .fakes import FakeBroker, OracleEngine
+
+sw = importlib.import_module("microservice-matchmaking_b200.search_worker")
+
+
+def boot(pkg, engine_cls, order=0):
+    cfg = pkg.synth.make_config(groups=pkg.synth.REFERENCE_GROUPS, order=order, capacity=10_000)
+    eng = engine_cls(cfg)
+    broker = FakeBroker()
+    pool = sw.SearchPool(eng, ["1v1", "5v5"], pkg.synth.REFERENCE_GROUP_NAMES)
+    workers = {}
+    for g in pkg.synth.REFERENCE_GROUP_NAMES:  # application.ex:26-40: one worker per rating group
+        ok, w = sw.SearchWorker.start_link(broker, pool, {"group_name": g, "channel_name": f"search.{g}"})
+        assert ok == "ok"
+        workers[g] = w
+    broker.bind(sw.EXCHANGE_FORWARD, sw.QUEUE_FORWARD, sw.QUEUE_FORWARD)  # the lobby stage's queue
+    return cfg, eng, broker, pool, workers
+
+
+def publish_player(pkg, broker, cfg, pid, rating, mode, extra=None):
+    """What Generic.Worker.consume/4 does (generic/worker.ex:55-69): route by rating group."""
+    from oracle import oracle as orc
+    gi = orc.find_rating_group(cfg, rating)
+    name = pkg.synth.REFERENCE_GROUP_NAMES[gi]
+    doc = {"id": pid, "rating": rating, "game-mode": mode, "response-queue": f"resp.{pid}", "event-name": "find-game"}
+    doc.update(extra or {})
+    broker.publish(sw.generate_exchange_name(name), sw.generate_queue_name(name), json.dumps(doc))
+
+
+def scenario(pkg, engine_cls):
+    cfg, eng, broker, pool, workers = boot(pkg, engine_cls)
+    assert workers["gold"].config["queue"]["name"] == "matchmaking.queues.gold"  # worker.ex:46-66
+    assert workers["gold"].config["exchange"]["name"] == "open-matchmaking.matchmaking.gold.direct"
+    assert workers["gold"].config["qos"] == {"prefetch_count": 10}
+    players = [("u1", 100, "1v1"), ("u2", 2100, "1v1"), ("u3", 150, "1v1"), ("u4", 2200, "1v1"),
+               ("u5", 4500, "1v1"), ("u1", 100, "1v1")]  # u1 twice: "already in the queue"
+    for pid, r, m in players:
+        publish_player(pkg, broker, cfg, pid, r, m)
+    assert broker.deliver_all() == 6
+    assert not broker.acked  # nothing is acked before the players are resident
+    assert pool.tick() == 2
+    assert len(broker.acked) == 6 and not broker.nacked
+    assert pool.stats == {"enqueued": 5, "duplicates": 1, "invalid": 0, "lobbies": 2}
+    lobbies = [json.loads(p) for p, _ in broker.queues[sw.QUEUE_FORWARD]]
+    props = [pr for _, pr in broker.queues[sw.QUEUE_FORWARD]]
+    assert all(pr == {"persistent": True, "content_type": "application/json"} for pr in props)  # worker.ex:254-258
+    assert [set(l) for l in lobbies] == [{"teams", "game-mode"}] * 2  # worker.ex:315-318
+    got = sorted(tuple(p["id"] for t in sorted(l["teams"]) for p in l["teams"][t]) for l in lobbies)
+    assert got == [("u1", "u3"), ("u2", "u4")]
+    l0 = lobbies[0]
+    assert l0["game-mode"] == "1v1" and set(l0["teams"]) == {"team 1", "team 2"}
+    p = l0["teams"]["team 1"][0]
+    assert "game-mode" not in p and p["response-queue"].startswith("resp.") and p["event-name"] == "find-game"
+    # the lobby stage's slot count (game-lobby/worker.ex:37-39)
+    assert sum(len(v) for v in l0["teams"].values()) == 2
+    # u5 is still searching; matched players stay "in queue" until the lobby stage removes them
+    assert pool.in_queue("u5") and pool.in_queue("u1")
+    assert pool.remove_user("u1") == ("ok", "removed") and not pool.in_queue("u1")
+    ok, st = workers["grandmaster"].status()
+    assert ok == "ok" and st["queue"] == "matchmaking.queues.grandmaster" and st["consumer_count"] == 1
+    # a leaver is never matched (search/worker.ex:267-280)
+    pool.remove_user("u5")
+    publish_player(pkg, broker, cfg, "u6", 4400, "1v1")
+    publish_player(pkg, broker, cfg, "u7", 4600, "1v1")
+    broker.deliver_all()
+    assert pool.tick() == 1
+    last = json.loads(broker.queues[sw.QUEUE_FORWARD][-1][0])
+    assert [p["id"] for t in ("team 1", "team 2") for p in last["teams"][t]] == ["u6", "u7"]
+    # 5v5: ten players of one group -> one lobby, team 1 = first five joiners
+    for i in range(10):
+        publish_player(pkg, broker, cfg, f"v{i}", 3000 + i, "5v5")
+    publish_player(pkg, broker, cfg, "bad", 3000, "7v7")  # unknown mode -> nack
+    broker.deliver_all()
+    assert pool.tick() == 1 and len(broker.nacked) == 1
+    last = json.loads(broker.queues[sw.QUEUE_FORWARD][-1][0])
+    assert last["game-mode"] == "5v5"
+    assert [p["id"] for p in last["teams"]["team 1"]] == [f"v{i}" for i in range(5)]
+    assert [p["id"] for p in last["teams"]["team 2"]] == [f"v{i}" for i in range(5, 10)]
+    eng.close()
+
+
+def test_worker_scenario_cpu(pkg):
+    scenario(pkg, OracleEngine)
+
+
+@pytest.mark.gpu
+def test_worker_scenario_gpu(pkg):
+    scenario(pkg, pkg.Engine)
+
+
+def test_start_link_contract(pkg):
+    with pytest.raises(RuntimeError, match="group_name"):
+        sw.prepare_config({})  # worker.ex:55-57
+    pool = sw.SearchPool(OracleEngine(pkg.synth.make_config(n_groups=7)), ["1v1"], list("abcdefg"))
+    assert sw.SearchWorker.start_link(None, pool, {"group_name": "gold"}) == ("error", "noconn")  # worker.ex:225-228
+
+
+def test_handle_info_clauses(pkg):
+    cfg, eng, broker, pool, workers = boot(pkg, OracleEngine)
+    w = workers["bronze"]
+    assert w.handle_info(("basic_consume_ok", {}))[0] == "noreply"
+    assert w.handle_info(("basic_cancel", {}))[:2] == ("stop", "normal")
+    assert w.handle_info(("basic_cancel_ok", {}))[0] == "noreply"
+    assert w.handle_info(("DOWN", None))[0] == "noreply" and "consumer" in w.meta
+
+
+def test_player_handle_is_stable_and_in_range():
+    h = sw.player_handle("c0a8012e-1c9b-4b7e-9d2f-5f1d3a2b4c6d")
+    assert h == sw.player_handle("c0a8012e-1c9b-4b7e-9d2f-5f1d3a2b4c6d") and 0 <= h < 2 ** 64 - 2
+    assert len({sw.player_handle(f"p{i}") for i in range(10000)}) == 10000
