@@ -165,7 +165,7 @@ def main():
     order = abi.MM_ORDER_RATING if args.order == "rating" else abi.MM_ORDER_ARRIVAL
     w, _ = workload_cfg(pkg, args.workload, order, rank, world, 1)
     n, L = w["n"], (2 if w["mode"] == 0 else 10)
-    cfg = pkg.synth.make_config(n_groups=w["n_groups"], order=order, capacity=n, device=local)
+    cfg = pkg.synth.make_config(n_groups=w["n_groups"], order=order, capacity=n + 65536, device=local)
     # rank r's shard of the N x n pool: its own seed stream (weak scaling, disjoint ids)
     ids, rating, mode, ts = pkg.synth.gen_pool(1, n, first=rank * n, mode=w["mode"])
 
@@ -278,7 +278,7 @@ def main():
                        "lobby_size": L, "order": args.order, "ratings": "uniform 0..5000, seed 1",
                        "parallelism": f"rating-group shards x{world}, no collective",
                        "l2": "flushed between steps (256 MiB write); pool 180 MB > L2",
-                       "timed_region": "mm_tick_device: k_hist+k_colscan+k_place+k_finish+k_headers, CUDA events "
+                       "timed_region": "mm_tick_device: k_hist+k_colscan+k_place+k_epilogue, CUDA events "
                                        "on the engine stream; snapshot restore + L2 flush between steps untimed"},
             "players_per_s": n * world * args.steps / tick_s,
             "wall_ms_per_step_incl_restore": 1e3 * wall_s / args.steps,
@@ -288,7 +288,7 @@ def main():
             "tick_roofline": {"bytes_per_player": B_ALG_TICK, "achieved": B_ALG_TICK * n * args.steps / tick_s / 1e9,
                               "frac": B_ALG_TICK * n * args.steps / tick_s / 1e9 / peak, "unit": "GB/s",
                               "frac_of_8000": B_ALG_TICK * n * args.steps / tick_s / 1e9 / 8000.0},
-            "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": 5 * args.steps, "clocks": clocks,
+            "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": 4 * args.steps, "clocks": clocks,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

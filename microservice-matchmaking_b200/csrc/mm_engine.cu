@@ -52,6 +52,7 @@ struct mm_engine {
   uint8_t* d_mode_tsize = nullptr;
   uint32_t* d_seg_bin_lo = nullptr;
   uint32_t* d_seg_L = nullptr;
+  uint16_t* d_bin_seg = nullptr;  // [Kp] bin -> (mode, group) segment
   uint32_t min_L = 1;
 
   // pool (double buffered) + snapshot
@@ -74,8 +75,11 @@ struct mm_engine {
   uint32_t R = 0;
   int rows_per_sm = 1;
   int rank_impl = 1;
+  int l2_hints = 1;
+  int place_debug = 0;
+  size_t persist_bytes = 0;
   uint32_t* d_M = nullptr;
-  uint32_t *d_tot = nullptr, *d_binbase = nullptr, *d_outbase = nullptr, *d_binlim = nullptr;
+  uint32_t *d_tot = nullptr, *d_binbase = nullptr, *d_seg_lim = nullptr;
   SegInfo* d_seg = nullptr;
   uint32_t* d_seg_shift = nullptr;
   uint64_t* d_members = nullptr;
@@ -215,6 +219,11 @@ int build_tables(mm_engine* e) {
     for (uint32_t g = 0; g < G; ++g) { seg_lo[m * G + g] = m * e->stride + first[g]; seg_L[m * G + g] = L; }
   }
   seg_lo[e->n_segs] = e->K;
+  std::vector<uint16_t> bin_seg(e->Kp, 0);
+  for (uint32_t sgi = 0; sgi < e->n_segs; ++sgi)
+    for (uint32_t b = seg_lo[sgi]; b < seg_lo[sgi + 1]; ++b) bin_seg[b] = (uint16_t)sgi;
+  CK(cudaMalloc(&e->d_bin_seg, e->Kp * 2));
+  CK(cudaMemcpy(e->d_bin_seg, bin_seg.data(), e->Kp * 2, cudaMemcpyHostToDevice));
   CK(cudaMalloc(&e->d_lut, e->KR * 2));
   CK(cudaMalloc(&e->d_grp_lut, e->KR));
   CK(cudaMalloc(&e->d_mode_tsize, MM_MAX_MODES));
@@ -316,9 +325,9 @@ int tick_phase_a(mm_engine* e, uint32_t n, uint32_t* chunk_out) {
   CK(cudaMemsetAsync(e->d_ctr, 0, sizeof(TickCtr), e->stream));
   CK(cudaEventRecord(e->ev[0], e->stream));
   k_hist<<<e->R, kBlock, hist_smem(e), e->stream>>>(p.v, n, chunk, bin_map(e), e->Kp, e->d_M);
-  k_colscan<<<(e->Kp + kScanBlock - 1) / kScanBlock, kScanBlock, 0, e->stream>>>(
-      e->R, e->Kp, e->K, e->d_M, e->d_tot, e->d_binbase, e->d_outbase, e->d_binlim, e->d_seg_bin_lo, e->d_seg_L,
-      e->n_segs, e->d_seg, e->d_seg_shift, e->d_ctr);
+  k_colscan<<<(e->Kp + 31) / 32, 1024, 0, e->stream>>>(e->R, e->Kp, e->K, e->d_M, e->d_tot, e->d_binbase, e->d_seg_bin_lo,
+                                                        e->d_seg_L, e->n_segs, e->d_seg, e->d_seg_shift, e->d_seg_lim,
+                                                        e->d_ctr);
   CK(cudaGetLastError());
   return MM_OK;
 }
@@ -328,18 +337,21 @@ int tick_phase_b(mm_engine* e, uint32_t n, uint32_t chunk, bool want_seq) {
   Pool& q = e->pool[e->cur ^ 1];
   uint32_t* src_idx = want_seq ? e->d_src_idx : nullptr;
   CK(cudaEventRecord(e->ev[1], e->stream));
-  if (e->rank_impl == 1)
-    k_place<1><<<e->R, kBlock, place_smem(e, 1), e->stream>>>(p.v, n, chunk, bin_map(e), e->Kp, e->R, e->d_M, e->d_tot,
-                                                              e->d_outbase, e->d_binlim, e->d_members, src_idx,
-                                                              e->d_resid_stage, e->d_rescnt, e->d_ctr);
-  else
-    k_place<0><<<e->R, kBlock, place_smem(e, 0), e->stream>>>(p.v, n, chunk, bin_map(e), e->Kp, e->R, e->d_M, e->d_tot,
-                                                              e->d_outbase, e->d_binlim, e->d_members, src_idx,
-                                                              e->d_resid_stage, e->d_rescnt, e->d_ctr);
+#define MM_PLACE(IMPL, DBG, HINT)                                                                                    \
+  k_place<IMPL, DBG, HINT><<<e->R, kBlock, place_smem(e, IMPL), e->stream>>>(                                         \
+      p.v, n, chunk, bin_map(e), e->Kp, e->R, e->d_M, e->d_tot, e->d_binbase, e->d_bin_seg, e->d_seg_shift,           \
+      e->d_seg_lim, e->n_segs, e->d_members, src_idx, e->d_resid_stage, e->d_rescnt, e->d_ctr)
+  if (e->rank_impl == 0) MM_PLACE(0, 0, false);
+  else if (e->place_debug == 1) MM_PLACE(1, 1, true);
+  else if (e->place_debug == 2) MM_PLACE(1, 2, true);
+  else if (e->place_debug == 3) MM_PLACE(1, 3, true);
+  else if (e->l2_hints) MM_PLACE(1, 0, true);
+  else MM_PLACE(1, 0, false);
+#undef MM_PLACE
   CK(cudaEventRecord(e->ev[2], e->stream));
-  k_finish<<<1, 1024, 0, e->stream>>>(p.v, q.v, e->R, e->d_rescnt, e->d_resid_stage, act_view(e), e->gen + 1, e->d_ctr);
-  k_headers<<<std::max(1, e->n_sms * 2), 256, 0, e->stream>>>(e->d_seg, e->d_seg_L, e->n_segs, e->cfg.n_groups, e->d_ctr,
-                                                              e->d_hdr, src_idx, want_seq ? e->d_emit_seq : nullptr);
+  k_epilogue<<<std::max(1, e->n_sms), 1024, 0, e->stream>>>(p.v, q.v, e->R, e->d_rescnt, e->d_resid_stage, act_view(e),
+                                                           e->gen + 1, e->d_seg, e->d_seg_L, e->n_segs, e->cfg.n_groups,
+                                                           e->d_hdr, src_idx, want_seq ? e->d_emit_seq : nullptr, e->d_ctr);
   CK(cudaGetLastError());
   CK(cudaEventRecord(e->ev[3], e->stream));
   CK(cudaMemcpyAsync(e->h_ctr, e->d_ctr, sizeof(TickCtr), cudaMemcpyDeviceToHost, e->stream));
@@ -355,7 +367,7 @@ int tick_commit(mm_engine* e, uint32_t n, mm_tick_stats* stats) {
   }
   mm_tick_stats st{};
   st.pool_before = n; st.n_lobbies = c.n_lobbies; st.n_matched = c.n_matched; st.n_residual = c.n_resid;
-  st.n_dead = c.n_dead; st.n_launches = 5;
+  st.n_dead = c.n_dead; st.n_launches = 4;
   float ms = 0;
   CK(cudaEventElapsedTime(&ms, e->ev[0], e->ev[3]));
   st.device_us = ms * 1000.f;
@@ -446,11 +458,18 @@ int mm_create(const mm_config* cfg, mm_engine** out) {
     std::snprintf(e->last_err, sizeof(e->last_err), "key domain too large for shared memory: %u bins", e->Kp);
     return bail(MM_E_ARG);
   }
-  if (cudaFuncSetAttribute(k_hist, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hist_smem(e)) != cudaSuccess ||
-      cudaFuncSetAttribute(k_place<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)place_smem(e, 0)) != cudaSuccess ||
-      (e->rank_impl == 1 &&
-       cudaFuncSetAttribute(k_place<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)place_smem(e, 1)) != cudaSuccess))
-    return bail(fail(e, cudaGetLastError(), "cudaFuncSetAttribute"));
+  {
+    const int s0 = (int)place_smem(e, 0), s1 = (int)place_smem(e, 1);
+    bool ok = cudaFuncSetAttribute(k_hist, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hist_smem(e)) == cudaSuccess &&
+              cudaFuncSetAttribute(k_place<0, 0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, s0) == cudaSuccess;
+    if (ok && e->rank_impl == 1)
+      ok = cudaFuncSetAttribute(k_place<1, 0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, s1) == cudaSuccess &&
+           cudaFuncSetAttribute(k_place<1, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, s1) == cudaSuccess &&
+           cudaFuncSetAttribute(k_place<1, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, s1) == cudaSuccess &&
+           cudaFuncSetAttribute(k_place<1, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, s1) == cudaSuccess &&
+           cudaFuncSetAttribute(k_place<1, 3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, s1) == cudaSuccess;
+    if (!ok) return bail(fail(e, cudaGetLastError(), "cudaFuncSetAttribute"));
+  }
   if ((rc = alloc_pool(e, e->pool[0], e->capacity)) || (rc = alloc_pool(e, e->pool[1], e->capacity))) return bail(rc);
   if (e->use_active) {
     uint64_t want = cfg->active_capacity ? cfg->active_capacity : 2ull * cfg->capacity;
@@ -466,7 +485,7 @@ int mm_create(const mm_config* cfg, mm_engine** out) {
   e->max_lobbies = e->capacity / e->min_L + 1;
   auto A = [&](void** p, size_t bytes) { return cudaMalloc(p, bytes) == cudaSuccess; };
   if (!A((void**)&e->d_tot, (e->Kp + 1) * 4) || !A((void**)&e->d_binbase, (e->Kp + 1) * 4) ||
-      !A((void**)&e->d_outbase, (e->Kp + 1) * 4) || !A((void**)&e->d_binlim, (e->Kp + 1) * 4) ||
+      !A((void**)&e->d_seg_lim, e->n_segs * 4) ||
       !A((void**)&e->d_seg, e->n_segs * sizeof(SegInfo)) || !A((void**)&e->d_seg_shift, e->n_segs * 4) ||
       !A((void**)&e->d_members, cap * 8) || !A((void**)&e->d_src_idx, cap * 4) ||
       !A((void**)&e->d_hdr, (size_t)e->max_lobbies * sizeof(mm_lobby_hdr)) ||
@@ -488,7 +507,7 @@ int mm_destroy(mm_engine* e) {
   free_pool(e->pool[0]); free_pool(e->pool[1]); free_pool(e->snap);
   for (auto& t : e->tab) { cudaFree(t.keys); cudaFree(t.vals); }
   cudaFree(e->d_lut); cudaFree(e->d_grp_lut); cudaFree(e->d_mode_tsize); cudaFree(e->d_seg_bin_lo); cudaFree(e->d_seg_L);
-  cudaFree(e->d_M); cudaFree(e->d_tot); cudaFree(e->d_binbase); cudaFree(e->d_outbase); cudaFree(e->d_binlim);
+  cudaFree(e->d_M); cudaFree(e->d_tot); cudaFree(e->d_binbase); cudaFree(e->d_seg_lim); cudaFree(e->d_bin_seg);
   cudaFree(e->d_seg); cudaFree(e->d_seg_shift); cudaFree(e->d_members); cudaFree(e->d_src_idx); cudaFree(e->d_hdr);
   cudaFree(e->d_emit_seq); cudaFree(e->d_resid_stage); cudaFree(e->d_rescnt); cudaFree(e->d_ctr); cudaFree(e->d_small);
   cudaFree(e->d_in_id); cudaFree(e->d_hslot); cudaFree(e->d_in_rating); cudaFree(e->d_in_mode); cudaFree(e->d_code);
@@ -521,8 +540,38 @@ int mm_set_option(mm_engine* e, const char* name, int64_t value) {
   if (!std::strcmp(name, "rank_impl")) {
     if (value != 0 && value != 1) return MM_E_ARG;
     if (value == 1 && place_smem(e, 1) > e->smem_optin) return MM_E_ARG;
-    if (value == 1) CK(cudaFuncSetAttribute(k_place<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)place_smem(e, 1)));
     e->rank_impl = (int)value;
+    return MM_OK;
+  }
+  if (!std::strcmp(name, "l2_hints")) { e->l2_hints = value != 0; return MM_OK; }
+  if (!std::strcmp(name, "place_debug")) {  // timing experiments only: results are NOT valid
+    if (value < 0 || value > 3) return MM_E_ARG;
+    e->place_debug = (int)value;
+    return MM_OK;
+  }
+  if (!std::strcmp(name, "persist_mb")) {  // pin member_ids in a persisting L2 carve-out
+    CK(cudaStreamSynchronize(e->stream));
+    cudaStreamAttrValue attr{};
+    if (value > 0) {
+      int max_persist = 0, max_win = 0;
+      CK(cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, e->device));
+      CK(cudaDeviceGetAttribute(&max_win, cudaDevAttrMaxAccessPolicyWindowSize, e->device));
+      size_t want = std::min<size_t>((size_t)value << 20, (size_t)max_persist);
+      CK(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want));
+      size_t win = std::min<size_t>({(size_t)e->capacity * 8, (size_t)max_win});
+      attr.accessPolicyWindow.base_ptr = e->d_members;
+      attr.accessPolicyWindow.num_bytes = win;
+      attr.accessPolicyWindow.hitRatio = win ? std::min(1.0f, (float)want / (float)win) : 0.f;
+      attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+      attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+      e->persist_bytes = want;
+      std::snprintf(e->last_err, sizeof(e->last_err), "persist: max_persist=%d max_window=%d set=%zu window=%zu",
+                    max_persist, max_win, want, win);
+    } else {
+      attr.accessPolicyWindow.num_bytes = 0;
+      e->persist_bytes = 0;
+    }
+    CK(cudaStreamSetAttribute(e->stream, cudaStreamAttributeAccessPolicyWindow, &attr));
     return MM_OK;
   }
   if (!std::strcmp(name, "rows_per_sm")) {

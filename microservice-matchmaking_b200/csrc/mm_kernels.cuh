@@ -12,8 +12,7 @@
 //   k_colscan  column prefix + bin bases + per-segment lobby arithmetic (tiny)
 //   k_place    stable rank inside the row -> final lobby-major slot; scatters
 //              player_id straight to member_ids (reads 13 B/player, writes 8 B)
-//   k_finish   residual players -> compacted pool (enqueue order kept)
-//   k_headers  lobby headers from the segment table
+//   k_epilogue residual players -> compacted pool (enqueue order kept) + lobby headers
 // Integer/HBM-bound work: no tensor cores (BASELINE.json north_star).
 #pragma once
 #include <cuda_runtime.h>
@@ -75,6 +74,38 @@ __device__ __forceinline__ uint64_t hash64(uint64_t x) {
   return x;
 }
 
+// L2 cache-policy hints.  The placement kernel scatters 8-byte ids into member_ids: the
+// 4 writes that complete a 32-byte sector arrive at unrelated times, so member_ids has to
+// stay L2-resident until the kernel ends (evict_last) while the input columns stream
+// through once (evict_first, no L1 allocation).
+__device__ __forceinline__ uint64_t policy_evict_first() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ uint64_t policy_evict_last() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ int32_t ld_stream_s32(const int32_t* a, uint64_t pol) {
+  int32_t v;
+  asm volatile("ld.global.L1::no_allocate.L2::cache_hint.s32 %0, [%1], %2;" : "=r"(v) : "l"(a), "l"(pol));
+  return v;
+}
+__device__ __forceinline__ uint32_t ld_stream_u8(const uint8_t* a, uint64_t pol) {
+  uint32_t v;
+  asm volatile("ld.global.L1::no_allocate.L2::cache_hint.u8 %0, [%1], %2;" : "=r"(v) : "l"(a), "l"(pol));
+  return v;
+}
+__device__ __forceinline__ uint64_t ld_stream_u64(const uint64_t* a, uint64_t pol) {
+  uint64_t v;
+  asm volatile("ld.global.L1::no_allocate.L2::cache_hint.u64 %0, [%1], %2;" : "=l"(v) : "l"(a), "l"(pol));
+  return v;
+}
+__device__ __forceinline__ void st_keep_u64(uint64_t* a, uint64_t v, uint64_t pol) {
+  asm volatile("st.global.L2::cache_hint.u64 [%0], %1, %2;" ::"l"(a), "l"(v), "l"(pol) : "memory");
+}
 
 // In-place exclusive scan of a shared-memory array a[0..n) by the whole CTA; returns the
 // total.  s_tmp must hold BLOCK words.  (n is a few hundred to a few thousand.)
@@ -123,16 +154,29 @@ __global__ void __launch_bounds__(kBlock) k_hist(PoolView p, uint32_t n, uint32_
   const uint64_t beg64 = (uint64_t)blockIdx.x * chunk;
   const uint32_t beg = beg64 < n ? (uint32_t)beg64 : n;
   const uint32_t end = (beg64 + chunk < n) ? (uint32_t)(beg64 + chunk) : n;
-  for (uint32_t i = beg + tid * 4; i < end; i += kBlock * 4) {
-    if (i + 4 <= end) {
-      const int4 r = __ldcs(reinterpret_cast<const int4*>(p.rating + i));
-      const uint32_t m = __ldcs(reinterpret_cast<const uint32_t*>(p.mode + i));
-      atomicAdd(&hist[bin_of(bm, s_lut, r.x, m & 0xFF)], 1u);
-      atomicAdd(&hist[bin_of(bm, s_lut, r.y, (m >> 8) & 0xFF)], 1u);
-      atomicAdd(&hist[bin_of(bm, s_lut, r.z, (m >> 16) & 0xFF)], 1u);
-      atomicAdd(&hist[bin_of(bm, s_lut, r.w, m >> 24)], 1u);
+  // plain (cacheable) loads: rating+mode are read again by k_place and 5 B/player fits L2
+  for (uint32_t i = beg + tid * 4; i < end; i += kBlock * 8) {
+    const uint32_t i2 = i + kBlock * 4;
+    int4 r0 = make_int4(0, 0, 0, 0), r1 = r0;
+    uint32_t m0 = 0, m1 = 0;
+    const bool f0 = i + 4 <= end, f1 = i2 + 4 <= end;
+    if (f0) { r0 = *reinterpret_cast<const int4*>(p.rating + i); m0 = *reinterpret_cast<const uint32_t*>(p.mode + i); }
+    if (f1) { r1 = *reinterpret_cast<const int4*>(p.rating + i2); m1 = *reinterpret_cast<const uint32_t*>(p.mode + i2); }
+    if (f0) {
+      atomicAdd(&hist[bin_of(bm, s_lut, r0.x, m0 & 0xFF)], 1u);
+      atomicAdd(&hist[bin_of(bm, s_lut, r0.y, (m0 >> 8) & 0xFF)], 1u);
+      atomicAdd(&hist[bin_of(bm, s_lut, r0.z, (m0 >> 16) & 0xFF)], 1u);
+      atomicAdd(&hist[bin_of(bm, s_lut, r0.w, m0 >> 24)], 1u);
     } else {
       for (uint32_t e = i; e < end; ++e) atomicAdd(&hist[bin_of(bm, s_lut, p.rating[e], p.mode[e])], 1u);
+    }
+    if (f1) {
+      atomicAdd(&hist[bin_of(bm, s_lut, r1.x, m1 & 0xFF)], 1u);
+      atomicAdd(&hist[bin_of(bm, s_lut, r1.y, (m1 >> 8) & 0xFF)], 1u);
+      atomicAdd(&hist[bin_of(bm, s_lut, r1.z, (m1 >> 16) & 0xFF)], 1u);
+      atomicAdd(&hist[bin_of(bm, s_lut, r1.w, m1 >> 24)], 1u);
+    } else {
+      for (uint32_t e = i2; e < end; ++e) atomicAdd(&hist[bin_of(bm, s_lut, p.rating[e], p.mode[e])], 1u);
     }
   }
   __syncthreads();
@@ -141,42 +185,46 @@ __global__ void __launch_bounds__(kBlock) k_hist(PoolView p, uint32_t n, uint32_
 }
 
 // ---------------------------------------------------------------------------------------
-// k_colscan: exclusive prefix down every column of M; the last block to finish then
-// scans the bin totals and does the per-segment lobby arithmetic:
-//   lobbies_s = n_s / L,  matched_s = lobbies_s * L,  residual_s = n_s - matched_s
-// outbase[bin] = sorted position of the bin's first player minus the residual players
-// of earlier segments (= its slot in member_ids); binlim[bin] = end of the segment's
-// matched slots.  A player whose slot is >= binlim stays queued.
+// k_colscan: exclusive prefix down every column of M.  A CTA is 32 bins wide (lanes =
+// consecutive bins, coalesced) and 32 row-slices deep (warps): every thread sums its
+// slice of rows, the slices are scanned through shared memory, then the slice is
+// rewritten as running prefixes — one round trip of latency instead of R.
+// The last CTA to finish scans the bin totals (-> binbase) and does the per-segment
+// lobby arithmetic:  lobbies_s = n_s / L, matched_s = lobbies_s * L, residual_s = n_s % L,
+//   seg_shift[s] = residual players of earlier segments (sorted position -> member slot)
+//   seg_lim[s]   = end of the segment's matched slots; a player at or past it stays queued.
 // ---------------------------------------------------------------------------------------
-constexpr int kScanBlock = 256;
 constexpr uint32_t kMaxSegs = MM_MAX_GROUPS * MM_MAX_MODES;
 
-__global__ void __launch_bounds__(kScanBlock) k_colscan(uint32_t R, uint32_t Kp, uint32_t K, uint32_t* __restrict__ M,
-                                                        uint32_t* __restrict__ tot, uint32_t* __restrict__ binbase,
-                                                        uint32_t* __restrict__ outbase, uint32_t* __restrict__ binlim,
-                                                        const uint32_t* __restrict__ seg_bin_lo,
-                                                        const uint32_t* __restrict__ seg_L, uint32_t n_segs,
-                                                        SegInfo* __restrict__ seg, uint32_t* __restrict__ seg_shift,
-                                                        TickCtr* ctr) {
-  const uint32_t tid = threadIdx.x;
-  const uint32_t b = blockIdx.x * kScanBlock + tid;
-  if (b < Kp) {
-    uint32_t run = 0;
-    uint32_t* col = M + b;
-    constexpr int kT = 16;  // rows loaded per step: keeps 16 independent loads in flight
-    for (uint32_t r0 = 0; r0 < R; r0 += kT) {
-      uint32_t v[kT];
-#pragma unroll
-      for (int t = 0; t < kT; ++t) v[t] = (r0 + t < R) ? __ldcg(col + (size_t)(r0 + t) * Kp) : 0u;
-#pragma unroll
-      for (int t = 0; t < kT; ++t) {
-        if (r0 + t < R) col[(size_t)(r0 + t) * Kp] = run;
-        run += v[t];
-      }
-    }
-    tot[b] = run;
-  }
+__global__ void __launch_bounds__(1024) k_colscan(uint32_t R, uint32_t Kp, uint32_t K, uint32_t* __restrict__ M,
+                                                  uint32_t* __restrict__ tot, uint32_t* __restrict__ binbase,
+                                                  const uint32_t* __restrict__ seg_bin_lo,
+                                                  const uint32_t* __restrict__ seg_L, uint32_t n_segs,
+                                                  SegInfo* __restrict__ seg, uint32_t* __restrict__ seg_shift,
+                                                  uint32_t* __restrict__ seg_lim, TickCtr* ctr) {
+  __shared__ uint32_t s_part[32][33];
+  __shared__ uint32_t s_tmp[1024];
   __shared__ uint32_t s_last;
+  const uint32_t tid = threadIdx.x, x = tid & 31, y = tid >> 5;
+  const uint32_t b = blockIdx.x * 32 + x;
+  const uint32_t rp = (R + 31) / 32;
+  const uint32_t r0 = y * rp < R ? y * rp : R, r1 = (r0 + rp < R) ? r0 + rp : R;
+  uint32_t sum = 0;
+  if (b < Kp)
+    for (uint32_t r = r0; r < r1; ++r) sum += __ldcg(M + (size_t)r * Kp + b);
+  s_part[y][x] = sum;
+  __syncthreads();
+  uint32_t run = 0;
+  for (uint32_t yy = 0; yy < y; ++yy) run += s_part[yy][x];
+  if (b < Kp) {
+    for (uint32_t r = r0; r < r1; ++r) {
+      uint32_t* p = M + (size_t)r * Kp + b;
+      const uint32_t v = __ldcg(p);
+      *p = run;
+      run += v;
+    }
+    if (y == 31) tot[b] = run;
+  }
   __threadfence();
   __syncthreads();
   if (tid == 0) s_last = (atomicAdd(&ctr->ticket, 1u) == gridDim.x - 1) ? 1u : 0u;
@@ -185,56 +233,47 @@ __global__ void __launch_bounds__(kScanBlock) k_colscan(uint32_t R, uint32_t Kp,
   __threadfence();
 
   // exclusive scan of tot[0..Kp) -> binbase[0..Kp]
-  __shared__ uint32_t s_sum[kScanBlock];
-  const uint32_t per = (Kp + kScanBlock - 1) / kScanBlock;
-  const uint32_t lo = tid * per, hi = (lo + per < Kp) ? lo + per : Kp;
-  uint32_t local = 0;
-  for (uint32_t i = lo; i < hi; ++i) local += __ldcg(&tot[i]);
-  s_sum[tid] = local;
-  __syncthreads();
-  for (int off = 1; off < kScanBlock; off <<= 1) {  // Hillis-Steele inclusive scan
-    uint32_t v = (tid >= (uint32_t)off) ? s_sum[tid - off] : 0;
+  {
+    const uint32_t per = (Kp + 1023) / 1024;
+    const uint32_t lo = tid * per < Kp ? tid * per : Kp, hi = (lo + per < Kp) ? lo + per : Kp;
+    uint32_t local = 0;
+    for (uint32_t i = lo; i < hi; ++i) local += __ldcg(&tot[i]);
+    s_tmp[tid] = local;
     __syncthreads();
-    s_sum[tid] += v;
+    for (int off = 1; off < 1024; off <<= 1) {
+      const uint32_t v = (tid >= (uint32_t)off) ? s_tmp[tid - off] : 0;
+      __syncthreads();
+      s_tmp[tid] += v;
+      __syncthreads();
+    }
+    uint32_t acc = s_tmp[tid] - local;
+    for (uint32_t i = lo; i < hi; ++i) { binbase[i] = acc; acc += __ldcg(&tot[i]); }
+    if (tid == 1023) binbase[Kp] = s_tmp[1023];
+    __threadfence_block();
     __syncthreads();
   }
-  uint32_t run = s_sum[tid] - local;
-  for (uint32_t i = lo; i < hi; ++i) { binbase[i] = run; run += __ldcg(&tot[i]); }
-  if (tid == kScanBlock - 1) binbase[Kp] = s_sum[kScanBlock - 1];
-  __threadfence_block();
-  __syncthreads();
-
   // per-segment arithmetic: three small scans over the <= modes*groups segments
   __shared__ uint32_t s_res[kMaxSegs], s_lob[kMaxSegs], s_n[kMaxSegs];
-  for (uint32_t s = tid; s < n_segs; s += kScanBlock) {
+  for (uint32_t s = tid; s < n_segs; s += 1024) {
     const uint32_t ns = binbase[seg_bin_lo[s + 1]] - binbase[seg_bin_lo[s]];
     const uint32_t nl = ns / seg_L[s];
     s_n[s] = ns; s_lob[s] = nl; s_res[s] = ns - nl * seg_L[s];
+    seg[s].n = ns; seg[s].n_lobbies = nl;
   }
   __syncthreads();
-  for (uint32_t s = tid; s < n_segs; s += kScanBlock) { seg[s].n = s_n[s]; seg[s].n_lobbies = s_lob[s]; }
-  const uint32_t tot_res = block_excl_scan<kScanBlock>(s_res, n_segs, s_sum);
-  const uint32_t tot_lob = block_excl_scan<kScanBlock>(s_lob, n_segs, s_sum);
-  const uint32_t tot_alive = block_excl_scan<kScanBlock>(s_n, n_segs, s_sum);
-  for (uint32_t s = tid; s < n_segs; s += kScanBlock) {
-    seg[s].member_base = binbase[seg_bin_lo[s]] - s_res[s];
+  const uint32_t tot_res = block_excl_scan<1024>(s_res, n_segs, s_tmp);
+  const uint32_t tot_lob = block_excl_scan<1024>(s_lob, n_segs, s_tmp);
+  const uint32_t tot_alive = block_excl_scan<1024>(s_n, n_segs, s_tmp);
+  for (uint32_t s = tid; s < n_segs; s += 1024) {
+    const uint32_t mb = binbase[seg_bin_lo[s]] - s_res[s];
+    seg[s].member_base = mb;
     seg[s].lobby_base = s_lob[s];
     seg_shift[s] = s_res[s];
+    seg_lim[s] = mb + seg[s].n_lobbies * seg_L[s];
   }
   if (tid == 0) {
     ctr->n_lobbies = tot_lob; ctr->n_matched = tot_alive - tot_res; ctr->n_alive = tot_alive;
     ctr->n_dead = __ldcg(&tot[K]);
-  }
-  __threadfence_block();
-  __syncthreads();
-  for (uint32_t i = tid; i < Kp; i += kScanBlock) {
-    if (i >= K) { outbase[i] = 0; binlim[i] = 0; continue; }
-    uint32_t a = 0, c = n_segs;  // last s with seg_bin_lo[s] <= i
-    while (c - a > 1) { const uint32_t mid = (a + c) >> 1; if (seg_bin_lo[mid] <= i) a = mid; else c = mid; }
-    // skip empty segments that share the same lower bound
-    while (a + 1 < n_segs && seg_bin_lo[a + 1] <= i) ++a;
-    outbase[i] = binbase[i] - seg_shift[a];
-    binlim[i] = seg[a].member_base + seg[a].n_lobbies * seg_L[a];
   }
 }
 
@@ -251,15 +290,19 @@ __global__ void __launch_bounds__(kScanBlock) k_colscan(uint32_t R, uint32_t Kp,
 //       slot = snapshot + sum(sizes of earlier groups) + rank inside the group.
 //       The first pusher advances cnt[bin] by the round's total.
 // Bit 31 of cnt marks a (row, bin) cell that reaches past the segment's matched range:
-// only those players consult binlim (the < L leftovers of a partition stay queued).
+// only those players consult seg_lim (the < L leftovers of a partition stay queued).
 // IMPL 0 is a slow warp-serial ranking kept as an on-device cross-check.
+// DBG != 0 are timing experiments (wrong results, never used by the ABI's tick):
+//   1 = rank but store coalesced, 2 = no rank + pseudo-random scatter, 3 = streaming copy.
 // ---------------------------------------------------------------------------------------
-template <int IMPL>
+template <int IMPL, int DBG, bool HINT>
 __global__ void __launch_bounds__(kBlock, 1)
     k_place(PoolView p, uint32_t n, uint32_t chunk, BinMap bm, uint32_t Kp, uint32_t R, const uint32_t* __restrict__ M,
-            const uint32_t* __restrict__ tot, const uint32_t* __restrict__ outbase, const uint32_t* __restrict__ binlim,
-            uint64_t* __restrict__ members, uint32_t* __restrict__ src_idx, uint32_t* __restrict__ resid_stage,
-            uint32_t* __restrict__ rescnt, TickCtr* ctr) {
+            const uint32_t* __restrict__ tot, const uint32_t* __restrict__ binbase,
+            const uint16_t* __restrict__ bin_seg, const uint32_t* __restrict__ seg_shift,
+            const uint32_t* __restrict__ seg_lim, uint32_t n_segs, uint64_t* __restrict__ members,
+            uint32_t* __restrict__ src_idx, uint32_t* __restrict__ resid_stage, uint32_t* __restrict__ rescnt,
+            TickCtr* ctr) {
   extern __shared__ __align__(16) uint32_t smem[];
   uint32_t* cnt = smem;
   uint32_t* head = cnt + Kp;                                 // IMPL 1 only
@@ -267,18 +310,26 @@ __global__ void __launch_bounds__(kBlock, 1)
   uint32_t* res_list = node + (IMPL == 1 ? kRound : 0);      // [kResCap]
   uint16_t* s_lut = reinterpret_cast<uint16_t*>(res_list + kResCap);
   __shared__ uint32_t s_nres;
+  __shared__ uint32_t s_shift[kMaxSegs], s_lim[kMaxSegs];
 
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t lt_mask = (1u << lane) - 1u;
   const uint32_t row = blockIdx.x;
+  const uint64_t pol_in = policy_evict_first(), pol_out = policy_evict_last();
+  for (uint32_t i = tid; i < n_segs; i += kBlock) { s_shift[i] = seg_shift[i]; s_lim[i] = seg_lim[i]; }
+  __syncthreads();
   {
     const uint32_t* mrow = M + (size_t)row * Kp;
     const uint32_t* mnext = (row + 1 < R) ? mrow + Kp : tot;  // prefix of the next row, or column total
     for (uint32_t i = tid; i < Kp; i += kBlock) {
-      const uint32_t pre = mrow[i], c = mnext[i] - pre;
-      const uint32_t start = outbase[i] + pre;
-      const uint32_t flag = (start + c > binlim[i]) ? 0x80000000u : 0u;
-      cnt[i] = start | flag;
+      uint32_t v = 0;
+      if (i < bm.K) {
+        const uint32_t pre = mrow[i], c = mnext[i] - pre;
+        const uint32_t sg = bin_seg[i];
+        const uint32_t start = binbase[i] - s_shift[sg] + pre;  // slot of the cell's first player
+        v = start | ((start + c > s_lim[sg]) ? 0x80000000u : 0u);
+      }
+      cnt[i] = v;
       if (IMPL == 1) head[i] = 0;
     }
     for (uint32_t i = tid; i < bm.KR; i += kBlock) s_lut[i] = bm.lut[i];
@@ -299,9 +350,16 @@ __global__ void __launch_bounds__(kBlock, 1)
     for (int j = 0; j < kJ; ++j) {
       const uint32_t e = base + j * kBlock + tid;
       if (e < end) {
-        const int32_t r = __ldcs(p.rating + e);
-        const uint32_t m = __ldcs(p.mode + e);
-        idv[j] = __ldcs(reinterpret_cast<const unsigned long long*>(p.id + e));
+        int32_t r; uint32_t m;
+        if (HINT) {
+          r = ld_stream_s32(p.rating + e, pol_in);
+          m = ld_stream_u8(p.mode + e, pol_in);
+          idv[j] = ld_stream_u64(p.id + e, pol_in);
+        } else {
+          r = __ldcs(p.rating + e);
+          m = __ldcs(p.mode + e);
+          idv[j] = __ldcs(reinterpret_cast<const unsigned long long*>(p.id + e));
+        }
         bin[j] = bin_of(bm, s_lut, r, m);
       } else {
         bin[j] = 0xFFFFFFFFu;
@@ -310,7 +368,10 @@ __global__ void __launch_bounds__(kBlock, 1)
     }
     uint32_t leader[kJ], rankw[kJ], base_g[kJ];
 
-    if (IMPL == 1) {
+    if (DBG >= 2) {
+#pragma unroll
+      for (int j = 0; j < kJ; ++j) { leader[j] = 0; rankw[j] = 0; base_g[j] = 0; }
+    } else if (IMPL == 1) {
       const uint32_t epoch = round + 1;
       uint32_t snap[kJ], mynode[kJ];
       bool isl[kJ], first[kJ];
@@ -374,11 +435,14 @@ __global__ void __launch_bounds__(kBlock, 1)
     for (int j = 0; j < kJ; ++j) {
       if (bin[j] < bm.K) {
         const uint32_t e = base + j * kBlock + tid;
-        const uint32_t slot = (base_g[j] & 0x7FFFFFFFu) + rankw[j];
+        uint32_t slot = (base_g[j] & 0x7FFFFFFFu) + rankw[j];
         bool matched = true;
-        if (base_g[j] >> 31) matched = slot < __ldg(&binlim[bin[j]]);
+        if (base_g[j] >> 31) matched = slot < s_lim[__ldg(&bin_seg[bin[j]])];
+        if (DBG == 1 || DBG == 3) { slot = e; matched = true; }
+        if (DBG == 2) { slot = (uint32_t)(((uint64_t)e * 2654435761ull) % n); matched = true; }
         if (matched) {
-          members[slot] = idv[j];
+          if (HINT) st_keep_u64(members + slot, idv[j], pol_out);
+          else members[slot] = idv[j];
           if (src_idx) src_idx[slot] = e;
         } else {
           const uint32_t k = atomicAdd(&s_nres, 1u);
@@ -406,23 +470,45 @@ __global__ void __launch_bounds__(kBlock, 1)
 }
 
 // ---------------------------------------------------------------------------------------
-// k_finish (one CTA): concatenate the rows' residual lists (rows are in enqueue order),
+// k_epilogue.  CTA 0: concatenate the rows' residual lists (rows are in enqueue order),
 // gather the five pool columns into the alternate pool buffer and re-stamp the residual
-// players' active-set entries with their new slot.  Replaces save_new_state/3
+// players' active-set entries with their new slot — replaces save_new_state/3
 // (search/worker.ex:282-289): the "partial lobby" is simply the players left resident.
+// Every CTA: lobby headers from the segment table — lobby c of segment s = members
+// [member_base + k*L, +L); replaces the payload assembly at search/worker.ex:315-319.
 // ---------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(1024) k_finish(PoolView src, PoolView dst, uint32_t R, const uint32_t* __restrict__ rescnt,
-                                                 const uint32_t* __restrict__ resid_stage,
-                                                 ActiveView act, uint32_t new_gen, TickCtr* ctr) {
+__global__ void __launch_bounds__(1024) k_epilogue(PoolView src, PoolView dst, uint32_t R, const uint32_t* __restrict__ rescnt,
+                                                   const uint32_t* __restrict__ resid_stage, ActiveView act, uint32_t new_gen,
+                                                   const SegInfo* __restrict__ seg, const uint32_t* __restrict__ seg_L,
+                                                   uint32_t n_segs, uint32_t n_groups, mm_lobby_hdr* __restrict__ hdr,
+                                                   const uint32_t* __restrict__ src_idx, uint32_t* __restrict__ emit_seq,
+                                                   TickCtr* ctr) {
   __shared__ uint32_t s_off[kMaxRows + 1];
   __shared__ uint32_t s_tmp[1024];
+  __shared__ uint32_t s_lbase[kMaxSegs + 1], s_mbase[kMaxSegs], s_L[kMaxSegs];
   const uint32_t tid = threadIdx.x;
+  for (uint32_t s = tid; s < n_segs; s += 1024) { s_lbase[s] = seg[s].lobby_base; s_mbase[s] = seg[s].member_base; s_L[s] = seg_L[s]; }
+  __syncthreads();
+  const uint32_t total_lob = ctr->n_lobbies;
+  for (uint32_t c = blockIdx.x * 1024 + tid; c < total_lob; c += gridDim.x * 1024) {
+    uint32_t a = 0, e = n_segs;  // last segment with lobby_base <= c
+    while (e - a > 1) { const uint32_t mid = (a + e) >> 1; if (s_lbase[mid] <= c) a = mid; else e = mid; }
+    const uint32_t L = s_L[a];
+    mm_lobby_hdr h;
+    h.first_member = s_mbase[a] + (c - s_lbase[a]) * L;
+    h.n_members = (uint16_t)L;
+    h.mode = (uint8_t)(a / n_groups);
+    h.group = (uint8_t)(a % n_groups);
+    hdr[c] = h;
+    if (emit_seq) emit_seq[c] = src_idx[h.first_member + L - 1];
+  }
+  if (blockIdx.x != 0) return;
+
   for (uint32_t r = tid; r < R; r += 1024) s_off[r] = rescnt[r];
   __syncthreads();
-  const uint32_t s_total = block_excl_scan<1024>(s_off, R, s_tmp);
-  if (tid == 0) { s_off[R] = s_total; ctr->n_resid = s_total; }
+  const uint32_t total = block_excl_scan<1024>(s_off, R, s_tmp);
+  if (tid == 0) { s_off[R] = total; ctr->n_resid = total; }
   __syncthreads();
-  const uint32_t total = s_total;
   for (uint32_t t = tid; t < total; t += 1024) {
     uint32_t a = 0, c = R;  // last row with s_off[row] <= t
     while (c - a > 1) { const uint32_t mid = (a + c) >> 1; if (s_off[mid] <= t) a = mid; else c = mid; }
@@ -439,27 +525,6 @@ __global__ void __launch_bounds__(1024) k_finish(PoolView src, PoolView dst, uin
         h = (h + 1) & act.mask;
       }
     }
-  }
-}
-
-// k_headers: lobby c of segment s = members [member_base + k*L, +L).  Replaces the
-// payload assembly at search/worker.ex:315-319 ({"teams": ..., "game-mode": ...}).
-__global__ void k_headers(const SegInfo* __restrict__ seg, const uint32_t* __restrict__ seg_L, uint32_t n_segs,
-                          uint32_t n_groups, const TickCtr* __restrict__ ctr, mm_lobby_hdr* __restrict__ hdr,
-                          const uint32_t* __restrict__ src_idx, uint32_t* __restrict__ emit_seq) {
-  const uint32_t total = ctr->n_lobbies;
-  for (uint32_t c = blockIdx.x * blockDim.x + threadIdx.x; c < total; c += gridDim.x * blockDim.x) {
-    uint32_t a = 0, e = n_segs;
-    while (e - a > 1) { const uint32_t mid = (a + e) >> 1; if (seg[mid].lobby_base <= c) a = mid; else e = mid; }
-    while (a + 1 < n_segs && seg[a + 1].lobby_base <= c) ++a;
-    const uint32_t L = seg_L[a];
-    mm_lobby_hdr h;
-    h.first_member = seg[a].member_base + (c - seg[a].lobby_base) * L;
-    h.n_members = (uint16_t)L;
-    h.mode = (uint8_t)(a / n_groups);
-    h.group = (uint8_t)(a % n_groups);
-    hdr[c] = h;
-    if (emit_seq) emit_seq[c] = src_idx[h.first_member + L - 1];
   }
 }
 

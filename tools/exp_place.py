@@ -1,0 +1,37 @@
+"""Timing experiments for the placement kernel (GPU).  Prints device/place microseconds
+for the L2-hint / persisting-window / debug variants on one workload."""
+import importlib, json, sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+pkg = importlib.import_module("microservice-matchmaking_b200")
+name = sys.argv[1] if len(sys.argv) > 1 else "config3_10m_g32_5v5"
+order = int(sys.argv[2]) if len(sys.argv) > 2 else 1
+w = pkg.synth.WORKLOADS[name]
+n = w["n"]
+cfg = pkg.synth.make_config(n_groups=w["n_groups"], order=order, capacity=n + 65536)
+ids, rating, mode, ts = pkg.synth.gen_pool(1, n, mode=w["mode"])
+eng = pkg.Engine(cfg)
+assert eng.enqueue(ids, rating, mode, ts).all()
+eng.snapshot()
+flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+def run(label, reps=6, **opts):
+    for k, v in opts.items():
+        eng.set_option(k, v)
+    dev, pl = [], []
+    for i in range(reps):
+        eng.restore(); flush.fill_(1); torch.cuda.synchronize()
+        st = eng.tick_device()
+        if i >= 2: dev.append(st.device_us); pl.append(st.place_us)
+    print(json.dumps({"variant": label, "workload": name, "order": order, "device_us": round(float(np.mean(dev)), 1),
+                      "place_us": round(float(np.mean(pl)), 1), "place_min": round(float(np.min(pl)), 1), "lobbies": st.n_lobbies}), flush=True)
+run("hints=0", l2_hints=0, place_debug=0, persist_mb=0)
+run("hints=1", l2_hints=1)
+run("hints=1 persist=96MB", persist_mb=96)
+print("persist info:", eng.lib.mm_last_error(eng.h).decode())
+run("hints=0 persist=96MB", l2_hints=0)
+run("hints=1 persist=64MB", l2_hints=1, persist_mb=64)
+run("dbg1 rank+coalesced store", persist_mb=0, place_debug=1)
+run("dbg2 norank+random scatter", place_debug=2)
+run("dbg2 + persist96", place_debug=2, persist_mb=96)
+run("dbg3 streaming copy", place_debug=3, persist_mb=0)
+run("rank_impl=0 (warp-serial)", place_debug=0, rank_impl=0)
