@@ -78,6 +78,8 @@ struct mm_engine {
   int l2_hints = 1;
   int place_debug = 0;
   size_t persist_bytes = 0;
+  uint32_t place2_stages = 0;  // 0 = k_place2 does not fit in shared memory
+  uint16_t* d_bins16 = nullptr;
   uint32_t* d_M = nullptr;
   uint32_t *d_tot = nullptr, *d_binbase = nullptr, *d_seg_lim = nullptr;
   SegInfo* d_seg = nullptr;
@@ -117,7 +119,7 @@ int fail(mm_engine* e, cudaError_t err, const char* what) {
   } while (0)
 
 int alloc_pool(mm_engine* e, Pool& p, uint32_t cap) {
-  const size_t c = (size_t)cap + 64;
+  const size_t c = (size_t)cap + 3 * kRound;  // TMA tiles are read whole: pad past the last row
   CK(cudaMalloc(&p.v.id, c * 8));
   CK(cudaMalloc(&p.v.rating, c * 4));
   CK(cudaMalloc(&p.v.mode, c));
@@ -171,6 +173,9 @@ int check_config(const mm_config* c) {
 size_t place_smem(const mm_engine* e, int impl) {
   size_t words = e->Kp + (impl == 1 ? (size_t)e->Kp + kRound : 0) + kResCap;
   return words * 4 + (size_t)e->KR * 2 + 16;
+}
+size_t place2_smem(const mm_engine* e, uint32_t stages) {
+  return (size_t)stages * kTileBytes + 64 + ((size_t)2 * e->Kp + kTile + kResCap) * 4;
 }
 size_t hist_smem(const mm_engine* e) { return (size_t)e->Kp * 4 + (size_t)e->KR * 2 + 16; }
 
@@ -316,6 +321,34 @@ int enqueue_device_locked(mm_engine* e, uint32_t n, const uint64_t* id, const in
   return MM_OK;
 }
 
+// Pin member_ids in a persisting L2 carve-out: the 8-byte scatter of k_place completes
+// 32-byte sectors at unrelated times, so the lines must survive in L2 until the kernel ends
+// (measured: -50 us and -79 MB of DRAM fill reads on the 10M-player tick).
+int set_persist(mm_engine* e, int64_t mb) {
+  CK(cudaStreamSynchronize(e->stream));
+  cudaStreamAttrValue attr{};
+  if (mb > 0) {
+    int max_persist = 0, max_win = 0;
+    CK(cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, e->device));
+    CK(cudaDeviceGetAttribute(&max_win, cudaDevAttrMaxAccessPolicyWindowSize, e->device));
+    const size_t want = std::min<size_t>((size_t)mb << 20, (size_t)max_persist);
+    if (want == 0) return MM_OK;
+    CK(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want));
+    const size_t win = std::min<size_t>({(size_t)e->capacity * 8, (size_t)max_win});
+    attr.accessPolicyWindow.base_ptr = e->d_members;
+    attr.accessPolicyWindow.num_bytes = win;
+    attr.accessPolicyWindow.hitRatio = win ? std::min(1.0f, (float)want / (float)win) : 0.f;
+    attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+    attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+    e->persist_bytes = want;
+  } else {
+    attr.accessPolicyWindow.num_bytes = 0;
+    e->persist_bytes = 0;
+  }
+  CK(cudaStreamSetAttribute(e->stream, cudaStreamAttributeAccessPolicyWindow, &attr));
+  return MM_OK;
+}
+
 // launches k_hist + k_colscan and returns the counters (phase A of a tick)
 int tick_phase_a(mm_engine* e, uint32_t n, uint32_t* chunk_out) {
   const Pool& p = e->pool[e->cur];
@@ -324,7 +357,8 @@ int tick_phase_a(mm_engine* e, uint32_t n, uint32_t* chunk_out) {
   *chunk_out = chunk;
   CK(cudaMemsetAsync(e->d_ctr, 0, sizeof(TickCtr), e->stream));
   CK(cudaEventRecord(e->ev[0], e->stream));
-  k_hist<<<e->R, kBlock, hist_smem(e), e->stream>>>(p.v, n, chunk, bin_map(e), e->Kp, e->d_M);
+  k_hist<<<e->R, kBlock, hist_smem(e), e->stream>>>(p.v, n, chunk, bin_map(e), e->Kp, e->d_M,
+                                                    e->rank_impl == 3 ? e->d_bins16 : nullptr);
   k_colscan<<<(e->Kp + 31) / 32, 1024, 0, e->stream>>>(e->R, e->Kp, e->K, e->d_M, e->d_tot, e->d_binbase, e->d_seg_bin_lo,
                                                         e->d_seg_L, e->n_segs, e->d_seg, e->d_seg_shift, e->d_seg_lim,
                                                         e->d_ctr);
@@ -341,7 +375,11 @@ int tick_phase_b(mm_engine* e, uint32_t n, uint32_t chunk, bool want_seq) {
   k_place<IMPL, DBG, HINT><<<e->R, kBlock, place_smem(e, IMPL), e->stream>>>(                                         \
       p.v, n, chunk, bin_map(e), e->Kp, e->R, e->d_M, e->d_tot, e->d_binbase, e->d_bin_seg, e->d_seg_shift,           \
       e->d_seg_lim, e->n_segs, e->d_members, src_idx, e->d_resid_stage, e->d_rescnt, e->d_ctr)
-  if (e->rank_impl == 0) MM_PLACE(0, 0, false);
+  if (e->rank_impl == 3)
+    k_place2<<<e->R, kBlock, place2_smem(e, e->place2_stages), e->stream>>>(
+        e->d_bins16, p.v.id, n, chunk, e->K, e->Kp, e->R, e->place2_stages, e->d_M, e->d_tot, e->d_binbase, e->d_bin_seg,
+        e->d_seg_shift, e->d_seg_lim, e->n_segs, e->d_members, src_idx, e->d_resid_stage, e->d_rescnt, e->d_ctr);
+  else if (e->rank_impl == 0) MM_PLACE(0, 0, false);
   else if (e->place_debug == 1) MM_PLACE(1, 1, true);
   else if (e->place_debug == 2) MM_PLACE(1, 2, true);
   else if (e->place_debug == 3) MM_PLACE(1, 3, true);
@@ -468,6 +506,14 @@ int mm_create(const mm_config* cfg, mm_engine** out) {
            cudaFuncSetAttribute(k_place<1, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, s1) == cudaSuccess &&
            cudaFuncSetAttribute(k_place<1, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, s1) == cudaSuccess &&
            cudaFuncSetAttribute(k_place<1, 3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, s1) == cudaSuccess;
+    // the TMA-fed kernel wants >= 2 ring stages next to its per-bin state
+    for (uint32_t st = kMaxStages; st >= 2 && e->rank_impl == 1 && e->Kp <= 65535u; --st)
+      if (place2_smem(e, st) + 8192 <= e->smem_optin) { e->place2_stages = st; break; }
+    if (ok && e->place2_stages) {
+      ok = cudaFuncSetAttribute(k_place2, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)place2_smem(e, e->place2_stages)) == cudaSuccess;
+      e->rank_impl = 3;
+    }
     if (!ok) return bail(fail(e, cudaGetLastError(), "cudaFuncSetAttribute"));
   }
   if ((rc = alloc_pool(e, e->pool[0], e->capacity)) || (rc = alloc_pool(e, e->pool[1], e->capacity))) return bail(rc);
@@ -488,6 +534,7 @@ int mm_create(const mm_config* cfg, mm_engine** out) {
       !A((void**)&e->d_seg_lim, e->n_segs * 4) ||
       !A((void**)&e->d_seg, e->n_segs * sizeof(SegInfo)) || !A((void**)&e->d_seg_shift, e->n_segs * 4) ||
       !A((void**)&e->d_members, cap * 8) || !A((void**)&e->d_src_idx, cap * 4) ||
+      !A((void**)&e->d_bins16, (cap + 3 * kRound) * 2) ||
       !A((void**)&e->d_hdr, (size_t)e->max_lobbies * sizeof(mm_lobby_hdr)) ||
       !A((void**)&e->d_emit_seq, (size_t)e->max_lobbies * 4) || !A((void**)&e->d_ctr, sizeof(TickCtr)) ||
       !A((void**)&e->d_small, 64))
@@ -495,6 +542,7 @@ int mm_create(const mm_config* cfg, mm_engine** out) {
   if (cudaMallocHost(&e->h_ctr, sizeof(TickCtr)) != cudaSuccess || cudaMallocHost(&e->h_small, 64) != cudaSuccess)
     return bail(MM_E_CUDA);
   if ((rc = alloc_tick_scratch(e))) return bail(rc);
+  if ((rc = set_persist(e, 1024))) return bail(rc);  // clamped to the device's persisting-L2 maximum
   if (cudaStreamSynchronize(e->stream) != cudaSuccess) return bail(MM_E_CUDA);
   *out = e;
   return MM_OK;
@@ -507,7 +555,7 @@ int mm_destroy(mm_engine* e) {
   free_pool(e->pool[0]); free_pool(e->pool[1]); free_pool(e->snap);
   for (auto& t : e->tab) { cudaFree(t.keys); cudaFree(t.vals); }
   cudaFree(e->d_lut); cudaFree(e->d_grp_lut); cudaFree(e->d_mode_tsize); cudaFree(e->d_seg_bin_lo); cudaFree(e->d_seg_L);
-  cudaFree(e->d_M); cudaFree(e->d_tot); cudaFree(e->d_binbase); cudaFree(e->d_seg_lim); cudaFree(e->d_bin_seg);
+  cudaFree(e->d_M); cudaFree(e->d_tot); cudaFree(e->d_binbase); cudaFree(e->d_seg_lim); cudaFree(e->d_bin_seg); cudaFree(e->d_bins16);
   cudaFree(e->d_seg); cudaFree(e->d_seg_shift); cudaFree(e->d_members); cudaFree(e->d_src_idx); cudaFree(e->d_hdr);
   cudaFree(e->d_emit_seq); cudaFree(e->d_resid_stage); cudaFree(e->d_rescnt); cudaFree(e->d_ctr); cudaFree(e->d_small);
   cudaFree(e->d_in_id); cudaFree(e->d_hslot); cudaFree(e->d_in_rating); cudaFree(e->d_in_mode); cudaFree(e->d_code);
@@ -530,7 +578,7 @@ int mm_set_stream(mm_engine* e, void* s) {
   if (e->own_stream && e->stream) cudaStreamDestroy(e->stream);
   e->stream = (cudaStream_t)s;
   e->own_stream = false;
-  return MM_OK;
+  return set_persist(e, e->persist_bytes ? (int64_t)(e->persist_bytes >> 20) : 0);
 }
 
 int mm_set_option(mm_engine* e, const char* name, int64_t value) {
@@ -538,8 +586,17 @@ int mm_set_option(mm_engine* e, const char* name, int64_t value) {
   std::lock_guard<std::mutex> lk(e->mu);
   CK(cudaSetDevice(e->device));
   if (!std::strcmp(name, "rank_impl")) {
-    if (value != 0 && value != 1) return MM_E_ARG;
+    if (value != 0 && value != 1 && value != 3) return MM_E_ARG;
     if (value == 1 && place_smem(e, 1) > e->smem_optin) return MM_E_ARG;
+    if (value == 1) {
+      const int s1 = (int)place_smem(e, 1);
+      CK(cudaFuncSetAttribute(k_place<1, 0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, s1));
+      CK(cudaFuncSetAttribute(k_place<1, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, s1));
+      CK(cudaFuncSetAttribute(k_place<1, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, s1));
+      CK(cudaFuncSetAttribute(k_place<1, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, s1));
+      CK(cudaFuncSetAttribute(k_place<1, 3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, s1));
+    }
+    if (value == 3 && !e->place2_stages) return MM_E_ARG;
     e->rank_impl = (int)value;
     return MM_OK;
   }
@@ -549,29 +606,11 @@ int mm_set_option(mm_engine* e, const char* name, int64_t value) {
     e->place_debug = (int)value;
     return MM_OK;
   }
-  if (!std::strcmp(name, "persist_mb")) {  // pin member_ids in a persisting L2 carve-out
-    CK(cudaStreamSynchronize(e->stream));
-    cudaStreamAttrValue attr{};
-    if (value > 0) {
-      int max_persist = 0, max_win = 0;
-      CK(cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, e->device));
-      CK(cudaDeviceGetAttribute(&max_win, cudaDevAttrMaxAccessPolicyWindowSize, e->device));
-      size_t want = std::min<size_t>((size_t)value << 20, (size_t)max_persist);
-      CK(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want));
-      size_t win = std::min<size_t>({(size_t)e->capacity * 8, (size_t)max_win});
-      attr.accessPolicyWindow.base_ptr = e->d_members;
-      attr.accessPolicyWindow.num_bytes = win;
-      attr.accessPolicyWindow.hitRatio = win ? std::min(1.0f, (float)want / (float)win) : 0.f;
-      attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
-      attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
-      e->persist_bytes = want;
-      std::snprintf(e->last_err, sizeof(e->last_err), "persist: max_persist=%d max_window=%d set=%zu window=%zu",
-                    max_persist, max_win, want, win);
-    } else {
-      attr.accessPolicyWindow.num_bytes = 0;
-      e->persist_bytes = 0;
-    }
-    CK(cudaStreamSetAttribute(e->stream, cudaStreamAttributeAccessPolicyWindow, &attr));
+  if (!std::strcmp(name, "persist_mb")) return set_persist(e, value);
+  if (!std::strcmp(name, "place2_stages")) {
+    if (value < 1 || value > (int64_t)kMaxStages || place2_smem(e, (uint32_t)value) + 8192 > e->smem_optin) return MM_E_ARG;
+    CK(cudaFuncSetAttribute(k_place2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)place2_smem(e, (uint32_t)value)));
+    e->place2_stages = (uint32_t)value;
     return MM_OK;
   }
   if (!std::strcmp(name, "rows_per_sm")) {

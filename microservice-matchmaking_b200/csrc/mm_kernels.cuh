@@ -28,6 +28,9 @@ constexpr uint32_t kRound = kBlock * kJ;
 constexpr uint32_t kNone = 0x1FFFu;   // list terminator (13-bit node ids)
 constexpr uint32_t kResCap = 2048;    // residual players one row may hold
 constexpr uint32_t kMaxRows = 2048;   // rows (CTAs) of the histogram matrix
+constexpr uint32_t kTile = 2048;      // players per TMA tile in k_place2
+constexpr uint32_t kMaxStages = 4;    // depth of the (bin, id) shared-memory ring
+constexpr uint32_t kTileBytes = kTile * (8 + 2);
 constexpr uint64_t kEmptyKey = 0xFFFFFFFFFFFFFFFFull;
 constexpr uint64_t kTombKey = 0xFFFFFFFFFFFFFFFEull;
 constexpr uint64_t kFreeVal = 0xFFFFFFFFFFFFFFFFull;
@@ -60,7 +63,7 @@ struct TickCtr {
   uint32_t ticket;
   uint32_t n_lobbies, n_matched, n_alive, n_dead, n_resid;
   uint32_t overflow;
-  uint32_t pad;
+  uint32_t heavy;  // some bin expects > 4 players per tile: use warp-aggregated ranking
 };
 
 struct ActiveView {
@@ -107,6 +110,35 @@ __device__ __forceinline__ void st_keep_u64(uint64_t* a, uint64_t v, uint64_t po
   asm volatile("st.global.L2::cache_hint.u64 [%0], %1, %2;" ::"l"(a), "l"(v), "l"(pol) : "memory");
 }
 
+// ---- TMA (1-D bulk copy) + mbarrier, CTA-local ------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE;\n"
+      "bra LAB_WAIT;\n"
+      "DONE:\n"
+      "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// global -> shared bulk copy (SASS: UBLKCP), completion counted on `bar`, L2 evict-first
+__device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar, uint64_t pol) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+          smem_u32(dst)),
+      "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(pol)
+      : "memory");
+}
+
 // In-place exclusive scan of a shared-memory array a[0..n) by the whole CTA; returns the
 // total.  s_tmp must hold BLOCK words.  (n is a few hundred to a few thousand.)
 template <int BLOCK>
@@ -139,11 +171,13 @@ __device__ __forceinline__ uint32_t bin_of(const BinMap& bm, const uint16_t* s_l
 }
 
 // ---------------------------------------------------------------------------------------
-// k_hist: M[row][bin] = number of the row's players in that bin.
-// Coalesced 128-bit rating loads (4 players per thread), 32-bit mode loads.
+// k_hist: M[row][bin] = number of the row's players in that bin, and the 16-bit bin column
+// bins16[] that k_place2 streams instead of re-deriving bins from rating + mode.
+// Coalesced 128-bit rating loads (4 players per thread, 4 such loads in flight), 32-bit
+// mode loads, 64-bit bin stores.
 // ---------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kBlock) k_hist(PoolView p, uint32_t n, uint32_t chunk, BinMap bm, uint32_t Kp,
-                                                 uint32_t* __restrict__ M) {
+                                                 uint32_t* __restrict__ M, uint16_t* __restrict__ bins16) {
   extern __shared__ __align__(16) uint32_t smem[];
   uint32_t* hist = smem;
   uint16_t* s_lut = reinterpret_cast<uint16_t*>(hist + Kp);
@@ -154,29 +188,33 @@ __global__ void __launch_bounds__(kBlock) k_hist(PoolView p, uint32_t n, uint32_
   const uint64_t beg64 = (uint64_t)blockIdx.x * chunk;
   const uint32_t beg = beg64 < n ? (uint32_t)beg64 : n;
   const uint32_t end = (beg64 + chunk < n) ? (uint32_t)(beg64 + chunk) : n;
-  // plain (cacheable) loads: rating+mode are read again by k_place and 5 B/player fits L2
-  for (uint32_t i = beg + tid * 4; i < end; i += kBlock * 8) {
-    const uint32_t i2 = i + kBlock * 4;
-    int4 r0 = make_int4(0, 0, 0, 0), r1 = r0;
-    uint32_t m0 = 0, m1 = 0;
-    const bool f0 = i + 4 <= end, f1 = i2 + 4 <= end;
-    if (f0) { r0 = *reinterpret_cast<const int4*>(p.rating + i); m0 = *reinterpret_cast<const uint32_t*>(p.mode + i); }
-    if (f1) { r1 = *reinterpret_cast<const int4*>(p.rating + i2); m1 = *reinterpret_cast<const uint32_t*>(p.mode + i2); }
-    if (f0) {
-      atomicAdd(&hist[bin_of(bm, s_lut, r0.x, m0 & 0xFF)], 1u);
-      atomicAdd(&hist[bin_of(bm, s_lut, r0.y, (m0 >> 8) & 0xFF)], 1u);
-      atomicAdd(&hist[bin_of(bm, s_lut, r0.z, (m0 >> 16) & 0xFF)], 1u);
-      atomicAdd(&hist[bin_of(bm, s_lut, r0.w, m0 >> 24)], 1u);
-    } else {
-      for (uint32_t e = i; e < end; ++e) atomicAdd(&hist[bin_of(bm, s_lut, p.rating[e], p.mode[e])], 1u);
+  constexpr int U = 4;
+  for (uint32_t i0 = beg + tid * 4; i0 < end; i0 += kBlock * 4 * U) {
+    int4 r[U];
+    uint32_t m[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const uint32_t i = i0 + u * kBlock * 4;
+      if (i + 4 <= end) {
+        r[u] = __ldcs(reinterpret_cast<const int4*>(p.rating + i));
+        m[u] = __ldcs(reinterpret_cast<const uint32_t*>(p.mode + i));
+      }
     }
-    if (f1) {
-      atomicAdd(&hist[bin_of(bm, s_lut, r1.x, m1 & 0xFF)], 1u);
-      atomicAdd(&hist[bin_of(bm, s_lut, r1.y, (m1 >> 8) & 0xFF)], 1u);
-      atomicAdd(&hist[bin_of(bm, s_lut, r1.z, (m1 >> 16) & 0xFF)], 1u);
-      atomicAdd(&hist[bin_of(bm, s_lut, r1.w, m1 >> 24)], 1u);
-    } else {
-      for (uint32_t e = i2; e < end; ++e) atomicAdd(&hist[bin_of(bm, s_lut, p.rating[e], p.mode[e])], 1u);
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const uint32_t i = i0 + u * kBlock * 4;
+      if (i + 4 <= end) {
+        const uint32_t b0 = bin_of(bm, s_lut, r[u].x, m[u] & 0xFF), b1 = bin_of(bm, s_lut, r[u].y, (m[u] >> 8) & 0xFF);
+        const uint32_t b2 = bin_of(bm, s_lut, r[u].z, (m[u] >> 16) & 0xFF), b3 = bin_of(bm, s_lut, r[u].w, m[u] >> 24);
+        atomicAdd(&hist[b0], 1u); atomicAdd(&hist[b1], 1u); atomicAdd(&hist[b2], 1u); atomicAdd(&hist[b3], 1u);
+        if (bins16) *reinterpret_cast<uint2*>(bins16 + i) = make_uint2(b0 | (b1 << 16), b2 | (b3 << 16));
+      } else if (i < end) {
+        for (uint32_t e = i; e < end; ++e) {
+          const uint32_t bb = bin_of(bm, s_lut, p.rating[e], p.mode[e]);
+          atomicAdd(&hist[bb], 1u);
+          if (bins16) bins16[e] = (uint16_t)bb;
+        }
+      }
     }
   }
   __syncthreads();
@@ -204,8 +242,9 @@ __global__ void __launch_bounds__(1024) k_colscan(uint32_t R, uint32_t Kp, uint3
                                                   uint32_t* __restrict__ seg_lim, TickCtr* ctr) {
   __shared__ uint32_t s_part[32][33];
   __shared__ uint32_t s_tmp[1024];
-  __shared__ uint32_t s_last;
+  __shared__ uint32_t s_last, s_max;
   const uint32_t tid = threadIdx.x, x = tid & 31, y = tid >> 5;
+  if (tid == 0) s_max = 0;
   const uint32_t b = blockIdx.x * 32 + x;
   const uint32_t rp = (R + 31) / 32;
   const uint32_t r0 = y * rp < R ? y * rp : R, r1 = (r0 + rp < R) ? r0 + rp : R;
@@ -236,8 +275,14 @@ __global__ void __launch_bounds__(1024) k_colscan(uint32_t R, uint32_t Kp, uint3
   {
     const uint32_t per = (Kp + 1023) / 1024;
     const uint32_t lo = tid * per < Kp ? tid * per : Kp, hi = (lo + per < Kp) ? lo + per : Kp;
-    uint32_t local = 0;
-    for (uint32_t i = lo; i < hi; ++i) local += __ldcg(&tot[i]);
+    uint32_t local = 0, lmax = 0;
+    for (uint32_t i = lo; i < hi; ++i) {
+      const uint32_t v = __ldcg(&tot[i]);
+      local += v;
+      if (i < K && v > lmax) lmax = v;
+    }
+    lmax = __reduce_max_sync(0xFFFFFFFFu, lmax);
+    if ((tid & 31) == 0 && lmax) atomicMax(&s_max, lmax);
     s_tmp[tid] = local;
     __syncthreads();
     for (int off = 1; off < 1024; off <<= 1) {
@@ -274,6 +319,9 @@ __global__ void __launch_bounds__(1024) k_colscan(uint32_t R, uint32_t Kp, uint3
   if (tid == 0) {
     ctr->n_lobbies = tot_lob; ctr->n_matched = tot_alive - tot_res; ctr->n_alive = tot_alive;
     ctr->n_dead = __ldcg(&tot[K]);
+    // expected players of the fullest bin per tile of one row (players spread evenly over rows)
+    const uint64_t npool = (uint64_t)tot_alive + ctr->n_dead;
+    ctr->heavy = ((uint64_t)s_max * kTile > 4ull * (npool ? npool : 1)) ? 1u : 0u;
   }
 }
 
@@ -451,6 +499,206 @@ __global__ void __launch_bounds__(kBlock, 1)
       }
     }
     if (IMPL == 1) __syncthreads();
+  }
+
+  // the row's residual players, in enqueue order
+  __syncthreads();
+  const uint32_t nres_all = s_nres;
+  const uint32_t nres = nres_all < kResCap ? nres_all : kResCap;
+  if (tid == 0) {
+    rescnt[row] = nres;
+    if (nres_all > kResCap) atomicExch(&ctr->overflow, 1u);
+  }
+  for (uint32_t t = tid; t < nres; t += kBlock) {
+    const uint32_t v = res_list[t];
+    uint32_t rank = 0;
+    for (uint32_t u = 0; u < nres; ++u) rank += (res_list[u] < v) ? 1u : 0u;
+    resid_stage[(size_t)row * kResCap + rank] = v;
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// k_place2: the production placement kernel (rank_impl 3).  Same contract as k_place, but
+//   * the row's (bin u16, id u64) columns arrive as 2 048-player tiles through a ring of
+//     TMA bulk copies (cp.async.bulk -> mbarrier), issued `stages` tiles ahead by one
+//     thread: DRAM latency never stalls the ranking, inputs stream with L2 evict-first;
+//   * light bins (the normal case with ~5k rating values per mode): ONE list node per
+//     player, no warp vote at all — push with a shared-memory atomicExch, barrier, walk
+//     the bin's round-local list counting nodes with a smaller tile position;
+//   * heavy bins (k_colscan flags the tick when some bin expects > 4 players per tile,
+//     e.g. everyone at the default rating): warp-aggregated groups as in k_place, so a
+//     list never exceeds 64 nodes;
+//   * ids are stored with an L2 evict-last policy: the 4 writes completing a 32-byte
+//     sector of member_ids arrive at unrelated times and must meet in L2, not in DRAM.
+// Shared memory: ring | mbarriers | cnt[Kp] | head[Kp] | node[kTile] | res_list.
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kBlock, 1)
+    k_place2(const uint16_t* __restrict__ bins16, const uint64_t* __restrict__ ids, uint32_t n, uint32_t chunk, uint32_t K,
+             uint32_t Kp, uint32_t R, uint32_t stages, const uint32_t* __restrict__ M, const uint32_t* __restrict__ tot,
+             const uint32_t* __restrict__ binbase, const uint16_t* __restrict__ bin_seg,
+             const uint32_t* __restrict__ seg_shift, const uint32_t* __restrict__ seg_lim, uint32_t n_segs,
+             uint64_t* __restrict__ members, uint32_t* __restrict__ src_idx, uint32_t* __restrict__ resid_stage,
+             uint32_t* __restrict__ rescnt, TickCtr* ctr) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  uint64_t* ring_ids = reinterpret_cast<uint64_t*>(smem_raw);                               // [stages][kTile]
+  uint16_t* ring_bins = reinterpret_cast<uint16_t*>(smem_raw + (size_t)stages * kTile * 8);  // [stages][kTile]
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + (size_t)stages * kTileBytes);      // [kMaxStages]
+  uint32_t* cnt = reinterpret_cast<uint32_t*>(smem_raw + (size_t)stages * kTileBytes + 64);
+  uint32_t* head = cnt + Kp;
+  uint32_t* node = head + Kp;          // [kTile]
+  uint32_t* res_list = node + kTile;   // [kResCap]
+  __shared__ uint32_t s_nres;
+  __shared__ uint32_t s_shift[kMaxSegs], s_lim[kMaxSegs];
+
+  const uint32_t tid = threadIdx.x, lane = tid & 31;
+  const uint32_t lt_mask = (1u << lane) - 1u;
+  const uint32_t row = blockIdx.x;
+  const uint64_t pol_in = policy_evict_first(), pol_out = policy_evict_last();
+
+  const uint64_t beg64 = (uint64_t)row * chunk;
+  const uint32_t beg = beg64 < n ? (uint32_t)beg64 : n;
+  const uint32_t end = (beg64 + chunk < n) ? (uint32_t)(beg64 + chunk) : n;
+  const uint32_t n_tiles = (end - beg + kTile - 1) / kTile;
+
+  if (tid == 0) {
+    for (uint32_t s = 0; s < stages; ++s) mbar_init(&full[s], 1);
+    mbar_fence_init();
+    s_nres = 0;
+  }
+  __syncthreads();
+  if (tid == 0) {  // prologue: fill the ring (whole tiles; the pool columns are padded past n)
+    for (uint32_t t = 0; t < stages && t < n_tiles; ++t) {
+      mbar_expect_tx(&full[t], kTileBytes);
+      tma_load_1d(ring_ids + (size_t)t * kTile, ids + beg + (size_t)t * kTile, kTile * 8, &full[t], pol_in);
+      tma_load_1d(ring_bins + (size_t)t * kTile, bins16 + beg + (size_t)t * kTile, kTile * 2, &full[t], pol_in);
+    }
+  }
+  for (uint32_t i = tid; i < n_segs; i += kBlock) { s_shift[i] = seg_shift[i]; s_lim[i] = seg_lim[i]; }
+  __syncthreads();
+  {
+    const uint32_t* mrow = M + (size_t)row * Kp;
+    const uint32_t* mnext = (row + 1 < R) ? mrow + Kp : tot;
+    for (uint32_t i = tid; i < Kp; i += kBlock) {
+      uint32_t v = 0;
+      if (i < K) {
+        const uint32_t pre = mrow[i], c = mnext[i] - pre;
+        const uint32_t sg = bin_seg[i];
+        const uint32_t start = binbase[i] - s_shift[sg] + pre;
+        v = start | ((start + c > s_lim[sg]) ? 0x80000000u : 0u);
+      }
+      cnt[i] = v;
+      head[i] = 0;
+    }
+  }
+  const bool heavy = ctr->heavy != 0;
+  __syncthreads();
+
+  for (uint32_t t = 0; t < n_tiles; ++t) {
+    const uint32_t st = t % stages;
+    const uint32_t tile_base = beg + t * kTile;
+    const uint16_t* tb = ring_bins + (size_t)st * kTile;
+    const uint64_t* ti = ring_ids + (size_t)st * kTile;
+    mbar_wait(&full[st], (t / stages) & 1u);
+    const uint32_t epoch = t + 1;
+    uint32_t bin[2], slot[2];
+    bool flag[2];
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const uint32_t pos = j * kBlock + tid;
+      bin[j] = (tile_base + pos < end) ? (uint32_t)tb[pos] : 0xFFFFu;
+      slot[j] = 0; flag[j] = false;
+    }
+    if (!heavy) {
+      uint32_t snap[2], pn[2];
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const uint32_t pos = j * kBlock + tid;
+        snap[j] = 0; pn[j] = 0;
+        if (bin[j] < K) {
+          snap[j] = cnt[bin[j]];
+          const uint32_t prev = atomicExch(&head[bin[j]], (epoch << 12) | pos);
+          pn[j] = ((prev >> 12) == epoch) ? (prev & 0xFFFu) : 0xFFFu;
+          node[pos] = pn[j];
+        }
+      }
+      __syncthreads();
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const uint32_t pos = j * kBlock + tid;
+        if (bin[j] < K) {
+          uint32_t cur = head[bin[j]] & 0xFFFu, lower = 0, total = 0;
+          while (cur != 0xFFFu) {
+            ++total;
+            lower += (cur < pos) ? 1u : 0u;
+            cur = node[cur];
+          }
+          slot[j] = (snap[j] & 0x7FFFFFFFu) + lower;
+          flag[j] = (snap[j] >> 31) != 0;
+          if (pn[j] == 0xFFFu) cnt[bin[j]] = snap[j] + total;
+        }
+      }
+    } else {
+      uint32_t snap[2], leader[2], rankw[2], mynode[2];
+      bool isl[2], first[2];
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const uint32_t mask = __match_any_sync(0xFFFFFFFFu, bin[j]);
+        leader[j] = __ffs(mask) - 1;
+        rankw[j] = __popc(mask & lt_mask);
+        isl[j] = (lane == leader[j]) && (bin[j] < K);
+        first[j] = false; snap[j] = 0;
+        mynode[j] = j * kBlock + tid;
+        if (isl[j]) {
+          snap[j] = cnt[bin[j]];
+          const uint32_t prev = atomicExch(&head[bin[j]], (epoch << 12) | mynode[j]);
+          const uint32_t prevnode = ((prev >> 12) == epoch) ? (prev & 0xFFFu) : 0xFFFu;
+          node[mynode[j]] = prevnode | ((uint32_t)__popc(mask) << 12);
+          first[j] = (prevnode == 0xFFFu);
+        }
+      }
+      __syncthreads();
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        uint32_t bg = 0;
+        if (isl[j]) {
+          uint32_t cur = head[bin[j]] & 0xFFFu, lower = 0, total = 0;
+          while (cur != 0xFFFu) {
+            const uint32_t nd = node[cur];
+            const uint32_t c = nd >> 12;
+            total += c;
+            if (cur < mynode[j]) lower += c;
+            cur = nd & 0xFFFu;
+          }
+          bg = snap[j] + lower;
+          if (first[j]) cnt[bin[j]] = snap[j] + total;
+        }
+        bg = __shfl_sync(0xFFFFFFFFu, bg, leader[j]);
+        slot[j] = (bg & 0x7FFFFFFFu) + rankw[j];
+        flag[j] = (bg >> 31) != 0;
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      if (bin[j] < K) {
+        const uint32_t pos = j * kBlock + tid;
+        bool matched = true;
+        if (flag[j]) matched = slot[j] < s_lim[__ldg(&bin_seg[bin[j]])];
+        if (matched) {
+          st_keep_u64(members + slot[j], ti[pos], pol_out);
+          if (src_idx) src_idx[slot[j]] = tile_base + pos;
+        } else {
+          const uint32_t k = atomicAdd(&s_nres, 1u);
+          if (k < kResCap) res_list[k] = tile_base + pos;
+        }
+      }
+    }
+    __syncthreads();  // everyone is done with stage st (and with this round's lists)
+    if (tid == 0 && t + stages < n_tiles) {
+      const uint32_t tn = t + stages;
+      mbar_expect_tx(&full[st], kTileBytes);
+      tma_load_1d(ring_ids + (size_t)st * kTile, ids + beg + (size_t)tn * kTile, kTile * 8, &full[st], pol_in);
+      tma_load_1d(ring_bins + (size_t)st * kTile, bins16 + beg + (size_t)tn * kTile, kTile * 2, &full[st], pol_in);
+    }
   }
 
   // the row's residual players, in enqueue order

@@ -35,7 +35,7 @@ def make_pool(pkg, seed, n, n_modes=2, bell=False, oor=0.01):
     return ids, rating, mode, ts
 
 
-@pytest.mark.parametrize("impl", [1, 0])
+@pytest.mark.parametrize("impl", [3, 1, 0])
 @pytest.mark.parametrize("order", [ARRIVAL, RATING])
 @pytest.mark.parametrize("n", [0, 1, 2, 9, 31, 33, 1000, 4095, 4096, 4097, 70001])
 def test_random_pool_matches_literal_oracle(pkg, oracle, n, order, impl):
@@ -73,13 +73,14 @@ def test_config2_and_both_rank_impls_agree(pkg, oracle):
     cfg = pkg.synth.make_config(n_groups=w["n_groups"], order=RATING, capacity=w["n"])
     ids, rating, mode, ts = pkg.synth.gen_pool(1, w["n"], mode=w["mode"])
     out = []
-    for impl in (1, 0):
+    for impl in (3, 1, 0):
         with pkg.Engine(cfg) as eng:
             eng.set_option("rank_impl", impl)
             assert eng.enqueue(ids, rating, mode, ts).all()
             lob, mem, seq, st = eng.tick()
             out.append((lob, mem, seq))
     assert all(np.array_equal(a, b) for a, b in zip(out[0], out[1]))
+    assert all(np.array_equal(a, b) for a, b in zip(out[0], out[2]))
     ref = oracle.run_closed_form(cfg, ids, rating, mode)
     assert np.array_equal(out[0][1], ref.member_ids) and np.array_equal(out[0][0], ref.lobbies)
 

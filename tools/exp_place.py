@@ -24,14 +24,9 @@ def run(label, reps=6, **opts):
         if i >= 2: dev.append(st.device_us); pl.append(st.place_us)
     print(json.dumps({"variant": label, "workload": name, "order": order, "device_us": round(float(np.mean(dev)), 1),
                       "place_us": round(float(np.mean(pl)), 1), "place_min": round(float(np.min(pl)), 1), "lobbies": st.n_lobbies}), flush=True)
-run("hints=0", l2_hints=0, place_debug=0, persist_mb=0)
-run("hints=1", l2_hints=1)
-run("hints=1 persist=96MB", persist_mb=96)
-print("persist info:", eng.lib.mm_last_error(eng.h).decode())
-run("hints=0 persist=96MB", l2_hints=0)
-run("hints=1 persist=64MB", l2_hints=1, persist_mb=64)
-run("dbg1 rank+coalesced store", persist_mb=0, place_debug=1)
-run("dbg2 norank+random scatter", place_debug=2)
-run("dbg2 + persist96", place_debug=2, persist_mb=96)
-run("dbg3 streaming copy", place_debug=3, persist_mb=0)
-run("rank_impl=0 (warp-serial)", place_debug=0, rank_impl=0)
+run("impl3 stages=4 persist", rank_impl=3, place2_stages=4)
+run("impl3 stages=3 persist", place2_stages=3)
+run("impl3 stages=2 persist", place2_stages=2)
+run("impl3 stages=4 nopersist", place2_stages=4, persist_mb=0)
+run("impl1 hints persist", rank_impl=1, l2_hints=1, persist_mb=1024)
+run("impl1 dbg3 streaming copy", place_debug=3)

@@ -11,7 +11,7 @@ timeout 600 python -m pytest tests -m gpu -q -k "config3" > gpurun_out/pytest_10
 tail -8 gpurun_out/pytest_10m.log
 timeout 600 compute-sanitizer --tool memcheck python -m pytest tests/test_engine_gpu.py -q -x -k "kat_leaver or dedupe or 4097 or capacity or multi_tick" > gpurun_out/memcheck.log 2>&1; echo "memcheck rc=$?"
 tail -6 gpurun_out/memcheck.log
-timeout 600 compute-sanitizer --tool racecheck python -m pytest tests/test_engine_gpu.py -q -x -k "4097 and 1-1" > gpurun_out/racecheck.log 2>&1; echo "racecheck rc=$?"
+timeout 600 compute-sanitizer --tool racecheck python -m pytest tests/test_engine_gpu.py -q -x -k "4097 and 1-3" > gpurun_out/racecheck.log 2>&1; echo "racecheck rc=$?"
 tail -6 gpurun_out/racecheck.log
 timeout 600 python bench.py --steps 10 --warmup 3 > gpurun_out/bench.log 2>&1; echo "bench rc=$?"
 tail -3 gpurun_out/bench.log
