@@ -135,7 +135,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="config3_10m_g32_5v5")
     ap.add_argument("--order", default="rating", choices=["rating", "arrival"])
-    ap.add_argument("--rank-impl", type=int, default=1)
+    ap.add_argument("--rank-impl", type=int, default=None)
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--ref-sample", type=int, default=10_000_000)
     ap.add_argument("--cpu-sample", type=int, default=10_000_000)
@@ -176,7 +176,8 @@ def main():
         torch.cuda.synchronize()
 
     eng = pkg.Engine(cfg)
-    eng.set_option("rank_impl", args.rank_impl)
+    if args.rank_impl is not None:
+        eng.set_option("rank_impl", args.rank_impl)
     acc = eng.enqueue(ids, rating, mode, ts)
     assert acc.all()
     eng.snapshot()
@@ -220,7 +221,8 @@ def main():
     if not args.no_e2e:
         eng.close()
         eng = pkg.Engine(cfg)
-        eng.set_option("rank_impl", args.rank_impl)
+        if args.rank_impl is not None:
+            eng.set_option("rank_impl", args.rank_impl)
         pin = lambda a: torch.from_numpy(a).pin_memory()
         h_ids, h_rating, h_mode, h_ts = pin(ids), pin(rating), pin(mode), pin(ts)
         h_acc = torch.empty(n, dtype=torch.uint8).pin_memory()

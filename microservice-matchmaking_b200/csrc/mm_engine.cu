@@ -38,7 +38,8 @@ struct mm_engine {
   std::mutex mu;
   int device = 0;
   int n_sms = 0;
-  size_t smem_optin = 0;
+  size_t smem_optin = 0, smem_sm = 0;
+  int block = 1024;  // threads per row CTA (512 when two rows share an SM)
   cudaStream_t stream = nullptr;
   bool own_stream = true;
   cudaEvent_t ev[4]{};
@@ -79,6 +80,7 @@ struct mm_engine {
   int place_debug = 0;
   size_t persist_bytes = 0;
   uint32_t place2_stages = 0;  // 0 = k_place2 does not fit in shared memory
+  int dense_ok = 1;            // allow the small-K dense ranking path
   uint16_t* d_bins16 = nullptr;
   uint32_t* d_M = nullptr;
   uint32_t *d_tot = nullptr, *d_binbase = nullptr, *d_seg_lim = nullptr;
@@ -174,8 +176,10 @@ size_t place_smem(const mm_engine* e, int impl) {
   size_t words = e->Kp + (impl == 1 ? (size_t)e->Kp + kRound : 0) + kResCap;
   return words * 4 + (size_t)e->KR * 2 + 16;
 }
+bool place2_dense(const mm_engine* e) { return e->Kp <= kDenseMaxBins; }
 size_t place2_smem(const mm_engine* e, uint32_t stages) {
-  return (size_t)stages * kTileBytes + 64 + ((size_t)2 * e->Kp + kTile + kResCap) * 4;
+  return (size_t)stages * kTileBytes + 64 + ((size_t)e->Kp + kHeadSlots + kTile + kRes2) * 4 + (size_t)kTile * 2 +
+         (place2_dense(e) ? (size_t)e->Kp * kDenseStride * 2 * 2 + (size_t)e->Kp * 4 : 0) + 16;
 }
 size_t hist_smem(const mm_engine* e) { return (size_t)e->Kp * 4 + (size_t)e->KR * 2 + 16; }
 
@@ -357,9 +361,13 @@ int tick_phase_a(mm_engine* e, uint32_t n, uint32_t* chunk_out) {
   *chunk_out = chunk;
   CK(cudaMemsetAsync(e->d_ctr, 0, sizeof(TickCtr), e->stream));
   CK(cudaEventRecord(e->ev[0], e->stream));
-  k_hist<<<e->R, kBlock, hist_smem(e), e->stream>>>(p.v, n, chunk, bin_map(e), e->Kp, e->d_M,
-                                                    e->rank_impl == 3 ? e->d_bins16 : nullptr);
-  k_colscan<<<(e->Kp + 31) / 32, 1024, 0, e->stream>>>(e->R, e->Kp, e->K, e->d_M, e->d_tot, e->d_binbase, e->d_seg_bin_lo,
+  if (e->block == 512)
+    k_hist<512><<<e->R, 512, hist_smem(e), e->stream>>>(p.v, n, chunk, bin_map(e), e->Kp, e->d_M, e->d_tot,
+                                                        e->rank_impl == 3 ? e->d_bins16 : nullptr);
+  else
+    k_hist<1024><<<e->R, 1024, hist_smem(e), e->stream>>>(p.v, n, chunk, bin_map(e), e->Kp, e->d_M, e->d_tot,
+                                                          e->rank_impl == 3 ? e->d_bins16 : nullptr);
+  k_colscan<<<(e->Kp + 31) / 32 + 1, kScanBlock, 0, e->stream>>>(e->R, e->Kp, e->K, e->d_M, e->d_tot, e->d_binbase, e->d_seg_bin_lo,
                                                         e->d_seg_L, e->n_segs, e->d_seg, e->d_seg_shift, e->d_seg_lim,
                                                         e->d_ctr);
   CK(cudaGetLastError());
@@ -375,10 +383,16 @@ int tick_phase_b(mm_engine* e, uint32_t n, uint32_t chunk, bool want_seq) {
   k_place<IMPL, DBG, HINT><<<e->R, kBlock, place_smem(e, IMPL), e->stream>>>(                                         \
       p.v, n, chunk, bin_map(e), e->Kp, e->R, e->d_M, e->d_tot, e->d_binbase, e->d_bin_seg, e->d_seg_shift,           \
       e->d_seg_lim, e->n_segs, e->d_members, src_idx, e->d_resid_stage, e->d_rescnt, e->d_ctr)
-  if (e->rank_impl == 3)
-    k_place2<<<e->R, kBlock, place2_smem(e, e->place2_stages), e->stream>>>(
-        e->d_bins16, p.v.id, n, chunk, e->K, e->Kp, e->R, e->place2_stages, e->d_M, e->d_tot, e->d_binbase, e->d_bin_seg,
-        e->d_seg_shift, e->d_seg_lim, e->n_segs, e->d_members, src_idx, e->d_resid_stage, e->d_rescnt, e->d_ctr);
+#define MM_PLACE2(BLK)                                                                                               \
+  k_place2<BLK><<<e->R, BLK, place2_smem(e, e->place2_stages), e->stream>>>(                                          \
+      e->d_bins16, p.v.id, n, chunk, e->K, e->Kp, e->R, e->place2_stages, (place2_dense(e) && e->dense_ok) ? 1u : 0u,  \
+      e->d_M, e->d_tot, e->d_binbase, e->d_bin_seg, e->d_seg_shift, e->d_seg_lim, e->d_members, src_idx,              \
+      e->d_resid_stage, e->d_rescnt, e->d_ctr)
+  if (e->rank_impl == 3) {
+    if (e->block == 512) MM_PLACE2(512);
+    else MM_PLACE2(1024);
+  }
+#undef MM_PLACE2
   else if (e->rank_impl == 0) MM_PLACE(0, 0, false);
   else if (e->place_debug == 1) MM_PLACE(1, 1, true);
   else if (e->place_debug == 2) MM_PLACE(1, 2, true);
@@ -389,7 +403,8 @@ int tick_phase_b(mm_engine* e, uint32_t n, uint32_t chunk, bool want_seq) {
   CK(cudaEventRecord(e->ev[2], e->stream));
   k_epilogue<<<std::max(1, e->n_sms), 1024, 0, e->stream>>>(p.v, q.v, e->R, e->d_rescnt, e->d_resid_stage, act_view(e),
                                                            e->gen + 1, e->d_seg, e->d_seg_L, e->n_segs, e->cfg.n_groups,
-                                                           e->d_hdr, src_idx, want_seq ? e->d_emit_seq : nullptr, e->d_ctr);
+                                                           e->d_hdr, src_idx, want_seq ? e->d_emit_seq : nullptr, e->d_tot,
+                                                           e->Kp, e->d_ctr);
   CK(cudaGetLastError());
   CK(cudaEventRecord(e->ev[3], e->stream));
   CK(cudaMemcpyAsync(e->h_ctr, e->d_ctr, sizeof(TickCtr), cudaMemcpyDeviceToHost, e->stream));
@@ -486,6 +501,7 @@ int mm_create(const mm_config* cfg, mm_engine** out) {
   if (cudaGetDeviceProperties(&prop, e->device) != cudaSuccess) return bail(MM_E_CUDA);
   e->n_sms = prop.multiProcessorCount;
   e->smem_optin = prop.sharedMemPerBlockOptin;
+  e->smem_sm = prop.sharedMemPerMultiprocessor;
   if (cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) != cudaSuccess) return bail(MM_E_CUDA);
   for (auto& ev : e->ev)
     if (cudaEventCreate(&ev) != cudaSuccess) return bail(MM_E_CUDA);
@@ -498,7 +514,7 @@ int mm_create(const mm_config* cfg, mm_engine** out) {
   }
   {
     const int s0 = (int)place_smem(e, 0), s1 = (int)place_smem(e, 1);
-    bool ok = cudaFuncSetAttribute(k_hist, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hist_smem(e)) == cudaSuccess &&
+    bool ok = cudaFuncSetAttribute(k_hist<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hist_smem(e)) == cudaSuccess &&
               cudaFuncSetAttribute(k_place<0, 0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, s0) == cudaSuccess;
     if (ok && e->rank_impl == 1)
       ok = cudaFuncSetAttribute(k_place<1, 0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, s1) == cudaSuccess &&
@@ -506,12 +522,19 @@ int mm_create(const mm_config* cfg, mm_engine** out) {
            cudaFuncSetAttribute(k_place<1, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, s1) == cudaSuccess &&
            cudaFuncSetAttribute(k_place<1, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, s1) == cudaSuccess &&
            cudaFuncSetAttribute(k_place<1, 3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, s1) == cudaSuccess;
-    // the TMA-fed kernel wants >= 2 ring stages next to its per-bin state
-    for (uint32_t st = kMaxStages; st >= 2 && e->rank_impl == 1 && e->Kp <= 65535u; --st)
-      if (place2_smem(e, st) + 8192 <= e->smem_optin) { e->place2_stages = st; break; }
+    ok = ok && cudaFuncSetAttribute(k_hist<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hist_smem(e)) == cudaSuccess;
+    // The TMA-fed kernel wants >= 2 ring stages next to its per-bin state; when two such CTAs
+    // (512 threads each) fit in one SM, rows = 2 x SMs so barrier phases of one overlap the other.
+    if (e->rank_impl == 1 && e->Kp <= 65535u) {
+      for (uint32_t st = 3; st >= 2 && !e->place2_stages; --st)
+        if (2 * (place2_smem(e, st) + 1024 + 256) <= e->smem_sm) { e->place2_stages = st; e->rows_per_sm = 2; e->block = 512; }
+      for (uint32_t st = kMaxStages; st >= 2 && !e->place2_stages; --st)
+        if (place2_smem(e, st) + 1024 <= e->smem_optin) { e->place2_stages = st; e->rows_per_sm = 1; e->block = 1024; }
+    }
     if (ok && e->place2_stages) {
-      ok = cudaFuncSetAttribute(k_place2, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                (int)place2_smem(e, e->place2_stages)) == cudaSuccess;
+      const int sz = (int)place2_smem(e, e->place2_stages);
+      ok = cudaFuncSetAttribute(k_place2<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, sz) == cudaSuccess &&
+           cudaFuncSetAttribute(k_place2<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, sz) == cudaSuccess;
       e->rank_impl = 3;
     }
     if (!ok) return bail(fail(e, cudaGetLastError(), "cudaFuncSetAttribute"));
@@ -542,6 +565,7 @@ int mm_create(const mm_config* cfg, mm_engine** out) {
   if (cudaMallocHost(&e->h_ctr, sizeof(TickCtr)) != cudaSuccess || cudaMallocHost(&e->h_small, 64) != cudaSuccess)
     return bail(MM_E_CUDA);
   if ((rc = alloc_tick_scratch(e))) return bail(rc);
+  if (cudaMemsetAsync(e->d_tot, 0, (e->Kp + 1) * 4, e->stream) != cudaSuccess) return bail(MM_E_CUDA);
   if ((rc = set_persist(e, 1024))) return bail(rc);  // clamped to the device's persisting-L2 maximum
   if (cudaStreamSynchronize(e->stream) != cudaSuccess) return bail(MM_E_CUDA);
   *out = e;
@@ -601,6 +625,7 @@ int mm_set_option(mm_engine* e, const char* name, int64_t value) {
     return MM_OK;
   }
   if (!std::strcmp(name, "l2_hints")) { e->l2_hints = value != 0; return MM_OK; }
+  if (!std::strcmp(name, "dense")) { e->dense_ok = value != 0; return MM_OK; }
   if (!std::strcmp(name, "place_debug")) {  // timing experiments only: results are NOT valid
     if (value < 0 || value > 3) return MM_E_ARG;
     e->place_debug = (int)value;
@@ -608,9 +633,16 @@ int mm_set_option(mm_engine* e, const char* name, int64_t value) {
   }
   if (!std::strcmp(name, "persist_mb")) return set_persist(e, value);
   if (!std::strcmp(name, "place2_stages")) {
-    if (value < 1 || value > (int64_t)kMaxStages || place2_smem(e, (uint32_t)value) + 8192 > e->smem_optin) return MM_E_ARG;
-    CK(cudaFuncSetAttribute(k_place2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)place2_smem(e, (uint32_t)value)));
+    if (value < 1 || value > (int64_t)kMaxStages || place2_smem(e, (uint32_t)value) + 1024 > e->smem_optin) return MM_E_ARG;
+    const int sz = (int)place2_smem(e, (uint32_t)value);
+    CK(cudaFuncSetAttribute(k_place2<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, sz));
+    CK(cudaFuncSetAttribute(k_place2<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, sz));
     e->place2_stages = (uint32_t)value;
+    return MM_OK;
+  }
+  if (!std::strcmp(name, "block")) {  // threads per row CTA
+    if (value != 512 && value != 1024) return MM_E_ARG;
+    e->block = (int)value;
     return MM_OK;
   }
   if (!std::strcmp(name, "rows_per_sm")) {
@@ -740,6 +772,8 @@ int mm_tick(mm_engine* e, uint64_t now, mm_lobby_hdr* lobbies, uint32_t lobby_ca
   if ((lobbies && e->h_ctr->n_lobbies > lobby_cap) || (member_ids && e->h_ctr->n_matched > member_cap)) {
     std::snprintf(e->last_err, sizeof(e->last_err), "need lobby_cap >= %u, member_cap >= %u", e->h_ctr->n_lobbies,
                   e->h_ctr->n_matched);
+    CK(cudaMemsetAsync(e->d_tot, 0, (e->Kp + 1) * 4, e->stream));  // the epilogue that re-zeroes it will not run
+    CK(cudaStreamSynchronize(e->stream));
     return MM_E_CAP;
   }
   if ((rc = tick_phase_b(e, n, chunk, emit_seq != nullptr))) return rc;

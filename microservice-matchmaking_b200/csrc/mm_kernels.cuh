@@ -31,6 +31,8 @@ constexpr uint32_t kMaxRows = 2048;   // rows (CTAs) of the histogram matrix
 constexpr uint32_t kTile = 2048;      // players per TMA tile in k_place2
 constexpr uint32_t kMaxStages = 4;    // depth of the (bin, id) shared-memory ring
 constexpr uint32_t kTileBytes = kTile * (8 + 2);
+constexpr uint32_t kDenseStride = 66;  // u16 per bin row of the dense group-size matrix (64 batches + pad)
+constexpr uint32_t kDenseMaxBins = 256;
 constexpr uint64_t kEmptyKey = 0xFFFFFFFFFFFFFFFFull;
 constexpr uint64_t kTombKey = 0xFFFFFFFFFFFFFFFEull;
 constexpr uint64_t kFreeVal = 0xFFFFFFFFFFFFFFFFull;
@@ -140,25 +142,36 @@ __device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t
 }
 
 // In-place exclusive scan of a shared-memory array a[0..n) by the whole CTA; returns the
-// total.  s_tmp must hold BLOCK words.  (n is a few hundred to a few thousand.)
+// total.  s_tmp must hold >= 33 words.  Warp-shuffle scan: 3 barriers.
 template <int BLOCK>
 __device__ __forceinline__ uint32_t block_excl_scan(uint32_t* a, uint32_t n, uint32_t* s_tmp) {
-  const uint32_t tid = threadIdx.x;
+  const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t per = (n + BLOCK - 1) / BLOCK;
   const uint32_t lo = tid * per < n ? tid * per : n, hi = (lo + per < n) ? lo + per : n;
   uint32_t local = 0;
   for (uint32_t i = lo; i < hi; ++i) local += a[i];
-  s_tmp[tid] = local;
-  __syncthreads();
-  for (int off = 1; off < BLOCK; off <<= 1) {
-    const uint32_t v = (tid >= (uint32_t)off) ? s_tmp[tid - off] : 0;
-    __syncthreads();
-    s_tmp[tid] += v;
-    __syncthreads();
+  uint32_t incl = local;
+#pragma unroll
+  for (int off = 1; off < 32; off <<= 1) {
+    const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, incl, off);
+    if (lane >= (uint32_t)off) incl += v;
   }
-  uint32_t run = s_tmp[tid] - local;
+  if (lane == 31) s_tmp[warp] = incl;
+  __syncthreads();
+  if (warp == 0) {
+    uint32_t w = lane < BLOCK / 32 ? s_tmp[lane] : 0, wi = w;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+      const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, wi, off);
+      if (lane >= (uint32_t)off) wi += v;
+    }
+    s_tmp[lane] = wi - w;                 // exclusive warp offsets
+    if (lane == 31) s_tmp[32] = wi;       // grand total
+  }
+  __syncthreads();
+  uint32_t run = s_tmp[warp] + incl - local;
   for (uint32_t i = lo; i < hi; ++i) { const uint32_t v = a[i]; a[i] = run; run += v; }
-  const uint32_t total = s_tmp[BLOCK - 1];
+  const uint32_t total = s_tmp[32];
   __syncthreads();
   return total;
 }
@@ -176,8 +189,11 @@ __device__ __forceinline__ uint32_t bin_of(const BinMap& bm, const uint16_t* s_l
 // Coalesced 128-bit rating loads (4 players per thread, 4 such loads in flight), 32-bit
 // mode loads, 64-bit bin stores.
 // ---------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kBlock) k_hist(PoolView p, uint32_t n, uint32_t chunk, BinMap bm, uint32_t Kp,
-                                                 uint32_t* __restrict__ M, uint16_t* __restrict__ bins16) {
+template <int BLOCK>
+__global__ void __launch_bounds__(BLOCK) k_hist(PoolView p, uint32_t n, uint32_t chunk, BinMap bm, uint32_t Kp,
+                                                uint32_t* __restrict__ M, uint32_t* __restrict__ tot,
+                                                uint16_t* __restrict__ bins16) {
+  constexpr uint32_t kBlock = BLOCK;
   extern __shared__ __align__(16) uint32_t smem[];
   uint32_t* hist = smem;
   uint16_t* s_lut = reinterpret_cast<uint16_t*>(hist + Kp);
@@ -219,62 +235,66 @@ __global__ void __launch_bounds__(kBlock) k_hist(PoolView p, uint32_t n, uint32_
   }
   __syncthreads();
   uint32_t* row = M + (size_t)blockIdx.x * Kp;
-  for (uint32_t i = tid; i < Kp; i += kBlock) row[i] = hist[i];
+  for (uint32_t i = tid; i < Kp; i += kBlock) {
+    const uint32_t v = hist[i];
+    row[i] = v;
+    if (v) atomicAdd(&tot[i], v);  // bin totals (tot[] is zeroed by the previous tick's epilogue)
+  }
 }
 
 // ---------------------------------------------------------------------------------------
-// k_colscan: exclusive prefix down every column of M.  A CTA is 32 bins wide (lanes =
-// consecutive bins, coalesced) and 32 row-slices deep (warps): every thread sums its
-// slice of rows, the slices are scanned through shared memory, then the slice is
+// k_colscan: exclusive prefix down every column of M.  A column CTA is 32 bins wide
+// (lanes = consecutive bins, coalesced) and 16 row-slices deep (warps): every thread sums
+// its slice of rows, the slices are scanned through shared memory, then the slice is
 // rewritten as running prefixes — one round trip of latency instead of R.
-// The last CTA to finish scans the bin totals (-> binbase) and does the per-segment
-// lobby arithmetic:  lobbies_s = n_s / L, matched_s = lobbies_s * L, residual_s = n_s % L,
+// The LAST CTA of the grid runs concurrently as the "tail": bin totals (accumulated by
+// k_hist with global reductions) -> exclusive scan binbase, then the per-segment lobby
+// arithmetic:  lobbies_s = n_s / L, matched_s = lobbies_s * L, residual_s = n_s % L,
 //   seg_shift[s] = residual players of earlier segments (sorted position -> member slot)
 //   seg_lim[s]   = end of the segment's matched slots; a player at or past it stays queued.
 // ---------------------------------------------------------------------------------------
 constexpr uint32_t kMaxSegs = MM_MAX_GROUPS * MM_MAX_MODES;
+constexpr int kScanBlock = 512;
 
-__global__ void __launch_bounds__(1024) k_colscan(uint32_t R, uint32_t Kp, uint32_t K, uint32_t* __restrict__ M,
-                                                  uint32_t* __restrict__ tot, uint32_t* __restrict__ binbase,
-                                                  const uint32_t* __restrict__ seg_bin_lo,
-                                                  const uint32_t* __restrict__ seg_L, uint32_t n_segs,
-                                                  SegInfo* __restrict__ seg, uint32_t* __restrict__ seg_shift,
-                                                  uint32_t* __restrict__ seg_lim, TickCtr* ctr) {
-  __shared__ uint32_t s_part[32][33];
-  __shared__ uint32_t s_tmp[1024];
-  __shared__ uint32_t s_last, s_max;
+__global__ void __launch_bounds__(kScanBlock) k_colscan(uint32_t R, uint32_t Kp, uint32_t K, uint32_t* __restrict__ M,
+                                                        const uint32_t* __restrict__ tot, uint32_t* __restrict__ binbase,
+                                                        const uint32_t* __restrict__ seg_bin_lo,
+                                                        const uint32_t* __restrict__ seg_L, uint32_t n_segs,
+                                                        SegInfo* __restrict__ seg, uint32_t* __restrict__ seg_shift,
+                                                        uint32_t* __restrict__ seg_lim, TickCtr* ctr) {
+  __shared__ uint32_t s_part[kScanBlock / 32][33];
+  __shared__ uint32_t s_tmp[64];
+  __shared__ uint32_t s_max;
+  __shared__ uint32_t s_res[kMaxSegs], s_lob[kMaxSegs], s_n[kMaxSegs];
   const uint32_t tid = threadIdx.x, x = tid & 31, y = tid >> 5;
-  if (tid == 0) s_max = 0;
-  const uint32_t b = blockIdx.x * 32 + x;
-  const uint32_t rp = (R + 31) / 32;
-  const uint32_t r0 = y * rp < R ? y * rp : R, r1 = (r0 + rp < R) ? r0 + rp : R;
-  uint32_t sum = 0;
-  if (b < Kp)
-    for (uint32_t r = r0; r < r1; ++r) sum += __ldcg(M + (size_t)r * Kp + b);
-  s_part[y][x] = sum;
-  __syncthreads();
-  uint32_t run = 0;
-  for (uint32_t yy = 0; yy < y; ++yy) run += s_part[yy][x];
-  if (b < Kp) {
-    for (uint32_t r = r0; r < r1; ++r) {
-      uint32_t* p = M + (size_t)r * Kp + b;
-      const uint32_t v = __ldcg(p);
-      *p = run;
-      run += v;
-    }
-    if (y == 31) tot[b] = run;
+  if (blockIdx.x + 1 < gridDim.x) {  // ---- column CTA ----
+    constexpr uint32_t NY = kScanBlock / 32;
+    const uint32_t b = blockIdx.x * 32 + x;
+    const uint32_t rp = (R + NY - 1) / NY;
+    const uint32_t r0 = y * rp < R ? y * rp : R, r1 = (r0 + rp < R) ? r0 + rp : R;
+    uint32_t sum = 0;
+    if (b < Kp)
+      for (uint32_t r = r0; r < r1; ++r) sum += __ldcg(M + (size_t)r * Kp + b);
+    s_part[y][x] = sum;
+    __syncthreads();
+    uint32_t run = 0;
+    for (uint32_t yy = 0; yy < y; ++yy) run += s_part[yy][x];
+    if (b < Kp)
+      for (uint32_t r = r0; r < r1; ++r) {
+        uint32_t* p = M + (size_t)r * Kp + b;
+        const uint32_t v = __ldcg(p);
+        *p = run;
+        run += v;
+      }
+    return;
   }
-  __threadfence();
+  // ---- tail CTA: scan of the bin totals ----
+  if (tid == 0) s_max = 0;
   __syncthreads();
-  if (tid == 0) s_last = (atomicAdd(&ctr->ticket, 1u) == gridDim.x - 1) ? 1u : 0u;
-  __syncthreads();
-  if (!s_last) return;
-  __threadfence();
-
-  // exclusive scan of tot[0..Kp) -> binbase[0..Kp]
   {
-    const uint32_t per = (Kp + 1023) / 1024;
+    const uint32_t per = (Kp + kScanBlock - 1) / kScanBlock;
     const uint32_t lo = tid * per < Kp ? tid * per : Kp, hi = (lo + per < Kp) ? lo + per : Kp;
+    const uint32_t lane = tid & 31, warp = tid >> 5;
     uint32_t local = 0, lmax = 0;
     for (uint32_t i = lo; i < hi; ++i) {
       const uint32_t v = __ldcg(&tot[i]);
@@ -282,34 +302,44 @@ __global__ void __launch_bounds__(1024) k_colscan(uint32_t R, uint32_t Kp, uint3
       if (i < K && v > lmax) lmax = v;
     }
     lmax = __reduce_max_sync(0xFFFFFFFFu, lmax);
-    if ((tid & 31) == 0 && lmax) atomicMax(&s_max, lmax);
-    s_tmp[tid] = local;
-    __syncthreads();
-    for (int off = 1; off < 1024; off <<= 1) {
-      const uint32_t v = (tid >= (uint32_t)off) ? s_tmp[tid - off] : 0;
-      __syncthreads();
-      s_tmp[tid] += v;
-      __syncthreads();
+    if (lane == 0 && lmax) atomicMax(&s_max, lmax);
+    uint32_t incl = local;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+      const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, incl, off);
+      if (lane >= (uint32_t)off) incl += v;
     }
-    uint32_t acc = s_tmp[tid] - local;
+    if (lane == 31) s_tmp[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+      uint32_t w = lane < kScanBlock / 32 ? s_tmp[lane] : 0, wi = w;
+#pragma unroll
+      for (int off = 1; off < 32; off <<= 1) {
+        const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, wi, off);
+        if (lane >= (uint32_t)off) wi += v;
+      }
+      s_tmp[lane] = wi - w;
+      if (lane == 31) s_tmp[32] = wi;
+    }
+    __syncthreads();
+    uint32_t acc = s_tmp[warp] + incl - local;
     for (uint32_t i = lo; i < hi; ++i) { binbase[i] = acc; acc += __ldcg(&tot[i]); }
-    if (tid == 1023) binbase[Kp] = s_tmp[1023];
+    if (tid == 0) binbase[Kp] = s_tmp[32];
     __threadfence_block();
     __syncthreads();
   }
   // per-segment arithmetic: three small scans over the <= modes*groups segments
-  __shared__ uint32_t s_res[kMaxSegs], s_lob[kMaxSegs], s_n[kMaxSegs];
-  for (uint32_t s = tid; s < n_segs; s += 1024) {
+  for (uint32_t s = tid; s < n_segs; s += kScanBlock) {
     const uint32_t ns = binbase[seg_bin_lo[s + 1]] - binbase[seg_bin_lo[s]];
     const uint32_t nl = ns / seg_L[s];
     s_n[s] = ns; s_lob[s] = nl; s_res[s] = ns - nl * seg_L[s];
     seg[s].n = ns; seg[s].n_lobbies = nl;
   }
   __syncthreads();
-  const uint32_t tot_res = block_excl_scan<1024>(s_res, n_segs, s_tmp);
-  const uint32_t tot_lob = block_excl_scan<1024>(s_lob, n_segs, s_tmp);
-  const uint32_t tot_alive = block_excl_scan<1024>(s_n, n_segs, s_tmp);
-  for (uint32_t s = tid; s < n_segs; s += 1024) {
+  const uint32_t tot_res = block_excl_scan<kScanBlock>(s_res, n_segs, s_tmp);
+  const uint32_t tot_lob = block_excl_scan<kScanBlock>(s_lob, n_segs, s_tmp);
+  const uint32_t tot_alive = block_excl_scan<kScanBlock>(s_n, n_segs, s_tmp);
+  for (uint32_t s = tid; s < n_segs; s += kScanBlock) {
     const uint32_t mb = binbase[seg_bin_lo[s]] - s_res[s];
     seg[s].member_base = mb;
     seg[s].lobby_base = s_lob[s];
@@ -317,10 +347,10 @@ __global__ void __launch_bounds__(1024) k_colscan(uint32_t R, uint32_t Kp, uint3
     seg_lim[s] = mb + seg[s].n_lobbies * seg_L[s];
   }
   if (tid == 0) {
-    ctr->n_lobbies = tot_lob; ctr->n_matched = tot_alive - tot_res; ctr->n_alive = tot_alive;
-    ctr->n_dead = __ldcg(&tot[K]);
+    const uint32_t dead = __ldcg(&tot[K]);
+    ctr->n_lobbies = tot_lob; ctr->n_matched = tot_alive - tot_res; ctr->n_alive = tot_alive; ctr->n_dead = dead;
     // expected players of the fullest bin per tile of one row (players spread evenly over rows)
-    const uint64_t npool = (uint64_t)tot_alive + ctr->n_dead;
+    const uint64_t npool = (uint64_t)tot_alive + dead;
     ctr->heavy = ((uint64_t)s_max * kTile > 4ull * (npool ? npool : 1)) ? 1u : 0u;
   }
 }
@@ -518,39 +548,53 @@ __global__ void __launch_bounds__(kBlock, 1)
 }
 
 // ---------------------------------------------------------------------------------------
-// k_place2: the production placement kernel (rank_impl 3).  Same contract as k_place, but
+// k_place2<BLOCK>: the production placement kernel (rank_impl 3).  Same contract as
+// k_place, but
 //   * the row's (bin u16, id u64) columns arrive as 2 048-player tiles through a ring of
 //     TMA bulk copies (cp.async.bulk -> mbarrier), issued `stages` tiles ahead by one
 //     thread: DRAM latency never stalls the ranking, inputs stream with L2 evict-first;
 //   * light bins (the normal case with ~5k rating values per mode): ONE list node per
-//     player, no warp vote at all — push with a shared-memory atomicExch, barrier, walk
-//     the bin's round-local list counting nodes with a smaller tile position;
+//     player, no warp vote — push on a HASHED head table (kHeadSlots entries, epoch-tagged,
+//     never cleared) with a shared-memory atomicExch, barrier, walk the slot's round-local
+//     list counting same-bin nodes with a smaller tile position; the lowest one advances
+//     the bin's slot counter.  Per-CTA state is 4 B/bin + 28 KB, so two CTAs share an SM
+//     and one CTA's barrier phases overlap the other's work;
 //   * heavy bins (k_colscan flags the tick when some bin expects > 4 players per tile,
-//     e.g. everyone at the default rating): warp-aggregated groups as in k_place, so a
-//     list never exceeds 64 nodes;
+//     e.g. everyone at the default rating): warp-aggregated groups, lists <= 64 nodes;
+//   * few bins (arrival order: bin = (mode, group), <= 256): dense per-(bin, warp-batch)
+//     group-size matrix + one warp-shuffle scan per bin;
 //   * ids are stored with an L2 evict-last policy: the 4 writes completing a 32-byte
 //     sector of member_ids arrive at unrelated times and must meet in L2, not in DRAM.
-// Shared memory: ring | mbarriers | cnt[Kp] | head[Kp] | node[kTile] | res_list.
+// Shared memory: ring | mbarriers | cnt[Kp] | head[kHeadSlots] | node[kTile] | nbin | res | dense.
 // ---------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kBlock, 1)
+constexpr uint32_t kHeadSlots = 4096;
+constexpr uint32_t kRes2 = 1024;  // residual players one row may hold (k_place2)
+
+template <int BLOCK>
+__global__ void __launch_bounds__(BLOCK, (BLOCK == 512 ? 2 : 1))
     k_place2(const uint16_t* __restrict__ bins16, const uint64_t* __restrict__ ids, uint32_t n, uint32_t chunk, uint32_t K,
-             uint32_t Kp, uint32_t R, uint32_t stages, const uint32_t* __restrict__ M, const uint32_t* __restrict__ tot,
-             const uint32_t* __restrict__ binbase, const uint16_t* __restrict__ bin_seg,
-             const uint32_t* __restrict__ seg_shift, const uint32_t* __restrict__ seg_lim, uint32_t n_segs,
-             uint64_t* __restrict__ members, uint32_t* __restrict__ src_idx, uint32_t* __restrict__ resid_stage,
-             uint32_t* __restrict__ rescnt, TickCtr* ctr) {
+             uint32_t Kp, uint32_t R, uint32_t stages, uint32_t dense, const uint32_t* __restrict__ M,
+             const uint32_t* __restrict__ tot, const uint32_t* __restrict__ binbase,
+             const uint16_t* __restrict__ bin_seg, const uint32_t* __restrict__ seg_shift,
+             const uint32_t* __restrict__ seg_lim, uint64_t* __restrict__ members, uint32_t* __restrict__ src_idx,
+             uint32_t* __restrict__ resid_stage, uint32_t* __restrict__ rescnt, TickCtr* ctr) {
+  constexpr int J = kTile / BLOCK;
+  constexpr int NW = BLOCK / 32;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   uint64_t* ring_ids = reinterpret_cast<uint64_t*>(smem_raw);                               // [stages][kTile]
   uint16_t* ring_bins = reinterpret_cast<uint16_t*>(smem_raw + (size_t)stages * kTile * 8);  // [stages][kTile]
   uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + (size_t)stages * kTileBytes);      // [kMaxStages]
-  uint32_t* cnt = reinterpret_cast<uint32_t*>(smem_raw + (size_t)stages * kTileBytes + 64);
-  uint32_t* head = cnt + Kp;
-  uint32_t* node = head + Kp;          // [kTile]
-  uint32_t* res_list = node + kTile;   // [kResCap]
+  uint32_t* cnt = reinterpret_cast<uint32_t*>(smem_raw + (size_t)stages * kTileBytes + 64);  // [Kp]
+  uint32_t* head = cnt + Kp;                 // [kHeadSlots]
+  uint32_t* node = head + kHeadSlots;        // [kTile]
+  uint32_t* res_list = node + kTile;         // [kRes2]
+  uint16_t* nbin = reinterpret_cast<uint16_t*>(res_list + kRes2);  // [kTile] heavy path: bin of a group node
+  uint16_t* wc = nbin + kTile;                                     // dense only: [Kp][kDenseStride] group sizes
+  uint16_t* pf = wc + (size_t)Kp * kDenseStride;                    // dense only: their exclusive prefixes
+  uint32_t* cbase = reinterpret_cast<uint32_t*>(pf + (size_t)Kp * kDenseStride);  // dense only: [Kp]
   __shared__ uint32_t s_nres;
-  __shared__ uint32_t s_shift[kMaxSegs], s_lim[kMaxSegs];
 
-  const uint32_t tid = threadIdx.x, lane = tid & 31;
+  const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t lt_mask = (1u << lane) - 1u;
   const uint32_t row = blockIdx.x;
   const uint64_t pol_in = policy_evict_first(), pol_out = policy_evict_last();
@@ -573,104 +617,147 @@ __global__ void __launch_bounds__(kBlock, 1)
       tma_load_1d(ring_bins + (size_t)t * kTile, bins16 + beg + (size_t)t * kTile, kTile * 2, &full[t], pol_in);
     }
   }
-  for (uint32_t i = tid; i < n_segs; i += kBlock) { s_shift[i] = seg_shift[i]; s_lim[i] = seg_lim[i]; }
-  __syncthreads();
   {
     const uint32_t* mrow = M + (size_t)row * Kp;
     const uint32_t* mnext = (row + 1 < R) ? mrow + Kp : tot;
-    for (uint32_t i = tid; i < Kp; i += kBlock) {
+    for (uint32_t i = tid; i < Kp; i += BLOCK) {
       uint32_t v = 0;
       if (i < K) {
         const uint32_t pre = mrow[i], c = mnext[i] - pre;
         const uint32_t sg = bin_seg[i];
-        const uint32_t start = binbase[i] - s_shift[sg] + pre;
-        v = start | ((start + c > s_lim[sg]) ? 0x80000000u : 0u);
+        const uint32_t start = binbase[i] - __ldg(&seg_shift[sg]) + pre;  // slot of the cell's first player
+        v = start | ((start + c > __ldg(&seg_lim[sg])) ? 0x80000000u : 0u);
       }
       cnt[i] = v;
-      head[i] = 0;
     }
+    for (uint32_t i = tid; i < kHeadSlots; i += BLOCK) head[i] = 0;
+    if (dense)
+      for (uint32_t i = tid; i < Kp * kDenseStride / 2; i += BLOCK) reinterpret_cast<uint32_t*>(wc)[i] = 0;
   }
   const bool heavy = ctr->heavy != 0;
   __syncthreads();
 
+  uint32_t st = 0, parity = 0;
   for (uint32_t t = 0; t < n_tiles; ++t) {
-    const uint32_t st = t % stages;
     const uint32_t tile_base = beg + t * kTile;
+    const uint32_t valid = end - tile_base;  // players of this tile inside the row (>= kTile except the last)
     const uint16_t* tb = ring_bins + (size_t)st * kTile;
     const uint64_t* ti = ring_ids + (size_t)st * kTile;
-    mbar_wait(&full[st], (t / stages) & 1u);
+    mbar_wait(&full[st], parity);
     const uint32_t epoch = t + 1;
-    uint32_t bin[2], slot[2];
-    bool flag[2];
+    uint32_t bin[J], slot[J];
+    bool flag[J];
 #pragma unroll
-    for (int j = 0; j < 2; ++j) {
-      const uint32_t pos = j * kBlock + tid;
-      bin[j] = (tile_base + pos < end) ? (uint32_t)tb[pos] : 0xFFFFu;
+    for (int j = 0; j < J; ++j) {
+      const uint32_t pos = j * BLOCK + tid;
+      bin[j] = (pos < valid) ? (uint32_t)tb[pos] : 0xFFFFu;
       slot[j] = 0; flag[j] = false;
     }
-    if (!heavy) {
-      uint32_t snap[2], pn[2];
+    if (dense) {
+      // per-(bin, warp-batch) group sizes in a small matrix, one shuffle scan per bin across
+      // the tile's 64 warp-batches (batch = j * NW + warp, increasing with tile position)
+      uint32_t rankw[J];
 #pragma unroll
-      for (int j = 0; j < 2; ++j) {
-        const uint32_t pos = j * kBlock + tid;
-        snap[j] = 0; pn[j] = 0;
+      for (int j = 0; j < J; ++j) {
+        const uint32_t mask = __match_any_sync(0xFFFFFFFFu, bin[j]);
+        rankw[j] = __popc(mask & lt_mask);
+        if (lane == (uint32_t)(__ffs(mask) - 1) && bin[j] < K)
+          wc[bin[j] * kDenseStride + j * NW + warp] = (uint16_t)__popc(mask);
+      }
+      __syncthreads();
+      for (uint32_t b = warp; b < K; b += NW) {  // lane l owns warp-batches 2l, 2l+1
+        uint32_t* w32 = reinterpret_cast<uint32_t*>(wc + b * kDenseStride) + lane;
+        const uint32_t two = *w32;
+        *w32 = 0;  // the matrix is all-zero again for the next tile
+        const uint32_t c0 = two & 0xFFFFu, c1 = two >> 16;
+        uint32_t incl = c0 + c1;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+          const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, incl, off);
+          if (lane >= (uint32_t)off) incl += v;
+        }
+        const uint32_t excl = incl - c0 - c1;
+        reinterpret_cast<uint32_t*>(pf + b * kDenseStride)[lane] = excl | ((excl + c0) << 16);
+        if (lane == 31) { const uint32_t base = cnt[b]; cbase[b] = base; cnt[b] = base + incl; }
+      }
+      __syncthreads();
+#pragma unroll
+      for (int j = 0; j < J; ++j) {
+        if (bin[j] < K) {
+          const uint32_t base = cbase[bin[j]];
+          slot[j] = (base & 0x7FFFFFFFu) + pf[bin[j] * kDenseStride + j * NW + warp] + rankw[j];
+          flag[j] = (base >> 31) != 0;
+        }
+      }
+    } else if (!heavy) {
+      uint32_t snap[J];
+#pragma unroll
+      for (int j = 0; j < J; ++j) {
+        const uint32_t pos = j * BLOCK + tid;
+        snap[j] = 0;
         if (bin[j] < K) {
           snap[j] = cnt[bin[j]];
-          const uint32_t prev = atomicExch(&head[bin[j]], (epoch << 12) | pos);
-          pn[j] = ((prev >> 12) == epoch) ? (prev & 0xFFFu) : 0xFFFu;
-          node[pos] = pn[j];
+          const uint32_t prev = atomicExch(&head[bin[j] & (kHeadSlots - 1)], (epoch << 12) | pos);
+          const uint32_t pn = ((prev >> 12) == epoch) ? (prev & 0xFFFu) : 0xFFFu;
+          node[pos] = pn | (bin[j] << 12);
         }
       }
       __syncthreads();
 #pragma unroll
-      for (int j = 0; j < 2; ++j) {
-        const uint32_t pos = j * kBlock + tid;
+      for (int j = 0; j < J; ++j) {
+        const uint32_t pos = j * BLOCK + tid;
         if (bin[j] < K) {
-          uint32_t cur = head[bin[j]] & 0xFFFu, lower = 0, total = 0;
+          uint32_t cur = head[bin[j] & (kHeadSlots - 1)] & 0xFFFu, lower = 0, total = 0;
           while (cur != 0xFFFu) {
-            ++total;
-            lower += (cur < pos) ? 1u : 0u;
-            cur = node[cur];
+            const uint32_t nd = node[cur];
+            if ((nd >> 12) == bin[j]) {  // the slot is shared by bins congruent mod kHeadSlots
+              ++total;
+              lower += (cur < pos) ? 1u : 0u;
+            }
+            cur = nd & 0xFFFu;
           }
           slot[j] = (snap[j] & 0x7FFFFFFFu) + lower;
           flag[j] = (snap[j] >> 31) != 0;
-          if (pn[j] == 0xFFFu) cnt[bin[j]] = snap[j] + total;
+          if (lower == 0) cnt[bin[j]] = snap[j] + total;  // the bin's earliest player of the tile
         }
       }
     } else {
-      uint32_t snap[2], leader[2], rankw[2], mynode[2];
-      bool isl[2], first[2];
+      uint32_t snap[J], leader[J], rankw[J];
+      bool isl[J];
 #pragma unroll
-      for (int j = 0; j < 2; ++j) {
+      for (int j = 0; j < J; ++j) {
+        const uint32_t pos = j * BLOCK + tid;
         const uint32_t mask = __match_any_sync(0xFFFFFFFFu, bin[j]);
         leader[j] = __ffs(mask) - 1;
         rankw[j] = __popc(mask & lt_mask);
         isl[j] = (lane == leader[j]) && (bin[j] < K);
-        first[j] = false; snap[j] = 0;
-        mynode[j] = j * kBlock + tid;
+        snap[j] = 0;
         if (isl[j]) {
           snap[j] = cnt[bin[j]];
-          const uint32_t prev = atomicExch(&head[bin[j]], (epoch << 12) | mynode[j]);
-          const uint32_t prevnode = ((prev >> 12) == epoch) ? (prev & 0xFFFu) : 0xFFFu;
-          node[mynode[j]] = prevnode | ((uint32_t)__popc(mask) << 12);
-          first[j] = (prevnode == 0xFFFu);
+          const uint32_t prev = atomicExch(&head[bin[j] & (kHeadSlots - 1)], (epoch << 12) | pos);
+          const uint32_t pn = ((prev >> 12) == epoch) ? (prev & 0xFFFu) : 0xFFFu;
+          node[pos] = pn | ((uint32_t)__popc(mask) << 12);
+          nbin[pos] = (uint16_t)bin[j];
         }
       }
       __syncthreads();
 #pragma unroll
-      for (int j = 0; j < 2; ++j) {
+      for (int j = 0; j < J; ++j) {
+        const uint32_t pos = j * BLOCK + tid;
         uint32_t bg = 0;
         if (isl[j]) {
-          uint32_t cur = head[bin[j]] & 0xFFFu, lower = 0, total = 0;
+          uint32_t cur = head[bin[j] & (kHeadSlots - 1)] & 0xFFFu, lower = 0, total = 0;
           while (cur != 0xFFFu) {
             const uint32_t nd = node[cur];
-            const uint32_t c = nd >> 12;
-            total += c;
-            if (cur < mynode[j]) lower += c;
+            if (nbin[cur] == bin[j]) {
+              const uint32_t c = nd >> 12;
+              total += c;
+              if (cur < pos) lower += c;
+            }
             cur = nd & 0xFFFu;
           }
           bg = snap[j] + lower;
-          if (first[j]) cnt[bin[j]] = snap[j] + total;
+          if (lower == 0) cnt[bin[j]] = snap[j] + total;
         }
         bg = __shfl_sync(0xFFFFFFFFu, bg, leader[j]);
         slot[j] = (bg & 0x7FFFFFFFu) + rankw[j];
@@ -678,17 +765,17 @@ __global__ void __launch_bounds__(kBlock, 1)
       }
     }
 #pragma unroll
-    for (int j = 0; j < 2; ++j) {
+    for (int j = 0; j < J; ++j) {
       if (bin[j] < K) {
-        const uint32_t pos = j * kBlock + tid;
+        const uint32_t pos = j * BLOCK + tid;
         bool matched = true;
-        if (flag[j]) matched = slot[j] < s_lim[__ldg(&bin_seg[bin[j]])];
+        if (flag[j]) matched = slot[j] < __ldg(&seg_lim[__ldg(&bin_seg[bin[j]])]);
         if (matched) {
           st_keep_u64(members + slot[j], ti[pos], pol_out);
           if (src_idx) src_idx[slot[j]] = tile_base + pos;
         } else {
           const uint32_t k = atomicAdd(&s_nres, 1u);
-          if (k < kResCap) res_list[k] = tile_base + pos;
+          if (k < kRes2) res_list[k] = tile_base + pos;
         }
       }
     }
@@ -699,17 +786,18 @@ __global__ void __launch_bounds__(kBlock, 1)
       tma_load_1d(ring_ids + (size_t)st * kTile, ids + beg + (size_t)tn * kTile, kTile * 8, &full[st], pol_in);
       tma_load_1d(ring_bins + (size_t)st * kTile, bins16 + beg + (size_t)tn * kTile, kTile * 2, &full[st], pol_in);
     }
+    if (++st == stages) { st = 0; parity ^= 1u; }
   }
 
   // the row's residual players, in enqueue order
   __syncthreads();
   const uint32_t nres_all = s_nres;
-  const uint32_t nres = nres_all < kResCap ? nres_all : kResCap;
+  const uint32_t nres = nres_all < kRes2 ? nres_all : kRes2;
   if (tid == 0) {
     rescnt[row] = nres;
-    if (nres_all > kResCap) atomicExch(&ctr->overflow, 1u);
+    if (nres_all > kRes2) atomicExch(&ctr->overflow, 1u);
   }
-  for (uint32_t t = tid; t < nres; t += kBlock) {
+  for (uint32_t t = tid; t < nres; t += BLOCK) {
     const uint32_t v = res_list[t];
     uint32_t rank = 0;
     for (uint32_t u = 0; u < nres; ++u) rank += (res_list[u] < v) ? 1u : 0u;
@@ -730,13 +818,14 @@ __global__ void __launch_bounds__(1024) k_epilogue(PoolView src, PoolView dst, u
                                                    const SegInfo* __restrict__ seg, const uint32_t* __restrict__ seg_L,
                                                    uint32_t n_segs, uint32_t n_groups, mm_lobby_hdr* __restrict__ hdr,
                                                    const uint32_t* __restrict__ src_idx, uint32_t* __restrict__ emit_seq,
-                                                   TickCtr* ctr) {
+                                                   uint32_t* __restrict__ tot, uint32_t Kp, TickCtr* ctr) {
   __shared__ uint32_t s_off[kMaxRows + 1];
   __shared__ uint32_t s_tmp[1024];
   __shared__ uint32_t s_lbase[kMaxSegs + 1], s_mbase[kMaxSegs], s_L[kMaxSegs];
   const uint32_t tid = threadIdx.x;
   for (uint32_t s = tid; s < n_segs; s += 1024) { s_lbase[s] = seg[s].lobby_base; s_mbase[s] = seg[s].member_base; s_L[s] = seg_L[s]; }
   __syncthreads();
+  for (uint32_t i = blockIdx.x * 1024 + tid; i < Kp; i += gridDim.x * 1024) tot[i] = 0;  // ready for the next tick
   const uint32_t total_lob = ctr->n_lobbies;
   for (uint32_t c = blockIdx.x * 1024 + tid; c < total_lob; c += gridDim.x * 1024) {
     uint32_t a = 0, e = n_segs;  // last segment with lobby_base <= c

@@ -24,9 +24,9 @@ def run(label, reps=6, **opts):
         if i >= 2: dev.append(st.device_us); pl.append(st.place_us)
     print(json.dumps({"variant": label, "workload": name, "order": order, "device_us": round(float(np.mean(dev)), 1),
                       "place_us": round(float(np.mean(pl)), 1), "place_min": round(float(np.min(pl)), 1), "lobbies": st.n_lobbies}), flush=True)
-run("impl3 stages=4 persist", rank_impl=3, place2_stages=4)
-run("impl3 stages=3 persist", place2_stages=3)
-run("impl3 stages=2 persist", place2_stages=2)
-run("impl3 stages=4 nopersist", place2_stages=4, persist_mb=0)
-run("impl1 hints persist", rank_impl=1, l2_hints=1, persist_mb=1024)
-run("impl1 dbg3 streaming copy", place_debug=3)
+run("impl3 auto (block512 x2 rows/SM)")
+run("impl3 block1024 rows1 stages4", rows_per_sm=1, block=1024, place2_stages=4)
+run("impl3 block512 rows1 stages4", block=512)
+run("impl3 block512 rows2 stages2", rows_per_sm=2, place2_stages=2)
+run("impl3 block512 rows2 stages2 dense=0", dense=0)
+run("impl1 legacy", rank_impl=1, rows_per_sm=1, block=1024)
