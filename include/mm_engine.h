@@ -98,6 +98,10 @@ typedef struct mm_tick_stats {
   uint32_t n_launches;    /* kernels launched by this tick                             */
   float device_us;        /* CUDA-event time of the whole tick on the engine's stream  */
   float place_us;         /* CUDA-event time of the dominant (placement) kernel        */
+  float hist_us;          /* ... of the histogram kernel                               */
+  float scan_us;          /* ... of the column-scan kernel                             */
+  float epilogue_us;      /* ... of the epilogue kernel (headers + pool compaction)    */
+  uint32_t reserved;
 } mm_tick_stats;
 
 typedef struct mm_engine mm_engine;

@@ -63,6 +63,10 @@ class TickStats(C.Structure):
         ("n_launches", C.c_uint32),
         ("device_us", C.c_float),
         ("place_us", C.c_float),
+        ("hist_us", C.c_float),
+        ("scan_us", C.c_float),
+        ("epilogue_us", C.c_float),
+        ("reserved", C.c_uint32),
     ]
 
 

@@ -42,7 +42,7 @@ struct mm_engine {
   int block = 1024;  // threads per row CTA (512 when two rows share an SM)
   cudaStream_t stream = nullptr;
   bool own_stream = true;
-  cudaEvent_t ev[4]{};
+  cudaEvent_t ev[5]{};  // tick start | after hist | after colscan | after place | after epilogue
   char last_err[512] = {0};
 
   // key domain
@@ -80,6 +80,8 @@ struct mm_engine {
   int place_debug = 0;
   size_t persist_bytes = 0;
   uint32_t place2_stages = 0;  // 0 = k_place2 does not fit in shared memory
+  uint32_t hist2_stages = 0;   // 0 = use the register-fed k_hist
+  int hist_impl = 2;
   int dense_ok = 1;            // allow the small-K dense ranking path
   uint16_t* d_bins16 = nullptr;
   uint32_t* d_M = nullptr;
@@ -180,6 +182,9 @@ bool place2_dense(const mm_engine* e) { return e->Kp <= kDenseMaxBins; }
 size_t place2_smem(const mm_engine* e, uint32_t stages) {
   return (size_t)stages * kTileBytes + 64 + ((size_t)e->Kp + kHeadSlots + kTile + kRes2) * 4 + (size_t)kTile * 2 +
          (place2_dense(e) ? (size_t)e->Kp * kDenseStride * 2 * 2 + (size_t)e->Kp * 4 : 0) + 16;
+}
+size_t hist2_smem(const mm_engine* e, uint32_t stages) {
+  return (size_t)stages * kHTileBytes + 64 + (size_t)e->Kp * 4 + (size_t)e->KR * 2 + 16;
 }
 size_t hist_smem(const mm_engine* e) { return (size_t)e->Kp * 4 + (size_t)e->KR * 2 + 16; }
 
@@ -361,12 +366,20 @@ int tick_phase_a(mm_engine* e, uint32_t n, uint32_t* chunk_out) {
   *chunk_out = chunk;
   CK(cudaMemsetAsync(e->d_ctr, 0, sizeof(TickCtr), e->stream));
   CK(cudaEventRecord(e->ev[0], e->stream));
-  if (e->block == 512)
+  if (e->rank_impl == 3 && e->hist_impl == 2 && e->hist2_stages) {
+    if (e->block == 512)
+      k_hist2<512><<<e->R, 512, hist2_smem(e, e->hist2_stages), e->stream>>>(p.v, n, chunk, bin_map(e), e->Kp,
+                                                                               e->hist2_stages, e->d_M, e->d_tot, e->d_bins16);
+    else
+      k_hist2<1024><<<e->R, 1024, hist2_smem(e, e->hist2_stages), e->stream>>>(p.v, n, chunk, bin_map(e), e->Kp,
+                                                                                 e->hist2_stages, e->d_M, e->d_tot, e->d_bins16);
+  } else if (e->block == 512)
     k_hist<512><<<e->R, 512, hist_smem(e), e->stream>>>(p.v, n, chunk, bin_map(e), e->Kp, e->d_M, e->d_tot,
                                                         e->rank_impl == 3 ? e->d_bins16 : nullptr);
   else
     k_hist<1024><<<e->R, 1024, hist_smem(e), e->stream>>>(p.v, n, chunk, bin_map(e), e->Kp, e->d_M, e->d_tot,
                                                           e->rank_impl == 3 ? e->d_bins16 : nullptr);
+  CK(cudaEventRecord(e->ev[1], e->stream));
   k_colscan<<<(e->Kp + 31) / 32 + 1, kScanBlock, 0, e->stream>>>(e->R, e->Kp, e->K, e->d_M, e->d_tot, e->d_binbase, e->d_seg_bin_lo,
                                                         e->d_seg_L, e->n_segs, e->d_seg, e->d_seg_shift, e->d_seg_lim,
                                                         e->d_ctr);
@@ -378,7 +391,7 @@ int tick_phase_b(mm_engine* e, uint32_t n, uint32_t chunk, bool want_seq) {
   const Pool& p = e->pool[e->cur];
   Pool& q = e->pool[e->cur ^ 1];
   uint32_t* src_idx = want_seq ? e->d_src_idx : nullptr;
-  CK(cudaEventRecord(e->ev[1], e->stream));
+  CK(cudaEventRecord(e->ev[2], e->stream));
 #define MM_PLACE(IMPL, DBG, HINT)                                                                                    \
   k_place<IMPL, DBG, HINT><<<e->R, kBlock, place_smem(e, IMPL), e->stream>>>(                                         \
       p.v, n, chunk, bin_map(e), e->Kp, e->R, e->d_M, e->d_tot, e->d_binbase, e->d_bin_seg, e->d_seg_shift,           \
@@ -400,13 +413,13 @@ int tick_phase_b(mm_engine* e, uint32_t n, uint32_t chunk, bool want_seq) {
   else if (e->l2_hints) MM_PLACE(1, 0, true);
   else MM_PLACE(1, 0, false);
 #undef MM_PLACE
-  CK(cudaEventRecord(e->ev[2], e->stream));
+  CK(cudaEventRecord(e->ev[3], e->stream));
   k_epilogue<<<std::max(1, e->n_sms), 1024, 0, e->stream>>>(p.v, q.v, e->R, e->d_rescnt, e->d_resid_stage, act_view(e),
                                                            e->gen + 1, e->d_seg, e->d_seg_L, e->n_segs, e->cfg.n_groups,
                                                            e->d_hdr, src_idx, want_seq ? e->d_emit_seq : nullptr, e->d_tot,
                                                            e->Kp, e->d_ctr);
   CK(cudaGetLastError());
-  CK(cudaEventRecord(e->ev[3], e->stream));
+  CK(cudaEventRecord(e->ev[4], e->stream));
   CK(cudaMemcpyAsync(e->h_ctr, e->d_ctr, sizeof(TickCtr), cudaMemcpyDeviceToHost, e->stream));
   CK(cudaStreamSynchronize(e->stream));
   return MM_OK;
@@ -422,10 +435,16 @@ int tick_commit(mm_engine* e, uint32_t n, mm_tick_stats* stats) {
   st.pool_before = n; st.n_lobbies = c.n_lobbies; st.n_matched = c.n_matched; st.n_residual = c.n_resid;
   st.n_dead = c.n_dead; st.n_launches = 4;
   float ms = 0;
-  CK(cudaEventElapsedTime(&ms, e->ev[0], e->ev[3]));
+  CK(cudaEventElapsedTime(&ms, e->ev[0], e->ev[4]));
   st.device_us = ms * 1000.f;
+  CK(cudaEventElapsedTime(&ms, e->ev[0], e->ev[1]));
+  st.hist_us = ms * 1000.f;
   CK(cudaEventElapsedTime(&ms, e->ev[1], e->ev[2]));
+  st.scan_us = ms * 1000.f;
+  CK(cudaEventElapsedTime(&ms, e->ev[2], e->ev[3]));
   st.place_us = ms * 1000.f;
+  CK(cudaEventElapsedTime(&ms, e->ev[3], e->ev[4]));
+  st.epilogue_us = ms * 1000.f;
   e->cur ^= 1;
   e->pool[e->cur].n = c.n_resid;
   e->gen += 1;
@@ -532,6 +551,16 @@ int mm_create(const mm_config* cfg, mm_engine** out) {
         if (place2_smem(e, st) + 1024 <= e->smem_optin) { e->place2_stages = st; e->rows_per_sm = 1; e->block = 1024; }
     }
     if (ok && e->place2_stages) {
+      for (uint32_t st = 3; st >= 2 && !e->hist2_stages; --st)
+        if ((size_t)e->rows_per_sm * (hist2_smem(e, st) + 1024 + 256) <= e->smem_sm && hist2_smem(e, st) + 1024 <= e->smem_optin)
+          e->hist2_stages = st;
+      if (e->hist2_stages) {
+        const int hs = (int)hist2_smem(e, e->hist2_stages);
+        ok = cudaFuncSetAttribute(k_hist2<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, hs) == cudaSuccess &&
+             cudaFuncSetAttribute(k_hist2<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, hs) == cudaSuccess;
+      }
+    }
+    if (ok && e->place2_stages) {
       const int sz = (int)place2_smem(e, e->place2_stages);
       ok = cudaFuncSetAttribute(k_place2<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, sz) == cudaSuccess &&
            cudaFuncSetAttribute(k_place2<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, sz) == cudaSuccess;
@@ -626,6 +655,7 @@ int mm_set_option(mm_engine* e, const char* name, int64_t value) {
   }
   if (!std::strcmp(name, "l2_hints")) { e->l2_hints = value != 0; return MM_OK; }
   if (!std::strcmp(name, "dense")) { e->dense_ok = value != 0; return MM_OK; }
+  if (!std::strcmp(name, "hist_impl")) { e->hist_impl = (int)value; return MM_OK; }
   if (!std::strcmp(name, "place_debug")) {  // timing experiments only: results are NOT valid
     if (value < 0 || value > 3) return MM_E_ARG;
     e->place_debug = (int)value;

@@ -243,6 +243,86 @@ __global__ void __launch_bounds__(BLOCK) k_hist(PoolView p, uint32_t n, uint32_t
 }
 
 // ---------------------------------------------------------------------------------------
+// k_hist2<BLOCK>: k_hist fed by a TMA ring.  One thread keeps `stages` bulk copies of
+// (rating i32[4096], mode u8[4096]) tiles in flight; the CTA only does shared-memory reads,
+// the LUT, shared-memory histogram atomics and the 64-bit bin stores — one barrier per tile.
+// ---------------------------------------------------------------------------------------
+constexpr uint32_t kHTile = 4096;
+constexpr uint32_t kHTileBytes = kHTile * 5;
+
+template <int BLOCK>
+__global__ void __launch_bounds__(BLOCK, (BLOCK == 512 ? 2 : 1))
+    k_hist2(PoolView p, uint32_t n, uint32_t chunk, BinMap bm, uint32_t Kp, uint32_t stages, uint32_t* __restrict__ M,
+            uint32_t* __restrict__ tot, uint16_t* __restrict__ bins16) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  int32_t* ring_r = reinterpret_cast<int32_t*>(smem_raw);                                   // [stages][kHTile]
+  uint8_t* ring_m = smem_raw + (size_t)stages * kHTile * 4;                                  // [stages][kHTile]
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + (size_t)stages * kHTileBytes);     // [kMaxStages]
+  uint32_t* hist = reinterpret_cast<uint32_t*>(smem_raw + (size_t)stages * kHTileBytes + 64);  // [Kp]
+  uint16_t* s_lut = reinterpret_cast<uint16_t*>(hist + Kp);                                  // [KR]
+  const uint32_t tid = threadIdx.x;
+  const uint64_t pol_in = policy_evict_first();
+  const uint64_t beg64 = (uint64_t)blockIdx.x * chunk;
+  const uint32_t beg = beg64 < n ? (uint32_t)beg64 : n;
+  const uint32_t end = (beg64 + chunk < n) ? (uint32_t)(beg64 + chunk) : n;
+  const uint32_t n_tiles = (end - beg + kHTile - 1) / kHTile;
+  if (tid == 0) {
+    for (uint32_t s = 0; s < stages; ++s) mbar_init(&full[s], 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+  if (tid == 0)
+    for (uint32_t t = 0; t < stages && t < n_tiles; ++t) {
+      mbar_expect_tx(&full[t], kHTileBytes);
+      tma_load_1d(ring_r + (size_t)t * kHTile, p.rating + beg + (size_t)t * kHTile, kHTile * 4, &full[t], pol_in);
+      tma_load_1d(ring_m + (size_t)t * kHTile, p.mode + beg + (size_t)t * kHTile, kHTile, &full[t], pol_in);
+    }
+  for (uint32_t i = tid; i < Kp; i += BLOCK) hist[i] = 0;
+  for (uint32_t i = tid; i < bm.KR; i += BLOCK) s_lut[i] = bm.lut[i];
+  __syncthreads();
+  uint32_t st = 0, parity = 0;
+  for (uint32_t t = 0; t < n_tiles; ++t) {
+    const uint32_t tile_base = beg + t * kHTile;
+    const uint32_t valid = end - tile_base;
+    const int32_t* tr = ring_r + (size_t)st * kHTile;
+    const uint8_t* tm = ring_m + (size_t)st * kHTile;
+    mbar_wait(&full[st], parity);
+#pragma unroll
+    for (uint32_t q = tid; q < kHTile / 4; q += BLOCK) {
+      const uint32_t o = q * 4;
+      if (o + 4 <= valid) {
+        const int4 r = *reinterpret_cast<const int4*>(tr + o);
+        const uint32_t m = *reinterpret_cast<const uint32_t*>(tm + o);
+        const uint32_t b0 = bin_of(bm, s_lut, r.x, m & 0xFF), b1 = bin_of(bm, s_lut, r.y, (m >> 8) & 0xFF);
+        const uint32_t b2 = bin_of(bm, s_lut, r.z, (m >> 16) & 0xFF), b3 = bin_of(bm, s_lut, r.w, m >> 24);
+        atomicAdd(&hist[b0], 1u); atomicAdd(&hist[b1], 1u); atomicAdd(&hist[b2], 1u); atomicAdd(&hist[b3], 1u);
+        *reinterpret_cast<uint2*>(bins16 + tile_base + o) = make_uint2(b0 | (b1 << 16), b2 | (b3 << 16));
+      } else if (o < valid) {
+        for (uint32_t k = o; k < valid; ++k) {
+          const uint32_t bb = bin_of(bm, s_lut, tr[k], tm[k]);
+          atomicAdd(&hist[bb], 1u);
+          bins16[tile_base + k] = (uint16_t)bb;
+        }
+      }
+    }
+    __syncthreads();
+    if (tid == 0 && t + stages < n_tiles) {
+      const uint32_t tn = t + stages;
+      mbar_expect_tx(&full[st], kHTileBytes);
+      tma_load_1d(ring_r + (size_t)st * kHTile, p.rating + beg + (size_t)tn * kHTile, kHTile * 4, &full[st], pol_in);
+      tma_load_1d(ring_m + (size_t)st * kHTile, p.mode + beg + (size_t)tn * kHTile, kHTile, &full[st], pol_in);
+    }
+    if (++st == stages) { st = 0; parity ^= 1u; }
+  }
+  uint32_t* row = M + (size_t)blockIdx.x * Kp;
+  for (uint32_t i = tid; i < Kp; i += BLOCK) {
+    const uint32_t v = hist[i];
+    row[i] = v;
+    if (v) atomicAdd(&tot[i], v);
+  }
+}
+
+// ---------------------------------------------------------------------------------------
 // k_colscan: exclusive prefix down every column of M.  A column CTA is 32 bins wide
 // (lanes = consecutive bins, coalesced) and 16 row-slices deep (warps): every thread sums
 // its slice of rows, the slices are scanned through shared memory, then the slice is
@@ -272,19 +352,30 @@ __global__ void __launch_bounds__(kScanBlock) k_colscan(uint32_t R, uint32_t Kp,
     const uint32_t b = blockIdx.x * 32 + x;
     const uint32_t rp = (R + NY - 1) / NY;
     const uint32_t r0 = y * rp < R ? y * rp : R, r1 = (r0 + rp < R) ? r0 + rp : R;
+    constexpr int kU = 8;  // independent loads in flight per thread
     uint32_t sum = 0;
     if (b < Kp)
-      for (uint32_t r = r0; r < r1; ++r) sum += __ldcg(M + (size_t)r * Kp + b);
+      for (uint32_t r = r0; r < r1; r += kU) {
+        uint32_t v[kU];
+#pragma unroll
+        for (int k = 0; k < kU; ++k) v[k] = (r + k < r1) ? __ldcg(M + (size_t)(r + k) * Kp + b) : 0u;
+#pragma unroll
+        for (int k = 0; k < kU; ++k) sum += v[k];
+      }
     s_part[y][x] = sum;
     __syncthreads();
     uint32_t run = 0;
     for (uint32_t yy = 0; yy < y; ++yy) run += s_part[yy][x];
     if (b < Kp)
-      for (uint32_t r = r0; r < r1; ++r) {
-        uint32_t* p = M + (size_t)r * Kp + b;
-        const uint32_t v = __ldcg(p);
-        *p = run;
-        run += v;
+      for (uint32_t r = r0; r < r1; r += kU) {
+        uint32_t v[kU];
+#pragma unroll
+        for (int k = 0; k < kU; ++k) v[k] = (r + k < r1) ? __ldcg(M + (size_t)(r + k) * Kp + b) : 0u;
+#pragma unroll
+        for (int k = 0; k < kU; ++k) {
+          if (r + k < r1) M[(size_t)(r + k) * Kp + b] = run;
+          run += v[k];
+        }
       }
     return;
   }
@@ -646,6 +737,7 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK == 512 ? 2 : 1))
     mbar_wait(&full[st], parity);
     const uint32_t epoch = t + 1;
     uint32_t bin[J], slot[J];
+    uint64_t idv[J];
     bool flag[J];
 #pragma unroll
     for (int j = 0; j < J; ++j) {
@@ -703,22 +795,35 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK == 512 ? 2 : 1))
         }
       }
       __syncthreads();
+      // walk the J lists in lockstep: J independent shared-memory loads in flight per step
+      uint32_t cur[J], lower[J], total[J];
 #pragma unroll
       for (int j = 0; j < J; ++j) {
-        const uint32_t pos = j * BLOCK + tid;
-        if (bin[j] < K) {
-          uint32_t cur = head[bin[j] & (kHeadSlots - 1)] & 0xFFFu, lower = 0, total = 0;
-          while (cur != 0xFFFu) {
-            const uint32_t nd = node[cur];
-            if ((nd >> 12) == bin[j]) {  // the slot is shared by bins congruent mod kHeadSlots
-              ++total;
-              lower += (cur < pos) ? 1u : 0u;
-            }
-            cur = nd & 0xFFFu;
+        cur[j] = (bin[j] < K) ? (head[bin[j] & (kHeadSlots - 1)] & 0xFFFu) : 0xFFFu;
+        lower[j] = 0; total[j] = 0;
+        idv[j] = ti[j * BLOCK + tid];
+      }
+      for (;;) {
+        bool more = false;
+#pragma unroll
+        for (int j = 0; j < J; ++j) {
+          if (cur[j] != 0xFFFu) {
+            const uint32_t nd = node[cur[j]];
+            const bool same = (nd >> 12) == bin[j];  // the slot is shared by bins congruent mod kHeadSlots
+            total[j] += same ? 1u : 0u;
+            lower[j] += (same && cur[j] < (uint32_t)(j * BLOCK) + tid) ? 1u : 0u;
+            cur[j] = nd & 0xFFFu;
+            more |= cur[j] != 0xFFFu;
           }
-          slot[j] = (snap[j] & 0x7FFFFFFFu) + lower;
+        }
+        if (!more) break;
+      }
+#pragma unroll
+      for (int j = 0; j < J; ++j) {
+        if (bin[j] < K) {
+          slot[j] = (snap[j] & 0x7FFFFFFFu) + lower[j];
           flag[j] = (snap[j] >> 31) != 0;
-          if (lower == 0) cnt[bin[j]] = snap[j] + total;  // the bin's earliest player of the tile
+          if (lower[j] == 0) cnt[bin[j]] = snap[j] + total[j];  // the bin's earliest player of the tile
         }
       }
     } else {
@@ -764,6 +869,10 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK == 512 ? 2 : 1))
         flag[j] = (bg >> 31) != 0;
       }
     }
+    if (dense || heavy) {
+#pragma unroll
+      for (int j = 0; j < J; ++j) idv[j] = ti[j * BLOCK + tid];
+    }
 #pragma unroll
     for (int j = 0; j < J; ++j) {
       if (bin[j] < K) {
@@ -771,7 +880,7 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK == 512 ? 2 : 1))
         bool matched = true;
         if (flag[j]) matched = slot[j] < __ldg(&seg_lim[__ldg(&bin_seg[bin[j]])]);
         if (matched) {
-          st_keep_u64(members + slot[j], ti[pos], pol_out);
+          st_keep_u64(members + slot[j], idv[j], pol_out);
           if (src_idx) src_idx[slot[j]] = tile_base + pos;
         } else {
           const uint32_t k = atomicAdd(&s_nres, 1u);

@@ -31,7 +31,7 @@ def test_header_symbols_all_exported(pkg, lib):
 def test_struct_layouts_match_header(pkg):
     abi = pkg.abi
     assert C.sizeof(abi.LobbyHdr) == 8
-    assert C.sizeof(abi.TickStats) == 32
+    assert C.sizeof(abi.TickStats) == 48
     assert C.sizeof(abi.ModeDesc) == 4
     assert C.sizeof(abi.Config) == 4 * 2 + 4 * 64 * 2 + 4 + 4 + 4 * 8 + 4 * 5
 

@@ -17,16 +17,15 @@ flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 def run(label, reps=6, **opts):
     for k, v in opts.items():
         eng.set_option(k, v)
-    dev, pl = [], []
+    dev, pl, hs, sc, ep = [], [], [], [], []
     for i in range(reps):
         eng.restore(); flush.fill_(1); torch.cuda.synchronize()
         st = eng.tick_device()
-        if i >= 2: dev.append(st.device_us); pl.append(st.place_us)
+        if i >= 2: dev.append(st.device_us); pl.append(st.place_us); hs.append(st.hist_us); sc.append(st.scan_us); ep.append(st.epilogue_us)
     print(json.dumps({"variant": label, "workload": name, "order": order, "device_us": round(float(np.mean(dev)), 1),
-                      "place_us": round(float(np.mean(pl)), 1), "place_min": round(float(np.min(pl)), 1), "lobbies": st.n_lobbies}), flush=True)
-run("impl3 auto (block512 x2 rows/SM)")
-run("impl3 block1024 rows1 stages4", rows_per_sm=1, block=1024, place2_stages=4)
-run("impl3 block512 rows1 stages4", block=512)
-run("impl3 block512 rows2 stages2", rows_per_sm=2, place2_stages=2)
-run("impl3 block512 rows2 stages2 dense=0", dense=0)
-run("impl1 legacy", rank_impl=1, rows_per_sm=1, block=1024)
+                      "place_us": round(float(np.mean(pl)), 1), "place_min": round(float(np.min(pl)), 1), "hist_us": round(float(np.mean(hs)), 1), "scan_us": round(float(np.mean(sc)), 1), "epi_us": round(float(np.mean(ep)), 1), "lobbies": st.n_lobbies}), flush=True)
+run("auto (block512 x2 rows/SM, hist2)")
+run("block512 rows2, hist_impl=1", hist_impl=1)
+run("block1024 rows1 stages4, hist2", hist_impl=2, rows_per_sm=1, block=1024, place2_stages=4)
+run("block1024 rows1 stages2, hist2", place2_stages=2)
+run("block512 rows1 stages4", block=512, place2_stages=4)

@@ -8,5 +8,5 @@ timeout 600 python tools/exp_place.py config3_10m_g32_5v5 1 > gpurun_out/exp_rat
 timeout 600 python tools/exp_place.py config3_10m_g32_5v5 0 > gpurun_out/exp_arrival.log 2>&1; tail -8 gpurun_out/exp_arrival.log
 timeout 600 python tools/exp_place.py config2_1m_g8_1v1 1 > gpurun_out/exp_1m.log 2>&1; tail -8 gpurun_out/exp_1m.log
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:"k_place|k_hist|k_colscan|k_epilogue" -s 4 -c 4 -o gpurun_out/prof_tick -f python tools/one_tick.py > gpurun_out/ncu_full.log 2>&1; echo "ncu rc=$?"
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 40 --csv --log-file gpurun_out/launches4.csv python tools/one_tick.py > gpurun_out/ncu_l.log 2>&1
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 40 --csv --log-file gpurun_out/launches5.csv python tools/one_tick.py > gpurun_out/ncu_l.log 2>&1
 timeout 600 python bench.py --steps 10 --warmup 3 > gpurun_out/bench.log 2>&1; echo "bench rc=$?"; tail -1 gpurun_out/bench.log
