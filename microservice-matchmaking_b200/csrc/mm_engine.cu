@@ -400,7 +400,7 @@ int tick_phase_b(mm_engine* e, uint32_t n, uint32_t chunk, bool want_seq) {
   k_place2<BLK><<<e->R, BLK, place2_smem(e, e->place2_stages), e->stream>>>(                                          \
       e->d_bins16, p.v.id, n, chunk, e->K, e->Kp, e->R, e->place2_stages, (place2_dense(e) && e->dense_ok) ? 1u : 0u,  \
       e->d_M, e->d_tot, e->d_binbase, e->d_bin_seg, e->d_seg_shift, e->d_seg_lim, e->d_members, src_idx,              \
-      e->d_resid_stage, e->d_rescnt, e->d_ctr)
+      e->d_resid_stage, e->d_rescnt, e->d_ctr, (uint32_t)e->place_debug)
   if (e->rank_impl == 3) {
     if (e->block == 512) MM_PLACE2(512);
     else MM_PLACE2(1024);

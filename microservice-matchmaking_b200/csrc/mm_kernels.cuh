@@ -668,7 +668,9 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK == 512 ? 2 : 1))
              const uint32_t* __restrict__ tot, const uint32_t* __restrict__ binbase,
              const uint16_t* __restrict__ bin_seg, const uint32_t* __restrict__ seg_shift,
              const uint32_t* __restrict__ seg_lim, uint64_t* __restrict__ members, uint32_t* __restrict__ src_idx,
-             uint32_t* __restrict__ resid_stage, uint32_t* __restrict__ rescnt, TickCtr* ctr) {
+             uint32_t* __restrict__ resid_stage, uint32_t* __restrict__ rescnt, TickCtr* ctr, uint32_t dbg) {
+  // dbg != 0: timing experiments only (results invalid): 1 = rank, no id store; 2 = no rank,
+  // coalesced store; 3 = no rank, pseudo-random scatter
   constexpr int J = kTile / BLOCK;
   constexpr int NW = BLOCK / 32;
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -745,7 +747,14 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK == 512 ? 2 : 1))
       bin[j] = (pos < valid) ? (uint32_t)tb[pos] : 0xFFFFu;
       slot[j] = 0; flag[j] = false;
     }
-    if (dense) {
+    if (dbg >= 2) {
+#pragma unroll
+      for (int j = 0; j < J; ++j) {
+        const uint32_t e = tile_base + j * BLOCK + tid;
+        slot[j] = dbg == 2 ? e : (uint32_t)(((uint64_t)e * 2654435761ull) % n);
+        idv[j] = ti[j * BLOCK + tid];
+      }
+    } else if (dense) {
       // per-(bin, warp-batch) group sizes in a small matrix, one shuffle scan per bin across
       // the tile's 64 warp-batches (batch = j * NW + warp, increasing with tile position)
       uint32_t rankw[J];
@@ -795,35 +804,24 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK == 512 ? 2 : 1))
         }
       }
       __syncthreads();
-      // walk the J lists in lockstep: J independent shared-memory loads in flight per step
-      uint32_t cur[J], lower[J], total[J];
+#pragma unroll
+      for (int j = 0; j < J; ++j) idv[j] = ti[j * BLOCK + tid];  // ids early: their latency hides behind the walks
 #pragma unroll
       for (int j = 0; j < J; ++j) {
-        cur[j] = (bin[j] < K) ? (head[bin[j] & (kHeadSlots - 1)] & 0xFFFu) : 0xFFFu;
-        lower[j] = 0; total[j] = 0;
-        idv[j] = ti[j * BLOCK + tid];
-      }
-      for (;;) {
-        bool more = false;
-#pragma unroll
-        for (int j = 0; j < J; ++j) {
-          if (cur[j] != 0xFFFu) {
-            const uint32_t nd = node[cur[j]];
-            const bool same = (nd >> 12) == bin[j];  // the slot is shared by bins congruent mod kHeadSlots
-            total[j] += same ? 1u : 0u;
-            lower[j] += (same && cur[j] < (uint32_t)(j * BLOCK) + tid) ? 1u : 0u;
-            cur[j] = nd & 0xFFFu;
-            more |= cur[j] != 0xFFFu;
-          }
-        }
-        if (!more) break;
-      }
-#pragma unroll
-      for (int j = 0; j < J; ++j) {
+        const uint32_t pos = j * BLOCK + tid;
         if (bin[j] < K) {
-          slot[j] = (snap[j] & 0x7FFFFFFFu) + lower[j];
+          uint32_t cur = head[bin[j] & (kHeadSlots - 1)] & 0xFFFu, lower = 0, total = 0;
+          while (cur != 0xFFFu) {
+            const uint32_t nd = node[cur];
+            if ((nd >> 12) == bin[j]) {  // the slot is shared by bins congruent mod kHeadSlots
+              ++total;
+              lower += (cur < pos) ? 1u : 0u;
+            }
+            cur = nd & 0xFFFu;
+          }
+          slot[j] = (snap[j] & 0x7FFFFFFFu) + lower;
           flag[j] = (snap[j] >> 31) != 0;
-          if (lower[j] == 0) cnt[bin[j]] = snap[j] + total[j];  // the bin's earliest player of the tile
+          if (lower == 0) cnt[bin[j]] = snap[j] + total;  // the bin's earliest player of the tile
         }
       }
     } else {
@@ -869,7 +867,7 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK == 512 ? 2 : 1))
         flag[j] = (bg >> 31) != 0;
       }
     }
-    if (dense || heavy) {
+    if (dbg < 2 && (dense || heavy)) {
 #pragma unroll
       for (int j = 0; j < J; ++j) idv[j] = ti[j * BLOCK + tid];
     }
@@ -879,6 +877,8 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK == 512 ? 2 : 1))
         const uint32_t pos = j * BLOCK + tid;
         bool matched = true;
         if (flag[j]) matched = slot[j] < __ldg(&seg_lim[__ldg(&bin_seg[bin[j]])]);
+        if (dbg == 1) matched = matched && slot[j] == 0xFFFFFFFFu;
+        if (dbg == 1 && !matched) continue;
         if (matched) {
           st_keep_u64(members + slot[j], idv[j], pol_out);
           if (src_idx) src_idx[slot[j]] = tile_base + pos;

@@ -25,7 +25,10 @@ def run(label, reps=6, **opts):
     print(json.dumps({"variant": label, "workload": name, "order": order, "device_us": round(float(np.mean(dev)), 1),
                       "place_us": round(float(np.mean(pl)), 1), "place_min": round(float(np.min(pl)), 1), "hist_us": round(float(np.mean(hs)), 1), "scan_us": round(float(np.mean(sc)), 1), "epi_us": round(float(np.mean(ep)), 1), "lobbies": st.n_lobbies}), flush=True)
 run("auto (block512 x2 rows/SM, hist2)")
-run("block512 rows2, hist_impl=1", hist_impl=1)
-run("block1024 rows1 stages4, hist2", hist_impl=2, rows_per_sm=1, block=1024, place2_stages=4)
-run("block1024 rows1 stages2, hist2", place2_stages=2)
-run("block512 rows1 stages4", block=512, place2_stages=4)
+run("512x2 dbg1 rank only (no id store)", place_debug=1)
+run("512x2 dbg2 no rank, coalesced store", place_debug=2)
+run("512x2 dbg3 no rank, random scatter", place_debug=3)
+run("1024x1 stages4", place_debug=0, rows_per_sm=1, block=1024, place2_stages=4)
+run("1024x1 dbg1 rank only", place_debug=1)
+run("1024x1 dbg2 copy", place_debug=2)
+run("1024x1 dbg3 scatter", place_debug=3)
