@@ -82,6 +82,7 @@ struct mm_engine {
   uint32_t place2_stages = 0;  // 0 = k_place2 does not fit in shared memory
   uint32_t hist2_stages = 0;   // 0 = use the register-fed k_hist
   int hist_impl = 2;
+  int warm_l2 = 1;  // bulk-prefetch member_ids into L2 during the histogram kernel
   int dense_ok = 1;            // allow the small-K dense ranking path
   uint16_t* d_bins16 = nullptr;
   uint32_t* d_M = nullptr;
@@ -369,10 +370,12 @@ int tick_phase_a(mm_engine* e, uint32_t n, uint32_t* chunk_out) {
   if (e->rank_impl == 3 && e->hist_impl == 2 && e->hist2_stages) {
     if (e->block == 512)
       k_hist2<512><<<e->R, 512, hist2_smem(e, e->hist2_stages), e->stream>>>(p.v, n, chunk, bin_map(e), e->Kp,
-                                                                               e->hist2_stages, e->d_M, e->d_tot, e->d_bins16);
+                                                                               e->hist2_stages, e->d_M, e->d_tot, e->d_bins16,
+                                                                               e->warm_l2 ? e->d_members : nullptr, n);
     else
       k_hist2<1024><<<e->R, 1024, hist2_smem(e, e->hist2_stages), e->stream>>>(p.v, n, chunk, bin_map(e), e->Kp,
-                                                                                 e->hist2_stages, e->d_M, e->d_tot, e->d_bins16);
+                                                                                 e->hist2_stages, e->d_M, e->d_tot, e->d_bins16,
+                                                                                 e->warm_l2 ? e->d_members : nullptr, n);
   } else if (e->block == 512)
     k_hist<512><<<e->R, 512, hist_smem(e), e->stream>>>(p.v, n, chunk, bin_map(e), e->Kp, e->d_M, e->d_tot,
                                                         e->rank_impl == 3 ? e->d_bins16 : nullptr);
@@ -656,6 +659,7 @@ int mm_set_option(mm_engine* e, const char* name, int64_t value) {
   if (!std::strcmp(name, "l2_hints")) { e->l2_hints = value != 0; return MM_OK; }
   if (!std::strcmp(name, "dense")) { e->dense_ok = value != 0; return MM_OK; }
   if (!std::strcmp(name, "hist_impl")) { e->hist_impl = (int)value; return MM_OK; }
+  if (!std::strcmp(name, "warm_l2")) { e->warm_l2 = value != 0; return MM_OK; }
   if (!std::strcmp(name, "place_debug")) {  // timing experiments only: results are NOT valid
     if (value < 0 || value > 3) return MM_E_ARG;
     e->place_debug = (int)value;

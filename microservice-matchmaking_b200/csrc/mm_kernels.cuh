@@ -141,6 +141,12 @@ __device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t
       : "memory");
 }
 
+// Bulk L2 prefetch (no SM data path): warms member_ids so the 8-byte scatter of k_place2 hits
+// resident lines instead of triggering a DRAM fill per partially written sector.
+__device__ __forceinline__ void l2_prefetch_bulk(const void* p, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
+
 // In-place exclusive scan of a shared-memory array a[0..n) by the whole CTA; returns the
 // total.  s_tmp must hold >= 33 words.  Warp-shuffle scan: 3 barriers.
 template <int BLOCK>
@@ -253,7 +259,7 @@ constexpr uint32_t kHTileBytes = kHTile * 5;
 template <int BLOCK>
 __global__ void __launch_bounds__(BLOCK, (BLOCK == 512 ? 2 : 1))
     k_hist2(PoolView p, uint32_t n, uint32_t chunk, BinMap bm, uint32_t Kp, uint32_t stages, uint32_t* __restrict__ M,
-            uint32_t* __restrict__ tot, uint16_t* __restrict__ bins16) {
+            uint32_t* __restrict__ tot, uint16_t* __restrict__ bins16, const uint64_t* __restrict__ warm, uint32_t warm_n) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   int32_t* ring_r = reinterpret_cast<int32_t*>(smem_raw);                                   // [stages][kHTile]
   uint8_t* ring_m = smem_raw + (size_t)stages * kHTile * 4;                                  // [stages][kHTile]
@@ -277,6 +283,14 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK == 512 ? 2 : 1))
       tma_load_1d(ring_r + (size_t)t * kHTile, p.rating + beg + (size_t)t * kHTile, kHTile * 4, &full[t], pol_in);
       tma_load_1d(ring_m + (size_t)t * kHTile, p.mode + beg + (size_t)t * kHTile, kHTile, &full[t], pol_in);
     }
+  if (tid == 32 && warm) {  // this CTA's slice of member_ids -> L2 (2 KB-aligned slices, 32 KB requests)
+    const uint64_t per = ((((uint64_t)warm_n * 8 + gridDim.x - 1) / gridDim.x) + 2047) & ~2047ull;
+    const uint64_t lo = per * blockIdx.x, hi = (lo + per < (uint64_t)warm_n * 8) ? lo + per : (uint64_t)warm_n * 8;
+    for (uint64_t o = lo; o < hi; o += 32768) {
+      const uint64_t sz = (hi - o < 32768) ? ((hi - o + 15) & ~15ull) : 32768;
+      l2_prefetch_bulk(reinterpret_cast<const char*>(warm) + o, (uint32_t)sz);
+    }
+  }
   for (uint32_t i = tid; i < Kp; i += BLOCK) hist[i] = 0;
   for (uint32_t i = tid; i < bm.KR; i += BLOCK) s_lut[i] = bm.lut[i];
   __syncthreads();
