@@ -82,7 +82,10 @@ struct mm_engine {
   uint32_t place2_stages = 0;  // 0 = k_place2 does not fit in shared memory
   uint32_t hist2_stages = 0;   // 0 = use the register-fed k_hist
   int hist_impl = 2;
-  int warm_l2 = 1;  // bulk-prefetch member_ids into L2 during the histogram kernel
+  int warm_l2 = 0;  // bulk-prefetch member_ids into L2 during the histogram kernel (measured: no gain)
+  int fused_ok = 0;  // k_tick<512> can be launched cooperatively with 2 CTAs per SM
+  int tick_impl = 1; // 1 = one fused cooperative launch when possible, 0 = four launches
+  size_t tick_smem = 0;
   int dense_ok = 1;            // allow the small-K dense ranking path
   uint16_t* d_bins16 = nullptr;
   uint32_t* d_M = nullptr;
@@ -108,6 +111,7 @@ struct mm_engine {
 
   // last tick
   mm_tick_stats last{};
+  bool last_fused = false;
 };
 
 namespace {
@@ -428,6 +432,38 @@ int tick_phase_b(mm_engine* e, uint32_t n, uint32_t chunk, bool want_seq) {
   return MM_OK;
 }
 
+bool use_fused(const mm_engine* e) {
+  return e->tick_impl == 1 && e->fused_ok && e->rank_impl == 3 && e->block == 512 && e->hist_impl == 2 &&
+         e->hist2_stages && e->rows_per_sm == 2;
+}
+
+// the whole tick in one cooperative launch (k_tick)
+int tick_fused(mm_engine* e, uint32_t n, bool want_seq) {
+  const Pool& p = e->pool[e->cur];
+  Pool& q = e->pool[e->cur ^ 1];
+  uint32_t chunk = (n + e->R - 1) / e->R;
+  chunk = std::max<uint32_t>(((chunk + kRound - 1) / kRound) * kRound, kRound);
+  TickArgs a{};
+  a.src = p.v; a.dst = q.v; a.bm = bin_map(e);
+  a.n = n; a.chunk = chunk; a.K = e->K; a.Kp = e->Kp; a.R = e->R; a.n_segs = e->n_segs; a.n_groups = e->cfg.n_groups;
+  a.hist_stages = e->hist2_stages; a.place_stages = e->place2_stages;
+  a.dense = (place2_dense(e) && e->dense_ok) ? 1u : 0u;
+  a.new_gen = e->gen + 1; a.dbg = (uint32_t)e->place_debug;
+  a.M = e->d_M; a.tot = e->d_tot; a.binbase = e->d_binbase; a.bins16 = e->d_bins16; a.bin_seg = e->d_bin_seg;
+  a.seg_bin_lo = e->d_seg_bin_lo; a.seg_L = e->d_seg_L; a.seg = e->d_seg; a.seg_shift = e->d_seg_shift;
+  a.seg_lim = e->d_seg_lim; a.members = e->d_members; a.src_idx = want_seq ? e->d_src_idx : nullptr; a.hdr = e->d_hdr;
+  a.emit_seq = want_seq ? e->d_emit_seq : nullptr; a.resid_stage = e->d_resid_stage; a.rescnt = e->d_rescnt;
+  a.act = act_view(e); a.ctr = e->d_ctr;
+  CK(cudaMemsetAsync(e->d_ctr, 0, sizeof(TickCtr), e->stream));
+  CK(cudaEventRecord(e->ev[0], e->stream));
+  void* params[] = {&a};
+  CK(cudaLaunchCooperativeKernel((const void*)k_tick<512>, dim3(e->R), dim3(512), params, e->tick_smem, e->stream));
+  CK(cudaEventRecord(e->ev[4], e->stream));
+  CK(cudaMemcpyAsync(e->h_ctr, e->d_ctr, sizeof(TickCtr), cudaMemcpyDeviceToHost, e->stream));
+  CK(cudaStreamSynchronize(e->stream));
+  return MM_OK;
+}
+
 int tick_commit(mm_engine* e, uint32_t n, mm_tick_stats* stats) {
   const TickCtr& c = *e->h_ctr;
   if (c.overflow) {
@@ -440,6 +476,19 @@ int tick_commit(mm_engine* e, uint32_t n, mm_tick_stats* stats) {
   float ms = 0;
   CK(cudaEventElapsedTime(&ms, e->ev[0], e->ev[4]));
   st.device_us = ms * 1000.f;
+  if (e->last_fused) {  // one launch: phase times from %globaltimer stamps of CTA 0
+    st.n_launches = 1;
+    st.hist_us = (float)(c.t[1] - c.t[0]) * 1e-3f;
+    st.scan_us = (float)(c.t[2] - c.t[1]) * 1e-3f;
+    st.place_us = (float)(c.t[3] - c.t[2]) * 1e-3f;
+    st.epilogue_us = (float)(c.t[4] - c.t[3]) * 1e-3f;
+    e->cur ^= 1;
+    e->pool[e->cur].n = c.n_resid;
+    e->gen += 1;
+    e->last = st;
+    if (stats) *stats = st;
+    return MM_OK;
+  }
   CK(cudaEventElapsedTime(&ms, e->ev[0], e->ev[1]));
   st.hist_us = ms * 1000.f;
   CK(cudaEventElapsedTime(&ms, e->ev[1], e->ev[2]));
@@ -597,6 +646,19 @@ int mm_create(const mm_config* cfg, mm_engine** out) {
   if (cudaMallocHost(&e->h_ctr, sizeof(TickCtr)) != cudaSuccess || cudaMallocHost(&e->h_small, 64) != cudaSuccess)
     return bail(MM_E_CUDA);
   if ((rc = alloc_tick_scratch(e))) return bail(rc);
+  if (e->rank_impl == 3 && e->block == 512 && e->hist2_stages && e->rows_per_sm == 2) {
+    size_t sz = std::max(hist2_smem(e, e->hist2_stages), place2_smem(e, e->place2_stages));
+    sz = std::max<size_t>(sz, (size_t)std::max(kEpiScratchWords, std::max(kTailScratchWords, kColScratchWords)) * 4);
+    int coop = 0, nb = 0;
+    cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, e->device);
+    if (coop && cudaFuncSetAttribute(k_tick<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sz) == cudaSuccess &&
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_tick<512>, 512, sz) == cudaSuccess &&
+        (uint32_t)nb * (uint32_t)e->n_sms >= e->R) {
+      e->fused_ok = 1;
+      e->tick_smem = sz;
+    }
+    cudaGetLastError();
+  }
   if (cudaMemsetAsync(e->d_tot, 0, (e->Kp + 1) * 4, e->stream) != cudaSuccess) return bail(MM_E_CUDA);
   if ((rc = set_persist(e, 1024))) return bail(rc);  // clamped to the device's persisting-L2 maximum
   if (cudaStreamSynchronize(e->stream) != cudaSuccess) return bail(MM_E_CUDA);
@@ -660,6 +722,7 @@ int mm_set_option(mm_engine* e, const char* name, int64_t value) {
   if (!std::strcmp(name, "dense")) { e->dense_ok = value != 0; return MM_OK; }
   if (!std::strcmp(name, "hist_impl")) { e->hist_impl = (int)value; return MM_OK; }
   if (!std::strcmp(name, "warm_l2")) { e->warm_l2 = value != 0; return MM_OK; }
+  if (!std::strcmp(name, "tick_impl")) { e->tick_impl = value != 0; return MM_OK; }
   if (!std::strcmp(name, "place_debug")) {  // timing experiments only: results are NOT valid
     if (value < 0 || value > 3) return MM_E_ARG;
     e->place_debug = (int)value;
@@ -776,6 +839,12 @@ int mm_tick_device(mm_engine* e, uint64_t now, mm_tick_stats* stats) {
   std::lock_guard<std::mutex> lk(e->mu);
   CK(cudaSetDevice(e->device));
   const uint32_t n = e->pool[e->cur].n;
+  e->last_fused = use_fused(e);
+  if (e->last_fused) {
+    int rc = tick_fused(e, n, false);
+    if (rc) return rc;
+    return tick_commit(e, n, stats);
+  }
   uint32_t chunk = 0;
   int rc = tick_phase_a(e, n, &chunk);
   if (rc) return rc;
@@ -798,7 +867,15 @@ int mm_tick(mm_engine* e, uint64_t now, mm_lobby_hdr* lobbies, uint32_t lobby_ca
   CK(cudaSetDevice(e->device));
   const uint32_t n = e->pool[e->cur].n;
   uint32_t chunk = 0;
-  int rc = tick_phase_a(e, n, &chunk);
+  int rc;
+  // worst-case output sizes known up front -> the fused single launch is safe
+  e->last_fused = use_fused(e) && (!lobbies || (uint64_t)lobby_cap >= n / e->min_L) && (!member_ids || member_cap >= n);
+  if (e->last_fused) {
+    if ((rc = tick_fused(e, n, emit_seq != nullptr))) return rc;
+    if ((rc = tick_commit(e, n, stats))) return rc;
+    goto copy_out;
+  }
+  rc = tick_phase_a(e, n, &chunk);
   if (rc) return rc;
   // the counts are final after phase A: check the caller's capacities before consuming
   CK(cudaMemcpyAsync(e->h_ctr, e->d_ctr, sizeof(TickCtr), cudaMemcpyDeviceToHost, e->stream));
@@ -812,6 +889,7 @@ int mm_tick(mm_engine* e, uint64_t now, mm_lobby_hdr* lobbies, uint32_t lobby_ca
   }
   if ((rc = tick_phase_b(e, n, chunk, emit_seq != nullptr))) return rc;
   if ((rc = tick_commit(e, n, stats))) return rc;
+copy_out:
   const TickCtr& c = *e->h_ctr;
   if (lobbies && c.n_lobbies)
     CK(cudaMemcpyAsync(lobbies, e->d_hdr, (size_t)c.n_lobbies * sizeof(mm_lobby_hdr), cudaMemcpyDeviceToHost, e->stream));

@@ -62,10 +62,11 @@ struct SegInfo {        // one (mode, group) partition
 };
 
 struct TickCtr {
-  uint32_t ticket;
+  uint32_t gbar;  // grid barrier of the fused tick kernel
   uint32_t n_lobbies, n_matched, n_alive, n_dead, n_resid;
   uint32_t overflow;
   uint32_t heavy;  // some bin expects > 4 players per tile: use warp-aggregated ranking
+  unsigned long long t[6];  // fused kernel: %globaltimer (ns) at phase boundaries, CTA 0
 };
 
 struct ActiveView {
@@ -131,6 +132,26 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       "bra LAB_WAIT;\n"
       "DONE:\n"
       "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void mbar_inval(uint64_t* bar) {
+  asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// order earlier generic-proxy accesses to shared memory before later async-proxy (TMA) writes
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+// Grid-wide barrier for the fused tick kernel (cooperative launch: all CTAs are co-resident).
+__device__ __forceinline__ void grid_barrier(unsigned int* bar, unsigned int target) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(bar, 1u);
+    unsigned int v;
+    do {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(bar) : "memory");
+      if (v < target) __nanosleep(32);
+    } while (v < target);
+    __threadfence();
+  }
+  __syncthreads();
 }
 // global -> shared bulk copy (SASS: UBLKCP), completion counted on `bar`, L2 evict-first
 __device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar, uint64_t pol) {
@@ -257,10 +278,10 @@ constexpr uint32_t kHTile = 4096;
 constexpr uint32_t kHTileBytes = kHTile * 5;
 
 template <int BLOCK>
-__global__ void __launch_bounds__(BLOCK, (BLOCK == 512 ? 2 : 1))
-    k_hist2(PoolView p, uint32_t n, uint32_t chunk, BinMap bm, uint32_t Kp, uint32_t stages, uint32_t* __restrict__ M,
-            uint32_t* __restrict__ tot, uint16_t* __restrict__ bins16, const uint64_t* __restrict__ warm, uint32_t warm_n) {
-  extern __shared__ __align__(128) unsigned char smem_raw[];
+__device__ __forceinline__ void hist2_body(unsigned char* smem_raw, PoolView p, uint32_t n, uint32_t chunk, BinMap bm,
+                                           uint32_t Kp, uint32_t stages, uint32_t* __restrict__ M,
+                                           uint32_t* __restrict__ tot, uint16_t* __restrict__ bins16,
+                                           const uint64_t* __restrict__ warm, uint32_t warm_n) {
   int32_t* ring_r = reinterpret_cast<int32_t*>(smem_raw);                                   // [stages][kHTile]
   uint8_t* ring_m = smem_raw + (size_t)stages * kHTile * 4;                                  // [stages][kHTile]
   uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + (size_t)stages * kHTileBytes);     // [kMaxStages]
@@ -276,6 +297,7 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK == 512 ? 2 : 1))
     for (uint32_t s = 0; s < stages; ++s) mbar_init(&full[s], 1);
     mbar_fence_init();
   }
+  fence_proxy_async();
   __syncthreads();
   if (tid == 0)
     for (uint32_t t = 0; t < stages && t < n_tiles; ++t) {
@@ -334,6 +356,16 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK == 512 ? 2 : 1))
     row[i] = v;
     if (v) atomicAdd(&tot[i], v);
   }
+  if (tid == 0)
+    for (uint32_t s = 0; s < stages; ++s) mbar_inval(&full[s]);
+}
+
+template <int BLOCK>
+__global__ void __launch_bounds__(BLOCK, (BLOCK == 512 ? 2 : 1))
+    k_hist2(PoolView p, uint32_t n, uint32_t chunk, BinMap bm, uint32_t Kp, uint32_t stages, uint32_t* __restrict__ M,
+            uint32_t* __restrict__ tot, uint16_t* __restrict__ bins16, const uint64_t* __restrict__ warm, uint32_t warm_n) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  hist2_body<BLOCK>(smem_raw, p, n, chunk, bm, Kp, stages, M, tot, bins16, warm, warm_n);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -349,52 +381,60 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK == 512 ? 2 : 1))
 // ---------------------------------------------------------------------------------------
 constexpr uint32_t kMaxSegs = MM_MAX_GROUPS * MM_MAX_MODES;
 constexpr int kScanBlock = 512;
+constexpr uint32_t kColScratchWords = (kScanBlock / 32) * 33;      // column CTA scratch
+constexpr uint32_t kTailScratchWords = 64 + 4 + 3 * kMaxSegs;      // tail CTA scratch
 
-__global__ void __launch_bounds__(kScanBlock) k_colscan(uint32_t R, uint32_t Kp, uint32_t K, uint32_t* __restrict__ M,
-                                                        const uint32_t* __restrict__ tot, uint32_t* __restrict__ binbase,
-                                                        const uint32_t* __restrict__ seg_bin_lo,
-                                                        const uint32_t* __restrict__ seg_L, uint32_t n_segs,
-                                                        SegInfo* __restrict__ seg, uint32_t* __restrict__ seg_shift,
-                                                        uint32_t* __restrict__ seg_lim, TickCtr* ctr) {
-  __shared__ uint32_t s_part[kScanBlock / 32][33];
-  __shared__ uint32_t s_tmp[64];
-  __shared__ uint32_t s_max;
-  __shared__ uint32_t s_res[kMaxSegs], s_lob[kMaxSegs], s_n[kMaxSegs];
+// one 32-bin column group: exclusive prefix down the rows of M (scratch: kColScratchWords)
+__device__ __forceinline__ void colscan_cols_body(uint32_t* scratch, uint32_t group, uint32_t R, uint32_t Kp,
+                                                  uint32_t* __restrict__ M) {
+  uint32_t(*s_part)[33] = reinterpret_cast<uint32_t(*)[33]>(scratch);
   const uint32_t tid = threadIdx.x, x = tid & 31, y = tid >> 5;
-  if (blockIdx.x + 1 < gridDim.x) {  // ---- column CTA ----
-    constexpr uint32_t NY = kScanBlock / 32;
-    const uint32_t b = blockIdx.x * 32 + x;
-    const uint32_t rp = (R + NY - 1) / NY;
-    const uint32_t r0 = y * rp < R ? y * rp : R, r1 = (r0 + rp < R) ? r0 + rp : R;
-    constexpr int kU = 8;  // independent loads in flight per thread
-    uint32_t sum = 0;
-    if (b < Kp)
-      for (uint32_t r = r0; r < r1; r += kU) {
-        uint32_t v[kU];
+  constexpr uint32_t NY = kScanBlock / 32;
+  const uint32_t b = group * 32 + x;
+  const uint32_t rp = (R + NY - 1) / NY;
+  const uint32_t r0 = y * rp < R ? y * rp : R, r1 = (r0 + rp < R) ? r0 + rp : R;
+  constexpr int kU = 8;  // independent loads in flight per thread
+  uint32_t sum = 0;
+  if (b < Kp)
+    for (uint32_t r = r0; r < r1; r += kU) {
+      uint32_t v[kU];
 #pragma unroll
-        for (int k = 0; k < kU; ++k) v[k] = (r + k < r1) ? __ldcg(M + (size_t)(r + k) * Kp + b) : 0u;
+      for (int k = 0; k < kU; ++k) v[k] = (r + k < r1) ? __ldcg(M + (size_t)(r + k) * Kp + b) : 0u;
 #pragma unroll
-        for (int k = 0; k < kU; ++k) sum += v[k];
+      for (int k = 0; k < kU; ++k) sum += v[k];
+    }
+  s_part[y][x] = sum;
+  __syncthreads();
+  uint32_t run = 0;
+  for (uint32_t yy = 0; yy < y; ++yy) run += s_part[yy][x];
+  if (b < Kp)
+    for (uint32_t r = r0; r < r1; r += kU) {
+      uint32_t v[kU];
+#pragma unroll
+      for (int k = 0; k < kU; ++k) v[k] = (r + k < r1) ? __ldcg(M + (size_t)(r + k) * Kp + b) : 0u;
+#pragma unroll
+      for (int k = 0; k < kU; ++k) {
+        if (r + k < r1) M[(size_t)(r + k) * Kp + b] = run;
+        run += v[k];
       }
-    s_part[y][x] = sum;
-    __syncthreads();
-    uint32_t run = 0;
-    for (uint32_t yy = 0; yy < y; ++yy) run += s_part[yy][x];
-    if (b < Kp)
-      for (uint32_t r = r0; r < r1; r += kU) {
-        uint32_t v[kU];
-#pragma unroll
-        for (int k = 0; k < kU; ++k) v[k] = (r + k < r1) ? __ldcg(M + (size_t)(r + k) * Kp + b) : 0u;
-#pragma unroll
-        for (int k = 0; k < kU; ++k) {
-          if (r + k < r1) M[(size_t)(r + k) * Kp + b] = run;
-          run += v[k];
-        }
-      }
-    return;
-  }
-  // ---- tail CTA: scan of the bin totals ----
-  if (tid == 0) s_max = 0;
+    }
+  __syncthreads();  // scratch may be reused by the next group
+}
+
+// the tail: bin totals -> binbase, per-segment lobby arithmetic, counters (scratch: kTailScratchWords)
+__device__ __forceinline__ void colscan_tail_body(uint32_t* scratch, uint32_t Kp, uint32_t K,
+                                                  const uint32_t* __restrict__ tot, uint32_t* __restrict__ binbase,
+                                                  const uint32_t* __restrict__ seg_bin_lo,
+                                                  const uint32_t* __restrict__ seg_L, uint32_t n_segs,
+                                                  SegInfo* __restrict__ seg, uint32_t* __restrict__ seg_shift,
+                                                  uint32_t* __restrict__ seg_lim, TickCtr* ctr) {
+  uint32_t* s_tmp = scratch;            // [64]
+  uint32_t* s_maxp = scratch + 64;      // [1]
+  uint32_t* s_res = scratch + 68;       // [kMaxSegs]
+  uint32_t* s_lob = s_res + kMaxSegs;
+  uint32_t* s_n = s_lob + kMaxSegs;
+  const uint32_t tid = threadIdx.x;
+  if (tid == 0) *s_maxp = 0;
   __syncthreads();
   {
     const uint32_t per = (Kp + kScanBlock - 1) / kScanBlock;
@@ -407,7 +447,7 @@ __global__ void __launch_bounds__(kScanBlock) k_colscan(uint32_t R, uint32_t Kp,
       if (i < K && v > lmax) lmax = v;
     }
     lmax = __reduce_max_sync(0xFFFFFFFFu, lmax);
-    if (lane == 0 && lmax) atomicMax(&s_max, lmax);
+    if (lane == 0 && lmax) atomicMax(s_maxp, lmax);
     uint32_t incl = local;
 #pragma unroll
     for (int off = 1; off < 32; off <<= 1) {
@@ -456,8 +496,20 @@ __global__ void __launch_bounds__(kScanBlock) k_colscan(uint32_t R, uint32_t Kp,
     ctr->n_lobbies = tot_lob; ctr->n_matched = tot_alive - tot_res; ctr->n_alive = tot_alive; ctr->n_dead = dead;
     // expected players of the fullest bin per tile of one row (players spread evenly over rows)
     const uint64_t npool = (uint64_t)tot_alive + dead;
-    ctr->heavy = ((uint64_t)s_max * kTile > 4ull * (npool ? npool : 1)) ? 1u : 0u;
+    ctr->heavy = ((uint64_t)(*s_maxp) * kTile > 4ull * (npool ? npool : 1)) ? 1u : 0u;
   }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(kScanBlock) k_colscan(uint32_t R, uint32_t Kp, uint32_t K, uint32_t* __restrict__ M,
+                                                        const uint32_t* __restrict__ tot, uint32_t* __restrict__ binbase,
+                                                        const uint32_t* __restrict__ seg_bin_lo,
+                                                        const uint32_t* __restrict__ seg_L, uint32_t n_segs,
+                                                        SegInfo* __restrict__ seg, uint32_t* __restrict__ seg_shift,
+                                                        uint32_t* __restrict__ seg_lim, TickCtr* ctr) {
+  __shared__ uint32_t scratch[(kTailScratchWords > kColScratchWords) ? kTailScratchWords : kColScratchWords];
+  if (blockIdx.x + 1 < gridDim.x) colscan_cols_body(scratch, blockIdx.x, R, Kp, M);
+  else colscan_tail_body(scratch, Kp, K, tot, binbase, seg_bin_lo, seg_L, n_segs, seg, seg_shift, seg_lim, ctr);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -676,18 +728,17 @@ constexpr uint32_t kHeadSlots = 4096;
 constexpr uint32_t kRes2 = 1024;  // residual players one row may hold (k_place2)
 
 template <int BLOCK>
-__global__ void __launch_bounds__(BLOCK, (BLOCK == 512 ? 2 : 1))
-    k_place2(const uint16_t* __restrict__ bins16, const uint64_t* __restrict__ ids, uint32_t n, uint32_t chunk, uint32_t K,
-             uint32_t Kp, uint32_t R, uint32_t stages, uint32_t dense, const uint32_t* __restrict__ M,
-             const uint32_t* __restrict__ tot, const uint32_t* __restrict__ binbase,
-             const uint16_t* __restrict__ bin_seg, const uint32_t* __restrict__ seg_shift,
-             const uint32_t* __restrict__ seg_lim, uint64_t* __restrict__ members, uint32_t* __restrict__ src_idx,
-             uint32_t* __restrict__ resid_stage, uint32_t* __restrict__ rescnt, TickCtr* ctr, uint32_t dbg) {
+__device__ __forceinline__ void place2_body(
+    unsigned char* smem_raw, const uint16_t* __restrict__ bins16, const uint64_t* __restrict__ ids, uint32_t n,
+    uint32_t chunk, uint32_t K, uint32_t Kp, uint32_t R, uint32_t stages, uint32_t dense, const uint32_t* __restrict__ M,
+    const uint32_t* __restrict__ tot, const uint32_t* __restrict__ binbase, const uint16_t* __restrict__ bin_seg,
+    const uint32_t* __restrict__ seg_shift, const uint32_t* __restrict__ seg_lim, uint64_t* __restrict__ members,
+    uint32_t* __restrict__ src_idx, uint32_t* __restrict__ resid_stage, uint32_t* __restrict__ rescnt, TickCtr* ctr,
+    uint32_t dbg) {
   // dbg != 0: timing experiments only (results invalid): 1 = rank, no id store; 2 = no rank,
   // coalesced store; 3 = no rank, pseudo-random scatter
   constexpr int J = kTile / BLOCK;
   constexpr int NW = BLOCK / 32;
-  extern __shared__ __align__(128) unsigned char smem_raw[];
   uint64_t* ring_ids = reinterpret_cast<uint64_t*>(smem_raw);                               // [stages][kTile]
   uint16_t* ring_bins = reinterpret_cast<uint16_t*>(smem_raw + (size_t)stages * kTile * 8);  // [stages][kTile]
   uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + (size_t)stages * kTileBytes);      // [kMaxStages]
@@ -716,6 +767,7 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK == 512 ? 2 : 1))
     mbar_fence_init();
     s_nres = 0;
   }
+  fence_proxy_async();
   __syncthreads();
   if (tid == 0) {  // prologue: fill the ring (whole tiles; the pool columns are padded past n)
     for (uint32_t t = 0; t < stages && t < n_tiles; ++t) {
@@ -729,11 +781,11 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK == 512 ? 2 : 1))
     const uint32_t* mnext = (row + 1 < R) ? mrow + Kp : tot;
     for (uint32_t i = tid; i < Kp; i += BLOCK) {
       uint32_t v = 0;
-      if (i < K) {
-        const uint32_t pre = mrow[i], c = mnext[i] - pre;
+      if (i < K) {  // __ldcg: these arrays are produced earlier in the same (fused) launch by other SMs
+        const uint32_t pre = __ldcg(&mrow[i]), c = __ldcg(&mnext[i]) - pre;
         const uint32_t sg = bin_seg[i];
-        const uint32_t start = binbase[i] - __ldg(&seg_shift[sg]) + pre;  // slot of the cell's first player
-        v = start | ((start + c > __ldg(&seg_lim[sg])) ? 0x80000000u : 0u);
+        const uint32_t start = __ldcg(&binbase[i]) - __ldcg(&seg_shift[sg]) + pre;  // slot of the cell's first player
+        v = start | ((start + c > __ldcg(&seg_lim[sg])) ? 0x80000000u : 0u);
       }
       cnt[i] = v;
     }
@@ -741,7 +793,7 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK == 512 ? 2 : 1))
     if (dense)
       for (uint32_t i = tid; i < Kp * kDenseStride / 2; i += BLOCK) reinterpret_cast<uint32_t*>(wc)[i] = 0;
   }
-  const bool heavy = ctr->heavy != 0;
+  const bool heavy = __ldcg(&ctr->heavy) != 0;
   __syncthreads();
 
   uint32_t st = 0, parity = 0;
@@ -890,7 +942,7 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK == 512 ? 2 : 1))
       if (bin[j] < K) {
         const uint32_t pos = j * BLOCK + tid;
         bool matched = true;
-        if (flag[j]) matched = slot[j] < __ldg(&seg_lim[__ldg(&bin_seg[bin[j]])]);
+        if (flag[j]) matched = slot[j] < __ldcg(&seg_lim[__ldg(&bin_seg[bin[j]])]);
         if (dbg == 1) matched = matched && slot[j] == 0xFFFFFFFFu;
         if (dbg == 1 && !matched) continue;
         if (matched) {
@@ -926,6 +978,21 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK == 512 ? 2 : 1))
     for (uint32_t u = 0; u < nres; ++u) rank += (res_list[u] < v) ? 1u : 0u;
     resid_stage[(size_t)row * kResCap + rank] = v;
   }
+  if (tid == 0)
+    for (uint32_t s = 0; s < stages; ++s) mbar_inval(&full[s]);
+}
+
+template <int BLOCK>
+__global__ void __launch_bounds__(BLOCK, (BLOCK == 512 ? 2 : 1))
+    k_place2(const uint16_t* __restrict__ bins16, const uint64_t* __restrict__ ids, uint32_t n, uint32_t chunk, uint32_t K,
+             uint32_t Kp, uint32_t R, uint32_t stages, uint32_t dense, const uint32_t* __restrict__ M,
+             const uint32_t* __restrict__ tot, const uint32_t* __restrict__ binbase,
+             const uint16_t* __restrict__ bin_seg, const uint32_t* __restrict__ seg_shift,
+             const uint32_t* __restrict__ seg_lim, uint64_t* __restrict__ members, uint32_t* __restrict__ src_idx,
+             uint32_t* __restrict__ resid_stage, uint32_t* __restrict__ rescnt, TickCtr* ctr, uint32_t dbg) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  place2_body<BLOCK>(smem_raw, bins16, ids, n, chunk, K, Kp, R, stages, dense, M, tot, binbase, bin_seg, seg_shift,
+                     seg_lim, members, src_idx, resid_stage, rescnt, ctr, dbg);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -936,21 +1003,29 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK == 512 ? 2 : 1))
 // Every CTA: lobby headers from the segment table — lobby c of segment s = members
 // [member_base + k*L, +L); replaces the payload assembly at search/worker.ex:315-319.
 // ---------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(1024) k_epilogue(PoolView src, PoolView dst, uint32_t R, const uint32_t* __restrict__ rescnt,
-                                                   const uint32_t* __restrict__ resid_stage, ActiveView act, uint32_t new_gen,
-                                                   const SegInfo* __restrict__ seg, const uint32_t* __restrict__ seg_L,
-                                                   uint32_t n_segs, uint32_t n_groups, mm_lobby_hdr* __restrict__ hdr,
-                                                   const uint32_t* __restrict__ src_idx, uint32_t* __restrict__ emit_seq,
-                                                   uint32_t* __restrict__ tot, uint32_t Kp, TickCtr* ctr) {
-  __shared__ uint32_t s_off[kMaxRows + 1];
-  __shared__ uint32_t s_tmp[1024];
-  __shared__ uint32_t s_lbase[kMaxSegs + 1], s_mbase[kMaxSegs], s_L[kMaxSegs];
+constexpr uint32_t kEpiScratchWords = (kMaxRows + 1) + 64 + (kMaxSegs + 1) + 2 * kMaxSegs;
+
+template <int BLOCK>
+__device__ __forceinline__ void epilogue_body(uint32_t* scratch, PoolView src, PoolView dst, uint32_t R,
+                                              const uint32_t* __restrict__ rescnt, const uint32_t* __restrict__ resid_stage,
+                                              ActiveView act, uint32_t new_gen, const SegInfo* __restrict__ seg,
+                                              const uint32_t* __restrict__ seg_L, uint32_t n_segs, uint32_t n_groups,
+                                              mm_lobby_hdr* __restrict__ hdr, const uint32_t* __restrict__ src_idx,
+                                              uint32_t* __restrict__ emit_seq, uint32_t* __restrict__ tot, uint32_t Kp,
+                                              TickCtr* ctr) {
+  uint32_t* s_off = scratch;                   // [kMaxRows + 1]
+  uint32_t* s_tmp = s_off + kMaxRows + 1;      // [64]
+  uint32_t* s_lbase = s_tmp + 64;              // [kMaxSegs + 1]
+  uint32_t* s_mbase = s_lbase + kMaxSegs + 1;  // [kMaxSegs]
+  uint32_t* s_L = s_mbase + kMaxSegs;          // [kMaxSegs]
   const uint32_t tid = threadIdx.x;
-  for (uint32_t s = tid; s < n_segs; s += 1024) { s_lbase[s] = seg[s].lobby_base; s_mbase[s] = seg[s].member_base; s_L[s] = seg_L[s]; }
+  for (uint32_t s = tid; s < n_segs; s += BLOCK) {
+    s_lbase[s] = __ldcg(&seg[s].lobby_base); s_mbase[s] = __ldcg(&seg[s].member_base); s_L[s] = seg_L[s];
+  }
   __syncthreads();
-  for (uint32_t i = blockIdx.x * 1024 + tid; i < Kp; i += gridDim.x * 1024) tot[i] = 0;  // ready for the next tick
-  const uint32_t total_lob = ctr->n_lobbies;
-  for (uint32_t c = blockIdx.x * 1024 + tid; c < total_lob; c += gridDim.x * 1024) {
+  for (uint32_t i = blockIdx.x * BLOCK + tid; i < Kp; i += gridDim.x * BLOCK) tot[i] = 0;  // ready for the next tick
+  const uint32_t total_lob = __ldcg(&ctr->n_lobbies);
+  for (uint32_t c = blockIdx.x * BLOCK + tid; c < total_lob; c += gridDim.x * BLOCK) {
     uint32_t a = 0, e = n_segs;  // last segment with lobby_base <= c
     while (e - a > 1) { const uint32_t mid = (a + e) >> 1; if (s_lbase[mid] <= c) a = mid; else e = mid; }
     const uint32_t L = s_L[a];
@@ -960,19 +1035,19 @@ __global__ void __launch_bounds__(1024) k_epilogue(PoolView src, PoolView dst, u
     h.mode = (uint8_t)(a / n_groups);
     h.group = (uint8_t)(a % n_groups);
     hdr[c] = h;
-    if (emit_seq) emit_seq[c] = src_idx[h.first_member + L - 1];
+    if (emit_seq) emit_seq[c] = __ldcg(&src_idx[h.first_member + L - 1]);
   }
   if (blockIdx.x != 0) return;
 
-  for (uint32_t r = tid; r < R; r += 1024) s_off[r] = rescnt[r];
+  for (uint32_t r = tid; r < R; r += BLOCK) s_off[r] = __ldcg(&rescnt[r]);
   __syncthreads();
-  const uint32_t total = block_excl_scan<1024>(s_off, R, s_tmp);
+  const uint32_t total = block_excl_scan<BLOCK>(s_off, R, s_tmp);
   if (tid == 0) { s_off[R] = total; ctr->n_resid = total; }
   __syncthreads();
-  for (uint32_t t = tid; t < total; t += 1024) {
+  for (uint32_t t = tid; t < total; t += BLOCK) {
     uint32_t a = 0, c = R;  // last row with s_off[row] <= t
     while (c - a > 1) { const uint32_t mid = (a + c) >> 1; if (s_off[mid] <= t) a = mid; else c = mid; }
-    const uint32_t idx = resid_stage[(size_t)a * kResCap + (t - s_off[a])];
+    const uint32_t idx = __ldcg(&resid_stage[(size_t)a * kResCap + (t - s_off[a])]);
     const uint64_t pid = src.id[idx];
     dst.id[t] = pid; dst.rating[t] = src.rating[idx]; dst.mode[t] = src.mode[idx];
     dst.tsize[t] = src.tsize[idx]; dst.ts[t] = src.ts[idx];
@@ -986,6 +1061,71 @@ __global__ void __launch_bounds__(1024) k_epilogue(PoolView src, PoolView dst, u
       }
     }
   }
+}
+
+__global__ void __launch_bounds__(1024) k_epilogue(PoolView src, PoolView dst, uint32_t R, const uint32_t* __restrict__ rescnt,
+                                                   const uint32_t* __restrict__ resid_stage, ActiveView act, uint32_t new_gen,
+                                                   const SegInfo* __restrict__ seg, const uint32_t* __restrict__ seg_L,
+                                                   uint32_t n_segs, uint32_t n_groups, mm_lobby_hdr* __restrict__ hdr,
+                                                   const uint32_t* __restrict__ src_idx, uint32_t* __restrict__ emit_seq,
+                                                   uint32_t* __restrict__ tot, uint32_t Kp, TickCtr* ctr) {
+  __shared__ uint32_t scratch[kEpiScratchWords];
+  epilogue_body<1024>(scratch, src, dst, R, rescnt, resid_stage, act, new_gen, seg, seg_L, n_segs, n_groups, hdr, src_idx,
+                      emit_seq, tot, Kp, ctr);
+}
+
+// ---------------------------------------------------------------------------------------
+// k_tick<512>: the whole search tick in ONE cooperative launch ("fully matched in one
+// launch", BASELINE.json).  Phases are the bodies above, separated by grid barriers; the
+// CTA's dynamic shared memory is re-used by every phase:
+//   hist (TMA ring of rating/mode tiles, row histogram, bin column)      | barrier 1
+//   column scan of M (all CTAs) + tail (last CTA: bin bases, segments)    | barrier 2
+//   placement (TMA ring of bin/id tiles, stable ranks, id scatter)        | barrier 3
+//   epilogue (lobby headers by all CTAs, pool compaction by CTA 0)
+// Saves three launch boundaries and their prologues (~10 us each on B200).
+// ---------------------------------------------------------------------------------------
+struct TickArgs {
+  PoolView src, dst;
+  BinMap bm;
+  uint32_t n, chunk, K, Kp, R, n_segs, n_groups, hist_stages, place_stages, dense, new_gen, dbg;
+  uint32_t* M; uint32_t* tot; uint32_t* binbase; uint16_t* bins16;
+  const uint16_t* bin_seg; const uint32_t* seg_bin_lo; const uint32_t* seg_L;
+  SegInfo* seg; uint32_t* seg_shift; uint32_t* seg_lim;
+  uint64_t* members; uint32_t* src_idx; mm_lobby_hdr* hdr; uint32_t* emit_seq;
+  uint32_t* resid_stage; uint32_t* rescnt; ActiveView act; TickCtr* ctr;
+};
+
+template <int BLOCK>
+__global__ void __launch_bounds__(BLOCK, 2) k_tick(const TickArgs a) {
+  static_assert(BLOCK == kScanBlock, "the column-scan phase is written for 512-thread CTAs");
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  uint32_t* scratch = reinterpret_cast<uint32_t*>(smem_raw);
+  const unsigned int G = gridDim.x;
+  auto stamp = [&](int k) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+      unsigned long long t;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+      a.ctr->t[k] = t;
+    }
+  };
+  stamp(0);
+  hist2_body<BLOCK>(smem_raw, a.src, a.n, a.chunk, a.bm, a.Kp, a.hist_stages, a.M, a.tot, a.bins16, nullptr, 0);
+  grid_barrier(&a.ctr->gbar, G);
+  stamp(1);
+  if (blockIdx.x == G - 1)
+    colscan_tail_body(scratch, a.Kp, a.K, a.tot, a.binbase, a.seg_bin_lo, a.seg_L, a.n_segs, a.seg, a.seg_shift, a.seg_lim,
+                      a.ctr);
+  for (uint32_t g = blockIdx.x; g < (a.Kp + 31) / 32; g += G) colscan_cols_body(scratch, g, a.R, a.Kp, a.M);
+  grid_barrier(&a.ctr->gbar, 2 * G);
+  stamp(2);
+  place2_body<BLOCK>(smem_raw, a.bins16, a.src.id, a.n, a.chunk, a.K, a.Kp, a.R, a.place_stages, a.dense, a.M, a.tot,
+                     a.binbase, a.bin_seg, a.seg_shift, a.seg_lim, a.members, a.src_idx, a.resid_stage, a.rescnt, a.ctr,
+                     a.dbg);
+  grid_barrier(&a.ctr->gbar, 3 * G);
+  stamp(3);
+  epilogue_body<BLOCK>(scratch, a.src, a.dst, a.R, a.rescnt, a.resid_stage, a.act, a.new_gen, a.seg, a.seg_L, a.n_segs,
+                       a.n_groups, a.hdr, a.src_idx, a.emit_seq, a.tot, a.Kp, a.ctr);
+  stamp(4);  // CTA 0 finishes last in practice (it also compacts the pool); informative only
 }
 
 // =======================================================================================

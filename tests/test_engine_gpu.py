@@ -85,6 +85,36 @@ def test_config2_and_both_rank_impls_agree(pkg, oracle):
     assert np.array_equal(out[0][1], ref.member_ids) and np.array_equal(out[0][0], ref.lobbies)
 
 
+@pytest.mark.parametrize("order", [ARRIVAL, RATING])
+@pytest.mark.parametrize("n", [0, 1, 7, 2047, 2049, 4097, 300_001, 2_000_003])
+def test_fused_single_launch_equals_split_and_oracle(pkg, oracle, n, order):
+    """k_tick (one cooperative launch) vs the four-kernel tick vs the oracle."""
+    cfg = pkg.synth.make_config(n_groups=8, order=order, capacity=max(n, 1) + 100)
+    ids, rating, mode, ts = make_pool(pkg, 100 + n, n, bell=(n % 2 == 1))
+    rng = np.random.default_rng(n)
+    alive = (rng.random(n) > 0.03).astype(np.uint8)
+    outs = []
+    for impl in (1, 0):
+        with pkg.Engine(cfg) as eng:
+            eng.set_option("tick_impl", impl)
+            assert eng.enqueue(ids, rating, mode, ts).all()
+            eng.remove(ids[alive == 0])
+            lob, mem, seq, st = eng.tick()
+            if impl == 1:
+                assert st.n_launches == 1, "the fused cooperative kernel was not used"
+            ref = oracle.run_closed_form(cfg, ids, rating, mode, alive)
+            assert_tick_matches(eng, ref, lob, mem, seq, st)
+            # second tick on the compacted pool + new arrivals
+            ids2, rating2, _, ts2 = pkg.synth.gen_pool(999, 5000, first=10 ** 9)
+            mode2 = (np.arange(5000) % 2).astype(np.uint8)
+            room = cfg.capacity - eng.pool_size()
+            k = min(5000, room)
+            assert eng.enqueue(ids2[:k], rating2[:k], mode2[:k], ts2[:k]).all()
+            st2 = eng.tick_device()
+            outs.append((lob, mem, seq, st2.n_lobbies, st2.n_matched, eng.pool_read()["id"]))
+    assert all(np.array_equal(a, b) for a, b in zip(outs[0], outs[1]))
+
+
 def test_degenerate_everyone_same_rating(pkg, oracle):
     n = 200_000
     cfg = pkg.synth.make_config(groups=pkg.synth.REFERENCE_GROUPS, order=RATING, capacity=n)

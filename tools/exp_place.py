@@ -24,9 +24,6 @@ def run(label, reps=6, **opts):
         if i >= 2: dev.append(st.device_us); pl.append(st.place_us); hs.append(st.hist_us); sc.append(st.scan_us); ep.append(st.epilogue_us)
     print(json.dumps({"variant": label, "workload": name, "order": order, "device_us": round(float(np.mean(dev)), 1),
                       "place_us": round(float(np.mean(pl)), 1), "place_min": round(float(np.min(pl)), 1), "hist_us": round(float(np.mean(hs)), 1), "scan_us": round(float(np.mean(sc)), 1), "epi_us": round(float(np.mean(ep)), 1), "lobbies": st.n_lobbies}), flush=True)
-run("auto 512x2 warm_l2=1")
-run("512x2 warm_l2=0", warm_l2=0)
-run("512x2 warm_l2=1 persist=0", warm_l2=1, persist_mb=0)
-run("512x2 warm_l2=0 persist=0", warm_l2=0)
-run("1024x1 stages4 warm persist", warm_l2=1, persist_mb=1024, rows_per_sm=1, block=1024, place2_stages=4)
-run("1024x1 dbg3 scatter warm", place_debug=3)
+run("fused k_tick (1 launch)", tick_impl=1)
+run("split 4 launches", tick_impl=0)
+run("fused again", tick_impl=1)
