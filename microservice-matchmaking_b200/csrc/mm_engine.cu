@@ -188,6 +188,9 @@ size_t place2_smem(const mm_engine* e, uint32_t stages) {
   return (size_t)stages * kTileBytes + 64 + ((size_t)e->Kp + kHeadSlots + kTile + kRes2) * 4 + (size_t)kTile * 2 +
          (place2_dense(e) ? (size_t)e->Kp * kDenseStride * 2 * 2 + (size_t)e->Kp * 4 : 0) + 16;
 }
+size_t colscan_smem(const mm_engine* e) {
+  return (size_t)std::max<uint32_t>(kColScratchWords, kTailScratchWords + e->Kp + 2) * 4;
+}
 size_t hist2_smem(const mm_engine* e, uint32_t stages) {
   return (size_t)stages * kHTileBytes + 64 + (size_t)e->Kp * 4 + (size_t)e->KR * 2 + 16;
 }
@@ -387,7 +390,7 @@ int tick_phase_a(mm_engine* e, uint32_t n, uint32_t* chunk_out) {
     k_hist<1024><<<e->R, 1024, hist_smem(e), e->stream>>>(p.v, n, chunk, bin_map(e), e->Kp, e->d_M, e->d_tot,
                                                           e->rank_impl == 3 ? e->d_bins16 : nullptr);
   CK(cudaEventRecord(e->ev[1], e->stream));
-  k_colscan<<<(e->Kp + 31) / 32 + 1, kScanBlock, 0, e->stream>>>(e->R, e->Kp, e->K, e->d_M, e->d_tot, e->d_binbase, e->d_seg_bin_lo,
+  k_colscan<<<(e->Kp + 31) / 32 + 1, kScanBlock, colscan_smem(e), e->stream>>>(e->R, e->Kp, e->K, e->d_M, e->d_tot, e->d_binbase, e->d_seg_bin_lo,
                                                         e->d_seg_L, e->n_segs, e->d_seg, e->d_seg_shift, e->d_seg_lim,
                                                         e->d_ctr);
   CK(cudaGetLastError());
@@ -482,6 +485,7 @@ int tick_commit(mm_engine* e, uint32_t n, mm_tick_stats* stats) {
     st.scan_us = (float)(c.t[2] - c.t[1]) * 1e-3f;
     st.place_us = (float)(c.t[3] - c.t[2]) * 1e-3f;
     st.epilogue_us = (float)(c.t[4] - c.t[3]) * 1e-3f;
+    st.reserved = (uint32_t)((c.t[5] - c.t[1]) / 10);  // tail CTA: barrier 1 -> tail done, in 10 ns units (debug)
     e->cur ^= 1;
     e->pool[e->cur].n = c.n_resid;
     e->gen += 1;
@@ -585,6 +589,8 @@ int mm_create(const mm_config* cfg, mm_engine** out) {
   }
   {
     const int s0 = (int)place_smem(e, 0), s1 = (int)place_smem(e, 1);
+    if (cudaFuncSetAttribute(k_colscan, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)colscan_smem(e)) != cudaSuccess)
+      return bail(fail(e, cudaGetLastError(), "cudaFuncSetAttribute(k_colscan)"));
     bool ok = cudaFuncSetAttribute(k_hist<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hist_smem(e)) == cudaSuccess &&
               cudaFuncSetAttribute(k_place<0, 0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, s0) == cudaSuccess;
     if (ok && e->rank_impl == 1)
@@ -648,7 +654,7 @@ int mm_create(const mm_config* cfg, mm_engine** out) {
   if ((rc = alloc_tick_scratch(e))) return bail(rc);
   if (e->rank_impl == 3 && e->block == 512 && e->hist2_stages && e->rows_per_sm == 2) {
     size_t sz = std::max(hist2_smem(e, e->hist2_stages), place2_smem(e, e->place2_stages));
-    sz = std::max<size_t>(sz, (size_t)std::max(kEpiScratchWords, std::max(kTailScratchWords, kColScratchWords)) * 4);
+    sz = std::max<size_t>(sz, std::max<size_t>((size_t)kEpiScratchWords * 4, colscan_smem(e)));
     int coop = 0, nb = 0;
     cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, e->device);
     if (coop && cudaFuncSetAttribute(k_tick<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sz) == cudaSuccess &&
@@ -724,7 +730,7 @@ int mm_set_option(mm_engine* e, const char* name, int64_t value) {
   if (!std::strcmp(name, "warm_l2")) { e->warm_l2 = value != 0; return MM_OK; }
   if (!std::strcmp(name, "tick_impl")) { e->tick_impl = value != 0; return MM_OK; }
   if (!std::strcmp(name, "place_debug")) {  // timing experiments only: results are NOT valid
-    if (value < 0 || value > 3) return MM_E_ARG;
+    if (value < 0 || value > 63) return MM_E_ARG;
     e->place_debug = (int)value;
     return MM_OK;
   }

@@ -281,7 +281,7 @@ template <int BLOCK>
 __device__ __forceinline__ void hist2_body(unsigned char* smem_raw, PoolView p, uint32_t n, uint32_t chunk, BinMap bm,
                                            uint32_t Kp, uint32_t stages, uint32_t* __restrict__ M,
                                            uint32_t* __restrict__ tot, uint16_t* __restrict__ bins16,
-                                           const uint64_t* __restrict__ warm, uint32_t warm_n) {
+                                           const uint64_t* __restrict__ warm, uint32_t warm_n, uint32_t dbg = 0) {
   int32_t* ring_r = reinterpret_cast<int32_t*>(smem_raw);                                   // [stages][kHTile]
   uint8_t* ring_m = smem_raw + (size_t)stages * kHTile * 4;                                  // [stages][kHTile]
   uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + (size_t)stages * kHTileBytes);     // [kMaxStages]
@@ -329,10 +329,15 @@ __device__ __forceinline__ void hist2_body(unsigned char* smem_raw, PoolView p, 
       if (o + 4 <= valid) {
         const int4 r = *reinterpret_cast<const int4*>(tr + o);
         const uint32_t m = *reinterpret_cast<const uint32_t*>(tm + o);
-        const uint32_t b0 = bin_of(bm, s_lut, r.x, m & 0xFF), b1 = bin_of(bm, s_lut, r.y, (m >> 8) & 0xFF);
-        const uint32_t b2 = bin_of(bm, s_lut, r.z, (m >> 16) & 0xFF), b3 = bin_of(bm, s_lut, r.w, m >> 24);
-        atomicAdd(&hist[b0], 1u); atomicAdd(&hist[b1], 1u); atomicAdd(&hist[b2], 1u); atomicAdd(&hist[b3], 1u);
-        *reinterpret_cast<uint2*>(bins16 + tile_base + o) = make_uint2(b0 | (b1 << 16), b2 | (b3 << 16));
+        uint32_t b0, b1, b2, b3;
+        if (dbg & 16) {  // timing experiment: no LUT
+          b0 = (uint32_t)r.x % bm.K; b1 = (uint32_t)r.y % bm.K; b2 = (uint32_t)r.z % bm.K; b3 = (uint32_t)r.w % bm.K;
+        } else {
+          b0 = bin_of(bm, s_lut, r.x, m & 0xFF); b1 = bin_of(bm, s_lut, r.y, (m >> 8) & 0xFF);
+          b2 = bin_of(bm, s_lut, r.z, (m >> 16) & 0xFF); b3 = bin_of(bm, s_lut, r.w, m >> 24);
+        }
+        if (!(dbg & 8)) { atomicAdd(&hist[b0], 1u); atomicAdd(&hist[b1], 1u); atomicAdd(&hist[b2], 1u); atomicAdd(&hist[b3], 1u); }
+        if (!(dbg & 32)) *reinterpret_cast<uint2*>(bins16 + tile_base + o) = make_uint2(b0 | (b1 << 16), b2 | (b3 << 16));
       } else if (o < valid) {
         for (uint32_t k = o; k < valid; ++k) {
           const uint32_t bb = bin_of(bm, s_lut, tr[k], tm[k]);
@@ -354,7 +359,7 @@ __device__ __forceinline__ void hist2_body(unsigned char* smem_raw, PoolView p, 
   for (uint32_t i = tid; i < Kp; i += BLOCK) {
     const uint32_t v = hist[i];
     row[i] = v;
-    if (v) atomicAdd(&tot[i], v);
+    if (v && !(dbg & 4)) atomicAdd(&tot[i], v);  // dbg&4: timing experiment without the reductions
   }
   if (tid == 0)
     for (uint32_t s = 0; s < stages; ++s) mbar_inval(&full[s]);
@@ -382,7 +387,7 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK == 512 ? 2 : 1))
 constexpr uint32_t kMaxSegs = MM_MAX_GROUPS * MM_MAX_MODES;
 constexpr int kScanBlock = 512;
 constexpr uint32_t kColScratchWords = (kScanBlock / 32) * 33;      // column CTA scratch
-constexpr uint32_t kTailScratchWords = 64 + 4 + 3 * kMaxSegs;      // tail CTA scratch
+constexpr uint32_t kTailScratchWords = 64 + 4 + 3 * kMaxSegs;      // tail CTA scratch (+ Kp + 1 words for the bin bases)
 
 // one 32-bin column group: exclusive prefix down the rows of M (scratch: kColScratchWords)
 __device__ __forceinline__ void colscan_cols_body(uint32_t* scratch, uint32_t group, uint32_t R, uint32_t Kp,
@@ -433,49 +438,28 @@ __device__ __forceinline__ void colscan_tail_body(uint32_t* scratch, uint32_t Kp
   uint32_t* s_res = scratch + 68;       // [kMaxSegs]
   uint32_t* s_lob = s_res + kMaxSegs;
   uint32_t* s_n = s_lob + kMaxSegs;
+  uint32_t* s_bb = s_n + kMaxSegs;      // [Kp + 1] bin totals -> bin bases (dynamic shared memory)
   const uint32_t tid = threadIdx.x;
   if (tid == 0) *s_maxp = 0;
   __syncthreads();
-  {
-    const uint32_t per = (Kp + kScanBlock - 1) / kScanBlock;
-    const uint32_t lo = tid * per < Kp ? tid * per : Kp, hi = (lo + per < Kp) ? lo + per : Kp;
-    const uint32_t lane = tid & 31, warp = tid >> 5;
-    uint32_t local = 0, lmax = 0;
-    for (uint32_t i = lo; i < hi; ++i) {
+  {  // coalesced, independent loads (the per-thread contiguous walk was latency-serialised: 25 us)
+    uint32_t lmax = 0;
+    for (uint32_t i = tid; i < Kp; i += kScanBlock) {
       const uint32_t v = __ldcg(&tot[i]);
-      local += v;
+      s_bb[i] = v;
       if (i < K && v > lmax) lmax = v;
     }
     lmax = __reduce_max_sync(0xFFFFFFFFu, lmax);
-    if (lane == 0 && lmax) atomicMax(s_maxp, lmax);
-    uint32_t incl = local;
-#pragma unroll
-    for (int off = 1; off < 32; off <<= 1) {
-      const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, incl, off);
-      if (lane >= (uint32_t)off) incl += v;
-    }
-    if (lane == 31) s_tmp[warp] = incl;
+    if ((tid & 31) == 0 && lmax) atomicMax(s_maxp, lmax);
     __syncthreads();
-    if (warp == 0) {
-      uint32_t w = lane < kScanBlock / 32 ? s_tmp[lane] : 0, wi = w;
-#pragma unroll
-      for (int off = 1; off < 32; off <<= 1) {
-        const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, wi, off);
-        if (lane >= (uint32_t)off) wi += v;
-      }
-      s_tmp[lane] = wi - w;
-      if (lane == 31) s_tmp[32] = wi;
-    }
+    const uint32_t total = block_excl_scan<kScanBlock>(s_bb, Kp, s_tmp);
+    if (tid == 0) s_bb[Kp] = total;
     __syncthreads();
-    uint32_t acc = s_tmp[warp] + incl - local;
-    for (uint32_t i = lo; i < hi; ++i) { binbase[i] = acc; acc += __ldcg(&tot[i]); }
-    if (tid == 0) binbase[Kp] = s_tmp[32];
-    __threadfence_block();
-    __syncthreads();
+    for (uint32_t i = tid; i <= Kp; i += kScanBlock) binbase[i] = s_bb[i];
   }
   // per-segment arithmetic: three small scans over the <= modes*groups segments
   for (uint32_t s = tid; s < n_segs; s += kScanBlock) {
-    const uint32_t ns = binbase[seg_bin_lo[s + 1]] - binbase[seg_bin_lo[s]];
+    const uint32_t ns = s_bb[seg_bin_lo[s + 1]] - s_bb[seg_bin_lo[s]];
     const uint32_t nl = ns / seg_L[s];
     s_n[s] = ns; s_lob[s] = nl; s_res[s] = ns - nl * seg_L[s];
     seg[s].n = ns; seg[s].n_lobbies = nl;
@@ -485,7 +469,7 @@ __device__ __forceinline__ void colscan_tail_body(uint32_t* scratch, uint32_t Kp
   const uint32_t tot_lob = block_excl_scan<kScanBlock>(s_lob, n_segs, s_tmp);
   const uint32_t tot_alive = block_excl_scan<kScanBlock>(s_n, n_segs, s_tmp);
   for (uint32_t s = tid; s < n_segs; s += kScanBlock) {
-    const uint32_t mb = binbase[seg_bin_lo[s]] - s_res[s];
+    const uint32_t mb = s_bb[seg_bin_lo[s]] - s_res[s];
     seg[s].member_base = mb;
     seg[s].lobby_base = s_lob[s];
     seg_shift[s] = s_res[s];
@@ -507,7 +491,7 @@ __global__ void __launch_bounds__(kScanBlock) k_colscan(uint32_t R, uint32_t Kp,
                                                         const uint32_t* __restrict__ seg_L, uint32_t n_segs,
                                                         SegInfo* __restrict__ seg, uint32_t* __restrict__ seg_shift,
                                                         uint32_t* __restrict__ seg_lim, TickCtr* ctr) {
-  __shared__ uint32_t scratch[(kTailScratchWords > kColScratchWords) ? kTailScratchWords : kColScratchWords];
+  extern __shared__ __align__(16) uint32_t scratch[];  // max(kColScratchWords, kTailScratchWords + Kp + 1) words
   if (blockIdx.x + 1 < gridDim.x) colscan_cols_body(scratch, blockIdx.x, R, Kp, M);
   else colscan_tail_body(scratch, Kp, K, tot, binbase, seg_bin_lo, seg_L, n_segs, seg, seg_shift, seg_lim, ctr);
 }
@@ -734,7 +718,8 @@ __device__ __forceinline__ void place2_body(
     const uint32_t* __restrict__ tot, const uint32_t* __restrict__ binbase, const uint16_t* __restrict__ bin_seg,
     const uint32_t* __restrict__ seg_shift, const uint32_t* __restrict__ seg_lim, uint64_t* __restrict__ members,
     uint32_t* __restrict__ src_idx, uint32_t* __restrict__ resid_stage, uint32_t* __restrict__ rescnt, TickCtr* ctr,
-    uint32_t dbg) {
+    uint32_t dbg_all) {
+  const uint32_t dbg = dbg_all & 3u;  // (higher bits are histogram-phase experiments)
   // dbg != 0: timing experiments only (results invalid): 1 = rank, no id store; 2 = no rank,
   // coalesced store; 3 = no rank, pseudo-random scatter
   constexpr int J = kTile / BLOCK;
@@ -1109,12 +1094,18 @@ __global__ void __launch_bounds__(BLOCK, 2) k_tick(const TickArgs a) {
     }
   };
   stamp(0);
-  hist2_body<BLOCK>(smem_raw, a.src, a.n, a.chunk, a.bm, a.Kp, a.hist_stages, a.M, a.tot, a.bins16, nullptr, 0);
+  hist2_body<BLOCK>(smem_raw, a.src, a.n, a.chunk, a.bm, a.Kp, a.hist_stages, a.M, a.tot, a.bins16, nullptr, 0, a.dbg);
   grid_barrier(&a.ctr->gbar, G);
   stamp(1);
-  if (blockIdx.x == G - 1)
+  if (blockIdx.x == G - 1) {
     colscan_tail_body(scratch, a.Kp, a.K, a.tot, a.binbase, a.seg_bin_lo, a.seg_L, a.n_segs, a.seg, a.seg_shift, a.seg_lim,
                       a.ctr);
+    if (threadIdx.x == 0) {
+      unsigned long long t;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+      a.ctr->t[5] = t;
+    }
+  }
   for (uint32_t g = blockIdx.x; g < (a.Kp + 31) / 32; g += G) colscan_cols_body(scratch, g, a.R, a.Kp, a.M);
   grid_barrier(&a.ctr->gbar, 2 * G);
   stamp(2);

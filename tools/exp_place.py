@@ -8,8 +8,14 @@ name = sys.argv[1] if len(sys.argv) > 1 else "config3_10m_g32_5v5"
 order = int(sys.argv[2]) if len(sys.argv) > 2 else 1
 w = pkg.synth.WORKLOADS[name]
 n = w["n"]
-cfg = pkg.synth.make_config(n_groups=w["n_groups"], order=order, capacity=n + 65536)
-ids, rating, mode, ts = pkg.synth.gen_pool(1, n, mode=w["mode"])
+single = len(sys.argv) > 3 and sys.argv[3] == "single"
+if single:  # only the workload's own game mode in the mode table
+    m = pkg.synth.MODES_DEFAULT[w["mode"]]
+    cfg = pkg.synth.make_config(n_groups=w["n_groups"], order=order, capacity=n + 65536, modes=(m,))
+    ids, rating, mode, ts = pkg.synth.gen_pool(1, n, mode=0)
+else:
+    cfg = pkg.synth.make_config(n_groups=w["n_groups"], order=order, capacity=n + 65536)
+    ids, rating, mode, ts = pkg.synth.gen_pool(1, n, mode=w["mode"])
 eng = pkg.Engine(cfg)
 assert eng.enqueue(ids, rating, mode, ts).all()
 eng.snapshot()
@@ -23,7 +29,10 @@ def run(label, reps=6, **opts):
         st = eng.tick_device()
         if i >= 2: dev.append(st.device_us); pl.append(st.place_us); hs.append(st.hist_us); sc.append(st.scan_us); ep.append(st.epilogue_us)
     print(json.dumps({"variant": label, "workload": name, "order": order, "device_us": round(float(np.mean(dev)), 1),
-                      "place_us": round(float(np.mean(pl)), 1), "place_min": round(float(np.min(pl)), 1), "hist_us": round(float(np.mean(hs)), 1), "scan_us": round(float(np.mean(sc)), 1), "epi_us": round(float(np.mean(ep)), 1), "lobbies": st.n_lobbies}), flush=True)
-run("fused k_tick (1 launch)", tick_impl=1)
-run("split 4 launches", tick_impl=0)
-run("fused again", tick_impl=1)
+                      "place_us": round(float(np.mean(pl)), 1), "place_min": round(float(np.min(pl)), 1), "hist_us": round(float(np.mean(hs)), 1), "scan_us": round(float(np.mean(sc)), 1), "epi_us": round(float(np.mean(ep)), 1), "tail_us": st.reserved / 100.0, "lobbies": st.n_lobbies}), flush=True)
+run("fused", tick_impl=1)
+run("fused hist: no ATOMS (dbg 8)", place_debug=8)
+run("fused hist: no LUT (dbg 16)", place_debug=16)
+run("fused hist: no bins16 store (dbg 32)", place_debug=32)
+run("fused hist: none of the three (dbg 56)", place_debug=56)
+run("split", tick_impl=0, place_debug=0)
