@@ -86,14 +86,6 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def workload_cfg(pkg, name, order, rank, world, capacity):
-    w = pkg.synth.WORKLOADS[name]
-    # weak scaling: every rank owns its own w["n_groups"] rating groups (a contiguous
-    # slice of a world*G-group ladder) and a full-size pool routed to them
-    cfg = pkg.synth.make_config(n_groups=w["n_groups"], order=order, capacity=capacity, device=0)
-    return w, cfg
-
-
 def run_reference(args, rank, world):
     """--impl reference: the CPU restatement of the reference loop on the host cores."""
     if rank != 0:
@@ -102,9 +94,10 @@ def run_reference(args, rank, world):
     orc = importlib.import_module("oracle.oracle")
     orc.build()
     order = pkg.abi.MM_ORDER_RATING if args.order == "rating" else pkg.abi.MM_ORDER_ARRIVAL
-    w, cfg = workload_cfg(pkg, args.workload, order, 0, 1, 1)
+    w = pkg.synth.WORKLOADS[args.workload]
+    cfg, mode_idx = pkg.synth.workload_config(args.workload, order, 1, single_mode=not getattr(args, "two_modes", False))
     n = min(w["n"], args.ref_sample)
-    ids, rating, mode, _ = pkg.synth.gen_pool(1, n, mode=w["mode"])
+    ids, rating, mode, _ = pkg.synth.gen_pool(1, n, mode=mode_idx)
     threads = max(1, min(os.cpu_count() or 1, cfg.n_groups))
     for _ in range(args.warmup):
         orc.time_literal(cfg, ids, rating, mode, threads)
@@ -141,6 +134,8 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=10_000_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--two-modes", action="store_true", help="configure both default modes (1v1, 5v5), not just the workload's")
+    ap.add_argument("--tick-impl", type=int, default=None, help="1 = one fused cooperative launch (default), 0 = four launches")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -163,11 +158,12 @@ def main():
     pkg = ge.build()
     abi = pkg.abi
     order = abi.MM_ORDER_RATING if args.order == "rating" else abi.MM_ORDER_ARRIVAL
-    w, _ = workload_cfg(pkg, args.workload, order, rank, world, 1)
+    w = pkg.synth.WORKLOADS[args.workload]
     n, L = w["n"], (2 if w["mode"] == 0 else 10)
-    cfg = pkg.synth.make_config(n_groups=w["n_groups"], order=order, capacity=n + 65536, device=local)
+    cfg, mode_idx = pkg.synth.workload_config(args.workload, order, n + 65536, device=local,
+                                              single_mode=not args.two_modes)
     # rank r's shard of the N x n pool: its own seed stream (weak scaling, disjoint ids)
-    ids, rating, mode, ts = pkg.synth.gen_pool(1, n, first=rank * n, mode=w["mode"])
+    ids, rating, mode, ts = pkg.synth.gen_pool(1, n, first=rank * n, mode=mode_idx)
 
     def barrier():
         torch.cuda.synchronize()
@@ -178,6 +174,8 @@ def main():
     eng = pkg.Engine(cfg)
     if args.rank_impl is not None:
         eng.set_option("rank_impl", args.rank_impl)
+    if args.tick_impl is not None:
+        eng.set_option("tick_impl", args.tick_impl)
     acc = eng.enqueue(ids, rating, mode, ts)
     assert acc.all()
     eng.snapshot()
@@ -195,10 +193,12 @@ def main():
     barrier()
     sampler.start()
     t_wall = time.perf_counter()
-    dev_us, place_us = [], []
+    dev_us, place_us, phases = [], [], []
     for _ in range(args.steps):
         st = one_step()
         dev_us.append(st.device_us); place_us.append(st.place_us)
+        phases.append((st.hist_us, st.scan_us, st.place_us, st.epilogue_us))
+    launches_per_tick = st.n_launches
     barrier()
     wall_s = time.perf_counter() - t_wall
     clocks = sampler.stop()
@@ -223,6 +223,8 @@ def main():
         eng = pkg.Engine(cfg)
         if args.rank_impl is not None:
             eng.set_option("rank_impl", args.rank_impl)
+        if args.tick_impl is not None:
+            eng.set_option("tick_impl", args.tick_impl)
         pin = lambda a: torch.from_numpy(a).pin_memory()
         h_ids, h_rating, h_mode, h_ts = pin(ids), pin(rating), pin(mode), pin(ts)
         h_acc = torch.empty(n, dtype=torch.uint8).pin_memory()
@@ -278,10 +280,14 @@ def main():
             "scaling": "weak", "vs_baseline": None, "dtype": "int32/u64", "data": "synthetic",
             "config": {"workload": args.workload, "players_per_gpu": n, "rating_groups_per_gpu": w["n_groups"],
                        "lobby_size": L, "order": args.order, "ratings": "uniform 0..5000, seed 1",
+                       "modes_configured": cfg.n_modes, "launches_per_tick": launches_per_tick,
                        "parallelism": f"rating-group shards x{world}, no collective",
                        "l2": "flushed between steps (256 MiB write); pool 180 MB > L2",
-                       "timed_region": "mm_tick_device: k_hist+k_colscan+k_place+k_epilogue, CUDA events "
-                                       "on the engine stream; snapshot restore + L2 flush between steps untimed"},
+                       "timed_region": "mm_tick_device: the whole tick (k_tick: hist | column scan | placement | "
+                                       "epilogue in one cooperative launch), CUDA events on the engine stream; "
+                                       "snapshot restore + L2 flush between steps untimed"},
+            "phase_us": dict(zip(("hist", "scan", "place", "epilogue"),
+                                 [round(sum(x) / len(x), 2) for x in zip(*phases)])),
             "players_per_s": n * world * args.steps / tick_s,
             "wall_ms_per_step_incl_restore": 1e3 * wall_s / args.steps,
             "roofline": {"bound": "hbm", "kernel": "k_place", "achieved": ach, "peak": peak, "unit": "GB/s",
@@ -290,7 +296,7 @@ def main():
             "tick_roofline": {"bytes_per_player": B_ALG_TICK, "achieved": B_ALG_TICK * n * args.steps / tick_s / 1e9,
                               "frac": B_ALG_TICK * n * args.steps / tick_s / 1e9 / peak, "unit": "GB/s",
                               "frac_of_8000": B_ALG_TICK * n * args.steps / tick_s / 1e9 / 8000.0},
-            "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": 4 * args.steps, "clocks": clocks,
+            "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches_per_tick * args.steps, "clocks": clocks,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -88,9 +88,20 @@ def make_config(n_groups=None, groups=None, modes=MODES_DEFAULT, order=abi.MM_OR
 REFERENCE_GROUPS = ((0, 1499), (1500, 1999), (2000, 2499), (2500, 2999), (3000, 3499), (3500, 3999), (4000, 5000))
 REFERENCE_GROUP_NAMES = ("bronze", "silver", "gold", "platinum", "diamond", "master", "grandmaster")
 
-# BASELINE.json configs (index = position in "configs")
+# BASELINE.json configs (index = position in "configs"); "mode" indexes MODES_DEFAULT
 WORKLOADS = {
     "config1_1k_g1_1v1": dict(n=1_000, n_groups=1, mode=0),
     "config2_1m_g8_1v1": dict(n=1_000_000, n_groups=8, mode=0),
     "config3_10m_g32_5v5": dict(n=10_000_000, n_groups=32, mode=1),
 }
+
+
+def workload_config(name, order, capacity, device=0, single_mode=True):
+    """(cfg, mode_index_in_cfg) for a BASELINE.json workload.  single_mode=True configures only the
+    game mode the workload names ("1v1" or "5v5"), which halves the engine's key domain."""
+    w = WORKLOADS[name]
+    if single_mode:
+        cfg = make_config(n_groups=w["n_groups"], modes=(MODES_DEFAULT[w["mode"]],), order=order, capacity=capacity,
+                          device=device)
+        return cfg, 0
+    return make_config(n_groups=w["n_groups"], order=order, capacity=capacity, device=device), w["mode"]
