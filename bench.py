@@ -266,10 +266,15 @@ def main():
     if rank == 0:
         peak, peak_src = peaks()
         place_avg_s = place_s / args.steps
-        ach = B_ALG_PLACE * n / place_avg_s / 1e9
+        tick_avg_s = tick_s / args.steps
+        fused = launches_per_tick == 1
+        # dominant kernel: the fused k_tick IS the tick (one launch processes the whole pool: N players x 22 B);
+        # with --tick-impl 0 it is k_place2 (13 B read + 8 B written per player)
+        dom_kernel, dom_bytes, dom_s = ("k_tick", B_ALG_TICK, tick_avg_s) if fused else ("k_place2", B_ALG_PLACE, place_avg_s)
+        ach = dom_bytes * n / dom_s / 1e9
         traffic = None
-        tp = os.path.join(ROOT, "profiles", "place_traffic.json")
-        if os.path.exists(tp):
+        tp = os.path.join(ROOT, "profiles", "tick_traffic.json")
+        if fused and os.path.exists(tp) and args.workload == "config3_10m_g32_5v5" and args.order == "rating":
             try:
                 traffic = json.load(open(tp)).get("dram_bytes_per_launch")
             except Exception:
@@ -290,9 +295,12 @@ def main():
                                  [round(sum(x) / len(x), 2) for x in zip(*phases)])),
             "players_per_s": n * world * args.steps / tick_s,
             "wall_ms_per_step_incl_restore": 1e3 * wall_s / args.steps,
-            "roofline": {"bound": "hbm", "kernel": "k_place", "achieved": ach, "peak": peak, "unit": "GB/s",
+            "roofline": {"bound": "hbm", "kernel": dom_kernel, "achieved": ach, "peak": peak, "unit": "GB/s",
                          "frac": ach / peak, "traffic": traffic, "peak_source": peak_src,
-                         "bytes_per_player": B_ALG_PLACE, "us_per_launch": 1e6 * place_avg_s},
+                         "bytes_per_player": dom_bytes, "players_per_launch": n, "us_per_launch": 1e6 * dom_s,
+                         "frac_of_8000": ach / 8000.0},
+            "place_phase": {"bytes_per_player": B_ALG_PLACE, "us": 1e6 * place_avg_s,
+                            "achieved": B_ALG_PLACE * n / place_avg_s / 1e9, "frac": B_ALG_PLACE * n / place_avg_s / 1e9 / peak},
             "tick_roofline": {"bytes_per_player": B_ALG_TICK, "achieved": B_ALG_TICK * n * args.steps / tick_s / 1e9,
                               "frac": B_ALG_TICK * n * args.steps / tick_s / 1e9 / peak, "unit": "GB/s",
                               "frac_of_8000": B_ALG_TICK * n * args.steps / tick_s / 1e9 / 8000.0},

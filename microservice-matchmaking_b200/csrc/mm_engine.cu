@@ -86,7 +86,7 @@ struct mm_engine {
   int fused_ok = 0;  // k_tick<512> can be launched cooperatively with 2 CTAs per SM
   int tick_impl = 1; // 1 = one fused cooperative launch when possible, 0 = four launches
   size_t tick_smem = 0;
-  int dense_ok = 1;            // allow the small-K dense ranking path
+  int dense_ok = 2;            // small-K ranking: 0 = off, 1 = MATCH-based matrix, 2 = private byte counters when possible
   uint16_t* d_bins16 = nullptr;
   uint32_t* d_M = nullptr;
   uint32_t *d_tot = nullptr, *d_binbase = nullptr, *d_seg_lim = nullptr;
@@ -184,9 +184,16 @@ size_t place_smem(const mm_engine* e, int impl) {
   return words * 4 + (size_t)e->KR * 2 + 16;
 }
 bool place2_dense(const mm_engine* e) { return e->Kp <= kDenseMaxBins; }
+// private byte counters c8[Kp][512] + lane bases + bases: only for very few bins and 512-thread CTAs
+bool place2_dense2(const mm_engine* e) { return e->Kp <= 96; }
+size_t place2_dense_bytes(const mm_engine* e) {
+  size_t a = place2_dense(e) ? (size_t)e->Kp * kDenseStride * 2 * 2 + (size_t)e->Kp * 4 : 0;
+  size_t b = place2_dense2(e) ? (size_t)e->Kp * 512 + (size_t)e->Kp * 64 + (size_t)e->Kp * 4 + 16 : 0;
+  return std::max(a, b);
+}
 size_t place2_smem(const mm_engine* e, uint32_t stages) {
   return (size_t)stages * kTileBytes + 64 + ((size_t)e->Kp + kHeadSlots + kTile + kRes2) * 4 + (size_t)kTile * 2 +
-         (place2_dense(e) ? (size_t)e->Kp * kDenseStride * 2 * 2 + (size_t)e->Kp * 4 : 0) + 16;
+         place2_dense_bytes(e) + 16;
 }
 size_t colscan_smem(const mm_engine* e) {
   return (size_t)std::max<uint32_t>(kColScratchWords, kTailScratchWords + e->Kp + 2) * 4;
@@ -366,6 +373,12 @@ int set_persist(mm_engine* e, int64_t mb) {
   return MM_OK;
 }
 
+uint32_t dense_mode(const mm_engine* e) {
+  if (!e->dense_ok) return 0u;
+  if (place2_dense2(e) && e->block == 512 && e->dense_ok != 1) return 2u;  // dense_ok: 1 = MATCH variant only
+  return place2_dense(e) ? 1u : 0u;
+}
+
 // launches k_hist + k_colscan and returns the counters (phase A of a tick)
 int tick_phase_a(mm_engine* e, uint32_t n, uint32_t* chunk_out) {
   const Pool& p = e->pool[e->cur];
@@ -408,7 +421,7 @@ int tick_phase_b(mm_engine* e, uint32_t n, uint32_t chunk, bool want_seq) {
       e->d_seg_lim, e->n_segs, e->d_members, src_idx, e->d_resid_stage, e->d_rescnt, e->d_ctr)
 #define MM_PLACE2(BLK)                                                                                               \
   k_place2<BLK><<<e->R, BLK, place2_smem(e, e->place2_stages), e->stream>>>(                                          \
-      e->d_bins16, p.v.id, n, chunk, e->K, e->Kp, e->R, e->place2_stages, (place2_dense(e) && e->dense_ok) ? 1u : 0u,  \
+      e->d_bins16, p.v.id, n, chunk, e->K, e->Kp, e->R, e->place2_stages, dense_mode(e),  \
       e->d_M, e->d_tot, e->d_binbase, e->d_bin_seg, e->d_seg_shift, e->d_seg_lim, e->d_members, src_idx,              \
       e->d_resid_stage, e->d_rescnt, e->d_ctr, (uint32_t)e->place_debug)
   if (e->rank_impl == 3) {
@@ -450,7 +463,7 @@ int tick_fused(mm_engine* e, uint32_t n, bool want_seq) {
   a.src = p.v; a.dst = q.v; a.bm = bin_map(e);
   a.n = n; a.chunk = chunk; a.K = e->K; a.Kp = e->Kp; a.R = e->R; a.n_segs = e->n_segs; a.n_groups = e->cfg.n_groups;
   a.hist_stages = e->hist2_stages; a.place_stages = e->place2_stages;
-  a.dense = (place2_dense(e) && e->dense_ok) ? 1u : 0u;
+  a.dense = dense_mode(e);
   a.new_gen = e->gen + 1; a.dbg = (uint32_t)e->place_debug;
   a.M = e->d_M; a.tot = e->d_tot; a.binbase = e->d_binbase; a.bins16 = e->d_bins16; a.bin_seg = e->d_bin_seg;
   a.seg_bin_lo = e->d_seg_bin_lo; a.seg_L = e->d_seg_L; a.seg = e->d_seg; a.seg_shift = e->d_seg_shift;
@@ -725,7 +738,7 @@ int mm_set_option(mm_engine* e, const char* name, int64_t value) {
     return MM_OK;
   }
   if (!std::strcmp(name, "l2_hints")) { e->l2_hints = value != 0; return MM_OK; }
-  if (!std::strcmp(name, "dense")) { e->dense_ok = value != 0; return MM_OK; }
+  if (!std::strcmp(name, "dense")) { e->dense_ok = (int)value; return MM_OK; }
   if (!std::strcmp(name, "hist_impl")) { e->hist_impl = (int)value; return MM_OK; }
   if (!std::strcmp(name, "warm_l2")) { e->warm_l2 = value != 0; return MM_OK; }
   if (!std::strcmp(name, "tick_impl")) { e->tick_impl = value != 0; return MM_OK; }

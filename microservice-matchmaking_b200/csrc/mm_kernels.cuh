@@ -789,13 +789,14 @@ __device__ __forceinline__ void place2_body(
     const uint64_t* ti = ring_ids + (size_t)st * kTile;
     mbar_wait(&full[st], parity);
     const uint32_t epoch = t + 1;
-    uint32_t bin[J], slot[J];
+    uint32_t bin[J], slot[J], pos_[J];
     uint64_t idv[J];
     bool flag[J];
 #pragma unroll
     for (int j = 0; j < J; ++j) {
-      const uint32_t pos = j * BLOCK + tid;
-      bin[j] = (pos < valid) ? (uint32_t)tb[pos] : 0xFFFFu;
+      // dense == 2 ranks a blocked arrangement (thread t owns J consecutive tile positions)
+      pos_[j] = (dense == 2) ? tid * J + j : j * BLOCK + tid;
+      bin[j] = (pos_[j] < valid) ? (uint32_t)tb[pos_[j]] : 0xFFFFu;
       slot[j] = 0; flag[j] = false;
     }
     if (dbg >= 2) {
@@ -804,6 +805,58 @@ __device__ __forceinline__ void place2_body(
         const uint32_t e = tile_base + j * BLOCK + tid;
         slot[j] = dbg == 2 ? e : (uint32_t)(((uint64_t)e * 2654435761ull) % n);
         idv[j] = ti[j * BLOCK + tid];
+      }
+    } else if (dense == 2) {
+      // Few bins, no warp vote (MATCH.ANY costs 64 cycles per warp instruction per SM on B200):
+      // every thread counts its own J consecutive players in private byte counters
+      // c8[bin][thread], one warp-shuffle scan per bin turns them into per-16-thread bases,
+      // and a thread's offset inside its 16-group is a masked byte sum (dp4a).
+      uint8_t* c8 = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(wc) + 15) & ~uintptr_t(15));  // [Kp][BLOCK]
+      uint16_t* lb = reinterpret_cast<uint16_t*>(c8 + (size_t)Kp * BLOCK);            // [Kp][32]
+      uint32_t* cb2 = reinterpret_cast<uint32_t*>(lb + (size_t)Kp * 32);              // [Kp]
+      for (uint32_t i = tid; i < Kp * (BLOCK / 16); i += BLOCK) reinterpret_cast<uint4*>(c8)[i] = make_uint4(0, 0, 0, 0);
+      __syncthreads();
+      uint32_t lrank[J];
+#pragma unroll
+      for (int j = 0; j < J; ++j) {
+        lrank[j] = 0;
+        if (bin[j] < K) {
+          uint8_t* c = c8 + bin[j] * BLOCK + tid;
+          lrank[j] = *c;
+          *c = (uint8_t)(lrank[j] + 1);
+        }
+      }
+      __syncthreads();
+      for (uint32_t b = warp; b < K; b += NW) {  // lane l sums the counters of threads 16l .. 16l+15
+        const uint4 v = reinterpret_cast<const uint4*>(c8 + b * BLOCK)[lane];
+        uint32_t incl = __dp4a(v.x, 0x01010101u, __dp4a(v.y, 0x01010101u, __dp4a(v.z, 0x01010101u, __dp4a(v.w, 0x01010101u, 0u))));
+        const uint32_t own = incl;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+          const uint32_t u = __shfl_up_sync(0xFFFFFFFFu, incl, off);
+          if (lane >= (uint32_t)off) incl += u;
+        }
+        lb[b * 32 + lane] = (uint16_t)(incl - own);
+        if (lane == 31) { const uint32_t base = cnt[b]; cb2[b] = base; cnt[b] = base + incl; }
+      }
+      __syncthreads();
+#pragma unroll
+      for (int j = 0; j < J; ++j) {
+        if (bin[j] < K) {
+          const uint32_t g = tid >> 4, k = tid & 15;
+          const uint4 v = reinterpret_cast<const uint4*>(c8 + bin[j] * BLOCK)[g];
+          const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+          uint32_t pre = 0;
+#pragma unroll
+          for (int wi = 0; wi < 4; ++wi) {
+            const uint32_t m = ((uint32_t)wi < (k >> 2)) ? 0x01010101u
+                               : ((uint32_t)wi == (k >> 2) ? (((1u << (8 * (k & 3))) - 1u) & 0x01010101u) : 0u);
+            pre = __dp4a(w[wi], m, pre);
+          }
+          const uint32_t base = cb2[bin[j]];
+          slot[j] = (base & 0x7FFFFFFFu) + lb[bin[j] * 32 + g] + pre + lrank[j];
+          flag[j] = (base >> 31) != 0;
+        }
       }
     } else if (dense) {
       // per-(bin, warp-batch) group sizes in a small matrix, one shuffle scan per bin across
@@ -920,12 +973,12 @@ __device__ __forceinline__ void place2_body(
     }
     if (dbg < 2 && (dense || heavy)) {
 #pragma unroll
-      for (int j = 0; j < J; ++j) idv[j] = ti[j * BLOCK + tid];
+      for (int j = 0; j < J; ++j) idv[j] = ti[pos_[j]];
     }
 #pragma unroll
     for (int j = 0; j < J; ++j) {
       if (bin[j] < K) {
-        const uint32_t pos = j * BLOCK + tid;
+        const uint32_t pos = pos_[j];
         bool matched = true;
         if (flag[j]) matched = slot[j] < __ldcg(&seg_lim[__ldg(&bin_seg[bin[j]])]);
         if (dbg == 1) matched = matched && slot[j] == 0xFFFFFFFFu;

@@ -115,6 +115,27 @@ def test_fused_single_launch_equals_split_and_oracle(pkg, oracle, n, order):
     assert all(np.array_equal(a, b) for a, b in zip(outs[0], outs[1]))
 
 
+@pytest.mark.parametrize("dense", [2, 1, 0])
+@pytest.mark.parametrize("n_groups,n_modes", [(7, 2), (32, 1), (32, 2), (45, 2), (64, 4)])
+def test_arrival_small_key_domain_variants(pkg, oracle, dense, n_groups, n_modes):
+    """ARRIVAL order has bin = (mode, group): exercises the private-counter (2), MATCH-matrix (1) and
+    list (0) rankings on the same pools, incl. a blocked (thread-contiguous) tile arrangement."""
+    modes = (("1v1", 2, 1), ("5v5", 2, 5), ("2v2", 2, 2), ("3v3", 2, 3))[:n_modes]
+    n = 150_001
+    cfg = pkg.synth.make_config(n_groups=n_groups, modes=modes, order=ARRIVAL, capacity=n)
+    ids, rating, mode, ts = make_pool(pkg, 7 * n_groups + n_modes, n, n_modes=n_modes, oor=0.0, bell=True)
+    rng = np.random.default_rng(1)
+    alive = (rng.random(n) > 0.02).astype(np.uint8)
+    for tick_impl in (1, 0):
+        with pkg.Engine(cfg) as eng:
+            eng.set_option("dense", dense)
+            eng.set_option("tick_impl", tick_impl)
+            assert eng.enqueue(ids, rating, mode, ts).all()
+            eng.remove(ids[alive == 0])
+            lob, mem, seq, st = eng.tick()
+            assert_tick_matches(eng, oracle.run_closed_form(cfg, ids, rating, mode, alive), lob, mem, seq, st)
+
+
 def test_degenerate_everyone_same_rating(pkg, oracle):
     n = 200_000
     cfg = pkg.synth.make_config(groups=pkg.synth.REFERENCE_GROUPS, order=RATING, capacity=n)
