@@ -188,7 +188,7 @@ bool place2_dense(const mm_engine* e) { return e->Kp <= kDenseMaxBins; }
 bool place2_dense2(const mm_engine* e) { return e->Kp <= 96; }
 size_t place2_dense_bytes(const mm_engine* e) {
   size_t a = place2_dense(e) ? (size_t)e->Kp * kDenseStride * 2 * 2 + (size_t)e->Kp * 4 : 0;
-  size_t b = place2_dense2(e) ? (size_t)e->Kp * 512 + (size_t)e->Kp * 64 + (size_t)e->Kp * 4 + 16 : 0;
+  size_t b = place2_dense2(e) ? (size_t)e->Kp * (512 + 16) + (size_t)e->Kp * 68 + (size_t)e->Kp * 4 + 32 : 0;
   return std::max(a, b);
 }
 size_t place2_smem(const mm_engine* e, uint32_t stages) {

@@ -792,12 +792,28 @@ __device__ __forceinline__ void place2_body(
     uint32_t bin[J], slot[J], pos_[J];
     uint64_t idv[J];
     bool flag[J];
+    if (J == 4 && dense == 2) {
+      // blocked arrangement (thread t owns 4 consecutive tile positions): one 64-bit load of the
+      // 4 bins, two 128-bit loads of the 4 ids — strided scalar loads would be 8-way bank conflicts
+      const uint2 bb = reinterpret_cast<const uint2*>(tb)[tid];
+      const uint4 i01 = reinterpret_cast<const uint4*>(ti)[2 * tid], i23 = reinterpret_cast<const uint4*>(ti)[2 * tid + 1];
+      const uint32_t b4[4] = {bb.x & 0xFFFFu, bb.x >> 16, bb.y & 0xFFFFu, bb.y >> 16};
+      const uint64_t i4[4] = {(uint64_t)i01.x | ((uint64_t)i01.y << 32), (uint64_t)i01.z | ((uint64_t)i01.w << 32),
+                              (uint64_t)i23.x | ((uint64_t)i23.y << 32), (uint64_t)i23.z | ((uint64_t)i23.w << 32)};
 #pragma unroll
-    for (int j = 0; j < J; ++j) {
-      // dense == 2 ranks a blocked arrangement (thread t owns J consecutive tile positions)
-      pos_[j] = (dense == 2) ? tid * J + j : j * BLOCK + tid;
-      bin[j] = (pos_[j] < valid) ? (uint32_t)tb[pos_[j]] : 0xFFFFu;
-      slot[j] = 0; flag[j] = false;
+      for (int j = 0; j < J; ++j) {
+        pos_[j] = tid * J + j;
+        bin[j] = (pos_[j] < valid) ? b4[j & 3] : 0xFFFFu;
+        idv[j] = i4[j & 3];
+        slot[j] = 0; flag[j] = false;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < J; ++j) {
+        pos_[j] = j * BLOCK + tid;
+        bin[j] = (pos_[j] < valid) ? (uint32_t)tb[pos_[j]] : 0xFFFFu;
+        slot[j] = 0; flag[j] = false;
+      }
     }
     if (dbg >= 2) {
 #pragma unroll
@@ -812,23 +828,25 @@ __device__ __forceinline__ void place2_body(
       // c8[bin][thread], one warp-shuffle scan per bin turns them into per-16-thread bases,
       // and a thread's offset inside its 16-group is a masked byte sum (dp4a).
       uint8_t* c8 = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(wc) + 15) & ~uintptr_t(15));  // [Kp][BLOCK]
-      uint16_t* lb = reinterpret_cast<uint16_t*>(c8 + (size_t)Kp * BLOCK);            // [Kp][32]
-      uint32_t* cb2 = reinterpret_cast<uint32_t*>(lb + (size_t)Kp * 32);              // [Kp]
-      for (uint32_t i = tid; i < Kp * (BLOCK / 16); i += BLOCK) reinterpret_cast<uint4*>(c8)[i] = make_uint4(0, 0, 0, 0);
+      // rows padded (+16 B, +2 entries) so that different bins fall into different banks
+      constexpr uint32_t CS = BLOCK + 16, LS = 34;
+      uint16_t* lb = reinterpret_cast<uint16_t*>(c8 + (size_t)Kp * CS);               // [Kp][LS]
+      uint32_t* cb2 = reinterpret_cast<uint32_t*>(lb + (size_t)Kp * LS);              // [Kp]
+      for (uint32_t i = tid; i < Kp * (CS / 16); i += BLOCK) reinterpret_cast<uint4*>(c8)[i] = make_uint4(0, 0, 0, 0);
       __syncthreads();
       uint32_t lrank[J];
 #pragma unroll
       for (int j = 0; j < J; ++j) {
         lrank[j] = 0;
         if (bin[j] < K) {
-          uint8_t* c = c8 + bin[j] * BLOCK + tid;
+          uint8_t* c = c8 + bin[j] * CS + tid;
           lrank[j] = *c;
           *c = (uint8_t)(lrank[j] + 1);
         }
       }
       __syncthreads();
       for (uint32_t b = warp; b < K; b += NW) {  // lane l sums the counters of threads 16l .. 16l+15
-        const uint4 v = reinterpret_cast<const uint4*>(c8 + b * BLOCK)[lane];
+        const uint4 v = reinterpret_cast<const uint4*>(c8 + b * CS)[lane];
         uint32_t incl = __dp4a(v.x, 0x01010101u, __dp4a(v.y, 0x01010101u, __dp4a(v.z, 0x01010101u, __dp4a(v.w, 0x01010101u, 0u))));
         const uint32_t own = incl;
 #pragma unroll
@@ -836,7 +854,7 @@ __device__ __forceinline__ void place2_body(
           const uint32_t u = __shfl_up_sync(0xFFFFFFFFu, incl, off);
           if (lane >= (uint32_t)off) incl += u;
         }
-        lb[b * 32 + lane] = (uint16_t)(incl - own);
+        lb[b * LS + lane] = (uint16_t)(incl - own);
         if (lane == 31) { const uint32_t base = cnt[b]; cb2[b] = base; cnt[b] = base + incl; }
       }
       __syncthreads();
@@ -844,7 +862,7 @@ __device__ __forceinline__ void place2_body(
       for (int j = 0; j < J; ++j) {
         if (bin[j] < K) {
           const uint32_t g = tid >> 4, k = tid & 15;
-          const uint4 v = reinterpret_cast<const uint4*>(c8 + bin[j] * BLOCK)[g];
+          const uint4 v = reinterpret_cast<const uint4*>(c8 + bin[j] * CS)[g];
           const uint32_t w[4] = {v.x, v.y, v.z, v.w};
           uint32_t pre = 0;
 #pragma unroll
@@ -854,7 +872,7 @@ __device__ __forceinline__ void place2_body(
             pre = __dp4a(w[wi], m, pre);
           }
           const uint32_t base = cb2[bin[j]];
-          slot[j] = (base & 0x7FFFFFFFu) + lb[bin[j] * 32 + g] + pre + lrank[j];
+          slot[j] = (base & 0x7FFFFFFFu) + lb[bin[j] * LS + g] + pre + lrank[j];
           flag[j] = (base >> 31) != 0;
         }
       }
@@ -971,7 +989,7 @@ __device__ __forceinline__ void place2_body(
         flag[j] = (bg >> 31) != 0;
       }
     }
-    if (dbg < 2 && (dense || heavy)) {
+    if (dbg < 2 && (dense == 1 || (!dense && heavy))) {
 #pragma unroll
       for (int j = 0; j < J; ++j) idv[j] = ti[pos_[j]];
     }
