@@ -230,16 +230,17 @@ def main():
         h_acc = torch.empty(n, dtype=torch.uint8).pin_memory()
         h_lob = torch.empty(n // L + 1, dtype=torch.int64).pin_memory()  # 8-byte mm_lobby_hdr
         h_mem = torch.empty(n, dtype=torch.int64).pin_memory()
-        times = []
+        times, t_enq = [], []
         for it in range(args.e2e_steps + 1):
             barrier()
             t0 = time.perf_counter()
             eng.enqueue_raw(n, h_ids.data_ptr(), h_rating.data_ptr(), h_mode.data_ptr(), h_ts.data_ptr(),
                             h_acc.data_ptr())
+            t1 = time.perf_counter()
             st2 = eng.tick_raw(h_lob.data_ptr(), n // L + 1, h_mem.data_ptr(), n)
             dt = time.perf_counter() - t0
             if it:  # first iteration = warm-up
-                times.append(dt)
+                times.append(dt); t_enq.append(t1 - t0)
             eng.remove(ids)  # what the lobby stage does later (game-lobby/worker.ex:80); untimed
         assert st2.n_lobbies == lobbies_per_step
         e2e_s = max(times) if False else sum(times) / len(times)
@@ -250,6 +251,7 @@ def main():
         e2e = {"value": total_lobbies_per_step / e2e_s, "unit": "lobbies/s",
                "h2d_bytes_per_step": n * (8 + 4 + 1 + 4), "d2h_bytes_per_step": n + st2.n_matched * 8 + st2.n_lobbies * 8,
                "ms_per_step": 1e3 * e2e_s, "steps": len(times),
+               "enqueue_ms": 1e3 * sum(t_enq) / len(t_enq), "tick_and_d2h_ms": 1e3 * (sum(times) - sum(t_enq)) / len(times),
                "call": "mm_enqueue(host columns) + mm_tick(host lobbies/member_ids)"}
     eng.close()
 

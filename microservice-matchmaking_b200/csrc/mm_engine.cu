@@ -42,6 +42,8 @@ struct mm_engine {
   int block = 1024;  // threads per row CTA (512 when two rows share an SM)
   cudaStream_t stream = nullptr;
   bool own_stream = true;
+  cudaStream_t copy_stream = nullptr;  // H2D of ingest chunks, overlapped with the claim kernels
+  cudaEvent_t ev_copy = nullptr;
   cudaEvent_t ev[5]{};  // tick start | after hist | after colscan | after place | after epilogue
   char last_err[512] = {0};
 
@@ -313,29 +315,39 @@ int rehash(mm_engine* e) {
   return MM_OK;
 }
 
-int enqueue_device_locked(mm_engine* e, uint32_t n, const uint64_t* id, const int32_t* rating, const uint8_t* mode,
-                          const uint32_t* ts, uint8_t* accepted, uint32_t* n_accepted) {
-  if (n_accepted) *n_accepted = 0;
-  if (n == 0) return MM_OK;
+// capacity checks + scratch for an ingest batch of n players
+int enq_prepare(mm_engine* e, uint32_t n) {
   int rc = ensure_enq_scratch(e, n);
   if (rc) return rc;
   if (e->use_active && (e->n_active + e->n_tomb + n) * 4 > e->hcap * 3) {
     if ((e->n_active + n) * 4 > e->hcap * 3) return MM_E_CAP;  // active set full
     if ((rc = rehash(e))) return rc;
   }
+  CK(cudaMemsetAsync(e->d_small, 0, 16, e->stream));
+  return MM_OK;
+}
+
+// E1 on batch indices [base, base + cnt): validate + claim in the active set
+int enq_claim(mm_engine* e, uint32_t base, uint32_t cnt, const uint64_t* id, const int32_t* rating, const uint8_t* mode) {
+  k_enq_claim<<<(cnt + 255) / 256, 256, 0, e->stream>>>(base, cnt, id, rating, mode, e->d_grp_lut, e->key_lo, e->KR,
+                                                         e->cfg.n_modes, act_view(e), e->d_hslot, e->d_code);
+  CK(cudaGetLastError());
+  return MM_OK;
+}
+
+// E2 + E3 over the whole batch: winners, stable append to the pool, commit, counters
+int enq_finish(mm_engine* e, uint32_t n, const uint64_t* id, const int32_t* rating, const uint8_t* mode, const uint32_t* ts,
+               uint8_t* accepted_dev, uint32_t* n_accepted) {
   const uint32_t nb = (n + 255) / 256;
   Pool& p = e->pool[e->cur];
   ActiveView av = act_view(e);
-  CK(cudaMemsetAsync(e->d_small, 0, 16, e->stream));
-  k_enq_claim<<<nb, 256, 0, e->stream>>>(n, id, rating, mode, e->d_grp_lut, e->key_lo, e->KR, e->cfg.n_modes, av,
-                                         e->d_hslot, e->d_code);
   k_enq_count<<<nb, 256, 0, e->stream>>>(n, av, e->d_hslot, e->d_code, e->d_blocksum);
   k_scan_small<<<1, 1024, 0, e->stream>>>(nb, e->d_blocksum, e->d_small);
   k_enq_append<<<nb, 256, 0, e->stream>>>(n, id, rating, mode, ts, e->d_mode_tsize, av, e->d_hslot, e->d_code,
                                           e->d_blocksum, p.v, p.n, e->capacity, e->gen, e->d_small + 1);
   CK(cudaGetLastError());
   CK(cudaMemcpyAsync(e->h_small, e->d_small, 16, cudaMemcpyDeviceToHost, e->stream));
-  if (accepted) CK(cudaMemcpyAsync(accepted, e->d_code, n, cudaMemcpyDeviceToDevice, e->stream));
+  if (accepted_dev) CK(cudaMemcpyAsync(accepted_dev, e->d_code, n, cudaMemcpyDeviceToDevice, e->stream));
   CK(cudaStreamSynchronize(e->stream));
   const uint32_t won = e->h_small[0], rej = e->h_small[1];
   const uint32_t acc = won - rej;
@@ -343,6 +355,16 @@ int enqueue_device_locked(mm_engine* e, uint32_t n, const uint64_t* id, const in
   if (e->use_active) { e->n_active += acc; e->n_tomb += rej; }
   if (n_accepted) *n_accepted = acc;
   return MM_OK;
+}
+
+int enqueue_device_locked(mm_engine* e, uint32_t n, const uint64_t* id, const int32_t* rating, const uint8_t* mode,
+                          const uint32_t* ts, uint8_t* accepted, uint32_t* n_accepted) {
+  if (n_accepted) *n_accepted = 0;
+  if (n == 0) return MM_OK;
+  int rc = enq_prepare(e, n);
+  if (rc) return rc;
+  if ((rc = enq_claim(e, 0, n, id, rating, mode))) return rc;
+  return enq_finish(e, n, id, rating, mode, ts, accepted, n_accepted);
 }
 
 // Pin member_ids in a persisting L2 carve-out: the 8-byte scatter of k_place completes
@@ -591,6 +613,9 @@ int mm_create(const mm_config* cfg, mm_engine** out) {
   e->smem_optin = prop.sharedMemPerBlockOptin;
   e->smem_sm = prop.sharedMemPerMultiprocessor;
   if (cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) != cudaSuccess) return bail(MM_E_CUDA);
+  if (cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreateWithFlags(&e->ev_copy, cudaEventDisableTiming) != cudaSuccess)
+    return bail(MM_E_CUDA);
   for (auto& ev : e->ev)
     if (cudaEventCreate(&ev) != cudaSuccess) return bail(MM_E_CUDA);
   if ((rc = build_tables(e))) return bail(rc);
@@ -702,6 +727,8 @@ int mm_destroy(mm_engine* e) {
   for (auto& ev : e->ev)
     if (ev) cudaEventDestroy(ev);
   if (e->stream && e->own_stream) cudaStreamDestroy(e->stream);
+  if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
+  if (e->ev_copy) cudaEventDestroy(e->ev_copy);
   cudaGetLastError();
   delete e;
   return MM_OK;
@@ -784,13 +811,26 @@ int mm_enqueue(mm_engine* e, uint32_t n, const uint64_t* id, const int32_t* rati
   if (n == 0) return MM_OK;
   std::lock_guard<std::mutex> lk(e->mu);
   CK(cudaSetDevice(e->device));
-  int rc = ensure_enq_scratch(e, n);
+  int rc = enq_prepare(e, n);
   if (rc) return rc;
-  CK(cudaMemcpyAsync(e->d_in_id, id, (size_t)n * 8, cudaMemcpyHostToDevice, e->stream));
-  CK(cudaMemcpyAsync(e->d_in_rating, rating, (size_t)n * 4, cudaMemcpyHostToDevice, e->stream));
-  CK(cudaMemcpyAsync(e->d_in_mode, mode, (size_t)n, cudaMemcpyHostToDevice, e->stream));
-  if (enq_ts) CK(cudaMemcpyAsync(e->d_in_ts, enq_ts, (size_t)n * 4, cudaMemcpyHostToDevice, e->stream));
-  rc = enqueue_device_locked(e, n, e->d_in_id, e->d_in_rating, e->d_in_mode, enq_ts ? e->d_in_ts : nullptr, nullptr, nullptr);
+  // Pipelined ingest: the host columns go up in chunks on the copy stream while the claim
+  // kernel of the previous chunk runs on the engine stream (the claim only needs id/rating/mode).
+  const uint32_t chunk = 1u << 20;
+  for (uint32_t base = 0; base < n; base += chunk) {
+    const uint32_t cnt = std::min(chunk, n - base);
+    CK(cudaMemcpyAsync(e->d_in_id + base, id + base, (size_t)cnt * 8, cudaMemcpyHostToDevice, e->copy_stream));
+    CK(cudaMemcpyAsync(e->d_in_rating + base, rating + base, (size_t)cnt * 4, cudaMemcpyHostToDevice, e->copy_stream));
+    CK(cudaMemcpyAsync(e->d_in_mode + base, mode + base, (size_t)cnt, cudaMemcpyHostToDevice, e->copy_stream));
+    CK(cudaEventRecord(e->ev_copy, e->copy_stream));
+    CK(cudaStreamWaitEvent(e->stream, e->ev_copy, 0));
+    if ((rc = enq_claim(e, base, cnt, e->d_in_id, e->d_in_rating, e->d_in_mode))) return rc;
+  }
+  if (enq_ts) {
+    CK(cudaMemcpyAsync(e->d_in_ts, enq_ts, (size_t)n * 4, cudaMemcpyHostToDevice, e->copy_stream));
+    CK(cudaEventRecord(e->ev_copy, e->copy_stream));
+    CK(cudaStreamWaitEvent(e->stream, e->ev_copy, 0));
+  }
+  rc = enq_finish(e, n, e->d_in_id, e->d_in_rating, e->d_in_mode, enq_ts ? e->d_in_ts : nullptr, nullptr, nullptr);
   if (rc) return rc;
   if (accepted) {
     CK(cudaMemcpyAsync(accepted, e->d_code, n, cudaMemcpyDeviceToHost, e->stream));

@@ -1199,12 +1199,13 @@ __global__ void __launch_bounds__(BLOCK, 2) k_tick(const TickArgs a) {
 
 // E1: validate + claim.  The lowest batch index wins a repeated id (atomicMin), which
 // is what a serialized in_queue?/add_user sequence (middleware/worker.ex:65-70) yields.
-__global__ void k_enq_claim(uint32_t n, const uint64_t* __restrict__ id, const int32_t* __restrict__ rating,
+__global__ void k_enq_claim(uint32_t base, uint32_t n, const uint64_t* __restrict__ id, const int32_t* __restrict__ rating,
                             const uint8_t* __restrict__ mode, const uint8_t* __restrict__ grp_lut, int32_t key_lo,
                             uint32_t KR, uint32_t n_modes, ActiveView act, uint64_t* __restrict__ hslot,
                             uint8_t* __restrict__ code) {
-  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;  // this launch covers batch indices [base, base + n)
+  if (t >= n) return;
+  const uint32_t i = base + t;
   const uint64_t pid = id[i];
   const int32_t hi = key_lo + (int32_t)KR - 1;
   const int32_t r = rating[i] < key_lo ? key_lo : (rating[i] > hi ? hi : rating[i]);
