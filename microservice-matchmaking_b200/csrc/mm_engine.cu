@@ -129,6 +129,17 @@ int fail(mm_engine* e, cudaError_t err, const char* what) {
     if (_err != cudaSuccess) return fail(e, _err, #call); \
   } while (0)
 
+// Allow a kernel the device's whole opt-in shared memory (minus its static part).  Function attributes are
+// process-global: an engine with a small key domain must never lower the limit another engine relies on.
+template <class F>
+cudaError_t allow_max_smem(const mm_engine* e, F* func) {
+  cudaFuncAttributes fa{};
+  cudaError_t err = cudaFuncGetAttributes(&fa, func);
+  if (err != cudaSuccess) return err;
+  return cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                              (int)(e->smem_optin - fa.sharedSizeBytes));
+}
+
 int alloc_pool(mm_engine* e, Pool& p, uint32_t cap) {
   const size_t c = (size_t)cap + 3 * kRound;  // TMA tiles are read whole: pad past the last row
   CK(cudaMalloc(&p.v.id, c * 8));
@@ -626,18 +637,19 @@ int mm_create(const mm_config* cfg, mm_engine** out) {
     return bail(MM_E_ARG);
   }
   {
-    const int s0 = (int)place_smem(e, 0), s1 = (int)place_smem(e, 1);
-    if (cudaFuncSetAttribute(k_colscan, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)colscan_smem(e)) != cudaSuccess)
-      return bail(fail(e, cudaGetLastError(), "cudaFuncSetAttribute(k_colscan)"));
-    bool ok = cudaFuncSetAttribute(k_hist<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hist_smem(e)) == cudaSuccess &&
-              cudaFuncSetAttribute(k_place<0, 0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, s0) == cudaSuccess;
+    // NOTE: function attributes are process-global.  Every kernel gets the device's opt-in maximum so that
+    // an engine with a small key domain never lowers the limit another engine of this process relies on.
+    if (allow_max_smem(e, k_colscan) != cudaSuccess)
+      return bail(fail(e, cudaGetLastError(), "allow_max_smem(e, k_colscan)"));
+    bool ok = allow_max_smem(e, k_hist<1024>) == cudaSuccess &&
+              allow_max_smem(e, k_place<0, 0, false>) == cudaSuccess;
     if (ok && e->rank_impl == 1)
-      ok = cudaFuncSetAttribute(k_place<1, 0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, s1) == cudaSuccess &&
-           cudaFuncSetAttribute(k_place<1, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, s1) == cudaSuccess &&
-           cudaFuncSetAttribute(k_place<1, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, s1) == cudaSuccess &&
-           cudaFuncSetAttribute(k_place<1, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, s1) == cudaSuccess &&
-           cudaFuncSetAttribute(k_place<1, 3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, s1) == cudaSuccess;
-    ok = ok && cudaFuncSetAttribute(k_hist<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hist_smem(e)) == cudaSuccess;
+      ok = allow_max_smem(e, k_place<1, 0, false>) == cudaSuccess &&
+           allow_max_smem(e, k_place<1, 0, true>) == cudaSuccess &&
+           allow_max_smem(e, k_place<1, 1, true>) == cudaSuccess &&
+           allow_max_smem(e, k_place<1, 2, true>) == cudaSuccess &&
+           allow_max_smem(e, k_place<1, 3, true>) == cudaSuccess;
+    ok = ok && allow_max_smem(e, k_hist<512>) == cudaSuccess;
     // The TMA-fed kernel wants >= 2 ring stages next to its per-bin state; when two such CTAs
     // (512 threads each) fit in one SM, rows = 2 x SMs so barrier phases of one overlap the other.
     if (e->rank_impl == 1 && e->Kp <= 65535u) {
@@ -652,14 +664,14 @@ int mm_create(const mm_config* cfg, mm_engine** out) {
           e->hist2_stages = st;
       if (e->hist2_stages) {
         const int hs = (int)hist2_smem(e, e->hist2_stages);
-        ok = cudaFuncSetAttribute(k_hist2<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, hs) == cudaSuccess &&
-             cudaFuncSetAttribute(k_hist2<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, hs) == cudaSuccess;
+        ok = allow_max_smem(e, k_hist2<512>) == cudaSuccess &&
+             allow_max_smem(e, k_hist2<1024>) == cudaSuccess;
       }
     }
     if (ok && e->place2_stages) {
       const int sz = (int)place2_smem(e, e->place2_stages);
-      ok = cudaFuncSetAttribute(k_place2<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, sz) == cudaSuccess &&
-           cudaFuncSetAttribute(k_place2<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, sz) == cudaSuccess;
+      ok = allow_max_smem(e, k_place2<512>) == cudaSuccess &&
+           allow_max_smem(e, k_place2<1024>) == cudaSuccess;
       e->rank_impl = 3;
     }
     if (!ok) return bail(fail(e, cudaGetLastError(), "cudaFuncSetAttribute"));
@@ -695,7 +707,7 @@ int mm_create(const mm_config* cfg, mm_engine** out) {
     sz = std::max<size_t>(sz, std::max<size_t>((size_t)kEpiScratchWords * 4, colscan_smem(e)));
     int coop = 0, nb = 0;
     cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, e->device);
-    if (coop && cudaFuncSetAttribute(k_tick<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sz) == cudaSuccess &&
+    if (coop && allow_max_smem(e, k_tick<512>) == cudaSuccess &&
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_tick<512>, 512, sz) == cudaSuccess &&
         (uint32_t)nb * (uint32_t)e->n_sms >= e->R) {
       e->fused_ok = 1;
@@ -754,11 +766,11 @@ int mm_set_option(mm_engine* e, const char* name, int64_t value) {
     if (value == 1 && place_smem(e, 1) > e->smem_optin) return MM_E_ARG;
     if (value == 1) {
       const int s1 = (int)place_smem(e, 1);
-      CK(cudaFuncSetAttribute(k_place<1, 0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, s1));
-      CK(cudaFuncSetAttribute(k_place<1, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, s1));
-      CK(cudaFuncSetAttribute(k_place<1, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, s1));
-      CK(cudaFuncSetAttribute(k_place<1, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, s1));
-      CK(cudaFuncSetAttribute(k_place<1, 3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, s1));
+      CK(allow_max_smem(e, k_place<1, 0, false>));
+      CK(allow_max_smem(e, k_place<1, 0, true>));
+      CK(allow_max_smem(e, k_place<1, 1, true>));
+      CK(allow_max_smem(e, k_place<1, 2, true>));
+      CK(allow_max_smem(e, k_place<1, 3, true>));
     }
     if (value == 3 && !e->place2_stages) return MM_E_ARG;
     e->rank_impl = (int)value;
@@ -778,8 +790,8 @@ int mm_set_option(mm_engine* e, const char* name, int64_t value) {
   if (!std::strcmp(name, "place2_stages")) {
     if (value < 1 || value > (int64_t)kMaxStages || place2_smem(e, (uint32_t)value) + 1024 > e->smem_optin) return MM_E_ARG;
     const int sz = (int)place2_smem(e, (uint32_t)value);
-    CK(cudaFuncSetAttribute(k_place2<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, sz));
-    CK(cudaFuncSetAttribute(k_place2<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, sz));
+    CK(allow_max_smem(e, k_place2<512>));
+    CK(allow_max_smem(e, k_place2<1024>));
     e->place2_stages = (uint32_t)value;
     return MM_OK;
   }

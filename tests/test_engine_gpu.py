@@ -364,3 +364,98 @@ def test_config3_ten_million_5v5(pkg, oracle):
         lm, lg, members, res = oracle.closed_form_numpy(cfg, ids, rating, mode)
         assert np.array_equal(members, mem) and np.array_equal(res, resid)
         assert np.array_equal(lg, lob["group"]) and np.array_equal(lm, lob["mode"])
+
+
+# ---- robustness of the boundary ------------------------------------------------------------------------
+def test_tombstone_rehash_and_reuse(pkg):
+    """Many enqueue/remove cycles on a small active set: tombstones accumulate, the table is rehashed,
+    membership stays exact (models/active_user.ex semantics)."""
+    cfg = pkg.synth.make_config(groups=pkg.synth.REFERENCE_GROUPS, order=ARRIVAL, capacity=4096, active_capacity=6000)
+    rng = np.random.default_rng(5)
+    with pkg.Engine(cfg) as eng:
+        live = set()
+        for step in range(40):
+            ids = rng.integers(1, 50_000, 1500).astype(np.uint64)
+            acc = eng.enqueue(ids, rng.integers(0, 5001, 1500), np.zeros(1500, np.uint8))
+            seen = set()
+            for p, a in zip(ids.tolist(), acc.tolist()):
+                if p in live or p in seen:
+                    assert a == 0
+                else:
+                    assert a in (1, 3)
+                    if a == 1:
+                        seen.add(p)
+            live |= seen
+            lob, mem, _, st = eng.tick()
+            assert set(mem.tolist()) <= live
+            gone = np.array(sorted(live), np.uint64)[::2]
+            assert eng.remove(gone) == len(gone)
+            live -= set(gone.tolist())
+            probe = rng.integers(1, 50_000, 500).astype(np.uint64)
+            assert list(eng.in_queue(probe)) == [p in live for p in probe.tolist()]
+            assert eng.active_size() == len(live)
+
+
+def test_active_set_full_is_reported(pkg):
+    cfg = pkg.synth.make_config(groups=pkg.synth.REFERENCE_GROUPS, order=ARRIVAL, capacity=1 << 16, active_capacity=1000)
+    with pkg.Engine(cfg) as eng:
+        with pytest.raises(pkg.EngineError) as ei:
+            eng.enqueue(np.arange(1, 60_001, dtype=np.uint64), np.full(60_000, 100), np.zeros(60_000, np.uint8))
+        assert ei.value.status == pkg.abi.MM_E_CAP and eng.pool_size() == 0
+
+
+def test_bad_options_and_state(pkg):
+    cfg = pkg.synth.make_config(groups=pkg.synth.REFERENCE_GROUPS, order=ARRIVAL, capacity=64)
+    with pkg.Engine(cfg) as eng:
+        for name, v in (("nope", 1), ("rank_impl", 7), ("block", 100), ("rows_per_sm", 0)):
+            with pytest.raises(pkg.EngineError):
+                eng.set_option(name, v)
+        with pytest.raises(pkg.EngineError) as ei:
+            eng.restore()  # no snapshot yet
+        assert ei.value.status == pkg.abi.MM_E_STATE
+
+
+def test_external_stream(pkg, oracle):
+    import torch
+    n = 30_000
+    cfg = pkg.synth.make_config(n_groups=8, order=RATING, capacity=n)
+    ids, rating, mode, ts = make_pool(pkg, 3, n)
+    s = torch.cuda.Stream()
+    with pkg.Engine(cfg) as eng:
+        eng.set_stream(s.cuda_stream)
+        assert eng.enqueue(ids, rating, mode, ts).all()
+        lob, mem, seq, st = eng.tick()
+        assert_tick_matches(eng, oracle.run_closed_form(cfg, ids, rating, mode), lob, mem, seq, st)
+
+
+def test_two_engines_and_threads(pkg, oracle):
+    """One writer per engine, several engines per process (one per rating-group shard)."""
+    import threading
+    n = 40_000
+    cfgs = [pkg.synth.make_config(n_groups=8, order=o, capacity=n) for o in (ARRIVAL, RATING)]
+    pools = [make_pool(pkg, 50 + i, n) for i in range(2)]
+    out = [None, None]
+
+    def work(i):
+        with pkg.Engine(cfgs[i]) as eng:
+            assert eng.enqueue(*pools[i]).all()
+            out[i] = eng.tick()
+
+    th = [threading.Thread(target=work, args=(i,)) for i in range(2)]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    for i in range(2):
+        ref = oracle.run_closed_form(cfgs[i], *pools[i][:3])
+        assert np.array_equal(out[i][1], ref.member_ids) and np.array_equal(out[i][0], ref.lobbies)
+
+
+def test_large_lobbies_and_many_groups(pkg, oracle):
+    modes = (("battle-royale", 1, 100), ("4x8", 4, 8))
+    n = 100_000
+    cfg = pkg.synth.make_config(n_groups=64, modes=modes, order=RATING, capacity=n)
+    ids, rating, mode, ts = make_pool(pkg, 77, n, n_modes=2, oor=0.0)
+    with pkg.Engine(cfg) as eng:
+        assert eng.enqueue(ids, rating, mode, ts).all()
+        lob, mem, seq, st = eng.tick()
+        assert_tick_matches(eng, oracle.run_literal(cfg, ids, rating, mode), lob, mem, seq, st)
+        assert set(np.unique(lob["n_members"])) <= {100, 32}
