@@ -55,7 +55,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.idx}", f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -201,7 +201,6 @@ def main():
     launches_per_tick = st.n_launches
     barrier()
     wall_s = time.perf_counter() - t_wall
-    clocks = sampler.stop()
     lobbies_per_step = st.n_lobbies
     tick_s = sum(dev_us) * 1e-6  # device time of the K timed ticks on this rank
     if world > 1:
@@ -254,6 +253,7 @@ def main():
                "enqueue_ms": 1e3 * sum(t_enq) / len(t_enq), "tick_and_d2h_ms": 1e3 * (sum(times) - sum(t_enq)) / len(times),
                "call": "mm_enqueue(host columns) + mm_tick(host lobbies/member_ids)"}
     eng.close()
+    clocks = sampler.stop()  # sampled across the device-timed ticks and the e2e steps
 
     # ---- CPU baseline (rank 0, N=1 only): the oracle's literal loop on a bounded sample ----
     cpu = None

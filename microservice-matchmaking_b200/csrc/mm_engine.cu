@@ -448,26 +448,24 @@ int tick_phase_b(mm_engine* e, uint32_t n, uint32_t chunk, bool want_seq) {
   Pool& q = e->pool[e->cur ^ 1];
   uint32_t* src_idx = want_seq ? e->d_src_idx : nullptr;
   CK(cudaEventRecord(e->ev[2], e->stream));
-#define MM_PLACE(IMPL, DBG, HINT)                                                                                    \
-  k_place<IMPL, DBG, HINT><<<e->R, kBlock, place_smem(e, IMPL), e->stream>>>(                                         \
+#define MM_PLACE(IMPL)                                                                                               \
+  k_place<IMPL><<<e->R, kBlock, place_smem(e, IMPL), e->stream>>>(                                                    \
       p.v, n, chunk, bin_map(e), e->Kp, e->R, e->d_M, e->d_tot, e->d_binbase, e->d_bin_seg, e->d_seg_shift,           \
       e->d_seg_lim, e->n_segs, e->d_members, src_idx, e->d_resid_stage, e->d_rescnt, e->d_ctr)
 #define MM_PLACE2(BLK)                                                                                               \
   k_place2<BLK><<<e->R, BLK, place2_smem(e, e->place2_stages), e->stream>>>(                                          \
-      e->d_bins16, p.v.id, n, chunk, e->K, e->Kp, e->R, e->place2_stages, dense_mode(e),  \
-      e->d_M, e->d_tot, e->d_binbase, e->d_bin_seg, e->d_seg_shift, e->d_seg_lim, e->d_members, src_idx,              \
-      e->d_resid_stage, e->d_rescnt, e->d_ctr, (uint32_t)e->place_debug)
+      e->d_bins16, p.v.id, n, chunk, e->K, e->Kp, e->R, e->place2_stages, dense_mode(e), e->d_M, e->d_tot,            \
+      e->d_binbase, e->d_bin_seg, e->d_seg_shift, e->d_seg_lim, e->d_members, src_idx, e->d_resid_stage, e->d_rescnt, \
+      e->d_ctr, (uint32_t)e->place_debug)
   if (e->rank_impl == 3) {
     if (e->block == 512) MM_PLACE2(512);
     else MM_PLACE2(1024);
+  } else if (e->rank_impl == 0) {
+    MM_PLACE(0);
+  } else {
+    MM_PLACE(1);
   }
 #undef MM_PLACE2
-  else if (e->rank_impl == 0) MM_PLACE(0, 0, false);
-  else if (e->place_debug == 1) MM_PLACE(1, 1, true);
-  else if (e->place_debug == 2) MM_PLACE(1, 2, true);
-  else if (e->place_debug == 3) MM_PLACE(1, 3, true);
-  else if (e->l2_hints) MM_PLACE(1, 0, true);
-  else MM_PLACE(1, 0, false);
 #undef MM_PLACE
   CK(cudaEventRecord(e->ev[3], e->stream));
   k_epilogue<<<std::max(1, e->n_sms), 1024, 0, e->stream>>>(p.v, q.v, e->R, e->d_rescnt, e->d_resid_stage, act_view(e),
@@ -642,13 +640,9 @@ int mm_create(const mm_config* cfg, mm_engine** out) {
     if (allow_max_smem(e, k_colscan) != cudaSuccess)
       return bail(fail(e, cudaGetLastError(), "allow_max_smem(e, k_colscan)"));
     bool ok = allow_max_smem(e, k_hist<1024>) == cudaSuccess &&
-              allow_max_smem(e, k_place<0, 0, false>) == cudaSuccess;
+              allow_max_smem(e, k_place<0>) == cudaSuccess;
     if (ok && e->rank_impl == 1)
-      ok = allow_max_smem(e, k_place<1, 0, false>) == cudaSuccess &&
-           allow_max_smem(e, k_place<1, 0, true>) == cudaSuccess &&
-           allow_max_smem(e, k_place<1, 1, true>) == cudaSuccess &&
-           allow_max_smem(e, k_place<1, 2, true>) == cudaSuccess &&
-           allow_max_smem(e, k_place<1, 3, true>) == cudaSuccess;
+      ok = allow_max_smem(e, k_place<1>) == cudaSuccess;
     ok = ok && allow_max_smem(e, k_hist<512>) == cudaSuccess;
     // The TMA-fed kernel wants >= 2 ring stages next to its per-bin state; when two such CTAs
     // (512 threads each) fit in one SM, rows = 2 x SMs so barrier phases of one overlap the other.
@@ -766,11 +760,7 @@ int mm_set_option(mm_engine* e, const char* name, int64_t value) {
     if (value == 1 && place_smem(e, 1) > e->smem_optin) return MM_E_ARG;
     if (value == 1) {
       const int s1 = (int)place_smem(e, 1);
-      CK(allow_max_smem(e, k_place<1, 0, false>));
-      CK(allow_max_smem(e, k_place<1, 0, true>));
-      CK(allow_max_smem(e, k_place<1, 1, true>));
-      CK(allow_max_smem(e, k_place<1, 2, true>));
-      CK(allow_max_smem(e, k_place<1, 3, true>));
+      CK(allow_max_smem(e, k_place<1>));
     }
     if (value == 3 && !e->place2_stages) return MM_E_ARG;
     e->rank_impl = (int)value;

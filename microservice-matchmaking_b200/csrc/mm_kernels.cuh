@@ -510,11 +510,10 @@ __global__ void __launch_bounds__(kScanBlock) k_colscan(uint32_t R, uint32_t Kp,
 //       The first pusher advances cnt[bin] by the round's total.
 // Bit 31 of cnt marks a (row, bin) cell that reaches past the segment's matched range:
 // only those players consult seg_lim (the < L leftovers of a partition stay queued).
-// IMPL 0 is a slow warp-serial ranking kept as an on-device cross-check.
-// DBG != 0 are timing experiments (wrong results, never used by the ABI's tick):
-//   1 = rank but store coalesced, 2 = no rank + pseudo-random scatter, 3 = streaming copy.
+// This is the round's first placement kernel, kept as an on-device cross-check of k_place2
+// (rank_impl 1 = this list ranking, rank_impl 0 = a slow warp-serial ranking).
 // ---------------------------------------------------------------------------------------
-template <int IMPL, int DBG, bool HINT>
+template <int IMPL>
 __global__ void __launch_bounds__(kBlock, 1)
     k_place(PoolView p, uint32_t n, uint32_t chunk, BinMap bm, uint32_t Kp, uint32_t R, const uint32_t* __restrict__ M,
             const uint32_t* __restrict__ tot, const uint32_t* __restrict__ binbase,
@@ -570,15 +569,9 @@ __global__ void __launch_bounds__(kBlock, 1)
       const uint32_t e = base + j * kBlock + tid;
       if (e < end) {
         int32_t r; uint32_t m;
-        if (HINT) {
-          r = ld_stream_s32(p.rating + e, pol_in);
-          m = ld_stream_u8(p.mode + e, pol_in);
-          idv[j] = ld_stream_u64(p.id + e, pol_in);
-        } else {
-          r = __ldcs(p.rating + e);
-          m = __ldcs(p.mode + e);
-          idv[j] = __ldcs(reinterpret_cast<const unsigned long long*>(p.id + e));
-        }
+        r = ld_stream_s32(p.rating + e, pol_in);
+        m = ld_stream_u8(p.mode + e, pol_in);
+        idv[j] = ld_stream_u64(p.id + e, pol_in);
         bin[j] = bin_of(bm, s_lut, r, m);
       } else {
         bin[j] = 0xFFFFFFFFu;
@@ -587,10 +580,7 @@ __global__ void __launch_bounds__(kBlock, 1)
     }
     uint32_t leader[kJ], rankw[kJ], base_g[kJ];
 
-    if (DBG >= 2) {
-#pragma unroll
-      for (int j = 0; j < kJ; ++j) { leader[j] = 0; rankw[j] = 0; base_g[j] = 0; }
-    } else if (IMPL == 1) {
+    if (IMPL == 1) {
       const uint32_t epoch = round + 1;
       uint32_t snap[kJ], mynode[kJ];
       bool isl[kJ], first[kJ];
@@ -657,11 +647,8 @@ __global__ void __launch_bounds__(kBlock, 1)
         uint32_t slot = (base_g[j] & 0x7FFFFFFFu) + rankw[j];
         bool matched = true;
         if (base_g[j] >> 31) matched = slot < s_lim[__ldg(&bin_seg[bin[j]])];
-        if (DBG == 1 || DBG == 3) { slot = e; matched = true; }
-        if (DBG == 2) { slot = (uint32_t)(((uint64_t)e * 2654435761ull) % n); matched = true; }
         if (matched) {
-          if (HINT) st_keep_u64(members + slot, idv[j], pol_out);
-          else members[slot] = idv[j];
+          st_keep_u64(members + slot, idv[j], pol_out);
           if (src_idx) src_idx[slot] = e;
         } else {
           const uint32_t k = atomicAdd(&s_nres, 1u);
