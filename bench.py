@@ -134,6 +134,9 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=10_000_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak (contract default): every rank holds a full-size pool over its own groups; strong "
+                         "(BASELINE configs[3]): ONE pool of the workload's size, rating groups dealt to the ranks")
     ap.add_argument("--two-modes", action="store_true", help="configure both default modes (1v1, 5v5), not just the workload's")
     ap.add_argument("--tick-impl", type=int, default=None, help="1 = one fused cooperative launch (default), 0 = four launches")
     args = ap.parse_args()
@@ -164,6 +167,13 @@ def main():
                                               single_mode=not args.two_modes)
     # rank r's shard of the N x n pool: its own seed stream (weak scaling, disjoint ids)
     ids, rating, mode, ts = pkg.synth.gen_pool(1, n, first=rank * n, mode=mode_idx)
+    if args.scaling == "strong" and world > 1:
+        # the Generic stage's routing (generic/worker.ex:46-69): this rank keeps the players of its groups
+        shard = importlib.import_module(PKG + ".shard")
+        ids, rating, mode, ts = pkg.synth.gen_pool(1, n, first=0, mode=mode_idx)
+        mine = shard.route(cfg, rating, world) == rank
+        ids, rating, mode, ts = ids[mine], rating[mine], mode[mine], ts[mine]
+        n = int(mine.sum())
 
     def barrier():
         torch.cuda.synchronize()
@@ -207,12 +217,12 @@ def main():
         t = torch.tensor([tick_s, float(sum(place_us)) * 1e-6], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         tick_s, place_s = t.tolist()
-        tl = torch.tensor([lobbies_per_step], device="cuda", dtype=torch.int64)
+        tl = torch.tensor([lobbies_per_step, n], device="cuda", dtype=torch.int64)
         dist.all_reduce(tl)
-        total_lobbies_per_step = int(tl.item())
+        total_lobbies_per_step, total_players = int(tl[0].item()), int(tl[1].item())
     else:
         place_s = sum(place_us) * 1e-6
-        total_lobbies_per_step = lobbies_per_step
+        total_lobbies_per_step, total_players = lobbies_per_step, n
     value = total_lobbies_per_step * args.steps / tick_s
 
     # ---- e2e through the C ABI with host buffers ------------------------------------
@@ -284,8 +294,10 @@ def main():
         line = {
             "metric": "matches/sec", "value": value, "unit": "lobbies/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * tick_s / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "int32/u64", "data": "synthetic",
-            "config": {"workload": args.workload, "players_per_gpu": n, "rating_groups_per_gpu": w["n_groups"],
+            "scaling": args.scaling, "vs_baseline": None, "dtype": "int32/u64", "data": "synthetic",
+            "config": {"workload": args.workload, "players_per_gpu": n,
+                       "rating_groups_per_gpu": w["n_groups"] if args.scaling == "weak" else w["n_groups"] // world,
+                       "players_total": total_players,
                        "lobby_size": L, "order": args.order, "ratings": "uniform 0..5000, seed 1",
                        "modes_configured": cfg.n_modes, "launches_per_tick": launches_per_tick,
                        "parallelism": f"rating-group shards x{world}, no collective",
@@ -295,7 +307,7 @@ def main():
                                        "snapshot restore + L2 flush between steps untimed"},
             "phase_us": dict(zip(("hist", "scan", "place", "epilogue"),
                                  [round(sum(x) / len(x), 2) for x in zip(*phases)])),
-            "players_per_s": n * world * args.steps / tick_s,
+            "players_per_s": total_players * args.steps / tick_s,
             "wall_ms_per_step_incl_restore": 1e3 * wall_s / args.steps,
             "roofline": {"bound": "hbm", "kernel": dom_kernel, "achieved": ach, "peak": peak, "unit": "GB/s",
                          "frac": ach / peak, "traffic": traffic, "peak_source": peak_src,

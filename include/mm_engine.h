@@ -188,9 +188,12 @@ int mm_restore(mm_engine* e);
 /* Use an externally owned CUDA stream (cudaStream_t passed as void*).              */
 int mm_set_stream(mm_engine* e, void* cuda_stream);
 
-/* Tuning / debugging knobs (name -> value); unknown name = MM_E_ARG.
- *   "rank_impl": 0 = warp-serial reference ranking, 1 = list ranking (default)
- *   "rows_per_sm": CTAs per SM for the histogram / placement kernels               */
+/* Tuning / debugging knobs (name -> value); unknown name or bad value = MM_E_ARG.
+ *   "tick_impl"     1 = whole tick in one cooperative launch (default when it fits), 0 = four launches
+ *   "rank_impl"     3 = TMA-fed tile kernel (default), 1 / 0 = first list / warp-serial kernels (cross-checks)
+ *   "dense"         small-key-domain ranking: 2 = private byte counters (default), 1 = vote matrix, 0 = lists
+ *   "rows_per_sm", "block", "place2_stages", "hist_impl", "persist_mb", "warm_l2"   occupancy / cache experiments
+ *   "place_debug"   timing experiments that switch parts of the tick off — results are then INVALID        */
 int mm_set_option(mm_engine* e, const char* name, int64_t value);
 
 const char* mm_strerror(int status);

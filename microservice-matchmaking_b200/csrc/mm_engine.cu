@@ -78,7 +78,6 @@ struct mm_engine {
   uint32_t R = 0;
   int rows_per_sm = 1;
   int rank_impl = 1;
-  int l2_hints = 1;
   int place_debug = 0;
   size_t persist_bytes = 0;
   uint32_t place2_stages = 0;  // 0 = k_place2 does not fit in shared memory
@@ -766,7 +765,6 @@ int mm_set_option(mm_engine* e, const char* name, int64_t value) {
     e->rank_impl = (int)value;
     return MM_OK;
   }
-  if (!std::strcmp(name, "l2_hints")) { e->l2_hints = value != 0; return MM_OK; }
   if (!std::strcmp(name, "dense")) { e->dense_ok = (int)value; return MM_OK; }
   if (!std::strcmp(name, "hist_impl")) { e->hist_impl = (int)value; return MM_OK; }
   if (!std::strcmp(name, "warm_l2")) { e->warm_l2 = value != 0; return MM_OK; }
