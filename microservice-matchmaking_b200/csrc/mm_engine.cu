@@ -81,14 +81,11 @@ struct mm_engine {
   int place_debug = 0;
   size_t persist_bytes = 0;
   uint32_t place2_stages = 0;  // 0 = k_place2 does not fit in shared memory
-  uint32_t hist2_stages = 0;   // 0 = use the register-fed k_hist
-  int hist_impl = 2;
-  int warm_l2 = 0;  // bulk-prefetch member_ids into L2 during the histogram kernel (measured: no gain)
+  uint32_t hist3_stages = 4;   // ring depth of the bin-column histogram
   int fused_ok = 0;  // k_tick<512> can be launched cooperatively with 2 CTAs per SM
   int tick_impl = 1; // 1 = one fused cooperative launch when possible, 0 = four launches
   size_t tick_smem = 0;
   int dense_ok = 2;            // small-K ranking: 0 = off, 1 = MATCH-based matrix, 2 = private byte counters when possible
-  uint16_t* d_bins16 = nullptr;
   uint32_t* d_M = nullptr;
   uint32_t *d_tot = nullptr, *d_binbase = nullptr, *d_seg_lim = nullptr;
   SegInfo* d_seg = nullptr;
@@ -146,11 +143,12 @@ int alloc_pool(mm_engine* e, Pool& p, uint32_t cap) {
   CK(cudaMalloc(&p.v.mode, c));
   CK(cudaMalloc(&p.v.tsize, c));
   CK(cudaMalloc(&p.v.ts, c * 4));
+  CK(cudaMalloc(&p.v.bin, c * 2));
   p.n = 0;
   return MM_OK;
 }
 void free_pool(Pool& p) {
-  cudaFree(p.v.id); cudaFree(p.v.rating); cudaFree(p.v.mode); cudaFree(p.v.tsize); cudaFree(p.v.ts);
+  cudaFree(p.v.id); cudaFree(p.v.rating); cudaFree(p.v.mode); cudaFree(p.v.tsize); cudaFree(p.v.ts); cudaFree(p.v.bin);
   p = Pool{};
 }
 
@@ -210,9 +208,7 @@ size_t place2_smem(const mm_engine* e, uint32_t stages) {
 size_t colscan_smem(const mm_engine* e) {
   return (size_t)std::max<uint32_t>(kColScratchWords, kTailScratchWords + e->Kp + 2) * 4;
 }
-size_t hist2_smem(const mm_engine* e, uint32_t stages) {
-  return (size_t)stages * kHTileBytes + 64 + (size_t)e->Kp * 4 + (size_t)e->KR * 2 + 16;
-}
+size_t hist3_smem(const mm_engine* e, uint32_t stages) { return (size_t)stages * kBTileBytes + 64 + (size_t)e->Kp * 4 + 16; }
 size_t hist_smem(const mm_engine* e) { return (size_t)e->Kp * 4 + (size_t)e->KR * 2 + 16; }
 
 // Build the key -> bin LUT and the (mode, group) segment table (see mm_kernels.cuh).
@@ -354,7 +350,7 @@ int enq_finish(mm_engine* e, uint32_t n, const uint64_t* id, const int32_t* rati
   k_enq_count<<<nb, 256, 0, e->stream>>>(n, av, e->d_hslot, e->d_code, e->d_blocksum);
   k_scan_small<<<1, 1024, 0, e->stream>>>(nb, e->d_blocksum, e->d_small);
   k_enq_append<<<nb, 256, 0, e->stream>>>(n, id, rating, mode, ts, e->d_mode_tsize, av, e->d_hslot, e->d_code,
-                                          e->d_blocksum, p.v, p.n, e->capacity, e->gen, e->d_small + 1);
+                                          e->d_blocksum, p.v, p.n, e->capacity, e->gen, e->d_small + 1, bin_map(e));
   CK(cudaGetLastError());
   CK(cudaMemcpyAsync(e->h_small, e->d_small, 16, cudaMemcpyDeviceToHost, e->stream));
   if (accepted_dev) CK(cudaMemcpyAsync(accepted_dev, e->d_code, n, cudaMemcpyDeviceToDevice, e->stream));
@@ -419,21 +415,18 @@ int tick_phase_a(mm_engine* e, uint32_t n, uint32_t* chunk_out) {
   *chunk_out = chunk;
   CK(cudaMemsetAsync(e->d_ctr, 0, sizeof(TickCtr), e->stream));
   CK(cudaEventRecord(e->ev[0], e->stream));
-  if (e->rank_impl == 3 && e->hist_impl == 2 && e->hist2_stages) {
+  if (e->rank_impl == 3) {
     if (e->block == 512)
-      k_hist2<512><<<e->R, 512, hist2_smem(e, e->hist2_stages), e->stream>>>(p.v, n, chunk, bin_map(e), e->Kp,
-                                                                               e->hist2_stages, e->d_M, e->d_tot, e->d_bins16,
-                                                                               e->warm_l2 ? e->d_members : nullptr, n);
+      k_hist3<512><<<e->R, 512, hist3_smem(e, e->hist3_stages), e->stream>>>(p.v.bin, n, chunk, e->Kp, e->hist3_stages, e->d_M,
+                                                                              e->d_tot);
     else
-      k_hist2<1024><<<e->R, 1024, hist2_smem(e, e->hist2_stages), e->stream>>>(p.v, n, chunk, bin_map(e), e->Kp,
-                                                                                 e->hist2_stages, e->d_M, e->d_tot, e->d_bins16,
-                                                                                 e->warm_l2 ? e->d_members : nullptr, n);
-  } else if (e->block == 512)
-    k_hist<512><<<e->R, 512, hist_smem(e), e->stream>>>(p.v, n, chunk, bin_map(e), e->Kp, e->d_M, e->d_tot,
-                                                        e->rank_impl == 3 ? e->d_bins16 : nullptr);
-  else
-    k_hist<1024><<<e->R, 1024, hist_smem(e), e->stream>>>(p.v, n, chunk, bin_map(e), e->Kp, e->d_M, e->d_tot,
-                                                          e->rank_impl == 3 ? e->d_bins16 : nullptr);
+      k_hist3<1024><<<e->R, 1024, hist3_smem(e, e->hist3_stages), e->stream>>>(p.v.bin, n, chunk, e->Kp, e->hist3_stages,
+                                                                                e->d_M, e->d_tot);
+  } else if (e->block == 512) {
+    k_hist<512><<<e->R, 512, hist_smem(e), e->stream>>>(p.v, n, chunk, bin_map(e), e->Kp, e->d_M, e->d_tot, nullptr);
+  } else {
+    k_hist<1024><<<e->R, 1024, hist_smem(e), e->stream>>>(p.v, n, chunk, bin_map(e), e->Kp, e->d_M, e->d_tot, nullptr);
+  }
   CK(cudaEventRecord(e->ev[1], e->stream));
   k_colscan<<<(e->Kp + 31) / 32 + 1, kScanBlock, colscan_smem(e), e->stream>>>(e->R, e->Kp, e->K, e->d_M, e->d_tot, e->d_binbase, e->d_seg_bin_lo,
                                                         e->d_seg_L, e->n_segs, e->d_seg, e->d_seg_shift, e->d_seg_lim,
@@ -453,7 +446,7 @@ int tick_phase_b(mm_engine* e, uint32_t n, uint32_t chunk, bool want_seq) {
       e->d_seg_lim, e->n_segs, e->d_members, src_idx, e->d_resid_stage, e->d_rescnt, e->d_ctr)
 #define MM_PLACE2(BLK)                                                                                               \
   k_place2<BLK><<<e->R, BLK, place2_smem(e, e->place2_stages), e->stream>>>(                                          \
-      e->d_bins16, p.v.id, n, chunk, e->K, e->Kp, e->R, e->place2_stages, dense_mode(e), e->d_M, e->d_tot,            \
+      p.v.bin, p.v.id, n, chunk, e->K, e->Kp, e->R, e->place2_stages, dense_mode(e), e->d_M, e->d_tot,                \
       e->d_binbase, e->d_bin_seg, e->d_seg_shift, e->d_seg_lim, e->d_members, src_idx, e->d_resid_stage, e->d_rescnt, \
       e->d_ctr, (uint32_t)e->place_debug)
   if (e->rank_impl == 3) {
@@ -479,8 +472,7 @@ int tick_phase_b(mm_engine* e, uint32_t n, uint32_t chunk, bool want_seq) {
 }
 
 bool use_fused(const mm_engine* e) {
-  return e->tick_impl == 1 && e->fused_ok && e->rank_impl == 3 && e->block == 512 && e->hist_impl == 2 &&
-         e->hist2_stages && e->rows_per_sm == 2;
+  return e->tick_impl == 1 && e->fused_ok && e->rank_impl == 3 && e->block == 512 && e->rows_per_sm == 2;
 }
 
 // the whole tick in one cooperative launch (k_tick)
@@ -492,10 +484,10 @@ int tick_fused(mm_engine* e, uint32_t n, bool want_seq) {
   TickArgs a{};
   a.src = p.v; a.dst = q.v; a.bm = bin_map(e);
   a.n = n; a.chunk = chunk; a.K = e->K; a.Kp = e->Kp; a.R = e->R; a.n_segs = e->n_segs; a.n_groups = e->cfg.n_groups;
-  a.hist_stages = e->hist2_stages; a.place_stages = e->place2_stages;
+  a.hist_stages = e->hist3_stages; a.place_stages = e->place2_stages;
   a.dense = dense_mode(e);
   a.new_gen = e->gen + 1; a.dbg = (uint32_t)e->place_debug;
-  a.M = e->d_M; a.tot = e->d_tot; a.binbase = e->d_binbase; a.bins16 = e->d_bins16; a.bin_seg = e->d_bin_seg;
+  a.M = e->d_M; a.tot = e->d_tot; a.binbase = e->d_binbase; a.bin_seg = e->d_bin_seg;
   a.seg_bin_lo = e->d_seg_bin_lo; a.seg_L = e->d_seg_L; a.seg = e->d_seg; a.seg_shift = e->d_seg_shift;
   a.seg_lim = e->d_seg_lim; a.members = e->d_members; a.src_idx = want_seq ? e->d_src_idx : nullptr; a.hdr = e->d_hdr;
   a.emit_seq = want_seq ? e->d_emit_seq : nullptr; a.resid_stage = e->d_resid_stage; a.rescnt = e->d_rescnt;
@@ -652,14 +644,10 @@ int mm_create(const mm_config* cfg, mm_engine** out) {
         if (place2_smem(e, st) + 1024 <= e->smem_optin) { e->place2_stages = st; e->rows_per_sm = 1; e->block = 1024; }
     }
     if (ok && e->place2_stages) {
-      for (uint32_t st = 3; st >= 2 && !e->hist2_stages; --st)
-        if ((size_t)e->rows_per_sm * (hist2_smem(e, st) + 1024 + 256) <= e->smem_sm && hist2_smem(e, st) + 1024 <= e->smem_optin)
-          e->hist2_stages = st;
-      if (e->hist2_stages) {
-        const int hs = (int)hist2_smem(e, e->hist2_stages);
-        ok = allow_max_smem(e, k_hist2<512>) == cudaSuccess &&
-             allow_max_smem(e, k_hist2<1024>) == cudaSuccess;
-      }
+      while (e->hist3_stages > 2 && ((size_t)e->rows_per_sm * (hist3_smem(e, e->hist3_stages) + 1280) > e->smem_sm ||
+                                     hist3_smem(e, e->hist3_stages) + 1024 > e->smem_optin))
+        --e->hist3_stages;
+      ok = allow_max_smem(e, k_hist3<512>) == cudaSuccess && allow_max_smem(e, k_hist3<1024>) == cudaSuccess;
     }
     if (ok && e->place2_stages) {
       const int sz = (int)place2_smem(e, e->place2_stages);
@@ -687,7 +675,6 @@ int mm_create(const mm_config* cfg, mm_engine** out) {
       !A((void**)&e->d_seg_lim, e->n_segs * 4) ||
       !A((void**)&e->d_seg, e->n_segs * sizeof(SegInfo)) || !A((void**)&e->d_seg_shift, e->n_segs * 4) ||
       !A((void**)&e->d_members, cap * 8) || !A((void**)&e->d_src_idx, cap * 4) ||
-      !A((void**)&e->d_bins16, (cap + 3 * kRound) * 2) ||
       !A((void**)&e->d_hdr, (size_t)e->max_lobbies * sizeof(mm_lobby_hdr)) ||
       !A((void**)&e->d_emit_seq, (size_t)e->max_lobbies * 4) || !A((void**)&e->d_ctr, sizeof(TickCtr)) ||
       !A((void**)&e->d_small, 64))
@@ -695,8 +682,8 @@ int mm_create(const mm_config* cfg, mm_engine** out) {
   if (cudaMallocHost(&e->h_ctr, sizeof(TickCtr)) != cudaSuccess || cudaMallocHost(&e->h_small, 64) != cudaSuccess)
     return bail(MM_E_CUDA);
   if ((rc = alloc_tick_scratch(e))) return bail(rc);
-  if (e->rank_impl == 3 && e->block == 512 && e->hist2_stages && e->rows_per_sm == 2) {
-    size_t sz = std::max(hist2_smem(e, e->hist2_stages), place2_smem(e, e->place2_stages));
+  if (e->rank_impl == 3 && e->block == 512 && e->rows_per_sm == 2) {
+    size_t sz = std::max(hist3_smem(e, e->hist3_stages), place2_smem(e, e->place2_stages));
     sz = std::max<size_t>(sz, std::max<size_t>((size_t)kEpiScratchWords * 4, colscan_smem(e)));
     int coop = 0, nb = 0;
     cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, e->device);
@@ -722,7 +709,7 @@ int mm_destroy(mm_engine* e) {
   free_pool(e->pool[0]); free_pool(e->pool[1]); free_pool(e->snap);
   for (auto& t : e->tab) { cudaFree(t.keys); cudaFree(t.vals); }
   cudaFree(e->d_lut); cudaFree(e->d_grp_lut); cudaFree(e->d_mode_tsize); cudaFree(e->d_seg_bin_lo); cudaFree(e->d_seg_L);
-  cudaFree(e->d_M); cudaFree(e->d_tot); cudaFree(e->d_binbase); cudaFree(e->d_seg_lim); cudaFree(e->d_bin_seg); cudaFree(e->d_bins16);
+  cudaFree(e->d_M); cudaFree(e->d_tot); cudaFree(e->d_binbase); cudaFree(e->d_seg_lim); cudaFree(e->d_bin_seg);
   cudaFree(e->d_seg); cudaFree(e->d_seg_shift); cudaFree(e->d_members); cudaFree(e->d_src_idx); cudaFree(e->d_hdr);
   cudaFree(e->d_emit_seq); cudaFree(e->d_resid_stage); cudaFree(e->d_rescnt); cudaFree(e->d_ctr); cudaFree(e->d_small);
   cudaFree(e->d_in_id); cudaFree(e->d_hslot); cudaFree(e->d_in_rating); cudaFree(e->d_in_mode); cudaFree(e->d_code);
@@ -766,8 +753,6 @@ int mm_set_option(mm_engine* e, const char* name, int64_t value) {
     return MM_OK;
   }
   if (!std::strcmp(name, "dense")) { e->dense_ok = (int)value; return MM_OK; }
-  if (!std::strcmp(name, "hist_impl")) { e->hist_impl = (int)value; return MM_OK; }
-  if (!std::strcmp(name, "warm_l2")) { e->warm_l2 = value != 0; return MM_OK; }
   if (!std::strcmp(name, "tick_impl")) { e->tick_impl = value != 0; return MM_OK; }
   if (!std::strcmp(name, "place_debug")) {  // timing experiments only: results are NOT valid
     if (value < 0 || value > 63) return MM_E_ARG;
@@ -851,7 +836,7 @@ int mm_remove(mm_engine* e, uint32_t n, const uint64_t* id, uint32_t* n_removed)
   const Pool& p = e->pool[e->cur];
   CK(cudaMemcpyAsync(e->d_in_id, id, (size_t)n * 8, cudaMemcpyHostToDevice, e->stream));
   CK(cudaMemsetAsync(e->d_small, 0, 16, e->stream));
-  k_remove<<<(n + 255) / 256, 256, 0, e->stream>>>(n, e->d_in_id, act_view(e), p.v, p.n, e->gen, e->d_small + 2);
+  k_remove<<<(n + 255) / 256, 256, 0, e->stream>>>(n, e->d_in_id, act_view(e), p.v, p.n, e->gen, e->K, e->d_small + 2);
   CK(cudaGetLastError());
   CK(cudaMemcpyAsync(e->h_small, e->d_small, 16, cudaMemcpyDeviceToHost, e->stream));
   CK(cudaStreamSynchronize(e->stream));
@@ -1009,6 +994,7 @@ int mm_snapshot(mm_engine* e) {
   CK(cudaMemcpyAsync(e->snap.v.mode, p.v.mode, n, cudaMemcpyDeviceToDevice, e->stream));
   CK(cudaMemcpyAsync(e->snap.v.tsize, p.v.tsize, n, cudaMemcpyDeviceToDevice, e->stream));
   CK(cudaMemcpyAsync(e->snap.v.ts, p.v.ts, n * 4, cudaMemcpyDeviceToDevice, e->stream));
+  CK(cudaMemcpyAsync(e->snap.v.bin, p.v.bin, n * 2, cudaMemcpyDeviceToDevice, e->stream));
   CK(cudaStreamSynchronize(e->stream));
   e->snap.n = p.n;
   e->has_snap = true;
@@ -1027,6 +1013,7 @@ int mm_restore(mm_engine* e) {
   CK(cudaMemcpyAsync(p.v.mode, e->snap.v.mode, n, cudaMemcpyDeviceToDevice, e->stream));
   CK(cudaMemcpyAsync(p.v.tsize, e->snap.v.tsize, n, cudaMemcpyDeviceToDevice, e->stream));
   CK(cudaMemcpyAsync(p.v.ts, e->snap.v.ts, n * 4, cudaMemcpyDeviceToDevice, e->stream));
+  CK(cudaMemcpyAsync(p.v.bin, e->snap.v.bin, n * 2, cudaMemcpyDeviceToDevice, e->stream));
   p.n = e->snap.n;
   e->gen += 1;
   if (e->use_active && p.n) {

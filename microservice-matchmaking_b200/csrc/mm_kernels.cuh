@@ -44,6 +44,7 @@ struct PoolView {
   uint8_t* mode;
   uint8_t* tsize;
   uint32_t* ts;
+  uint16_t* bin;  // derived at ingest: mode * stride + lut[clamp(rating)]; K = removed while queued
 };
 
 struct BinMap {
@@ -162,12 +163,6 @@ __device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t
       : "memory");
 }
 
-// Bulk L2 prefetch (no SM data path): warms member_ids so the 8-byte scatter of k_place2 hits
-// resident lines instead of triggering a DRAM fill per partially written sector.
-__device__ __forceinline__ void l2_prefetch_bulk(const void* p, uint32_t bytes) {
-  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
-}
-
 // In-place exclusive scan of a shared-memory array a[0..n) by the whole CTA; returns the
 // total.  s_tmp must hold >= 33 words.  Warp-shuffle scan: 3 barriers.
 template <int BLOCK>
@@ -270,29 +265,26 @@ __global__ void __launch_bounds__(BLOCK) k_hist(PoolView p, uint32_t n, uint32_t
 }
 
 // ---------------------------------------------------------------------------------------
-// k_hist2<BLOCK>: k_hist fed by a TMA ring.  One thread keeps `stages` bulk copies of
-// (rating i32[4096], mode u8[4096]) tiles in flight; the CTA only does shared-memory reads,
-// the LUT, shared-memory histogram atomics and the 64-bit bin stores — one barrier per tile.
+// hist3_body<BLOCK>: row histogram straight from the resident 16-bit bin column (maintained
+// at ingest by k_enq_append / k_remove / the epilogue's compaction), streamed through a TMA
+// ring of 4 096-player (8 KB) tiles: the tick never touches rating / mode.
 // ---------------------------------------------------------------------------------------
-constexpr uint32_t kHTile = 4096;
-constexpr uint32_t kHTileBytes = kHTile * 5;
+constexpr uint32_t kBTile = 4096;
+constexpr uint32_t kBTileBytes = kBTile * 2;
 
 template <int BLOCK>
-__device__ __forceinline__ void hist2_body(unsigned char* smem_raw, PoolView p, uint32_t n, uint32_t chunk, BinMap bm,
-                                           uint32_t Kp, uint32_t stages, uint32_t* __restrict__ M,
-                                           uint32_t* __restrict__ tot, uint16_t* __restrict__ bins16,
-                                           const uint64_t* __restrict__ warm, uint32_t warm_n, uint32_t dbg = 0) {
-  int32_t* ring_r = reinterpret_cast<int32_t*>(smem_raw);                                   // [stages][kHTile]
-  uint8_t* ring_m = smem_raw + (size_t)stages * kHTile * 4;                                  // [stages][kHTile]
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + (size_t)stages * kHTileBytes);     // [kMaxStages]
-  uint32_t* hist = reinterpret_cast<uint32_t*>(smem_raw + (size_t)stages * kHTileBytes + 64);  // [Kp]
-  uint16_t* s_lut = reinterpret_cast<uint16_t*>(hist + Kp);                                  // [KR]
+__device__ __forceinline__ void hist3_body(unsigned char* smem_raw, const uint16_t* __restrict__ bins16, uint32_t n,
+                                           uint32_t chunk, uint32_t Kp, uint32_t stages, uint32_t* __restrict__ M,
+                                           uint32_t* __restrict__ tot) {
+  uint16_t* ring = reinterpret_cast<uint16_t*>(smem_raw);                                      // [stages][kBTile]
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + (size_t)stages * kBTileBytes);       // [kMaxStages]
+  uint32_t* hist = reinterpret_cast<uint32_t*>(smem_raw + (size_t)stages * kBTileBytes + 64);  // [Kp]
   const uint32_t tid = threadIdx.x;
   const uint64_t pol_in = policy_evict_first();
   const uint64_t beg64 = (uint64_t)blockIdx.x * chunk;
   const uint32_t beg = beg64 < n ? (uint32_t)beg64 : n;
   const uint32_t end = (beg64 + chunk < n) ? (uint32_t)(beg64 + chunk) : n;
-  const uint32_t n_tiles = (end - beg + kHTile - 1) / kHTile;
+  const uint32_t n_tiles = (end - beg + kBTile - 1) / kBTile;
   if (tid == 0) {
     for (uint32_t s = 0; s < stages; ++s) mbar_init(&full[s], 1);
     mbar_fence_init();
@@ -301,57 +293,33 @@ __device__ __forceinline__ void hist2_body(unsigned char* smem_raw, PoolView p, 
   __syncthreads();
   if (tid == 0)
     for (uint32_t t = 0; t < stages && t < n_tiles; ++t) {
-      mbar_expect_tx(&full[t], kHTileBytes);
-      tma_load_1d(ring_r + (size_t)t * kHTile, p.rating + beg + (size_t)t * kHTile, kHTile * 4, &full[t], pol_in);
-      tma_load_1d(ring_m + (size_t)t * kHTile, p.mode + beg + (size_t)t * kHTile, kHTile, &full[t], pol_in);
+      mbar_expect_tx(&full[t], kBTileBytes);
+      tma_load_1d(ring + (size_t)t * kBTile, bins16 + beg + (size_t)t * kBTile, kBTileBytes, &full[t], pol_in);
     }
-  if (tid == 32 && warm) {  // this CTA's slice of member_ids -> L2 (2 KB-aligned slices, 32 KB requests)
-    const uint64_t per = ((((uint64_t)warm_n * 8 + gridDim.x - 1) / gridDim.x) + 2047) & ~2047ull;
-    const uint64_t lo = per * blockIdx.x, hi = (lo + per < (uint64_t)warm_n * 8) ? lo + per : (uint64_t)warm_n * 8;
-    for (uint64_t o = lo; o < hi; o += 32768) {
-      const uint64_t sz = (hi - o < 32768) ? ((hi - o + 15) & ~15ull) : 32768;
-      l2_prefetch_bulk(reinterpret_cast<const char*>(warm) + o, (uint32_t)sz);
-    }
-  }
   for (uint32_t i = tid; i < Kp; i += BLOCK) hist[i] = 0;
-  for (uint32_t i = tid; i < bm.KR; i += BLOCK) s_lut[i] = bm.lut[i];
   __syncthreads();
   uint32_t st = 0, parity = 0;
   for (uint32_t t = 0; t < n_tiles; ++t) {
-    const uint32_t tile_base = beg + t * kHTile;
-    const uint32_t valid = end - tile_base;
-    const int32_t* tr = ring_r + (size_t)st * kHTile;
-    const uint8_t* tm = ring_m + (size_t)st * kHTile;
+    const uint32_t valid = end - (beg + t * kBTile);
+    const uint16_t* tb = ring + (size_t)st * kBTile;
     mbar_wait(&full[st], parity);
 #pragma unroll
-    for (uint32_t q = tid; q < kHTile / 4; q += BLOCK) {
-      const uint32_t o = q * 4;
-      if (o + 4 <= valid) {
-        const int4 r = *reinterpret_cast<const int4*>(tr + o);
-        const uint32_t m = *reinterpret_cast<const uint32_t*>(tm + o);
-        uint32_t b0, b1, b2, b3;
-        if (dbg & 16) {  // timing experiment: no LUT
-          b0 = (uint32_t)r.x % bm.K; b1 = (uint32_t)r.y % bm.K; b2 = (uint32_t)r.z % bm.K; b3 = (uint32_t)r.w % bm.K;
-        } else {
-          b0 = bin_of(bm, s_lut, r.x, m & 0xFF); b1 = bin_of(bm, s_lut, r.y, (m >> 8) & 0xFF);
-          b2 = bin_of(bm, s_lut, r.z, (m >> 16) & 0xFF); b3 = bin_of(bm, s_lut, r.w, m >> 24);
-        }
-        if (!(dbg & 8)) { atomicAdd(&hist[b0], 1u); atomicAdd(&hist[b1], 1u); atomicAdd(&hist[b2], 1u); atomicAdd(&hist[b3], 1u); }
-        if (!(dbg & 32)) *reinterpret_cast<uint2*>(bins16 + tile_base + o) = make_uint2(b0 | (b1 << 16), b2 | (b3 << 16));
-      } else if (o < valid) {
-        for (uint32_t k = o; k < valid; ++k) {
-          const uint32_t bb = bin_of(bm, s_lut, tr[k], tm[k]);
-          atomicAdd(&hist[bb], 1u);
-          bins16[tile_base + k] = (uint16_t)bb;
-        }
+    for (uint32_t q = tid; q < kBTile / 8; q += BLOCK) {  // 8 bins (128 bits) per thread per step
+      const uint32_t o = q * 8;
+      if (o + 8 <= valid) {
+        const uint4 v = *reinterpret_cast<const uint4*>(tb + o);
+        atomicAdd(&hist[v.x & 0xFFFFu], 1u); atomicAdd(&hist[v.x >> 16], 1u);
+        atomicAdd(&hist[v.y & 0xFFFFu], 1u); atomicAdd(&hist[v.y >> 16], 1u);
+        atomicAdd(&hist[v.z & 0xFFFFu], 1u); atomicAdd(&hist[v.z >> 16], 1u);
+        atomicAdd(&hist[v.w & 0xFFFFu], 1u); atomicAdd(&hist[v.w >> 16], 1u);
+      } else {
+        for (uint32_t k = o; k < valid; ++k) atomicAdd(&hist[tb[k]], 1u);
       }
     }
     __syncthreads();
     if (tid == 0 && t + stages < n_tiles) {
-      const uint32_t tn = t + stages;
-      mbar_expect_tx(&full[st], kHTileBytes);
-      tma_load_1d(ring_r + (size_t)st * kHTile, p.rating + beg + (size_t)tn * kHTile, kHTile * 4, &full[st], pol_in);
-      tma_load_1d(ring_m + (size_t)st * kHTile, p.mode + beg + (size_t)tn * kHTile, kHTile, &full[st], pol_in);
+      mbar_expect_tx(&full[st], kBTileBytes);
+      tma_load_1d(ring + (size_t)st * kBTile, bins16 + beg + (size_t)(t + stages) * kBTile, kBTileBytes, &full[st], pol_in);
     }
     if (++st == stages) { st = 0; parity ^= 1u; }
   }
@@ -359,7 +327,7 @@ __device__ __forceinline__ void hist2_body(unsigned char* smem_raw, PoolView p, 
   for (uint32_t i = tid; i < Kp; i += BLOCK) {
     const uint32_t v = hist[i];
     row[i] = v;
-    if (v && !(dbg & 4)) atomicAdd(&tot[i], v);  // dbg&4: timing experiment without the reductions
+    if (v) atomicAdd(&tot[i], v);
   }
   if (tid == 0)
     for (uint32_t s = 0; s < stages; ++s) mbar_inval(&full[s]);
@@ -367,10 +335,10 @@ __device__ __forceinline__ void hist2_body(unsigned char* smem_raw, PoolView p, 
 
 template <int BLOCK>
 __global__ void __launch_bounds__(BLOCK, (BLOCK == 512 ? 2 : 1))
-    k_hist2(PoolView p, uint32_t n, uint32_t chunk, BinMap bm, uint32_t Kp, uint32_t stages, uint32_t* __restrict__ M,
-            uint32_t* __restrict__ tot, uint16_t* __restrict__ bins16, const uint64_t* __restrict__ warm, uint32_t warm_n) {
+    k_hist3(const uint16_t* __restrict__ bins16, uint32_t n, uint32_t chunk, uint32_t Kp, uint32_t stages,
+            uint32_t* __restrict__ M, uint32_t* __restrict__ tot) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  hist2_body<BLOCK>(smem_raw, p, n, chunk, bm, Kp, stages, M, tot, bins16, warm, warm_n);
+  hist3_body<BLOCK>(smem_raw, bins16, n, chunk, Kp, stages, M, tot);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -1093,7 +1061,7 @@ __device__ __forceinline__ void epilogue_body(uint32_t* scratch, PoolView src, P
     const uint32_t idx = __ldcg(&resid_stage[(size_t)a * kResCap + (t - s_off[a])]);
     const uint64_t pid = src.id[idx];
     dst.id[t] = pid; dst.rating[t] = src.rating[idx]; dst.mode[t] = src.mode[idx];
-    dst.tsize[t] = src.tsize[idx]; dst.ts[t] = src.ts[idx];
+    dst.tsize[t] = src.tsize[idx]; dst.ts[t] = src.ts[idx]; dst.bin[t] = src.bin[idx];
     if (act.mask) {
       uint64_t h = hash64(pid) & act.mask;
       for (uint64_t probe = 0; probe <= act.mask; ++probe) {
@@ -1131,7 +1099,7 @@ struct TickArgs {
   PoolView src, dst;
   BinMap bm;
   uint32_t n, chunk, K, Kp, R, n_segs, n_groups, hist_stages, place_stages, dense, new_gen, dbg;
-  uint32_t* M; uint32_t* tot; uint32_t* binbase; uint16_t* bins16;
+  uint32_t* M; uint32_t* tot; uint32_t* binbase;
   const uint16_t* bin_seg; const uint32_t* seg_bin_lo; const uint32_t* seg_L;
   SegInfo* seg; uint32_t* seg_shift; uint32_t* seg_lim;
   uint64_t* members; uint32_t* src_idx; mm_lobby_hdr* hdr; uint32_t* emit_seq;
@@ -1152,7 +1120,7 @@ __global__ void __launch_bounds__(BLOCK, 2) k_tick(const TickArgs a) {
     }
   };
   stamp(0);
-  hist2_body<BLOCK>(smem_raw, a.src, a.n, a.chunk, a.bm, a.Kp, a.hist_stages, a.M, a.tot, a.bins16, nullptr, 0, a.dbg);
+  hist3_body<BLOCK>(smem_raw, a.src.bin, a.n, a.chunk, a.Kp, a.hist_stages, a.M, a.tot);
   grid_barrier(&a.ctr->gbar, G);
   stamp(1);
   if (blockIdx.x == G - 1) {
@@ -1167,7 +1135,7 @@ __global__ void __launch_bounds__(BLOCK, 2) k_tick(const TickArgs a) {
   for (uint32_t g = blockIdx.x; g < (a.Kp + 31) / 32; g += G) colscan_cols_body(scratch, g, a.R, a.Kp, a.M);
   grid_barrier(&a.ctr->gbar, 2 * G);
   stamp(2);
-  place2_body<BLOCK>(smem_raw, a.bins16, a.src.id, a.n, a.chunk, a.K, a.Kp, a.R, a.place_stages, a.dense, a.M, a.tot,
+  place2_body<BLOCK>(smem_raw, a.src.bin, a.src.id, a.n, a.chunk, a.K, a.Kp, a.R, a.place_stages, a.dense, a.M, a.tot,
                      a.binbase, a.bin_seg, a.seg_shift, a.seg_lim, a.members, a.src_idx, a.resid_stage, a.rescnt, a.ctr,
                      a.dbg);
   grid_barrier(&a.ctr->gbar, 3 * G);
@@ -1261,7 +1229,8 @@ __global__ void k_enq_append(uint32_t n, const uint64_t* __restrict__ id, const 
                              const uint8_t* __restrict__ mode, const uint32_t* __restrict__ ts,
                              const uint8_t* __restrict__ mode_tsize, ActiveView act, const uint64_t* __restrict__ hslot,
                              uint8_t* __restrict__ code, const uint32_t* __restrict__ blockoff, PoolView pool,
-                             uint32_t n_pool, uint32_t capacity, uint32_t gen, uint32_t* __restrict__ n_rejected_cap) {
+                             uint32_t n_pool, uint32_t capacity, uint32_t gen, uint32_t* __restrict__ n_rejected_cap,
+                             BinMap bm) {
   __shared__ uint32_t s_warp[32];
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -1281,6 +1250,7 @@ __global__ void k_enq_append(uint32_t n, const uint64_t* __restrict__ id, const 
   }
   pool.id[slot] = id[i]; pool.rating[slot] = rating[i]; pool.mode[slot] = mode[i];
   pool.tsize[slot] = mode_tsize[mode[i]]; pool.ts[slot] = ts ? ts[i] : 0u;
+  pool.bin[slot] = (uint16_t)bin_of(bm, bm.lut, rating[i], mode[i]);  // the tick's sort key, derived once at ingest
   if (act.mask) act.vals[hslot[i]] = ((unsigned long long)gen << 32) | slot;
 }
 
@@ -1288,7 +1258,7 @@ __global__ void k_enq_append(uint32_t n, const uint64_t* __restrict__ id, const 
 // queued is tombstoned in the pool (mode byte = DEAD) so the next tick drops it the way
 // remove_inactive_players/1 (search/worker.ex:267-280) filters it.
 __global__ void k_remove(uint32_t n, const uint64_t* __restrict__ id, ActiveView act, PoolView pool, uint32_t n_pool,
-                         uint32_t gen, uint32_t* __restrict__ n_removed) {
+                         uint32_t gen, uint32_t dead_bin, uint32_t* __restrict__ n_removed) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n || !act.mask) return;
   const uint64_t pid = id[i];
@@ -1302,7 +1272,10 @@ __global__ void k_remove(uint32_t n, const uint64_t* __restrict__ id, ActiveView
       if (atomicCAS(&act.keys[h], (unsigned long long)pid, kTombKey) != pid) return;  // a twin in this batch won
       act.vals[h] = kFreeVal;
       const uint32_t slot = (uint32_t)v, g = (uint32_t)(v >> 32);
-      if (v < kPending && g == gen && slot < n_pool && pool.id[slot] == pid) pool.mode[slot] = MM_MODE_DEAD;
+      if (v < kPending && g == gen && slot < n_pool && pool.id[slot] == pid) {
+        pool.mode[slot] = MM_MODE_DEAD;
+        pool.bin[slot] = (uint16_t)dead_bin;
+      }
       atomicAdd(n_removed, 1u);
       return;
     }

@@ -31,8 +31,4 @@ def run(label, reps=6, **opts):
     print(json.dumps({"variant": label, "workload": name, "order": order, "device_us": round(float(np.mean(dev)), 1),
                       "place_us": round(float(np.mean(pl)), 1), "place_min": round(float(np.min(pl)), 1), "hist_us": round(float(np.mean(hs)), 1), "scan_us": round(float(np.mean(sc)), 1), "epi_us": round(float(np.mean(ep)), 1), "tail_us": st.reserved / 100.0, "lobbies": st.n_lobbies}), flush=True)
 run("fused", tick_impl=1)
-run("dbg1 rank, no id store", place_debug=1)
-run("dbg2 no rank, coalesced store", place_debug=2)
-run("dbg3 no rank, random scatter", place_debug=3)
-run("dense=1 (MATCH matrix)", place_debug=0, dense=1)
-run("dense=0 (lists)", dense=0)
+run("split", tick_impl=0)
