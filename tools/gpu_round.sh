@@ -11,4 +11,4 @@ timeout 300 python bench.py --steps 10 --warmup 3 --two-modes --no-cpu-baseline 
 timeout 300 python bench.py --steps 10 --warmup 3 --tick-impl 0 --no-cpu-baseline --no-e2e > gpurun_out/bench_split.log 2>&1; tail -1 gpurun_out/bench_split.log | cut -c1-600
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/ncu_b.log 2>&1; echo "ncu list rc=$?"
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:"k_tick" -s 3 -c 1 -o gpurun_out/prof_tick -f python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/ncu_full.log 2>&1; echo "ncu full rc=$?"
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:"k_place2|k_hist2|k_colscan|k_epilogue" -s 12 -c 4 -o gpurun_out/prof_split -f python bench.py --steps 2 --warmup 3 --tick-impl 0 --no-cpu-baseline --no-e2e > gpurun_out/ncu_full2.log 2>&1; echo "ncu split rc=$?"
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:"k_place2|k_hist3|k_colscan|k_epilogue" -s 12 -c 4 -o gpurun_out/prof_split -f python bench.py --steps 2 --warmup 3 --tick-impl 0 --no-cpu-baseline --no-e2e > gpurun_out/ncu_full2.log 2>&1; echo "ncu split rc=$?"
