@@ -87,15 +87,17 @@ struct mm_engine {
   size_t tick_smem = 0;
   int dense_ok = 2;            // small-K ranking: 0 = off, 1 = MATCH-based matrix, 2 = private byte counters when possible
   uint32_t* d_M = nullptr;
-  uint32_t *d_tot = nullptr, *d_binbase = nullptr, *d_seg_lim = nullptr;
+  uint32_t *d_tot = nullptr, *d_outbase = nullptr, *d_binlim = nullptr;
+  uint16_t* d_bin_key = nullptr;
+  int32_t max_spread = -1;  // < 0: policy S0 (reference behaviour); >= 0: policy S1 (extension)
   SegInfo* d_seg = nullptr;
-  uint32_t* d_seg_shift = nullptr;
+  uint32_t* d_left_bits = nullptr;  // one bit per pool slot: stays queued after the tick
   uint64_t* d_members = nullptr;
   uint32_t* d_src_idx = nullptr;
   mm_lobby_hdr* d_hdr = nullptr;
   uint32_t* d_emit_seq = nullptr;
   uint32_t max_lobbies = 0;
-  uint32_t *d_resid_stage = nullptr, *d_rescnt = nullptr;
+  uint32_t* d_rescnt = nullptr;
   TickCtr* d_ctr = nullptr;
   TickCtr* h_ctr = nullptr;  // pinned
 
@@ -190,7 +192,7 @@ int check_config(const mm_config* c) {
 }
 
 size_t place_smem(const mm_engine* e, int impl) {
-  size_t words = e->Kp + (impl == 1 ? (size_t)e->Kp + kRound : 0) + kResCap;
+  size_t words = e->Kp + (impl == 1 ? (size_t)e->Kp + kRound : 0);
   return words * 4 + (size_t)e->KR * 2 + 16;
 }
 bool place2_dense(const mm_engine* e) { return e->Kp <= kDenseMaxBins; }
@@ -202,11 +204,18 @@ size_t place2_dense_bytes(const mm_engine* e) {
   return std::max(a, b);
 }
 size_t place2_smem(const mm_engine* e, uint32_t stages) {
-  return (size_t)stages * kTileBytes + 64 + ((size_t)e->Kp + kHeadSlots + kTile + kRes2) * 4 + (size_t)kTile * 2 +
+  return (size_t)stages * kTileBytes + 64 + ((size_t)e->Kp + kHeadSlots + kTile) * 4 + (size_t)kTile * 2 +
          place2_dense_bytes(e) + 16;
 }
+// Shared-memory layout of the scan tail: everything on chip up to ~100 KB (so that it never exceeds the placement
+// phase's footprint in the fused kernel), else keys from global memory, else matched counts parked in global too.
+uint32_t tail_layout(const mm_engine* e) {
+  if ((size_t)tail_words(e->Kp, 3) * 4 <= 100 * 1024) return 3;
+  if ((size_t)tail_words(e->Kp, 1) * 4 + 1024 <= e->smem_optin) return 1;
+  return 0;
+}
 size_t colscan_smem(const mm_engine* e) {
-  return (size_t)std::max<uint32_t>(kColScratchWords, kTailScratchWords + e->Kp + 2) * 4;
+  return (size_t)std::max<uint32_t>(kColScratchWords, tail_words(e->Kp, tail_layout(e))) * 4;
 }
 size_t hist3_smem(const mm_engine* e, uint32_t stages) { return (size_t)stages * kBTileBytes + 64 + (size_t)e->Kp * 4 + 16; }
 size_t hist_smem(const mm_engine* e) { return (size_t)e->Kp * 4 + (size_t)e->KR * 2 + 16; }
@@ -228,13 +237,14 @@ int build_tables(mm_engine* e) {
   }
   std::vector<uint16_t> lut(e->KR, 0);
   std::vector<uint32_t> first(G + 1, 0);
+  std::vector<uint16_t> key_of;  // rating order: bin (inside a mode) -> clamp key
   if (c.order_mode == MM_ORDER_RATING) {
     // bins ordered by (group, clamp key): the partition of a group is its keys ascending
     uint32_t next = 0;
     for (uint32_t g = 0; g < G; ++g) {
       first[g] = next;
       for (uint32_t k = 0; k < e->KR; ++k)
-        if (grp[k] == g) lut[k] = (uint16_t)next++;
+        if (grp[k] == g) { lut[k] = (uint16_t)next++; key_of.push_back((uint16_t)k); }
     }
     first[G] = next;
     e->stride = std::max(next, 1u);
@@ -259,8 +269,13 @@ int build_tables(mm_engine* e) {
   std::vector<uint16_t> bin_seg(e->Kp, 0);
   for (uint32_t sgi = 0; sgi < e->n_segs; ++sgi)
     for (uint32_t b = seg_lo[sgi]; b < seg_lo[sgi + 1]; ++b) bin_seg[b] = (uint16_t)sgi;
+  std::vector<uint16_t> bin_key(e->Kp, 0);
+  if (!key_of.empty())
+    for (uint32_t b = 0; b < e->K; ++b) bin_key[b] = key_of[b % e->stride];
   CK(cudaMalloc(&e->d_bin_seg, e->Kp * 2));
   CK(cudaMemcpy(e->d_bin_seg, bin_seg.data(), e->Kp * 2, cudaMemcpyHostToDevice));
+  CK(cudaMalloc(&e->d_bin_key, e->Kp * 2));
+  CK(cudaMemcpy(e->d_bin_key, bin_key.data(), e->Kp * 2, cudaMemcpyHostToDevice));
   CK(cudaMalloc(&e->d_lut, e->KR * 2));
   CK(cudaMalloc(&e->d_grp_lut, e->KR));
   CK(cudaMalloc(&e->d_mode_tsize, MM_MAX_MODES));
@@ -283,9 +298,8 @@ BinMap bin_map(const mm_engine* e) {
 int alloc_tick_scratch(mm_engine* e) {
   e->R = (uint32_t)e->n_sms * (uint32_t)e->rows_per_sm;
   if (e->R > kMaxRows) e->R = kMaxRows;
-  if (e->d_M) { cudaFree(e->d_M); cudaFree(e->d_resid_stage); cudaFree(e->d_rescnt); }
+  if (e->d_M) { cudaFree(e->d_M); cudaFree(e->d_rescnt); }
   CK(cudaMalloc(&e->d_M, (size_t)e->R * e->Kp * 4));
-  CK(cudaMalloc(&e->d_resid_stage, (size_t)e->R * kResCap * 4));
   CK(cudaMalloc(&e->d_rescnt, (size_t)(e->R + 1) * 4));
   return MM_OK;
 }
@@ -407,6 +421,14 @@ uint32_t dense_mode(const mm_engine* e) {
   return place2_dense(e) ? 1u : 0u;
 }
 
+TailArgs tail_args(const mm_engine* e) {
+  TailArgs t{};
+  t.Kp = e->Kp; t.K = e->K; t.n_segs = e->n_segs; t.max_spread = e->max_spread; t.layout = tail_layout(e);
+  t.tot = e->d_tot; t.seg_bin_lo = e->d_seg_bin_lo; t.seg_L = e->d_seg_L; t.bin_seg = e->d_bin_seg;
+  t.bin_key = e->d_bin_key; t.outbase = e->d_outbase; t.binlim = e->d_binlim; t.seg = e->d_seg; t.ctr = e->d_ctr;
+  return t;
+}
+
 // launches k_hist + k_colscan and returns the counters (phase A of a tick)
 int tick_phase_a(mm_engine* e, uint32_t n, uint32_t* chunk_out) {
   const Pool& p = e->pool[e->cur];
@@ -428,9 +450,7 @@ int tick_phase_a(mm_engine* e, uint32_t n, uint32_t* chunk_out) {
     k_hist<1024><<<e->R, 1024, hist_smem(e), e->stream>>>(p.v, n, chunk, bin_map(e), e->Kp, e->d_M, e->d_tot, nullptr);
   }
   CK(cudaEventRecord(e->ev[1], e->stream));
-  k_colscan<<<(e->Kp + 31) / 32 + 1, kScanBlock, colscan_smem(e), e->stream>>>(e->R, e->Kp, e->K, e->d_M, e->d_tot, e->d_binbase, e->d_seg_bin_lo,
-                                                        e->d_seg_L, e->n_segs, e->d_seg, e->d_seg_shift, e->d_seg_lim,
-                                                        e->d_ctr);
+  k_colscan<<<(e->Kp + 31) / 32 + 1, kScanBlock, colscan_smem(e), e->stream>>>(e->R, e->d_M, tail_args(e));
   CK(cudaGetLastError());
   return MM_OK;
 }
@@ -442,13 +462,13 @@ int tick_phase_b(mm_engine* e, uint32_t n, uint32_t chunk, bool want_seq) {
   CK(cudaEventRecord(e->ev[2], e->stream));
 #define MM_PLACE(IMPL)                                                                                               \
   k_place<IMPL><<<e->R, kBlock, place_smem(e, IMPL), e->stream>>>(                                                    \
-      p.v, n, chunk, bin_map(e), e->Kp, e->R, e->d_M, e->d_tot, e->d_binbase, e->d_bin_seg, e->d_seg_shift,           \
-      e->d_seg_lim, e->n_segs, e->d_members, src_idx, e->d_resid_stage, e->d_rescnt, e->d_ctr)
+      p.v, n, chunk, bin_map(e), e->Kp, e->R, e->d_M, e->d_tot, e->d_outbase, e->d_binlim, e->d_members, src_idx,     \
+      e->d_left_bits, e->d_rescnt, e->d_ctr)
 #define MM_PLACE2(BLK)                                                                                               \
   k_place2<BLK><<<e->R, BLK, place2_smem(e, e->place2_stages), e->stream>>>(                                          \
       p.v.bin, p.v.id, n, chunk, e->K, e->Kp, e->R, e->place2_stages, dense_mode(e), e->d_M, e->d_tot,                \
-      e->d_binbase, e->d_bin_seg, e->d_seg_shift, e->d_seg_lim, e->d_members, src_idx, e->d_resid_stage, e->d_rescnt, \
-      e->d_ctr, (uint32_t)e->place_debug)
+      e->d_outbase, e->d_binlim, e->d_members, src_idx, e->d_left_bits, e->d_rescnt, e->d_ctr,                        \
+      (uint32_t)e->place_debug)
   if (e->rank_impl == 3) {
     if (e->block == 512) MM_PLACE2(512);
     else MM_PLACE2(1024);
@@ -460,7 +480,7 @@ int tick_phase_b(mm_engine* e, uint32_t n, uint32_t chunk, bool want_seq) {
 #undef MM_PLACE2
 #undef MM_PLACE
   CK(cudaEventRecord(e->ev[3], e->stream));
-  k_epilogue<<<std::max(1, e->n_sms), 1024, 0, e->stream>>>(p.v, q.v, e->R, e->d_rescnt, e->d_resid_stage, act_view(e),
+  k_epilogue<<<std::max(1, e->n_sms), 1024, 0, e->stream>>>(p.v, q.v, n, chunk, e->R, e->d_rescnt, e->d_left_bits, act_view(e),
                                                            e->gen + 1, e->d_seg, e->d_seg_L, e->n_segs, e->cfg.n_groups,
                                                            e->d_hdr, src_idx, want_seq ? e->d_emit_seq : nullptr, e->d_tot,
                                                            e->Kp, e->d_ctr);
@@ -482,16 +502,15 @@ int tick_fused(mm_engine* e, uint32_t n, bool want_seq) {
   uint32_t chunk = (n + e->R - 1) / e->R;
   chunk = std::max<uint32_t>(((chunk + kRound - 1) / kRound) * kRound, kRound);
   TickArgs a{};
-  a.src = p.v; a.dst = q.v; a.bm = bin_map(e);
-  a.n = n; a.chunk = chunk; a.K = e->K; a.Kp = e->Kp; a.R = e->R; a.n_segs = e->n_segs; a.n_groups = e->cfg.n_groups;
+  a.src = p.v; a.dst = q.v; a.left_bits = e->d_left_bits;
+  a.n = n; a.chunk = chunk; a.R = e->R; a.n_groups = e->cfg.n_groups;
   a.hist_stages = e->hist3_stages; a.place_stages = e->place2_stages;
   a.dense = dense_mode(e);
   a.new_gen = e->gen + 1; a.dbg = (uint32_t)e->place_debug;
-  a.M = e->d_M; a.tot = e->d_tot; a.binbase = e->d_binbase; a.bin_seg = e->d_bin_seg;
-  a.seg_bin_lo = e->d_seg_bin_lo; a.seg_L = e->d_seg_L; a.seg = e->d_seg; a.seg_shift = e->d_seg_shift;
-  a.seg_lim = e->d_seg_lim; a.members = e->d_members; a.src_idx = want_seq ? e->d_src_idx : nullptr; a.hdr = e->d_hdr;
-  a.emit_seq = want_seq ? e->d_emit_seq : nullptr; a.resid_stage = e->d_resid_stage; a.rescnt = e->d_rescnt;
-  a.act = act_view(e); a.ctr = e->d_ctr;
+  a.M = e->d_M; a.tot = e->d_tot; a.tail = tail_args(e);
+  a.members = e->d_members; a.src_idx = want_seq ? e->d_src_idx : nullptr; a.hdr = e->d_hdr;
+  a.emit_seq = want_seq ? e->d_emit_seq : nullptr; a.rescnt = e->d_rescnt;
+  a.act = act_view(e);
   CK(cudaMemsetAsync(e->d_ctr, 0, sizeof(TickCtr), e->stream));
   CK(cudaEventRecord(e->ev[0], e->stream));
   void* params[] = {&a};
@@ -504,10 +523,6 @@ int tick_fused(mm_engine* e, uint32_t n, bool want_seq) {
 
 int tick_commit(mm_engine* e, uint32_t n, mm_tick_stats* stats) {
   const TickCtr& c = *e->h_ctr;
-  if (c.overflow) {
-    std::snprintf(e->last_err, sizeof(e->last_err), "a row held more than %u residual players", kResCap);
-    return MM_E_CAP;
-  }
   mm_tick_stats st{};
   st.pool_before = n; st.n_lobbies = c.n_lobbies; st.n_matched = c.n_matched; st.n_residual = c.n_resid;
   st.n_dead = c.n_dead; st.n_launches = 4;
@@ -519,8 +534,9 @@ int tick_commit(mm_engine* e, uint32_t n, mm_tick_stats* stats) {
     st.hist_us = (float)(c.t[1] - c.t[0]) * 1e-3f;
     st.scan_us = (float)(c.t[2] - c.t[1]) * 1e-3f;
     st.place_us = (float)(c.t[3] - c.t[2]) * 1e-3f;
-    st.epilogue_us = (float)(c.t[4] - c.t[3]) * 1e-3f;
-    st.reserved = (uint32_t)((c.t[5] - c.t[1]) / 10);  // tail CTA: barrier 1 -> tail done, in 10 ns units (debug)
+    st.epilogue_us = (float)(c.t[6] - c.t[3]) * 1e-3f;  // until the last CTA is done
+    // debug: lobby headers done (max over CTAs) after barrier 3, in 10 ns units
+    st.reserved = (uint32_t)((c.t[7] - c.t[3]) / 10);
     e->cur ^= 1;
     e->pool[e->cur].n = c.n_resid;
     e->gen += 1;
@@ -658,6 +674,7 @@ int mm_create(const mm_config* cfg, mm_engine** out) {
     if (!ok) return bail(fail(e, cudaGetLastError(), "cudaFuncSetAttribute"));
   }
   if ((rc = alloc_pool(e, e->pool[0], e->capacity)) || (rc = alloc_pool(e, e->pool[1], e->capacity))) return bail(rc);
+  if (cudaMalloc(&e->d_left_bits, (((size_t)e->capacity + 3 * kRound) / 32 + 64) * 4) != cudaSuccess) return bail(MM_E_CUDA);
   if (e->use_active) {
     uint64_t want = cfg->active_capacity ? cfg->active_capacity : 2ull * cfg->capacity;
     uint64_t h = 1024;
@@ -671,9 +688,8 @@ int mm_create(const mm_config* cfg, mm_engine** out) {
   const size_t cap = (size_t)e->capacity + 64;
   e->max_lobbies = e->capacity / e->min_L + 1;
   auto A = [&](void** p, size_t bytes) { return cudaMalloc(p, bytes) == cudaSuccess; };
-  if (!A((void**)&e->d_tot, (e->Kp + 1) * 4) || !A((void**)&e->d_binbase, (e->Kp + 1) * 4) ||
-      !A((void**)&e->d_seg_lim, e->n_segs * 4) ||
-      !A((void**)&e->d_seg, e->n_segs * sizeof(SegInfo)) || !A((void**)&e->d_seg_shift, e->n_segs * 4) ||
+  if (!A((void**)&e->d_tot, (e->Kp + 1) * 4) || !A((void**)&e->d_outbase, (e->Kp + 1) * 4) ||
+      !A((void**)&e->d_binlim, (e->Kp + 1) * 4) || !A((void**)&e->d_seg, e->n_segs * sizeof(SegInfo)) ||
       !A((void**)&e->d_members, cap * 8) || !A((void**)&e->d_src_idx, cap * 4) ||
       !A((void**)&e->d_hdr, (size_t)e->max_lobbies * sizeof(mm_lobby_hdr)) ||
       !A((void**)&e->d_emit_seq, (size_t)e->max_lobbies * 4) || !A((void**)&e->d_ctr, sizeof(TickCtr)) ||
@@ -706,12 +722,12 @@ int mm_destroy(mm_engine* e) {
   if (!e) return MM_OK;
   cudaSetDevice(e->device);
   if (e->stream) cudaStreamSynchronize(e->stream);
-  free_pool(e->pool[0]); free_pool(e->pool[1]); free_pool(e->snap);
+  free_pool(e->pool[0]); free_pool(e->pool[1]); free_pool(e->snap); cudaFree(e->d_left_bits);
   for (auto& t : e->tab) { cudaFree(t.keys); cudaFree(t.vals); }
   cudaFree(e->d_lut); cudaFree(e->d_grp_lut); cudaFree(e->d_mode_tsize); cudaFree(e->d_seg_bin_lo); cudaFree(e->d_seg_L);
-  cudaFree(e->d_M); cudaFree(e->d_tot); cudaFree(e->d_binbase); cudaFree(e->d_seg_lim); cudaFree(e->d_bin_seg);
-  cudaFree(e->d_seg); cudaFree(e->d_seg_shift); cudaFree(e->d_members); cudaFree(e->d_src_idx); cudaFree(e->d_hdr);
-  cudaFree(e->d_emit_seq); cudaFree(e->d_resid_stage); cudaFree(e->d_rescnt); cudaFree(e->d_ctr); cudaFree(e->d_small);
+  cudaFree(e->d_M); cudaFree(e->d_tot); cudaFree(e->d_outbase); cudaFree(e->d_binlim); cudaFree(e->d_bin_seg);
+  cudaFree(e->d_bin_key); cudaFree(e->d_seg); cudaFree(e->d_members); cudaFree(e->d_src_idx); cudaFree(e->d_hdr);
+  cudaFree(e->d_emit_seq); cudaFree(e->d_rescnt); cudaFree(e->d_ctr); cudaFree(e->d_small);
   cudaFree(e->d_in_id); cudaFree(e->d_hslot); cudaFree(e->d_in_rating); cudaFree(e->d_in_mode); cudaFree(e->d_code);
   cudaFree(e->d_in_ts); cudaFree(e->d_blocksum);
   if (e->h_ctr) cudaFreeHost(e->h_ctr);
@@ -753,6 +769,14 @@ int mm_set_option(mm_engine* e, const char* name, int64_t value) {
     return MM_OK;
   }
   if (!std::strcmp(name, "dense")) { e->dense_ok = (int)value; return MM_OK; }
+  if (!std::strcmp(name, "max_spread")) {
+    // EXTENSION (policy S1): a lobby spans at most `value` rating points; < 0 restores the reference behaviour.
+    // Defined on the rating-sorted partition, so MM_ORDER_RATING only (oracle: orc_run_windowed).
+    if (value >= 0 && e->cfg.order_mode != MM_ORDER_RATING) return MM_E_ARG;
+    if (value > 0x7FFFFFFF) return MM_E_ARG;
+    e->max_spread = value < 0 ? -1 : (int32_t)value;
+    return MM_OK;
+  }
   if (!std::strcmp(name, "tick_impl")) { e->tick_impl = value != 0; return MM_OK; }
   if (!std::strcmp(name, "place_debug")) {  // timing experiments only: results are NOT valid
     if (value < 0 || value > 63) return MM_E_ARG;

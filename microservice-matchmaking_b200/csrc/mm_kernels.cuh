@@ -26,7 +26,6 @@ constexpr int kBlock = 1024;          // threads per CTA for hist / place
 constexpr int kJ = 4;                 // batches per round in k_place
 constexpr uint32_t kRound = kBlock * kJ;
 constexpr uint32_t kNone = 0x1FFFu;   // list terminator (13-bit node ids)
-constexpr uint32_t kResCap = 2048;    // residual players one row may hold
 constexpr uint32_t kMaxRows = 2048;   // rows (CTAs) of the histogram matrix
 constexpr uint32_t kTile = 2048;      // players per TMA tile in k_place2
 constexpr uint32_t kMaxStages = 4;    // depth of the (bin, id) shared-memory ring
@@ -65,9 +64,9 @@ struct SegInfo {        // one (mode, group) partition
 struct TickCtr {
   uint32_t gbar;  // grid barrier of the fused tick kernel
   uint32_t n_lobbies, n_matched, n_alive, n_dead, n_resid;
-  uint32_t overflow;
+  uint32_t reserved0;
   uint32_t heavy;  // some bin expects > 4 players per tile: use warp-aggregated ranking
-  unsigned long long t[6];  // fused kernel: %globaltimer (ns) at phase boundaries, CTA 0
+  unsigned long long t[8];  // fused kernel: %globaltimer (ns) at phase boundaries, CTA 0; [6],[7]: max over CTAs
 };
 
 struct ActiveView {
@@ -347,15 +346,15 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK == 512 ? 2 : 1))
 // its slice of rows, the slices are scanned through shared memory, then the slice is
 // rewritten as running prefixes — one round trip of latency instead of R.
 // The LAST CTA of the grid runs concurrently as the "tail": bin totals (accumulated by
-// k_hist with global reductions) -> exclusive scan binbase, then the per-segment lobby
-// arithmetic:  lobbies_s = n_s / L, matched_s = lobbies_s * L, residual_s = n_s % L,
-//   seg_shift[s] = residual players of earlier segments (sorted position -> member slot)
-//   seg_lim[s]   = end of the segment's matched slots; a player at or past it stays queued.
+// k_hist with global reductions) -> sorted position of every bin -> how many players of every
+// bin are matched under the tick's policy (always a PREFIX of the bin in enqueue order) ->
+//   outbase[v] = member slot of bin v's first player (exclusive scan of the matched counts)
+//   binlim[v]  = outbase[v] + matched players of bin v; a player at or past it stays queued.
 // ---------------------------------------------------------------------------------------
 constexpr uint32_t kMaxSegs = MM_MAX_GROUPS * MM_MAX_MODES;
 constexpr int kScanBlock = 512;
 constexpr uint32_t kColScratchWords = (kScanBlock / 32) * 33;      // column CTA scratch
-constexpr uint32_t kTailScratchWords = 64 + 4 + 3 * kMaxSegs;      // tail CTA scratch (+ Kp + 1 words for the bin bases)
+constexpr uint32_t kTailScratchWords = 64 + 4 + 4 * kMaxSegs + 4;  // tail CTA scratch, fixed part
 
 // one 32-bin column group: exclusive prefix down the rows of M (scratch: kColScratchWords)
 __device__ __forceinline__ void colscan_cols_body(uint32_t* scratch, uint32_t group, uint32_t R, uint32_t Kp,
@@ -394,74 +393,156 @@ __device__ __forceinline__ void colscan_cols_body(uint32_t* scratch, uint32_t gr
   __syncthreads();  // scratch may be reused by the next group
 }
 
-// the tail: bin totals -> binbase, per-segment lobby arithmetic, counters (scratch: kTailScratchWords)
-__device__ __forceinline__ void colscan_tail_body(uint32_t* scratch, uint32_t Kp, uint32_t K,
-                                                  const uint32_t* __restrict__ tot, uint32_t* __restrict__ binbase,
-                                                  const uint32_t* __restrict__ seg_bin_lo,
-                                                  const uint32_t* __restrict__ seg_L, uint32_t n_segs,
-                                                  SegInfo* __restrict__ seg, uint32_t* __restrict__ seg_shift,
-                                                  uint32_t* __restrict__ seg_lim, TickCtr* ctr) {
+// arguments of the tail (shared by k_colscan and the fused k_tick)
+struct TailArgs {
+  uint32_t Kp, K, n_segs;
+  uint32_t layout;                    // bit 0: matched counts in shared memory; bit 1: bin keys too (tail_words)
+  int32_t max_spread;                 // < 0: unlimited (policy S0); >= 0: policy S1, rating order only
+  const uint32_t* tot;                // [Kp] bin totals (k_hist)
+  const uint32_t* seg_bin_lo;         // [n_segs + 1]
+  const uint32_t* seg_L;              // [n_segs]
+  const uint16_t* bin_seg;            // [Kp] bin -> segment
+  const uint16_t* bin_key;            // [Kp] bin -> clamp key (rating order: ascending inside a segment)
+  uint32_t* outbase;                  // [Kp] out: member slot of the bin's first player
+  uint32_t* binlim;                   // [Kp] out: outbase + matched players of the bin
+  SegInfo* seg;                       // [n_segs] out
+  TickCtr* ctr;
+};
+// shared-memory words of the tail for a layout: bases | matched counts (bit 0) | keys (bit 1)
+__host__ __device__ constexpr uint32_t tail_words(uint32_t Kp, uint32_t layout) {
+  return kTailScratchWords + (Kp + 2) + ((layout & 1u) ? (Kp + 2) : 0u) + ((layout & 2u) ? (Kp + 3) / 2 : 0u);
+}
+
+// The tail.  One pipeline for both policies:
+//   bin totals -> bases s_bb -> matched prefix of every bin -> member slot of the bin's first player.
+// S0 (reference behaviour): a (mode, group) partition of n players emits floor(n/L) lobbies, the n mod L
+//   highest-ranked players stay queued: member slot = sorted position - leftovers of earlier partitions,
+//   clipped at the partition's matched end (closed form, only a scan over the partitions).
+// S1 (extension): greedy windowed walk over the partition (oracle: orc_run_windowed).  Players of one bin have
+//   the same key, so the walk runs on the histogram: from position cur in bin v, lobbies are seeded at
+//   cur, cur+L, ... while the seed is still in bin v and its L-th player has key <= key_v + W; whatever is
+//   left of bin v afterwards cannot seed and stays queued.  Two-pointer over the bins of the segment.
+// Very large key domains (layout bit 0 clear) park m_v in global memory and scan it in place of the bases.
+__device__ __forceinline__ void colscan_tail_body(uint32_t* scratch, const TailArgs t) {
+  constexpr uint32_t NW = kScanBlock / 32;
   uint32_t* s_tmp = scratch;            // [64]
-  uint32_t* s_maxp = scratch + 64;      // [1]
-  uint32_t* s_res = scratch + 68;       // [kMaxSegs]
-  uint32_t* s_lob = s_res + kMaxSegs;
-  uint32_t* s_n = s_lob + kMaxSegs;
-  uint32_t* s_bb = s_n + kMaxSegs;      // [Kp + 1] bin totals -> bin bases (dynamic shared memory)
-  const uint32_t tid = threadIdx.x;
-  if (tid == 0) *s_maxp = 0;
+  uint32_t* s_misc = scratch + 64;      // [4] fullest bin
+  uint32_t* s_a = scratch + 68;         // [kMaxSegs] leftovers of earlier segments / member base
+  uint32_t* s_lob = s_a + kMaxSegs;     // [kMaxSegs] lobbies of earlier segments
+  uint32_t* s_nl = s_lob + kMaxSegs;    // [kMaxSegs] lobbies of the segment
+  uint32_t* s_lo = s_nl + kMaxSegs;     // [kMaxSegs + 1] first bin of the segment
+  uint32_t* s_bb = scratch + kTailScratchWords;  // [Kp + 1] sorted position of the bin's first player
+  const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, Kp = t.Kp, K = t.K, n_segs = t.n_segs;
+  if (tid == 0) s_misc[0] = 0;
+  for (uint32_t sg = tid; sg <= n_segs; sg += kScanBlock) s_lo[sg] = t.seg_bin_lo[sg];
   __syncthreads();
-  {  // coalesced, independent loads (the per-thread contiguous walk was latency-serialised: 25 us)
-    uint32_t lmax = 0;
-    for (uint32_t i = tid; i < Kp; i += kScanBlock) {
-      const uint32_t v = __ldcg(&tot[i]);
-      s_bb[i] = v;
-      if (i < K && v > lmax) lmax = v;
+  uint32_t lmax = 0;
+  for (uint32_t i = tid; i < Kp; i += kScanBlock) {  // coalesced, independent loads
+    const uint32_t v = __ldcg(&t.tot[i]);
+    s_bb[i] = v;
+    if (i < K && v > lmax) lmax = v;
+  }
+  lmax = __reduce_max_sync(0xFFFFFFFFu, lmax);
+  if ((tid & 31) == 0 && lmax) atomicMax(&s_misc[0], lmax);
+  __syncthreads();
+  const uint32_t total = block_excl_scan<kScanBlock>(s_bb, Kp, s_tmp);
+  if (tid == 0) s_bb[Kp] = total;
+  __syncthreads();
+  const uint32_t alive = s_bb[K], dead = total - alive;
+  uint32_t n_matched, tot_lob;
+
+  if (t.max_spread < 0) {
+    // S0: lobbies_s = n_s / L; the partition's first lobbies_s * L sorted positions are matched.
+    for (uint32_t sg = tid; sg < n_segs; sg += kScanBlock) {
+      const uint32_t ns = s_bb[s_lo[sg + 1]] - s_bb[s_lo[sg]], nl = ns / t.seg_L[sg];
+      s_nl[sg] = nl; s_lob[sg] = nl; s_a[sg] = ns - nl * t.seg_L[sg];
+      t.seg[sg].n = ns; t.seg[sg].n_lobbies = nl;
     }
-    lmax = __reduce_max_sync(0xFFFFFFFFu, lmax);
-    if ((tid & 31) == 0 && lmax) atomicMax(s_maxp, lmax);
     __syncthreads();
-    const uint32_t total = block_excl_scan<kScanBlock>(s_bb, Kp, s_tmp);
-    if (tid == 0) s_bb[Kp] = total;
+    const uint32_t n_left = block_excl_scan<kScanBlock>(s_a, n_segs, s_tmp);   // -> leftovers of earlier segments
+    tot_lob = block_excl_scan<kScanBlock>(s_lob, n_segs, s_tmp);               // -> lobbies of earlier segments
+    n_matched = alive - n_left;
+    for (uint32_t sg = warp; sg < n_segs; sg += NW) {  // one warp per partition: no bin -> segment lookups
+      const uint32_t lo = s_lo[sg], hi = s_lo[sg + 1], start = s_bb[lo], shift = s_a[sg];
+      const uint32_t mend = start + s_nl[sg] * t.seg_L[sg];  // end of the partition's matched positions
+      for (uint32_t v = lo + lane; v < hi; v += 32) {
+        const uint32_t b0 = s_bb[v], b1 = s_bb[v + 1];
+        t.outbase[v] = (b0 < mend ? b0 : mend) - shift;
+        t.binlim[v] = (b1 < mend ? b1 : mend) - shift;
+      }
+      if (lane == 0) { t.seg[sg].member_base = start - shift; t.seg[sg].lobby_base = s_lob[sg]; }
+    }
+    for (uint32_t v = K + tid; v < Kp; v += kScanBlock) { t.outbase[v] = n_matched; t.binlim[v] = n_matched; }
+  } else {
+    // S1: greedy windowed walk on the histogram, one thread per partition (see above), then a second scan.
+    const bool m_smem = (t.layout & 1u) != 0, key_smem = (t.layout & 2u) != 0;
+    uint32_t* s_m = m_smem ? s_bb + Kp + 2 : t.binlim;  // [Kp + 1] matched players of the bin
+    uint16_t* s_key = reinterpret_cast<uint16_t*>(s_bb + (m_smem ? 2 : 1) * (Kp + 2));
+    const uint16_t* keys = key_smem ? s_key : t.bin_key;
+    if (key_smem)
+      for (uint32_t v = tid; v < K; v += kScanBlock) s_key[v] = t.bin_key[v];
+    for (uint32_t v = K + tid; v < Kp; v += kScanBlock) s_m[v] = 0;
     __syncthreads();
-    for (uint32_t i = tid; i <= Kp; i += kScanBlock) binbase[i] = s_bb[i];
-  }
-  // per-segment arithmetic: three small scans over the <= modes*groups segments
-  for (uint32_t s = tid; s < n_segs; s += kScanBlock) {
-    const uint32_t ns = s_bb[seg_bin_lo[s + 1]] - s_bb[seg_bin_lo[s]];
-    const uint32_t nl = ns / seg_L[s];
-    s_n[s] = ns; s_lob[s] = nl; s_res[s] = ns - nl * seg_L[s];
-    seg[s].n = ns; seg[s].n_lobbies = nl;
-  }
-  __syncthreads();
-  const uint32_t tot_res = block_excl_scan<kScanBlock>(s_res, n_segs, s_tmp);
-  const uint32_t tot_lob = block_excl_scan<kScanBlock>(s_lob, n_segs, s_tmp);
-  const uint32_t tot_alive = block_excl_scan<kScanBlock>(s_n, n_segs, s_tmp);
-  for (uint32_t s = tid; s < n_segs; s += kScanBlock) {
-    const uint32_t mb = s_bb[seg_bin_lo[s]] - s_res[s];
-    seg[s].member_base = mb;
-    seg[s].lobby_base = s_lob[s];
-    seg_shift[s] = s_res[s];
-    seg_lim[s] = mb + seg[s].n_lobbies * seg_L[s];
+    const int32_t W = t.max_spread;
+    for (uint32_t sg = tid; sg < n_segs; sg += kScanBlock) {
+      const uint32_t lo = s_lo[sg], hi = s_lo[sg + 1], L = t.seg_L[sg];
+      uint32_t pos = s_bb[lo], vmax = lo;
+      for (uint32_t v = lo; v < hi; ++v) {
+        const uint32_t b0 = s_bb[v], b1 = s_bb[v + 1];
+        if (b1 == b0) { s_m[v] = 0; continue; }
+        const uint32_t cur = pos > b0 ? pos : b0;
+        if (cur >= b1) { s_m[v] = b1 - b0; continue; }  // consumed by lobbies seeded in earlier bins
+        if (vmax < v) vmax = v;
+        const int32_t kv = (int32_t)keys[v];
+        while (vmax + 1 < hi && (int32_t)keys[vmax + 1] - kv <= W) ++vmax;
+        const uint32_t reach = s_bb[vmax + 1];  // positions < reach have key <= key_v + W
+        uint32_t k = 0;
+        if (cur + L <= reach) {
+          const uint32_t kw = (reach - L - cur) / L + 1, kb = (b1 - 1 - cur) / L + 1;
+          k = kw < kb ? kw : kb;
+        }
+        pos = cur + k * L;
+        if (pos >= b1) s_m[v] = b1 - b0;
+        else { s_m[v] = pos - b0; pos = b1; }
+      }
+      t.seg[sg].n = s_bb[hi] - s_bb[lo];
+    }
+    __syncthreads();
+    if (!m_smem) {  // very large key domain: the counts were parked in global memory; scan them in place of the bases
+      for (uint32_t v = tid; v < Kp; v += kScanBlock) s_bb[v] = s_m[v];
+      s_m = s_bb;
+      __syncthreads();
+    }
+    // member slots = exclusive scan of the matched counts (members of successive partitions are contiguous)
+    n_matched = block_excl_scan<kScanBlock>(s_m, Kp, s_tmp);
+    if (tid == 0) s_m[Kp] = n_matched;
+    __syncthreads();
+    for (uint32_t v = tid; v < Kp; v += kScanBlock) {
+      t.outbase[v] = s_m[v];
+      t.binlim[v] = s_m[v + 1];  // = outbase + matched players of the bin
+    }
+    for (uint32_t sg = tid; sg < n_segs; sg += kScanBlock) {
+      const uint32_t mb = s_m[s_lo[sg]], nl = (s_m[s_lo[sg + 1]] - mb) / t.seg_L[sg];
+      s_lob[sg] = nl;
+      t.seg[sg].n_lobbies = nl; t.seg[sg].member_base = mb;
+    }
+    __syncthreads();
+    tot_lob = block_excl_scan<kScanBlock>(s_lob, n_segs, s_tmp);
+    for (uint32_t sg = tid; sg < n_segs; sg += kScanBlock) t.seg[sg].lobby_base = s_lob[sg];
   }
   if (tid == 0) {
-    const uint32_t dead = __ldcg(&tot[K]);
-    ctr->n_lobbies = tot_lob; ctr->n_matched = tot_alive - tot_res; ctr->n_alive = tot_alive; ctr->n_dead = dead;
+    t.ctr->n_lobbies = tot_lob; t.ctr->n_matched = n_matched; t.ctr->n_alive = alive; t.ctr->n_dead = dead;
     // expected players of the fullest bin per tile of one row (players spread evenly over rows)
-    const uint64_t npool = (uint64_t)tot_alive + dead;
-    ctr->heavy = ((uint64_t)(*s_maxp) * kTile > 4ull * (npool ? npool : 1)) ? 1u : 0u;
+    const uint64_t npool = (uint64_t)alive + dead;
+    t.ctr->heavy = ((uint64_t)s_misc[0] * kTile > 4ull * (npool ? npool : 1)) ? 1u : 0u;
   }
   __syncthreads();
 }
 
-__global__ void __launch_bounds__(kScanBlock) k_colscan(uint32_t R, uint32_t Kp, uint32_t K, uint32_t* __restrict__ M,
-                                                        const uint32_t* __restrict__ tot, uint32_t* __restrict__ binbase,
-                                                        const uint32_t* __restrict__ seg_bin_lo,
-                                                        const uint32_t* __restrict__ seg_L, uint32_t n_segs,
-                                                        SegInfo* __restrict__ seg, uint32_t* __restrict__ seg_shift,
-                                                        uint32_t* __restrict__ seg_lim, TickCtr* ctr) {
-  extern __shared__ __align__(16) uint32_t scratch[];  // max(kColScratchWords, kTailScratchWords + Kp + 1) words
-  if (blockIdx.x + 1 < gridDim.x) colscan_cols_body(scratch, blockIdx.x, R, Kp, M);
-  else colscan_tail_body(scratch, Kp, K, tot, binbase, seg_bin_lo, seg_L, n_segs, seg, seg_shift, seg_lim, ctr);
+__global__ void __launch_bounds__(kScanBlock) k_colscan(uint32_t R, uint32_t* __restrict__ M, const TailArgs t) {
+  extern __shared__ __align__(16) uint32_t scratch[];  // max(kColScratchWords, tail_words(Kp, layout)) words
+  if (blockIdx.x + 1 < gridDim.x) colscan_cols_body(scratch, blockIdx.x, R, t.Kp, M);
+  else colscan_tail_body(scratch, t);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -476,34 +557,28 @@ __global__ void __launch_bounds__(kScanBlock) k_colscan(uint32_t R, uint32_t Kp,
 //       come earlier in enqueue order (node id = batch*kBlock + tid), so
 //       slot = snapshot + sum(sizes of earlier groups) + rank inside the group.
 //       The first pusher advances cnt[bin] by the round's total.
-// Bit 31 of cnt marks a (row, bin) cell that reaches past the segment's matched range:
-// only those players consult seg_lim (the < L leftovers of a partition stay queued).
+// Bit 31 of cnt marks a (row, bin) cell that reaches past the bin's matched prefix:
+// only those players consult binlim (the leftovers of a partition stay queued, marked in left_bits).
 // This is the round's first placement kernel, kept as an on-device cross-check of k_place2
 // (rank_impl 1 = this list ranking, rank_impl 0 = a slow warp-serial ranking).
 // ---------------------------------------------------------------------------------------
 template <int IMPL>
 __global__ void __launch_bounds__(kBlock, 1)
     k_place(PoolView p, uint32_t n, uint32_t chunk, BinMap bm, uint32_t Kp, uint32_t R, const uint32_t* __restrict__ M,
-            const uint32_t* __restrict__ tot, const uint32_t* __restrict__ binbase,
-            const uint16_t* __restrict__ bin_seg, const uint32_t* __restrict__ seg_shift,
-            const uint32_t* __restrict__ seg_lim, uint32_t n_segs, uint64_t* __restrict__ members,
-            uint32_t* __restrict__ src_idx, uint32_t* __restrict__ resid_stage, uint32_t* __restrict__ rescnt,
-            TickCtr* ctr) {
+            const uint32_t* __restrict__ tot, const uint32_t* __restrict__ outbase,
+            const uint32_t* __restrict__ binlim, uint64_t* __restrict__ members, uint32_t* __restrict__ src_idx,
+            uint32_t* __restrict__ left_bits, uint32_t* __restrict__ rescnt, TickCtr* ctr) {
   extern __shared__ __align__(16) uint32_t smem[];
   uint32_t* cnt = smem;
   uint32_t* head = cnt + Kp;                                 // IMPL 1 only
   uint32_t* node = head + (IMPL == 1 ? Kp : 0);              // [kRound]
-  uint32_t* res_list = node + (IMPL == 1 ? kRound : 0);      // [kResCap]
-  uint16_t* s_lut = reinterpret_cast<uint16_t*>(res_list + kResCap);
+  uint16_t* s_lut = reinterpret_cast<uint16_t*>(node + (IMPL == 1 ? kRound : 0));
   __shared__ uint32_t s_nres;
-  __shared__ uint32_t s_shift[kMaxSegs], s_lim[kMaxSegs];
 
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t lt_mask = (1u << lane) - 1u;
   const uint32_t row = blockIdx.x;
   const uint64_t pol_in = policy_evict_first(), pol_out = policy_evict_last();
-  for (uint32_t i = tid; i < n_segs; i += kBlock) { s_shift[i] = seg_shift[i]; s_lim[i] = seg_lim[i]; }
-  __syncthreads();
   {
     const uint32_t* mrow = M + (size_t)row * Kp;
     const uint32_t* mnext = (row + 1 < R) ? mrow + Kp : tot;  // prefix of the next row, or column total
@@ -511,9 +586,8 @@ __global__ void __launch_bounds__(kBlock, 1)
       uint32_t v = 0;
       if (i < bm.K) {
         const uint32_t pre = mrow[i], c = mnext[i] - pre;
-        const uint32_t sg = bin_seg[i];
-        const uint32_t start = binbase[i] - s_shift[sg] + pre;  // slot of the cell's first player
-        v = start | ((start + c > s_lim[sg]) ? 0x80000000u : 0u);
+        const uint32_t start = outbase[i] + pre;  // slot of the cell's first player
+        v = start | ((start + c > binlim[i]) ? 0x80000000u : 0u);
       }
       cnt[i] = v;
       if (IMPL == 1) head[i] = 0;
@@ -528,6 +602,7 @@ __global__ void __launch_bounds__(kBlock, 1)
   const uint32_t end = (beg64 + chunk < n) ? (uint32_t)(beg64 + chunk) : n;
   const uint32_t n_rounds = (end - beg + kRound - 1) / kRound;
 
+  uint32_t nleft = 0;
   for (uint32_t round = 0; round < n_rounds; ++round) {
     const uint32_t base = beg + round * kRound;
     uint32_t bin[kJ];
@@ -610,37 +685,28 @@ __global__ void __launch_bounds__(kBlock, 1)
 
 #pragma unroll
     for (int j = 0; j < kJ; ++j) {
+      bool left = false;
       if (bin[j] < bm.K) {
         const uint32_t e = base + j * kBlock + tid;
         uint32_t slot = (base_g[j] & 0x7FFFFFFFu) + rankw[j];
         bool matched = true;
-        if (base_g[j] >> 31) matched = slot < s_lim[__ldg(&bin_seg[bin[j]])];
+        if (base_g[j] >> 31) matched = slot < __ldg(&binlim[bin[j]]);
         if (matched) {
           st_keep_u64(members + slot, idv[j], pol_out);
           if (src_idx) src_idx[slot] = e;
         } else {
-          const uint32_t k = atomicAdd(&s_nres, 1u);
-          if (k < kResCap) res_list[k] = e;
+          left = true;
         }
       }
+      // one bit per player that stays queued; the warp's 32 positions of a batch are one word
+      const uint32_t wv = __ballot_sync(0xFFFFFFFFu, left);
+      if (lane == 0) { left_bits[(base + j * kBlock + warp * 32) >> 5] = wv; nleft += __popc(wv); }
     }
     if (IMPL == 1) __syncthreads();
   }
-
-  // the row's residual players, in enqueue order
+  if (lane == 0 && nleft) atomicAdd(&s_nres, nleft);
   __syncthreads();
-  const uint32_t nres_all = s_nres;
-  const uint32_t nres = nres_all < kResCap ? nres_all : kResCap;
-  if (tid == 0) {
-    rescnt[row] = nres;
-    if (nres_all > kResCap) atomicExch(&ctr->overflow, 1u);
-  }
-  for (uint32_t t = tid; t < nres; t += kBlock) {
-    const uint32_t v = res_list[t];
-    uint32_t rank = 0;
-    for (uint32_t u = 0; u < nres; ++u) rank += (res_list[u] < v) ? 1u : 0u;
-    resid_stage[(size_t)row * kResCap + rank] = v;
-  }
+  if (tid == 0) rescnt[row] = s_nres;
 }
 
 // ---------------------------------------------------------------------------------------
@@ -661,19 +727,17 @@ __global__ void __launch_bounds__(kBlock, 1)
 //     group-size matrix + one warp-shuffle scan per bin;
 //   * ids are stored with an L2 evict-last policy: the 4 writes completing a 32-byte
 //     sector of member_ids arrive at unrelated times and must meet in L2, not in DRAM.
-// Shared memory: ring | mbarriers | cnt[Kp] | head[kHeadSlots] | node[kTile] | nbin | res | dense.
+// Shared memory: ring | mbarriers | cnt[Kp] | head[kHeadSlots] | node[kTile] | nbin | dense.
 // ---------------------------------------------------------------------------------------
 constexpr uint32_t kHeadSlots = 4096;
-constexpr uint32_t kRes2 = 1024;  // residual players one row may hold (k_place2)
 
 template <int BLOCK>
 __device__ __forceinline__ void place2_body(
     unsigned char* smem_raw, const uint16_t* __restrict__ bins16, const uint64_t* __restrict__ ids, uint32_t n,
     uint32_t chunk, uint32_t K, uint32_t Kp, uint32_t R, uint32_t stages, uint32_t dense, const uint32_t* __restrict__ M,
-    const uint32_t* __restrict__ tot, const uint32_t* __restrict__ binbase, const uint16_t* __restrict__ bin_seg,
-    const uint32_t* __restrict__ seg_shift, const uint32_t* __restrict__ seg_lim, uint64_t* __restrict__ members,
-    uint32_t* __restrict__ src_idx, uint32_t* __restrict__ resid_stage, uint32_t* __restrict__ rescnt, TickCtr* ctr,
-    uint32_t dbg_all) {
+    const uint32_t* __restrict__ tot, const uint32_t* __restrict__ outbase, const uint32_t* __restrict__ binlim,
+    uint64_t* __restrict__ members, uint32_t* __restrict__ src_idx, uint32_t* __restrict__ left_bits,
+    uint32_t* __restrict__ rescnt, TickCtr* ctr, uint32_t dbg_all) {
   const uint32_t dbg = dbg_all & 3u;  // (higher bits are histogram-phase experiments)
   // dbg != 0: timing experiments only (results invalid): 1 = rank, no id store; 2 = no rank,
   // coalesced store; 3 = no rank, pseudo-random scatter
@@ -685,8 +749,7 @@ __device__ __forceinline__ void place2_body(
   uint32_t* cnt = reinterpret_cast<uint32_t*>(smem_raw + (size_t)stages * kTileBytes + 64);  // [Kp]
   uint32_t* head = cnt + Kp;                 // [kHeadSlots]
   uint32_t* node = head + kHeadSlots;        // [kTile]
-  uint32_t* res_list = node + kTile;         // [kRes2]
-  uint16_t* nbin = reinterpret_cast<uint16_t*>(res_list + kRes2);  // [kTile] heavy path: bin of a group node
+  uint16_t* nbin = reinterpret_cast<uint16_t*>(node + kTile);  // [kTile] heavy path: bin of a group node
   uint16_t* wc = nbin + kTile;                                     // dense only: [Kp][kDenseStride] group sizes
   uint16_t* pf = wc + (size_t)Kp * kDenseStride;                    // dense only: their exclusive prefixes
   uint32_t* cbase = reinterpret_cast<uint32_t*>(pf + (size_t)Kp * kDenseStride);  // dense only: [Kp]
@@ -723,9 +786,8 @@ __device__ __forceinline__ void place2_body(
       uint32_t v = 0;
       if (i < K) {  // __ldcg: these arrays are produced earlier in the same (fused) launch by other SMs
         const uint32_t pre = __ldcg(&mrow[i]), c = __ldcg(&mnext[i]) - pre;
-        const uint32_t sg = bin_seg[i];
-        const uint32_t start = __ldcg(&binbase[i]) - __ldcg(&seg_shift[sg]) + pre;  // slot of the cell's first player
-        v = start | ((start + c > __ldcg(&seg_lim[sg])) ? 0x80000000u : 0u);
+        const uint32_t start = __ldcg(&outbase[i]) + pre;  // slot of the cell's first player
+        v = start | ((start + c > __ldcg(&binlim[i])) ? 0x80000000u : 0u);
       }
       cnt[i] = v;
     }
@@ -737,6 +799,7 @@ __device__ __forceinline__ void place2_body(
   __syncthreads();
 
   uint32_t st = 0, parity = 0;
+  uint32_t nleft = 0;  // lane 0: players of this warp's positions that stay queued
   for (uint32_t t = 0; t < n_tiles; ++t) {
     const uint32_t tile_base = beg + t * kTile;
     const uint32_t valid = end - tile_base;  // players of this tile inside the row (>= kTile except the last)
@@ -948,24 +1011,45 @@ __device__ __forceinline__ void place2_body(
 #pragma unroll
       for (int j = 0; j < J; ++j) idv[j] = ti[pos_[j]];
     }
+    // ---- store matched ids; players past their bin's matched prefix stay queued: one bit per player in
+    // left_bits (every word of the row is written every tick, no atomics, no cold branch in this loop) ----
+    uint32_t lmask = 0;
 #pragma unroll
     for (int j = 0; j < J; ++j) {
       if (bin[j] < K) {
-        const uint32_t pos = pos_[j];
         bool matched = true;
-        if (flag[j]) matched = slot[j] < __ldcg(&seg_lim[__ldg(&bin_seg[bin[j]])]);
-        if (dbg == 1) matched = matched && slot[j] == 0xFFFFFFFFu;
-        if (dbg == 1 && !matched) continue;
+        if (flag[j]) matched = slot[j] < __ldcg(&binlim[bin[j]]);
+        if (dbg == 1) continue;
         if (matched) {
           st_keep_u64(members + slot[j], idv[j], pol_out);
-          if (src_idx) src_idx[slot[j]] = tile_base + pos;
+          if (src_idx) src_idx[slot[j]] = tile_base + pos_[j];
         } else {
-          const uint32_t k = atomicAdd(&s_nres, 1u);
-          if (k < kRes2) res_list[k] = tile_base + pos;
+          lmask |= 1u << j;
         }
       }
     }
-    __syncthreads();  // everyone is done with stage st (and with this round's lists)
+    {
+      uint32_t* lw = left_bits + ((tile_base + warp * (32 * J)) >> 5);
+      if (J == 4 && dense == 2) {  // blocked: the warp owns 128 consecutive positions, lane l the bits 4l .. 4l+3
+        const uint32_t mine = lmask << ((lane & 7u) * 4u);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const uint32_t wv = __reduce_or_sync(0xFFFFFFFFu, (lane >> 3) == (uint32_t)k ? mine : 0u);
+          if (lane == 0) { lw[k] = wv; nleft += __popc(wv); }
+        }
+      } else {                     // strided: batch j of the warp = positions j*BLOCK + 32*warp .. +31 = one word
+        uint32_t mine = 0, all = 0;    // lane j stores batch j's word: one store instruction per warp and tile
+#pragma unroll
+        for (int j = 0; j < J; ++j) {
+          const uint32_t wv = __ballot_sync(0xFFFFFFFFu, (lmask >> j) & 1u);
+          if (lane == (uint32_t)j) mine = wv;
+          all += __popc(wv);
+        }
+        if (lane < (uint32_t)J) left_bits[(tile_base + lane * BLOCK + warp * 32) >> 5] = mine;
+        if (lane == 0) nleft += all;
+      }
+    }
+    __syncthreads();  // everyone is done with stage st and with this round's lists
     if (tid == 0 && t + stages < n_tiles) {
       const uint32_t tn = t + stages;
       mbar_expect_tx(&full[st], kTileBytes);
@@ -975,20 +1059,9 @@ __device__ __forceinline__ void place2_body(
     if (++st == stages) { st = 0; parity ^= 1u; }
   }
 
-  // the row's residual players, in enqueue order
+  if (lane == 0 && nleft) atomicAdd(&s_nres, nleft);
   __syncthreads();
-  const uint32_t nres_all = s_nres;
-  const uint32_t nres = nres_all < kRes2 ? nres_all : kRes2;
-  if (tid == 0) {
-    rescnt[row] = nres;
-    if (nres_all > kRes2) atomicExch(&ctr->overflow, 1u);
-  }
-  for (uint32_t t = tid; t < nres; t += BLOCK) {
-    const uint32_t v = res_list[t];
-    uint32_t rank = 0;
-    for (uint32_t u = 0; u < nres; ++u) rank += (res_list[u] < v) ? 1u : 0u;
-    resid_stage[(size_t)row * kResCap + rank] = v;
-  }
+  if (tid == 0) rescnt[row] = s_nres;  // players of this row that stay queued
   if (tid == 0)
     for (uint32_t s = 0; s < stages; ++s) mbar_inval(&full[s]);
 }
@@ -997,44 +1070,131 @@ template <int BLOCK>
 __global__ void __launch_bounds__(BLOCK, (BLOCK == 512 ? 2 : 1))
     k_place2(const uint16_t* __restrict__ bins16, const uint64_t* __restrict__ ids, uint32_t n, uint32_t chunk, uint32_t K,
              uint32_t Kp, uint32_t R, uint32_t stages, uint32_t dense, const uint32_t* __restrict__ M,
-             const uint32_t* __restrict__ tot, const uint32_t* __restrict__ binbase,
-             const uint16_t* __restrict__ bin_seg, const uint32_t* __restrict__ seg_shift,
-             const uint32_t* __restrict__ seg_lim, uint64_t* __restrict__ members, uint32_t* __restrict__ src_idx,
-             uint32_t* __restrict__ resid_stage, uint32_t* __restrict__ rescnt, TickCtr* ctr, uint32_t dbg) {
+             const uint32_t* __restrict__ tot, const uint32_t* __restrict__ outbase,
+             const uint32_t* __restrict__ binlim, uint64_t* __restrict__ members, uint32_t* __restrict__ src_idx,
+             uint32_t* __restrict__ left_bits, uint32_t* __restrict__ rescnt, TickCtr* ctr, uint32_t dbg) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  place2_body<BLOCK>(smem_raw, bins16, ids, n, chunk, K, Kp, R, stages, dense, M, tot, binbase, bin_seg, seg_shift,
-                     seg_lim, members, src_idx, resid_stage, rescnt, ctr, dbg);
+  place2_body<BLOCK>(smem_raw, bins16, ids, n, chunk, K, Kp, R, stages, dense, M, tot, outbase, binlim, members, src_idx,
+                     left_bits, rescnt, ctr, dbg);
 }
 
 // ---------------------------------------------------------------------------------------
-// k_epilogue.  CTA 0: concatenate the rows' residual lists (rows are in enqueue order),
-// gather the five pool columns into the alternate pool buffer and re-stamp the residual
-// players' active-set entries with their new slot — replaces save_new_state/3
-// (search/worker.ex:282-289): the "partial lobby" is simply the players left resident.
-// Every CTA: lobby headers from the segment table — lobby c of segment s = members
+// k_epilogue.  Lobby headers from the segment table — lobby c of segment s = members
 // [member_base + k*L, +L); replaces the payload assembly at search/worker.ex:315-319.
+// Pool compaction, row-parallel and order-preserving: the placement pass left one bit per
+// player that stays queued (left_bits) and the count per row; every CTA scans the R row
+// counts, then walks the bit words of its rows — popcount prefix, slots of the set bits
+// enumerated into shared memory, one thread per leftover player gathers its record from the
+// old pool buffer into the alternate one and re-stamps the player's active-set entry.
+// Replaces save_new_state/3 (search/worker.ex:282-289): the "partial lobby" is the players
+// left resident.
 // ---------------------------------------------------------------------------------------
-constexpr uint32_t kEpiScratchWords = (kMaxRows + 1) + 64 + (kMaxSegs + 1) + 2 * kMaxSegs;
+constexpr uint32_t kLeftList = 2048;  // leftover players handled per step of the compaction
+constexpr uint32_t kEpiScratchWords = (kMaxRows + 1) + 64 + (kMaxSegs + 1) + 2 * kMaxSegs + kLeftList;
 
 template <int BLOCK>
-__device__ __forceinline__ void epilogue_body(uint32_t* scratch, PoolView src, PoolView dst, uint32_t R,
-                                              const uint32_t* __restrict__ rescnt, const uint32_t* __restrict__ resid_stage,
-                                              ActiveView act, uint32_t new_gen, const SegInfo* __restrict__ seg,
-                                              const uint32_t* __restrict__ seg_L, uint32_t n_segs, uint32_t n_groups,
-                                              mm_lobby_hdr* __restrict__ hdr, const uint32_t* __restrict__ src_idx,
-                                              uint32_t* __restrict__ emit_seq, uint32_t* __restrict__ tot, uint32_t Kp,
-                                              TickCtr* ctr) {
+__device__ __forceinline__ void epilogue_body(uint32_t* scratch, PoolView src, PoolView dst, uint32_t n, uint32_t chunk,
+                                              uint32_t R, const uint32_t* __restrict__ rescnt,
+                                              const uint32_t* __restrict__ left_bits, ActiveView act, uint32_t new_gen,
+                                              const SegInfo* __restrict__ seg, const uint32_t* __restrict__ seg_L,
+                                              uint32_t n_segs, uint32_t n_groups, mm_lobby_hdr* __restrict__ hdr,
+                                              const uint32_t* __restrict__ src_idx, uint32_t* __restrict__ emit_seq,
+                                              uint32_t* __restrict__ tot, uint32_t Kp, TickCtr* ctr,
+                                              unsigned long long* t_mid = nullptr) {
+  constexpr uint32_t NW = BLOCK / 32;
   uint32_t* s_off = scratch;                   // [kMaxRows + 1]
   uint32_t* s_tmp = s_off + kMaxRows + 1;      // [64]
   uint32_t* s_lbase = s_tmp + 64;              // [kMaxSegs + 1]
   uint32_t* s_mbase = s_lbase + kMaxSegs + 1;  // [kMaxSegs]
   uint32_t* s_L = s_mbase + kMaxSegs;          // [kMaxSegs]
-  const uint32_t tid = threadIdx.x;
+  uint32_t* s_list = s_L + kMaxSegs;           // [kLeftList]
+  const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   for (uint32_t s = tid; s < n_segs; s += BLOCK) {
     s_lbase[s] = __ldcg(&seg[s].lobby_base); s_mbase[s] = __ldcg(&seg[s].member_base); s_L[s] = seg_L[s];
   }
+  for (uint32_t r = tid; r < R; r += BLOCK) s_off[r] = __ldcg(&rescnt[r]);
   __syncthreads();
   for (uint32_t i = blockIdx.x * BLOCK + tid; i < Kp; i += gridDim.x * BLOCK) tot[i] = 0;  // ready for the next tick
+  const uint32_t total = block_excl_scan<BLOCK>(s_off, R, s_tmp);
+  if (tid == 0) {
+    s_off[R] = total;
+    if (blockIdx.x == 0) ctr->n_resid = total;
+  }
+  __syncthreads();
+  for (uint32_t row = blockIdx.x; row < R; row += gridDim.x) {
+    const uint32_t off = s_off[row], cnt = s_off[row + 1] - off;
+    if (cnt == 0) continue;  // uniform for the CTA
+    const uint64_t beg64 = (uint64_t)row * chunk;
+    const uint32_t beg = beg64 < n ? (uint32_t)beg64 : n;
+    const uint32_t end = (beg64 + chunk < n) ? (uint32_t)(beg64 + chunk) : n;
+    const uint32_t nwords = (end - beg + 31) >> 5;  // beg is a multiple of 32 (chunk is a multiple of kRound)
+    const uint32_t* bits = left_bits + (beg >> 5);
+    // The slots of the set bits are enumerated into a shared-memory list (no memory latency); whenever the
+    // list is full, and at the end of the row, one thread per listed player gathers its record into the
+    // alternate pool buffer and re-stamps its active-set entry — all the dependent gather / hash-probe
+    // chains of a flush run in parallel, and neighbouring threads touch neighbouring slots.
+    uint32_t tbase = off, fill = 0;  // destination of s_list[0]; entries in the list (uniform)
+    __syncthreads();  // the previous row's last flush may still be reading s_list
+    auto flush = [&](uint32_t count, bool last) {
+      __syncthreads();
+      for (uint32_t e = tid; e < count; e += BLOCK) {
+        const uint32_t i = beg + s_list[e], t = tbase + e;
+        const uint64_t pid = src.id[i];
+        dst.id[t] = pid; dst.rating[t] = src.rating[i]; dst.mode[t] = src.mode[i];
+        dst.tsize[t] = src.tsize[i]; dst.ts[t] = src.ts[i]; dst.bin[t] = src.bin[i];
+        if (act.mask) {
+          uint64_t h = hash64(pid) & act.mask;
+          for (uint64_t probe = 0; probe <= act.mask; ++probe) {
+            const unsigned long long k2 = act.keys[h];
+            if (k2 == pid) { act.vals[h] = ((unsigned long long)new_gen << 32) | t; break; }
+            if (k2 == kEmptyKey) break;
+            h = (h + 1) & act.mask;
+          }
+        }
+      }
+      tbase += count;
+      if (!last) __syncthreads();  // the row's last flush runs on into the lobby headers: the few threads
+                                   // waiting on their gather / probe chains do not hold up the others
+    };
+    for (uint32_t w0 = 0; w0 < nwords; w0 += BLOCK) {  // BLOCK words = 32 * BLOCK players per step
+      const uint32_t wi = w0 + tid;
+      const uint32_t w = wi < nwords ? __ldcg(&bits[wi]) : 0u;
+      const uint32_t c = __popc(w);
+      uint32_t incl = c;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t u = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+        if (lane >= (uint32_t)o) incl += u;
+      }
+      if (lane == 31) s_tmp[warp] = incl;
+      __syncthreads();
+      uint32_t wbase = 0, wtot = 0;
+      for (uint32_t k = 0; k < NW; ++k) { const uint32_t v = s_tmp[k]; if (k < warp) wbase += v; wtot += v; }
+      const uint32_t lpre = wbase + incl - c;  // rank of this word's first leftover player within the step
+      if (fill + wtot > kLeftList && fill) { flush(fill, false); fill = 0; }
+      for (uint32_t p0 = 0; p0 < wtot; p0 += kLeftList) {  // one pass unless the step alone overflows the list
+        const uint32_t cp = wtot - p0 < kLeftList ? wtot - p0 : kLeftList;
+        if (c && lpre < p0 + cp && lpre + c > p0) {
+          uint32_t ww = w, r = lpre;
+          while (ww) {
+            const uint32_t bpos = __ffs(ww) - 1;
+            ww &= ww - 1;
+            if (r >= p0 && r < p0 + cp) s_list[fill + r - p0] = (wi << 5) + bpos;
+            ++r;
+          }
+        }
+        fill += cp;
+        if (p0 + cp < wtot) { flush(fill, false); fill = 0; }
+      }
+      __syncthreads();  // s_tmp is rewritten by the next step
+    }
+    if (fill) flush(fill, true);
+  }
+  if (t_mid && tid == 0) {
+    unsigned long long tm;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tm));
+    atomicMax(t_mid, tm);
+  }
   const uint32_t total_lob = __ldcg(&ctr->n_lobbies);
   for (uint32_t c = blockIdx.x * BLOCK + tid; c < total_lob; c += gridDim.x * BLOCK) {
     uint32_t a = 0, e = n_segs;  // last segment with lobby_base <= c
@@ -1048,41 +1208,18 @@ __device__ __forceinline__ void epilogue_body(uint32_t* scratch, PoolView src, P
     hdr[c] = h;
     if (emit_seq) emit_seq[c] = __ldcg(&src_idx[h.first_member + L - 1]);
   }
-  if (blockIdx.x != 0) return;
-
-  for (uint32_t r = tid; r < R; r += BLOCK) s_off[r] = __ldcg(&rescnt[r]);
-  __syncthreads();
-  const uint32_t total = block_excl_scan<BLOCK>(s_off, R, s_tmp);
-  if (tid == 0) { s_off[R] = total; ctr->n_resid = total; }
-  __syncthreads();
-  for (uint32_t t = tid; t < total; t += BLOCK) {
-    uint32_t a = 0, c = R;  // last row with s_off[row] <= t
-    while (c - a > 1) { const uint32_t mid = (a + c) >> 1; if (s_off[mid] <= t) a = mid; else c = mid; }
-    const uint32_t idx = __ldcg(&resid_stage[(size_t)a * kResCap + (t - s_off[a])]);
-    const uint64_t pid = src.id[idx];
-    dst.id[t] = pid; dst.rating[t] = src.rating[idx]; dst.mode[t] = src.mode[idx];
-    dst.tsize[t] = src.tsize[idx]; dst.ts[t] = src.ts[idx]; dst.bin[t] = src.bin[idx];
-    if (act.mask) {
-      uint64_t h = hash64(pid) & act.mask;
-      for (uint64_t probe = 0; probe <= act.mask; ++probe) {
-        const unsigned long long k = act.keys[h];
-        if (k == pid) { act.vals[h] = ((unsigned long long)new_gen << 32) | t; break; }
-        if (k == kEmptyKey) break;
-        h = (h + 1) & act.mask;
-      }
-    }
-  }
 }
 
-__global__ void __launch_bounds__(1024) k_epilogue(PoolView src, PoolView dst, uint32_t R, const uint32_t* __restrict__ rescnt,
-                                                   const uint32_t* __restrict__ resid_stage, ActiveView act, uint32_t new_gen,
+__global__ void __launch_bounds__(1024) k_epilogue(PoolView src, PoolView dst, uint32_t n, uint32_t chunk, uint32_t R,
+                                                   const uint32_t* __restrict__ rescnt,
+                                                   const uint32_t* __restrict__ left_bits, ActiveView act, uint32_t new_gen,
                                                    const SegInfo* __restrict__ seg, const uint32_t* __restrict__ seg_L,
                                                    uint32_t n_segs, uint32_t n_groups, mm_lobby_hdr* __restrict__ hdr,
                                                    const uint32_t* __restrict__ src_idx, uint32_t* __restrict__ emit_seq,
                                                    uint32_t* __restrict__ tot, uint32_t Kp, TickCtr* ctr) {
   __shared__ uint32_t scratch[kEpiScratchWords];
-  epilogue_body<1024>(scratch, src, dst, R, rescnt, resid_stage, act, new_gen, seg, seg_L, n_segs, n_groups, hdr, src_idx,
-                      emit_seq, tot, Kp, ctr);
+  epilogue_body<1024>(scratch, src, dst, n, chunk, R, rescnt, left_bits, act, new_gen, seg, seg_L, n_segs, n_groups, hdr,
+                      src_idx, emit_seq, tot, Kp, ctr);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -1097,13 +1234,13 @@ __global__ void __launch_bounds__(1024) k_epilogue(PoolView src, PoolView dst, u
 // ---------------------------------------------------------------------------------------
 struct TickArgs {
   PoolView src, dst;
-  BinMap bm;
-  uint32_t n, chunk, K, Kp, R, n_segs, n_groups, hist_stages, place_stages, dense, new_gen, dbg;
-  uint32_t* M; uint32_t* tot; uint32_t* binbase;
-  const uint16_t* bin_seg; const uint32_t* seg_bin_lo; const uint32_t* seg_L;
-  SegInfo* seg; uint32_t* seg_shift; uint32_t* seg_lim;
+  uint32_t n, chunk, R, n_groups, hist_stages, place_stages, dense, new_gen, dbg;
+  uint32_t* M;
+  TailArgs tail;  // Kp, K, n_segs, tot, segment tables, outbase / binlim, counters
+  uint32_t* tot;  // = tail.tot (written by the histogram and re-zeroed by the epilogue)
   uint64_t* members; uint32_t* src_idx; mm_lobby_hdr* hdr; uint32_t* emit_seq;
-  uint32_t* resid_stage; uint32_t* rescnt; ActiveView act; TickCtr* ctr;
+  uint32_t* left_bits;  // one bit per pool slot: the player stays queued after this tick
+  uint32_t* rescnt; ActiveView act;
 };
 
 template <int BLOCK>
@@ -1112,37 +1249,42 @@ __global__ void __launch_bounds__(BLOCK, 2) k_tick(const TickArgs a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   uint32_t* scratch = reinterpret_cast<uint32_t*>(smem_raw);
   const unsigned int G = gridDim.x;
+  const uint32_t Kp = a.tail.Kp, K = a.tail.K;
+  TickCtr* ctr = a.tail.ctr;
   auto stamp = [&](int k) {
     if (blockIdx.x == 0 && threadIdx.x == 0) {
       unsigned long long t;
       asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-      a.ctr->t[k] = t;
+      ctr->t[k] = t;
     }
   };
   stamp(0);
-  hist3_body<BLOCK>(smem_raw, a.src.bin, a.n, a.chunk, a.Kp, a.hist_stages, a.M, a.tot);
-  grid_barrier(&a.ctr->gbar, G);
+  hist3_body<BLOCK>(smem_raw, a.src.bin, a.n, a.chunk, Kp, a.hist_stages, a.M, a.tot);
+  grid_barrier(&ctr->gbar, G);
   stamp(1);
   if (blockIdx.x == G - 1) {
-    colscan_tail_body(scratch, a.Kp, a.K, a.tot, a.binbase, a.seg_bin_lo, a.seg_L, a.n_segs, a.seg, a.seg_shift, a.seg_lim,
-                      a.ctr);
+    colscan_tail_body(scratch, a.tail);
     if (threadIdx.x == 0) {
       unsigned long long t;
       asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-      a.ctr->t[5] = t;
+      ctr->t[5] = t;
     }
   }
-  for (uint32_t g = blockIdx.x; g < (a.Kp + 31) / 32; g += G) colscan_cols_body(scratch, g, a.R, a.Kp, a.M);
-  grid_barrier(&a.ctr->gbar, 2 * G);
+  for (uint32_t g = blockIdx.x; g < (Kp + 31) / 32; g += G) colscan_cols_body(scratch, g, a.R, Kp, a.M);
+  grid_barrier(&ctr->gbar, 2 * G);
   stamp(2);
-  place2_body<BLOCK>(smem_raw, a.src.bin, a.src.id, a.n, a.chunk, a.K, a.Kp, a.R, a.place_stages, a.dense, a.M, a.tot,
-                     a.binbase, a.bin_seg, a.seg_shift, a.seg_lim, a.members, a.src_idx, a.resid_stage, a.rescnt, a.ctr,
-                     a.dbg);
-  grid_barrier(&a.ctr->gbar, 3 * G);
+  place2_body<BLOCK>(smem_raw, a.src.bin, a.src.id, a.n, a.chunk, K, Kp, a.R, a.place_stages, a.dense, a.M, a.tot,
+                     a.tail.outbase, a.tail.binlim, a.members, a.src_idx, a.left_bits, a.rescnt, ctr, a.dbg);
+  grid_barrier(&ctr->gbar, 3 * G);
   stamp(3);
-  epilogue_body<BLOCK>(scratch, a.src, a.dst, a.R, a.rescnt, a.resid_stage, a.act, a.new_gen, a.seg, a.seg_L, a.n_segs,
-                       a.n_groups, a.hdr, a.src_idx, a.emit_seq, a.tot, a.Kp, a.ctr);
-  stamp(4);  // CTA 0 finishes last in practice (it also compacts the pool); informative only
+  epilogue_body<BLOCK>(scratch, a.src, a.dst, a.n, a.chunk, a.R, a.rescnt, a.left_bits, a.act, a.new_gen, a.tail.seg,
+                       a.tail.seg_L, a.tail.n_segs, a.n_groups, a.hdr, a.src_idx, a.emit_seq, a.tot, Kp, ctr, &ctr->t[7]);
+  stamp(4);  // CTA 0's view
+  if (threadIdx.x == 0) {  // the last CTA to finish closes the epilogue phase
+    unsigned long long tm;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tm));
+    atomicMax(&ctr->t[6], tm);
+  }
 }
 
 // =======================================================================================

@@ -489,6 +489,87 @@ done:
 }
 
 /* ------------------------------------------------------------------------- */
+/* EXTENSION — policy S1 (rating window), see mm_oracle.h                       */
+/* ------------------------------------------------------------------------- */
+int orc_run_windowed(const mm_config* cfg, int32_t max_spread, uint32_t n, const uint64_t* id, const int32_t* rating,
+                     const uint8_t* mode, const uint8_t* alive, orc_result* out) {
+  int rc = orc_check_cfg(cfg);
+  if (rc) return rc;
+  memset(out, 0, sizeof(*out));
+  const uint32_t G = cfg->n_groups, NS = cfg->n_modes * G;
+  int32_t rmin, rmax; orc_rating_span(cfg, &rmin, &rmax);
+  uint8_t* grp = (uint8_t*)malloc((size_t)n + 1);
+  uint32_t* feed = orc_feed_order(cfg, MM_ORDER_RATING, n, rating, mode);
+  uint32_t* cnt = (uint32_t*)calloc((size_t)NS + 1, sizeof(uint32_t));
+  uint32_t* part = (uint32_t*)malloc(((size_t)n + 1) * sizeof(uint32_t));
+  uint8_t* is_res = (uint8_t*)calloc((size_t)n + 1, 1);
+  orc_emit* emits = NULL; uint64_t* members = NULL;
+  if (!grp || !feed || !cnt || !part || !is_res) { rc = MM_E_CAP; goto done; }
+  for (uint32_t i = 0; i < n; ++i) {
+    if (mode[i] >= cfg->n_modes) { rc = MM_E_ARG; goto done; }
+    int g = orc_find_rating_group(cfg, (double)rating[i]);
+    if (g < 0) { rc = MM_E_ARG; goto done; }
+    grp[i] = (uint8_t)g;
+  }
+  uint32_t dead = 0;
+  for (uint32_t i = 0; i < n; ++i) {
+    if (alive && !alive[i]) { dead++; continue; }
+    cnt[(uint32_t)mode[i] * G + grp[i] + 1]++;
+  }
+  for (uint32_t s = 0; s < NS; ++s) cnt[s + 1] += cnt[s];
+  {
+    uint32_t* cur = (uint32_t*)malloc(((size_t)NS + 1) * sizeof(uint32_t));
+    if (!cur) { rc = MM_E_CAP; goto done; }
+    memcpy(cur, cnt, ((size_t)NS + 1) * sizeof(uint32_t));
+    for (uint32_t k = 0; k < n; ++k) {
+      uint32_t i = feed[k];
+      if (alive && !alive[i]) continue;
+      part[cur[(uint32_t)mode[i] * G + grp[i]]++] = i;
+    }
+    free(cur);
+  }
+  emits = (orc_emit*)malloc(((size_t)n + 1) * sizeof(orc_emit));
+  members = (uint64_t*)malloc(((size_t)n + 1) * sizeof(uint64_t));
+  if (!emits || !members) { rc = MM_E_CAP; goto done; }
+  uint32_t n_emits = 0; uint64_t n_mem = 0;
+#define ORC_CK(i) ((rating[i] < rmin - 1 ? rmin - 1 : (rating[i] > rmax + 1 ? rmax + 1 : rating[i])))
+  for (uint32_t s = 0; s < NS; ++s) {
+    const uint32_t L = (uint32_t)cfg->modes[s / G].teams * cfg->modes[s / G].team_size;
+    const uint32_t a = cnt[s], len = cnt[s + 1] - cnt[s];
+    uint32_t i = 0;
+    while (i + L <= len) {
+      const int64_t spread = (int64_t)ORC_CK(part[a + i + L - 1]) - (int64_t)ORC_CK(part[a + i]);
+      if (max_spread < 0 || spread <= max_spread) {
+        orc_emit* e = &emits[n_emits++];
+        e->mode = (uint8_t)(s / G); e->group = (uint8_t)(s % G); e->n_members = (uint16_t)L;
+        e->emit_seq = part[a + i + L - 1]; e->first_member = n_mem;
+        for (uint32_t j = 0; j < L; ++j) members[n_mem++] = id[part[a + i + j]];
+        i += L;
+      } else {
+        is_res[part[a + i]] = 1;
+        i += 1;
+      }
+    }
+    for (; i < len; ++i) is_res[part[a + i]] = 1;
+  }
+#undef ORC_CK
+  rc = orc_assemble(cfg, emits, n_emits, members, n_mem, out);
+  if (rc == MM_OK) {
+    uint32_t nres = 0;
+    for (uint32_t i = 0; i < n; ++i) nres += is_res[i];
+    out->residual_ids = (uint64_t*)malloc(((size_t)nres + 1) * sizeof(uint64_t));
+    if (!out->residual_ids) { rc = MM_E_CAP; goto done; }
+    uint32_t k = 0;
+    for (uint32_t i = 0; i < n; ++i) if (is_res[i]) out->residual_ids[k++] = id[i];
+    out->n_residual = k; out->n_dead = dead;
+  }
+done:
+  free(grp); free(feed); free(cnt); free(part); free(is_res); free(emits); free(members);
+  if (rc) orc_result_free(out);
+  return rc;
+}
+
+/* ------------------------------------------------------------------------- */
 /* timed legs                                                                   */
 /* ------------------------------------------------------------------------- */
 static double orc_now(void) {

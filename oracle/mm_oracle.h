@@ -72,6 +72,14 @@ int orc_run_closed_form(const mm_config* cfg, uint32_t order_mode, uint32_t n,
                         const uint64_t* id, const int32_t* rating, const uint8_t* mode,
                         const uint8_t* alive, orc_result* out);
 
+/* EXTENSION (not reference behaviour): strategist policy S1 — "a lobby may not span more
+ * than max_spread rating points".  Defined directly on the sorted partition, RATING order only: per (mode, group)
+ * partition sorted by (clamp(rating), enqueue order), i = 0; while i + L <= n: if key[i+L-1] - key[i] <= max_spread
+ * emit players i .. i+L-1 as a lobby and i += L, else player i stays queued and i += 1.  max_spread < 0 = unlimited
+ * (identical to S0).  Everything else (dead players, canonical lobby order, residual in enqueue order) as above.    */
+int orc_run_windowed(const mm_config* cfg, int32_t max_spread, uint32_t n, const uint64_t* id, const int32_t* rating,
+                     const uint8_t* mode, const uint8_t* alive, orc_result* out);
+
 /* Timed legs for bench.py.  Both run the LITERAL loop and return wall seconds
  * (setup — building the active set, routing by group — is outside the timer, as the
  * middleware / generic stages are outside the search stage).  n_threads==1: one

@@ -65,6 +65,8 @@ def lib():
             fn = getattr(L, name)
             fn.restype = C.c_int
             fn.argtypes = [C.POINTER(abi.Config), C.c_uint32, C.c_uint32, vp, vp, vp, vp, C.POINTER(OrcResult)]
+        L.orc_run_windowed.restype = C.c_int
+        L.orc_run_windowed.argtypes = [C.POINTER(abi.Config), C.c_int32, C.c_uint32, vp, vp, vp, vp, C.POINTER(OrcResult)]
         L.orc_result_free.restype = None
         L.orc_result_free.argtypes = [C.POINTER(OrcResult)]
         L.orc_time_literal.restype = C.c_double
@@ -124,6 +126,24 @@ def run_literal(cfg, ids, rating, mode, alive=None, order=None):
 def run_closed_form(cfg, ids, rating, mode, alive=None, order=None):
     return _run(lib().orc_run_closed_form, cfg, cfg.order_mode if order is None else order, ids, rating, mode, alive,
                 False)
+
+
+def run_windowed(cfg, max_spread, ids, rating, mode, alive=None):
+    """EXTENSION: policy S1 (a lobby spans at most max_spread rating points), RATING order; < 0 = unlimited."""
+    ids = np.ascontiguousarray(ids, dtype=np.uint64)
+    rating = np.ascontiguousarray(rating, dtype=np.int32)
+    mode = np.ascontiguousarray(mode, dtype=np.uint8)
+    if alive is not None:
+        alive = np.ascontiguousarray(alive, dtype=np.uint8)
+    r = OrcResult()
+    rc = lib().orc_run_windowed(C.byref(cfg), int(max_spread), len(ids), _ptr(ids), _ptr(rating), _ptr(mode), _ptr(alive),
+                                C.byref(r))
+    if rc != 0:
+        raise ValueError(f"oracle returned {rc}")
+    try:
+        return Result(r, True)
+    finally:
+        lib().orc_result_free(C.byref(r))
 
 
 def time_literal(cfg, ids, rating, mode, n_threads=1, order=None):

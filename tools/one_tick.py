@@ -18,4 +18,5 @@ flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 for i in range(2):
     eng.restore(); flush.fill_(1); torch.cuda.synchronize()
     st = eng.tick_device()
-    print(i, st.n_lobbies, st.device_us, st.place_us)
+    print(i, st.n_lobbies, "resid", st.n_residual, "dev", round(st.device_us, 1), "hist", round(st.hist_us, 1), "scan", round(st.scan_us, 1),
+          "place", round(st.place_us, 1), "epi", round(st.epilogue_us, 1), "dbg", st.reserved / 100.0)
