@@ -139,6 +139,8 @@ def main():
                          "(BASELINE configs[3]): ONE pool of the workload's size, rating groups dealt to the ranks")
     ap.add_argument("--two-modes", action="store_true", help="configure both default modes (1v1, 5v5), not just the workload's")
     ap.add_argument("--tick-impl", type=int, default=None, help="1 = one fused cooperative launch (default), 0 = four launches")
+    ap.add_argument("--max-spread", type=int, default=None,
+                    help="EXTENSION (policy S1, not the BASELINE workload): a lobby spans at most W rating points")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -163,7 +165,8 @@ def main():
     order = abi.MM_ORDER_RATING if args.order == "rating" else abi.MM_ORDER_ARRIVAL
     w = pkg.synth.WORKLOADS[args.workload]
     n, L = w["n"], (2 if w["mode"] == 0 else 10)
-    cfg, mode_idx = pkg.synth.workload_config(args.workload, order, n + 65536, device=local,
+    cap = n + 65536 + (n if (args.max_spread is not None and args.max_spread >= 0) else 0)  # S1 leaves players queued
+    cfg, mode_idx = pkg.synth.workload_config(args.workload, order, cap, device=local,
                                               single_mode=not args.two_modes)
     # rank r's shard of the N x n pool: its own seed stream (weak scaling, disjoint ids)
     ids, rating, mode, ts = pkg.synth.gen_pool(1, n, first=rank * n, mode=mode_idx)
@@ -186,6 +189,8 @@ def main():
         eng.set_option("rank_impl", args.rank_impl)
     if args.tick_impl is not None:
         eng.set_option("tick_impl", args.tick_impl)
+    if args.max_spread is not None:
+        eng.set_option("max_spread", args.max_spread)
     acc = eng.enqueue(ids, rating, mode, ts)
     assert acc.all()
     eng.snapshot()
@@ -234,6 +239,8 @@ def main():
             eng.set_option("rank_impl", args.rank_impl)
         if args.tick_impl is not None:
             eng.set_option("tick_impl", args.tick_impl)
+        if args.max_spread is not None:
+            eng.set_option("max_spread", args.max_spread)
         pin = lambda a: torch.from_numpy(a).pin_memory()
         h_ids, h_rating, h_mode, h_ts = pin(ids), pin(rating), pin(mode), pin(ts)
         h_acc = torch.empty(n, dtype=torch.uint8).pin_memory()
@@ -300,6 +307,9 @@ def main():
                        "players_total": total_players,
                        "lobby_size": L, "order": args.order, "ratings": "uniform 0..5000, seed 1",
                        "modes_configured": cfg.n_modes, "launches_per_tick": launches_per_tick,
+                       "policy": ("S0 (reference behaviour)" if args.max_spread is None or args.max_spread < 0 else
+                                  f"S1 extension: max lobby spread {args.max_spread} rating points"),
+                       "players_left_queued_per_step": int(st.n_residual),
                        "parallelism": f"rating-group shards x{world}, no collective",
                        "l2": "flushed between steps (256 MiB write); pool 180 MB > L2",
                        "timed_region": "mm_tick_device: the whole tick (k_tick: hist | column scan | placement | "

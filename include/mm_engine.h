@@ -192,6 +192,10 @@ int mm_set_stream(mm_engine* e, void* cuda_stream);
  *   "tick_impl"     1 = whole tick in one cooperative launch (default when it fits), 0 = four launches
  *   "rank_impl"     3 = TMA-fed tile kernel (default), 1 / 0 = first list / warp-serial kernels (cross-checks)
  *   "dense"         small-key-domain ranking: 2 = private byte counters (default), 1 = vote matrix, 0 = lists
+ *   "max_spread"    EXTENSION beyond the reference (strategist policy S1): a lobby may span at most
+ *                   `value` rating points — greedy walk over the rating-sorted partition, a player whose window cannot
+ *                   be filled stays queued (oracle: orc_run_windowed).  < 0 (default) = reference behaviour (S0).
+ *                   MM_ORDER_RATING only (MM_E_ARG otherwise).  Takes effect from the next tick.
  *   "rows_per_sm", "block", "place2_stages", "persist_mb"      occupancy / cache experiments
  *   "place_debug"   timing experiments that switch parts of the tick off — results are then INVALID        */
 int mm_set_option(mm_engine* e, const char* name, int64_t value);

@@ -119,6 +119,16 @@ static ERL_NIF_TERM nif_status(ErlNifEnv* env, int argc, const ERL_NIF_TERM argv
   return enif_make_tuple2(env, atom(env, "ok"), m);
 }
 
+/* set_max_spread(ref, w): extension knob (strategist policy S1); w < 0 restores the reference behaviour */
+static ERL_NIF_TERM nif_set_max_spread(ErlNifEnv* env, int argc, const ERL_NIF_TERM argv[]) {
+  engine_res* r; ErlNifSInt64 w = -1;
+  (void)argc;
+  if (!enif_get_resource(env, argv[0], ENGINE_T, (void**)&r) || !enif_get_int64(env, argv[1], &w))
+    return enif_make_badarg(env);
+  int rc = mm_set_option(r->e, "max_spread", (int64_t)w);
+  return rc ? err(env, rc) : atom(env, "ok");
+}
+
 static ErlNifFunc funcs[] = {
   {"new", 1, nif_new, ERL_NIF_DIRTY_JOB_CPU_BOUND},
   {"enqueue", 4, nif_enqueue, ERL_NIF_DIRTY_JOB_CPU_BOUND},
@@ -126,5 +136,6 @@ static ErlNifFunc funcs[] = {
   {"in_queue?", 2, nif_in_queue, ERL_NIF_DIRTY_JOB_CPU_BOUND},
   {"tick", 2, nif_tick, ERL_NIF_DIRTY_JOB_CPU_BOUND},
   {"status", 1, nif_status, 0},
+  {"set_max_spread", 2, nif_set_max_spread, 0},
 };
 ERL_NIF_INIT(Elixir.Matchmaking.Search.Engine, funcs, load, NULL, NULL, NULL)

@@ -47,4 +47,7 @@ defmodule Matchmaking.Search.Engine do
   def in_queue?(_ref, _id), do: :erlang.nif_error(:nif_not_loaded)
   def tick(_ref, _now_ms), do: :erlang.nif_error(:nif_not_loaded)
   def status(_ref), do: :erlang.nif_error(:nif_not_loaded)
+
+  @doc "Extension (not reference behaviour): maximum rating spread of a lobby for the following ticks; < 0 = off."
+  def set_max_spread(_ref, _w), do: :erlang.nif_error(:nif_not_loaded)
 end

@@ -484,28 +484,62 @@ __device__ __forceinline__ void colscan_tail_body(uint32_t* scratch, const TailA
     for (uint32_t v = K + tid; v < Kp; v += kScanBlock) s_m[v] = 0;
     __syncthreads();
     const int32_t W = t.max_spread;
-    for (uint32_t sg = tid; sg < n_segs; sg += kScanBlock) {
-      const uint32_t lo = s_lo[sg], hi = s_lo[sg + 1], L = t.seg_L[sg];
-      uint32_t pos = s_bb[lo], vmax = lo;
-      for (uint32_t v = lo; v < hi; ++v) {
-        const uint32_t b0 = s_bb[v], b1 = s_bb[v + 1];
-        if (b1 == b0) { s_m[v] = 0; continue; }
-        const uint32_t cur = pos > b0 ? pos : b0;
-        if (cur >= b1) { s_m[v] = b1 - b0; continue; }  // consumed by lobbies seeded in earlier bins
-        if (vmax < v) vmax = v;
-        const int32_t kv = (int32_t)keys[v];
-        while (vmax + 1 < hi && (int32_t)keys[vmax + 1] - kv <= W) ++vmax;
-        const uint32_t reach = s_bb[vmax + 1];  // positions < reach have key <= key_v + W
-        uint32_t k = 0;
-        if (cur + L <= reach) {
-          const uint32_t kw = (reach - L - cur) / L + 1, kb = (b1 - 1 - cur) / L + 1;
-          k = kw < kb ? kw : kb;
-        }
-        pos = cur + k * L;
-        if (pos >= b1) s_m[v] = b1 - b0;
-        else { s_m[v] = pos - b0; pos = b1; }
+    // One warp walks TWO partitions at a time (two independent carry chains in flight).  Per bin, off the chain:
+    //   reach  = sorted position where keys exceed key_v + W (binary search over the partition's keys)
+    //   rsel   = min(reach, b1 - 1 + L): the seeds of bin v are cur, cur + L, ... < min(b1, reach - L + 1), so with
+    //            a = rsel - cur the bin seeds a / L lobbies and p2 = rsel - a mod L is the next unconsumed position
+    // and on the chain only: cur = max(pos, b0); a; a mod L by a reciprocal multiply; p2; select.  Empty bins
+    // fall out of the same arithmetic (cur >= b1), so the 32 bins of a batch are visited by an unrolled loop.
+    for (uint32_t sg0 = warp; sg0 < n_segs; sg0 += 2 * NW) {
+      uint32_t lo[2], hi[2], L[2], Mrec[2], pos[2];
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        const uint32_t sg = sg0 + q * NW;
+        const bool on = sg < n_segs;
+        lo[q] = on ? s_lo[sg] : 0u; hi[q] = on ? s_lo[sg + 1] : 0u; L[q] = on ? t.seg_L[sg] : 1u;
+        Mrec[q] = 0xFFFFFFFFu / L[q];  // umulhi(a, Mrec) is a / L or a / L - 1 for every 32-bit a
+        pos[q] = s_bb[lo[q]];
+        if (on && lane == 0) t.seg[sg].n = s_bb[hi[q]] - s_bb[lo[q]];
       }
-      t.seg[sg].n = s_bb[hi] - s_bb[lo];
+      const uint32_t span0 = hi[0] - lo[0], span1 = hi[1] - lo[1], span = span0 > span1 ? span0 : span1;
+      for (uint32_t off = 0; off < span; off += 32) {
+        uint32_t b0[2], b1[2], rs[2], mine[2];
+        bool valid[2];
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          const uint32_t v = lo[q] + off + lane;
+          valid[q] = v < hi[q];
+          b0[q] = b1[q] = rs[q] = 0u; mine[q] = 0u;
+          if (valid[q]) {
+            b0[q] = s_bb[v]; b1[q] = s_bb[v + 1];
+            const int32_t lim = (int32_t)keys[v] + W;
+            uint32_t a = v, e = hi[q];  // last bin in [v, hi) with key <= lim
+            while (e - a > 1) { const uint32_t mid = (a + e) >> 1; if ((int32_t)keys[mid] <= lim) a = mid; else e = mid; }
+            const uint32_t reach = s_bb[a + 1], cap = b1[q] - 1 + L[q];
+            rs[q] = reach < cap ? reach : cap;
+          }
+        }
+#pragma unroll 8
+        for (int l = 0; l < 32; ++l) {
+#pragma unroll
+          for (int q = 0; q < 2; ++q) {
+            const uint32_t B0 = __shfl_sync(0xFFFFFFFFu, b0[q], l), B1 = __shfl_sync(0xFFFFFFFFu, b1[q], l);
+            const uint32_t RS = __shfl_sync(0xFFFFFFFFu, rs[q], l);
+            const uint32_t cur = pos[q] > B0 ? pos[q] : B0;
+            const uint32_t a = RS - cur;                      // meaningful when cur < B1 (then RS > cur)
+            uint32_t rem = a - __umulhi(a, Mrec[q]) * L[q];   // a mod L, or a mod L + L
+            rem = rem < rem - L[q] ? rem : rem - L[q];        // unsigned: picks the one below L
+            const uint32_t p2 = RS - rem;                     // next unconsumed position after this bin's lobbies
+            const bool inside = cur < B1, full = p2 >= B1;
+            const uint32_t m = (!inside || full) ? B1 - B0 : p2 - B0;  // matched players of the bin (a prefix)
+            pos[q] = !inside ? pos[q] : (full ? p2 : B1);     // the rest of a partly matched bin stays queued
+            if ((int)lane == l) mine[q] = m;
+          }
+        }
+#pragma unroll
+        for (int q = 0; q < 2; ++q)
+          if (valid[q]) s_m[lo[q] + off + lane] = mine[q];
+      }
     }
     __syncthreads();
     if (!m_smem) {  // very large key domain: the counts were parked in global memory; scan them in place of the bases
@@ -1121,24 +1155,22 @@ __device__ __forceinline__ void epilogue_body(uint32_t* scratch, PoolView src, P
     if (blockIdx.x == 0) ctr->n_resid = total;
   }
   __syncthreads();
-  for (uint32_t row = blockIdx.x; row < R; row += gridDim.x) {
-    const uint32_t off = s_off[row], cnt = s_off[row + 1] - off;
-    if (cnt == 0) continue;  // uniform for the CTA
-    const uint64_t beg64 = (uint64_t)row * chunk;
-    const uint32_t beg = beg64 < n ? (uint32_t)beg64 : n;
-    const uint32_t end = (beg64 + chunk < n) ? (uint32_t)(beg64 + chunk) : n;
-    const uint32_t nwords = (end - beg + 31) >> 5;  // beg is a multiple of 32 (chunk is a multiple of kRound)
-    const uint32_t* bits = left_bits + (beg >> 5);
-    // The slots of the set bits are enumerated into a shared-memory list (no memory latency); whenever the
-    // list is full, and at the end of the row, one thread per listed player gathers its record into the
-    // alternate pool buffer and re-stamps its active-set entry — all the dependent gather / hash-probe
-    // chains of a flush run in parallel, and neighbouring threads touch neighbouring slots.
-    uint32_t tbase = off, fill = 0;  // destination of s_list[0]; entries in the list (uniform)
-    __syncthreads();  // the previous row's last flush may still be reading s_list
+  // Work is split by leftover RANK, not by row: under policy S0 the leftovers are the latest arrivals of every
+  // partition and sit in the last rows of the pool.  CTA b moves the players with global rank [r0, r1); it walks
+  // the bit words of the rows holding them (popcount prefix from the start of the row), enumerates the pool
+  // slots of its ranks into a shared-memory list (no memory latency) and then, one thread per listed player,
+  // gathers the record into the alternate pool buffer and re-stamps the player's active-set entry — all the
+  // dependent gather / hash-probe chains run in parallel, neighbouring threads touch neighbouring slots.
+  const uint32_t per = (total + gridDim.x - 1) / gridDim.x;
+  const uint32_t r0 = (uint64_t)blockIdx.x * per < total ? blockIdx.x * per : total;
+  const uint32_t r1 = r0 + per < total ? r0 + per : total;
+  if (r1 > r0) {
+    uint32_t tbase = r0, fill = 0;  // global rank of s_list[0]; entries in the list (uniform)
+    uint32_t row_beg = 0;           // pool slot of the current row's first player
     auto flush = [&](uint32_t count, bool last) {
       __syncthreads();
       for (uint32_t e = tid; e < count; e += BLOCK) {
-        const uint32_t i = beg + s_list[e], t = tbase + e;
+        const uint32_t i = s_list[e], t = tbase + e;
         const uint64_t pid = src.id[i];
         dst.id[t] = pid; dst.rating[t] = src.rating[i]; dst.mode[t] = src.mode[i];
         dst.tsize[t] = src.tsize[i]; dst.ts[t] = src.ts[i]; dst.bin[t] = src.bin[i];
@@ -1153,40 +1185,61 @@ __device__ __forceinline__ void epilogue_body(uint32_t* scratch, PoolView src, P
         }
       }
       tbase += count;
-      if (!last) __syncthreads();  // the row's last flush runs on into the lobby headers: the few threads
-                                   // waiting on their gather / probe chains do not hold up the others
+      if (!last) __syncthreads();  // the last flush runs on into the lobby headers: the few threads waiting on
+                                   // their gather / probe chains do not hold up the others
     };
-    for (uint32_t w0 = 0; w0 < nwords; w0 += BLOCK) {  // BLOCK words = 32 * BLOCK players per step
-      const uint32_t wi = w0 + tid;
-      const uint32_t w = wi < nwords ? __ldcg(&bits[wi]) : 0u;
-      const uint32_t c = __popc(w);
-      uint32_t incl = c;
+    uint32_t row = 0;
+    {  // first row holding rank r0: smallest row with s_off[row + 1] > r0
+      uint32_t a = 0, e = R;
+      while (a < e) { const uint32_t mid = (a + e) >> 1; if (s_off[mid + 1] > r0) e = mid; else a = mid + 1; }
+      row = a;
+    }
+    for (; row < R && s_off[row] < r1; ++row) {
+      const uint32_t off = s_off[row], cnt = s_off[row + 1] - off;
+      if (cnt == 0) continue;  // uniform for the CTA
+      const uint64_t beg64 = (uint64_t)row * chunk;
+      const uint32_t beg = beg64 < n ? (uint32_t)beg64 : n;
+      const uint32_t end = (beg64 + chunk < n) ? (uint32_t)(beg64 + chunk) : n;
+      const uint32_t nwords = (end - beg + 31) >> 5;  // beg is a multiple of 32 (chunk is a multiple of kRound)
+      const uint32_t* bits = left_bits + (beg >> 5);
+      row_beg = beg;
+      const uint32_t lo_l = (r0 > off ? r0 : off) - off, hi_l = (r1 < off + cnt ? r1 : off + cnt) - off;  // row-local ranks
+      uint32_t run_l = 0;  // row-local rank of the step's first leftover player
+      for (uint32_t w0 = 0; w0 < nwords && run_l < hi_l; w0 += BLOCK) {  // BLOCK words = 32 * BLOCK players per step
+        const uint32_t wi = w0 + tid;
+        const uint32_t w = wi < nwords ? __ldcg(&bits[wi]) : 0u;
+        const uint32_t c = __popc(w);
+        uint32_t incl = c;
 #pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const uint32_t u = __shfl_up_sync(0xFFFFFFFFu, incl, o);
-        if (lane >= (uint32_t)o) incl += u;
-      }
-      if (lane == 31) s_tmp[warp] = incl;
-      __syncthreads();
-      uint32_t wbase = 0, wtot = 0;
-      for (uint32_t k = 0; k < NW; ++k) { const uint32_t v = s_tmp[k]; if (k < warp) wbase += v; wtot += v; }
-      const uint32_t lpre = wbase + incl - c;  // rank of this word's first leftover player within the step
-      if (fill + wtot > kLeftList && fill) { flush(fill, false); fill = 0; }
-      for (uint32_t p0 = 0; p0 < wtot; p0 += kLeftList) {  // one pass unless the step alone overflows the list
-        const uint32_t cp = wtot - p0 < kLeftList ? wtot - p0 : kLeftList;
-        if (c && lpre < p0 + cp && lpre + c > p0) {
-          uint32_t ww = w, r = lpre;
-          while (ww) {
-            const uint32_t bpos = __ffs(ww) - 1;
-            ww &= ww - 1;
-            if (r >= p0 && r < p0 + cp) s_list[fill + r - p0] = (wi << 5) + bpos;
-            ++r;
-          }
+        for (int o = 1; o < 32; o <<= 1) {
+          const uint32_t u = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+          if (lane >= (uint32_t)o) incl += u;
         }
-        fill += cp;
-        if (p0 + cp < wtot) { flush(fill, false); fill = 0; }
+        if (lane == 31) s_tmp[warp] = incl;
+        __syncthreads();
+        uint32_t wbase = 0, wtot = 0;
+        for (uint32_t k = 0; k < NW; ++k) { const uint32_t v = s_tmp[k]; if (k < warp) wbase += v; wtot += v; }
+        const uint32_t lpre = run_l + wbase + incl - c;  // row-local rank of this word's first leftover player
+        uint32_t q = lo_l > run_l ? lo_l : run_l;
+        const uint32_t q_end = hi_l < run_l + wtot ? hi_l : run_l + wtot;
+        while (q < q_end) {  // (uniform) ranks [q, q_end) of this step are mine
+          if (fill == kLeftList) { flush(fill, false); fill = 0; }
+          const uint32_t room = kLeftList - fill, take = q_end - q < room ? q_end - q : room;
+          if (c && lpre < q + take && lpre + c > q) {
+            uint32_t ww = w, r = lpre;
+            while (ww) {
+              const uint32_t bpos = __ffs(ww) - 1;
+              ww &= ww - 1;
+              if (r >= q && r < q + take) s_list[fill + (r - q)] = row_beg + (wi << 5) + bpos;
+              ++r;
+            }
+          }
+          fill += take;
+          q += take;
+        }
+        run_l += wtot;
+        __syncthreads();  // s_tmp is rewritten by the next step
       }
-      __syncthreads();  // s_tmp is rewritten by the next step
     }
     if (fill) flush(fill, true);
   }

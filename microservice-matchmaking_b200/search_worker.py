@@ -70,14 +70,42 @@ def player_handle(player_id):
     return h if h < 0xFFFFFFFFFFFFFFFE else h - 2
 
 
+class WindowSchedule:
+    """EXTENSION beyond the reference: time-expanded search window.
+
+    The reference stamps `created_at` on every queued player (active_user.ex:47) and never
+    reads it; its strategist decides without a notion of waiting time.  This schedule turns
+    the wait of the LONGEST-waiting queued player into the tick's maximum lobby spread
+    (strategist policy S1, mm_set_option("max_spread")):
+
+        W(now) = min(w_max, w0 + growth_per_s * (now - enqueue_time(oldest queued player)))
+
+    so a sparse pool relaxes until its oldest player can be matched and tightens again once
+    it has left.  One window per tick for the whole pool: the per-player form needs the
+    sorted order on the device first and is future work."""
+
+    def __init__(self, w0, growth_per_s, w_max):
+        self.w0, self.growth_per_s, self.w_max = int(w0), float(growth_per_s), int(w_max)
+
+    def spread(self, now, oldest_enqueued_at):
+        wait = 0.0 if oldest_enqueued_at is None else max(0.0, float(now) - float(oldest_enqueued_at))
+        return int(min(self.w_max, self.w0 + self.growth_per_s * wait))
+
+
 class SearchPool:
     """Owner of the GPU pool shared by every search worker of this node.
 
     engine: an object with the `Engine` API (enqueue / tick / remove / in_queue /
-    pool_size); mode_names: index -> "1v1", ...; group_names: index -> "bronze", ...
+    pool_size / set_option); mode_names: index -> "1v1", ...; group_names: index -> "bronze", ...
+    window: optional WindowSchedule (extension; needs MM_ORDER_RATING); clock: () -> seconds.
     """
 
-    def __init__(self, engine, mode_names, group_names, max_batch=65536):
+    def __init__(self, engine, mode_names, group_names, max_batch=65536, window=None, clock=None):
+        import time
+        self.window = window
+        self.clock = clock or time.monotonic
+        self.enqueued_at = {}  # handle -> clock() when the player became resident (insertion = enqueue order)
+        self.last_spread = None
         self.engine = engine
         self.mode_names = list(mode_names)
         self.mode_index = {m: i for i, m in enumerate(self.mode_names)}
@@ -97,6 +125,7 @@ class SearchPool:
         h = player_handle(player_id)
         self.engine.remove([h])
         self.players.pop(h, None)
+        self.enqueued_at.pop(h, None)
         return ("ok", "removed")
 
     # -- ingest -----------------------------------------------------------------------------
@@ -114,9 +143,12 @@ class SearchPool:
         rating = np.clip(np.array([s[1] for s in staged], np.int64), -(2 ** 31), 2 ** 31 - 1).astype(np.int32)
         mode = np.array([self.mode_index.get(s[2], 255) for s in staged], np.uint8)
         acc = self.engine.enqueue(ids, rating, mode, None)
+        t_resident = self.clock() if self.window else None
         for code, (h, _r, _m, player, worker, tag) in zip(acc, staged):
             if code == 1:
                 self.players[h] = player
+                if self.window:
+                    self.enqueued_at[h] = t_resident
                 self.stats["enqueued"] += 1
                 worker.ack(worker.channel_name, tag)       # worker.ex:323
             elif code == 0:                                 # "You are already in the queue."
@@ -131,12 +163,19 @@ class SearchPool:
     def tick(self, now=0):
         """One search tick; publishes each lobby like prepare_game_lobby/4. -> lobbies emitted"""
         self.flush()
+        if self.window:  # the oldest queued player is the first key: dicts keep insertion (= enqueue) order
+            oldest = next(iter(self.enqueued_at.values()), None)
+            self.last_spread = self.window.spread(self.clock(), oldest)
+            self.engine.set_option("max_spread", self.last_spread)
         lob, mem, _seq, _st = self.engine.tick(now)
         for h in lob:
             mode_name = self.mode_names[h["mode"]]
             group_name = self.group_names[h["group"]]
             first, n = int(h["first_member"]), int(h["n_members"])
             members = [self.players.pop(int(x)) for x in mem[first:first + n]]
+            if self.window:
+                for x in mem[first:first + n]:
+                    self.enqueued_at.pop(int(x), None)
             size = n // self._teams_of(h["mode"])
             teams = {f"team {t + 1}": members[t * size:(t + 1) * size] for t in range(n // size)}
             payload = json.dumps({"teams": teams, "game-mode": mode_name})      # worker.ex:315-318

@@ -90,6 +90,14 @@ class OracleEngine:
         self.q = [np.zeros(0, np.uint64), np.zeros(0, np.int32), np.zeros(0, np.uint8)]
         self.alive = np.zeros(0, np.uint8)
         self.active = set()
+        self.max_spread = -1
+
+    def set_option(self, name, value):
+        if name != "max_spread":
+            raise ValueError(name)
+        if value >= 0 and self.cfg.order_mode != self.abi.MM_ORDER_RATING:
+            raise ValueError("max_spread needs MM_ORDER_RATING")
+        self.max_spread = int(value)
 
     def enqueue(self, ids, rating, mode, enq_ts=None):
         ids = np.asarray(ids, np.uint64); rating = np.asarray(rating, np.int32); mode = np.asarray(mode, np.uint8)
@@ -126,7 +134,10 @@ class OracleEngine:
         return len(self.q[0])
 
     def tick(self, now=0):
-        ref = self.oracle.run_literal(self.cfg, *self.q, alive=self.alive)
+        if self.max_spread >= 0:
+            ref = self.oracle.run_windowed(self.cfg, self.max_spread, *self.q, alive=self.alive)
+        else:
+            ref = self.oracle.run_literal(self.cfg, *self.q, alive=self.alive)
         keep = np.isin(self.q[0], ref.residual_ids)
         self.q = [a[keep] for a in self.q]
         self.alive = np.ones(len(self.q[0]), np.uint8)

@@ -97,6 +97,49 @@ def test_worker_scenario_gpu(pkg):
     scenario(pkg, pkg.Engine)
 
 
+def window_scenario(pkg, engine_cls):
+    """EXTENSION: the pool-level time-expanded window (WindowSchedule) drives policy S1 tick by tick."""
+    cfg = pkg.synth.make_config(groups=pkg.synth.REFERENCE_GROUPS, order=1, capacity=10_000)
+    eng = engine_cls(cfg)
+    broker = FakeBroker()
+    now = [100.0]
+    pool = sw.SearchPool(eng, ["1v1", "5v5"], pkg.synth.REFERENCE_GROUP_NAMES,
+                         window=sw.WindowSchedule(w0=10, growth_per_s=20, w_max=400), clock=lambda: now[0])
+    for g in pkg.synth.REFERENCE_GROUP_NAMES:
+        sw.SearchWorker.start_link(broker, pool, {"group_name": g, "channel_name": f"search.{g}"})
+    broker.bind(sw.EXCHANGE_FORWARD, sw.QUEUE_FORWARD, sw.QUEUE_FORWARD)
+    for pid, r in (("a", 1000), ("b", 1008), ("c", 1100), ("d", 1300)):
+        publish_player(pkg, broker, cfg, pid, r, "1v1")
+    broker.deliver_all()
+    assert pool.tick() == 1 and pool.last_spread == 10         # a-b are 8 apart; c, d wait
+    last = json.loads(broker.queues[sw.QUEUE_FORWARD][-1][0])
+    assert [p["id"] for t in ("team 1", "team 2") for p in last["teams"][t]] == ["a", "b"]
+    now[0] += 2.0                                              # oldest queued (c) has waited 2 s -> W = 50
+    assert pool.tick() == 0 and pool.last_spread == 50
+    now[0] += 8.0                                              # 10 s -> W = 210 >= 200
+    assert pool.tick() == 1 and pool.last_spread == 210
+    last = json.loads(broker.queues[sw.QUEUE_FORWARD][-1][0])
+    assert [p["id"] for t in ("team 1", "team 2") for p in last["teams"][t]] == ["c", "d"]
+    publish_player(pkg, broker, cfg, "e", 1400, "1v1")
+    broker.deliver_all()
+    now[0] += 100.0
+    assert pool.tick() == 0 and pool.last_spread == 10         # e just arrived: the window is tight again
+    assert pool.in_queue("e") and not pool.enqueued_at.keys() - {sw.player_handle("e")}
+    pool.remove_user("e")
+    assert not pool.enqueued_at
+    assert pool.tick() == 0 and pool.last_spread == 10
+    eng.close()
+
+
+def test_window_schedule_cpu(pkg):
+    window_scenario(pkg, OracleEngine)
+
+
+@pytest.mark.gpu
+def test_window_schedule_gpu(pkg):
+    window_scenario(pkg, pkg.Engine)
+
+
 def test_start_link_contract(pkg):
     with pytest.raises(RuntimeError, match="group_name"):
         sw.prepare_config({})  # worker.ex:55-57

@@ -6,7 +6,9 @@ tick every `dt_ms`, p50/p99/p99.9 of the per-player queue->match latency
 measured in real time (the loop is paced with the wall clock; a tick that overruns its period is counted).
 Strict-parity mode: there are no time-expanded windows, so a player waits only until L-1 more
 players of its (mode, group) partition have arrived and the next tick fires.
-usage: python tools/stream_bench.py [rate=1e6] [seconds=2] [dt_ms=1,5] [groups=32] [mode=5v5]"""
+With max_spread=W (extension, policy S1) a lobby may span at most W rating points, so the pool accumulates the
+players whose neighbourhood is still sparse and the latency distribution grows a tail.
+usage: python tools/stream_bench.py [rate=1e6] [seconds=2] [dt_ms=1,5] [groups=32] [mode=5v5] [max_spread=-1]"""
 import importlib, json, os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
@@ -18,6 +20,7 @@ dts = [float(x) for x in args.get("dt_ms", "1,5").split(",")]
 G = int(args.get("groups", 32)); mode_name = args.get("mode", "5v5")
 modes = (("1v1", 2, 1),) if mode_name == "1v1" else (("5v5", 2, 5),)
 L = modes[0][1] * modes[0][2]
+W = int(args.get("max_spread", -1))
 
 for dt_ms in dts:
     dt = dt_ms * 1e-3
@@ -29,6 +32,7 @@ for dt_ms in dts:
     cfg = pkg.synth.make_config(n_groups=G, modes=modes, order=pkg.abi.MM_ORDER_RATING, capacity=1 << 20,
                                 active_capacity=4 * n_total)
     eng = pkg.Engine(cfg)
+    eng.set_option("max_spread", W)
     eng.enqueue(ids[:10], rating[:10], mode[:10]); eng.tick(); eng.remove(ids[:10])   # warm-up / allocation
     matched_at = np.full(n_total, np.nan)
     order = np.argsort(ids, kind="stable"); sorted_ids = ids[order]
@@ -55,7 +59,7 @@ for dt_ms in dts:
     lat = (matched_at - arrive)[10:lo]
     ok = ~np.isnan(lat)
     q = lambda p: float(np.percentile(lat[ok], p) * 1e3)
-    print(json.dumps({"workload": "stream", "rate_per_s": rate, "dt_ms": dt_ms, "seconds": seconds, "groups": G, "mode": mode_name,
+    print(json.dumps({"workload": "stream", "rate_per_s": rate, "dt_ms": dt_ms, "seconds": seconds, "groups": G, "mode": mode_name, "max_spread": W,
                       "players_enqueued": int(lo - 10), "matched": int(ok.sum()), "still_queued": int((~ok).sum()),
                       "latency_ms": {"p50": q(50), "p99": q(99), "p99.9": q(99.9), "max": q(100)},
                       "players_per_tick_mean": float(np.mean(per_tick)), "tick_device_us_mean": float(np.mean(tick_us)),
