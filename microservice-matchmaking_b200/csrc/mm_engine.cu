@@ -27,8 +27,7 @@ struct Pool {
 };
 
 struct Table {
-  unsigned long long* keys = nullptr;
-  unsigned long long* vals = nullptr;
+  unsigned long long* kv = nullptr;  // hcap x {key, value}
 };
 
 }  // namespace
@@ -156,13 +155,12 @@ void free_pool(Pool& p) {
 
 ActiveView act_view(mm_engine* e) {
   ActiveView a{};
-  if (e->use_active) { a.keys = e->tab[e->tcur].keys; a.vals = e->tab[e->tcur].vals; a.mask = e->hcap - 1; }
+  if (e->use_active) { a.keys.p = e->tab[e->tcur].kv; a.vals.p = e->tab[e->tcur].kv + 1; a.mask = e->hcap - 1; }
   return a;
 }
 
 int clear_table(mm_engine* e, Table& t) {
-  k_fill64<<<1024, 256, 0, e->stream>>>(t.keys, e->hcap, kEmptyKey);
-  k_fill64<<<1024, 256, 0, e->stream>>>(t.vals, e->hcap, kFreeVal);
+  k_fill_kv<<<1024, 256, 0, e->stream>>>(reinterpret_cast<ulonglong2*>(t.kv), e->hcap, kEmptyKey, kFreeVal);
   CK(cudaGetLastError());
   return MM_OK;
 }
@@ -326,7 +324,7 @@ int rehash(mm_engine* e) {
   Table& nt = e->tab[e->tcur ^ 1];
   int rc = clear_table(e, nt);
   if (rc) return rc;
-  ActiveView oldv = act_view(e), newv{nt.keys, nt.vals, e->hcap - 1};
+  ActiveView oldv = act_view(e), newv{{nt.kv}, {nt.kv + 1}, e->hcap - 1};
   k_rehash<<<2048, 256, 0, e->stream>>>(oldv, newv);
   CK(cudaGetLastError());
   CK(cudaStreamSynchronize(e->stream));
@@ -355,17 +353,24 @@ int enq_claim(mm_engine* e, uint32_t base, uint32_t cnt, const uint64_t* id, con
   return MM_OK;
 }
 
-// E2 + E3 over the whole batch: winners, stable append to the pool, commit, counters
-int enq_finish(mm_engine* e, uint32_t n, const uint64_t* id, const int32_t* rating, const uint8_t* mode, const uint32_t* ts,
-               uint8_t* accepted_dev, uint32_t* n_accepted) {
-  const uint32_t nb = (n + 255) / 256;
+// E2 + E3 on batch indices [base, base + cnt): winners, stable append to the pool (after the winners of the
+// earlier chunks: the running total lives in d_small[0]), commit
+int enq_append(mm_engine* e, uint32_t base, uint32_t cnt, const uint64_t* id, const int32_t* rating, const uint8_t* mode,
+               const uint32_t* ts) {
+  const uint32_t nb = (cnt + 255) / 256;
   Pool& p = e->pool[e->cur];
   ActiveView av = act_view(e);
-  k_enq_count<<<nb, 256, 0, e->stream>>>(n, av, e->d_hslot, e->d_code, e->d_blocksum);
+  k_enq_count<<<nb, 256, 0, e->stream>>>(base, cnt, av, e->d_hslot, e->d_code, e->d_blocksum);
   k_scan_small<<<1, 1024, 0, e->stream>>>(nb, e->d_blocksum, e->d_small);
-  k_enq_append<<<nb, 256, 0, e->stream>>>(n, id, rating, mode, ts, e->d_mode_tsize, av, e->d_hslot, e->d_code,
+  k_enq_append<<<nb, 256, 0, e->stream>>>(base, cnt, id, rating, mode, ts, e->d_mode_tsize, av, e->d_hslot, e->d_code,
                                           e->d_blocksum, p.v, p.n, e->capacity, e->gen, e->d_small + 1, bin_map(e));
   CK(cudaGetLastError());
+  return MM_OK;
+}
+
+// counters of the finished batch -> host state
+int enq_finish(mm_engine* e, uint32_t n, uint8_t* accepted_dev, uint32_t* n_accepted) {
+  Pool& p = e->pool[e->cur];
   CK(cudaMemcpyAsync(e->h_small, e->d_small, 16, cudaMemcpyDeviceToHost, e->stream));
   if (accepted_dev) CK(cudaMemcpyAsync(accepted_dev, e->d_code, n, cudaMemcpyDeviceToDevice, e->stream));
   CK(cudaStreamSynchronize(e->stream));
@@ -384,7 +389,8 @@ int enqueue_device_locked(mm_engine* e, uint32_t n, const uint64_t* id, const in
   int rc = enq_prepare(e, n);
   if (rc) return rc;
   if ((rc = enq_claim(e, 0, n, id, rating, mode))) return rc;
-  return enq_finish(e, n, id, rating, mode, ts, accepted, n_accepted);
+  if ((rc = enq_append(e, 0, n, id, rating, mode, ts))) return rc;
+  return enq_finish(e, n, accepted, n_accepted);
 }
 
 // Pin member_ids in a persisting L2 carve-out: the 8-byte scatter of k_place completes
@@ -681,7 +687,7 @@ int mm_create(const mm_config* cfg, mm_engine** out) {
     while (h * 3 < want * 4 + 64) h <<= 1;  // load factor <= 0.75 at active_capacity
     e->hcap = h;
     for (auto& t : e->tab) {
-      if (cudaMalloc(&t.keys, h * 8) != cudaSuccess || cudaMalloc(&t.vals, h * 8) != cudaSuccess) return bail(MM_E_CUDA);
+      if (cudaMalloc(&t.kv, h * 16) != cudaSuccess) return bail(MM_E_CUDA);
     }
     if ((rc = clear_table(e, e->tab[0]))) return bail(rc);
   }
@@ -723,7 +729,7 @@ int mm_destroy(mm_engine* e) {
   cudaSetDevice(e->device);
   if (e->stream) cudaStreamSynchronize(e->stream);
   free_pool(e->pool[0]); free_pool(e->pool[1]); free_pool(e->snap); cudaFree(e->d_left_bits);
-  for (auto& t : e->tab) { cudaFree(t.keys); cudaFree(t.vals); }
+  for (auto& t : e->tab) cudaFree(t.kv);
   cudaFree(e->d_lut); cudaFree(e->d_grp_lut); cudaFree(e->d_mode_tsize); cudaFree(e->d_seg_bin_lo); cudaFree(e->d_seg_L);
   cudaFree(e->d_M); cudaFree(e->d_tot); cudaFree(e->d_outbase); cudaFree(e->d_binlim); cudaFree(e->d_bin_seg);
   cudaFree(e->d_bin_key); cudaFree(e->d_seg); cudaFree(e->d_members); cudaFree(e->d_src_idx); cudaFree(e->d_hdr);
@@ -822,24 +828,23 @@ int mm_enqueue(mm_engine* e, uint32_t n, const uint64_t* id, const int32_t* rati
   CK(cudaSetDevice(e->device));
   int rc = enq_prepare(e, n);
   if (rc) return rc;
-  // Pipelined ingest: the host columns go up in chunks on the copy stream while the claim
-  // kernel of the previous chunk runs on the engine stream (the claim only needs id/rating/mode).
+  // Pipelined ingest: the host columns go up in chunks on the copy stream while the previous chunk's
+  // claim / dedupe / append kernels run on the engine stream — the whole device side of the ingest hides
+  // behind the PCIe transfer except for the last chunk.
   const uint32_t chunk = 1u << 20;
   for (uint32_t base = 0; base < n; base += chunk) {
     const uint32_t cnt = std::min(chunk, n - base);
     CK(cudaMemcpyAsync(e->d_in_id + base, id + base, (size_t)cnt * 8, cudaMemcpyHostToDevice, e->copy_stream));
     CK(cudaMemcpyAsync(e->d_in_rating + base, rating + base, (size_t)cnt * 4, cudaMemcpyHostToDevice, e->copy_stream));
     CK(cudaMemcpyAsync(e->d_in_mode + base, mode + base, (size_t)cnt, cudaMemcpyHostToDevice, e->copy_stream));
+    if (enq_ts)
+      CK(cudaMemcpyAsync(e->d_in_ts + base, enq_ts + base, (size_t)cnt * 4, cudaMemcpyHostToDevice, e->copy_stream));
     CK(cudaEventRecord(e->ev_copy, e->copy_stream));
     CK(cudaStreamWaitEvent(e->stream, e->ev_copy, 0));
     if ((rc = enq_claim(e, base, cnt, e->d_in_id, e->d_in_rating, e->d_in_mode))) return rc;
+    if ((rc = enq_append(e, base, cnt, e->d_in_id, e->d_in_rating, e->d_in_mode, enq_ts ? e->d_in_ts : nullptr))) return rc;
   }
-  if (enq_ts) {
-    CK(cudaMemcpyAsync(e->d_in_ts, enq_ts, (size_t)n * 4, cudaMemcpyHostToDevice, e->copy_stream));
-    CK(cudaEventRecord(e->ev_copy, e->copy_stream));
-    CK(cudaStreamWaitEvent(e->stream, e->ev_copy, 0));
-  }
-  rc = enq_finish(e, n, e->d_in_id, e->d_in_rating, e->d_in_mode, enq_ts ? e->d_in_ts : nullptr, nullptr, nullptr);
+  rc = enq_finish(e, n, nullptr, nullptr);
   if (rc) return rc;
   if (accepted) {
     CK(cudaMemcpyAsync(accepted, e->d_code, n, cudaMemcpyDeviceToHost, e->stream));

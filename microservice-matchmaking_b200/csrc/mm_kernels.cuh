@@ -69,10 +69,16 @@ struct TickCtr {
   unsigned long long t[8];  // fused kernel: %globaltimer (ns) at phase boundaries, CTA 0; [6],[7]: max over CTAs
 };
 
+// Active set slot = {key, value} adjacent in one 16-byte pair: the claim's CAS on the key and atomicMin on the
+// value, the winner check and the commit all touch the same 32-byte sector (one DRAM access instead of four).
+struct Strided64 {
+  unsigned long long* p;
+  __device__ __forceinline__ unsigned long long& operator[](uint64_t h) const { return p[2 * h]; }
+};
 struct ActiveView {
-  unsigned long long* keys;
-  unsigned long long* vals;
-  uint64_t mask;  // capacity - 1, 0 = no active set
+  Strided64 keys;  // keys[h] = kv[2h]
+  Strided64 vals;  // vals[h] = kv[2h + 1]
+  uint64_t mask;   // capacity - 1, 0 = no active set
 };
 
 __device__ __forceinline__ uint64_t hash64(uint64_t x) {
@@ -1380,14 +1386,18 @@ __global__ void k_enq_claim(uint32_t base, uint32_t n, const uint64_t* __restric
 }
 
 // E2: winners = entries whose PENDING index is their own; per-block winner counts.
-__global__ void k_enq_count(uint32_t n, ActiveView act, const uint64_t* __restrict__ hslot, uint8_t* __restrict__ code,
-                            uint32_t* __restrict__ blocksum) {
+// E2 / E3 run per ingest chunk — batch indices [base, base + n) — so that they overlap the
+// host-to-device copy of the next chunk; the lowest batch index wins a repeated id, and a chunk's
+// winners are final once every lower index has claimed.
+__global__ void k_enq_count(uint32_t base, uint32_t n, ActiveView act, const uint64_t* __restrict__ hslot,
+                            uint8_t* __restrict__ code, uint32_t* __restrict__ blocksum) {
   __shared__ uint32_t s_cnt;
   if (threadIdx.x == 0) s_cnt = 0;
   __syncthreads();
-  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t i = base + t;
   bool win = false;
-  if (i < n && code[i] == 1) {
+  if (t < n && code[i] == 1) {
     win = !act.mask || act.vals[hslot[i]] == (kPending | i);
     if (!win) code[i] = 0;  // a lower batch index holds the id
   }
@@ -1397,10 +1407,12 @@ __global__ void k_enq_count(uint32_t n, ActiveView act, const uint64_t* __restri
   if (threadIdx.x == 0) blocksum[blockIdx.x] = s_cnt;
 }
 
-// exclusive scan of blocksum (single CTA; nblocks is at most a few 10k)
+// exclusive scan of blocksum (single CTA; nblocks is at most a few 10k), continued from the
+// running total of the earlier chunks of the batch (*total), which it then advances
 __global__ void __launch_bounds__(1024) k_scan_small(uint32_t nb, uint32_t* __restrict__ v, uint32_t* __restrict__ total) {
   __shared__ uint32_t s_sum[1024];
   const uint32_t tid = threadIdx.x;
+  const uint32_t before = *total;
   const uint32_t per = (nb + 1023) / 1024;
   const uint32_t lo = tid * per, hi = (lo + per < nb) ? lo + per : nb;
   uint32_t local = 0;
@@ -1413,23 +1425,25 @@ __global__ void __launch_bounds__(1024) k_scan_small(uint32_t nb, uint32_t* __re
     s_sum[tid] += x;
     __syncthreads();
   }
-  uint32_t run = s_sum[tid] - local;
+  uint32_t run = before + s_sum[tid] - local;
   for (uint32_t i = lo; i < hi && i < nb; ++i) { const uint32_t x = v[i]; v[i] = run; run += x; }
-  if (tid == 1023) *total = s_sum[1023];
+  __syncthreads();  // everyone has read *total
+  if (tid == 1023) *total = before + s_sum[1023];
 }
 
 // E3: append winners to the pool in batch order (= enqueue order) and commit their
 // active-set entries.  Players past the pool capacity are rolled back with code 3.
-__global__ void k_enq_append(uint32_t n, const uint64_t* __restrict__ id, const int32_t* __restrict__ rating,
+__global__ void k_enq_append(uint32_t base, uint32_t n, const uint64_t* __restrict__ id, const int32_t* __restrict__ rating,
                              const uint8_t* __restrict__ mode, const uint32_t* __restrict__ ts,
                              const uint8_t* __restrict__ mode_tsize, ActiveView act, const uint64_t* __restrict__ hslot,
                              uint8_t* __restrict__ code, const uint32_t* __restrict__ blockoff, PoolView pool,
                              uint32_t n_pool, uint32_t capacity, uint32_t gen, uint32_t* __restrict__ n_rejected_cap,
                              BinMap bm) {
   __shared__ uint32_t s_warp[32];
-  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t i = base + t;
   const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const bool win = i < n && code[i] == 1;
+  const bool win = t < n && code[i] == 1;
   const uint32_t b = __ballot_sync(0xFFFFFFFFu, win);
   if (lane == 0) s_warp[warp] = __popc(b);
   __syncthreads();
@@ -1524,8 +1538,10 @@ __global__ void k_restamp(PoolView pool, uint32_t n_pool, ActiveView act, uint32
   }
 }
 
-__global__ void k_fill64(unsigned long long* p, uint64_t n, unsigned long long v) {
-  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) p[i] = v;
+// empty active set: every slot {EMPTY key, FREE value}
+__global__ void k_fill_kv(ulonglong2* p, uint64_t n, unsigned long long k, unsigned long long v) {
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
+    p[i] = make_ulonglong2(k, v);
 }
 
 }  // namespace mm
