@@ -188,6 +188,39 @@ def test_window_multi_tick_accumulation(pkg, oracle):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("n_modes", [5, 8])
+@pytest.mark.parametrize("W", [-1, 30])
+def test_large_key_domains_use_the_fallback_tail_layouts(pkg, oracle, n_modes, W):
+    """5 x 5003 bins: the scan tail reads the bin keys from global memory; 8 x 5003 bins: it also parks the matched
+    counts there (and the placement falls back to the first list / warp-serial kernels).  Both policies."""
+    shapes = (("1v1", 2, 1), ("2v2", 2, 2), ("3v3", 2, 3), ("5v5", 2, 5), ("solo4", 4, 1), ("duo3", 3, 2), ("6v6", 2, 6),
+              ("solo3", 3, 1))[:n_modes]
+    n = 120_011
+    cfg = pkg.synth.make_config(groups=pkg.synth.REFERENCE_GROUPS, modes=shapes, order=RATING, capacity=n)
+    ids, rating, mode, ts = small_pool(pkg, 31 + n_modes, n, n_modes=n_modes)
+    with pkg.Engine(cfg) as eng:
+        eng.set_option("max_spread", W)
+        assert eng.enqueue(ids, rating, mode, ts).all()
+        lob, mem, seq, st = eng.tick()
+        check(eng, oracle.run_windowed(cfg, W, ids, rating, mode), lob, mem, seq, st)
+
+
+@pytest.mark.gpu
+def test_window_many_partitions(pkg, oracle):
+    """64 groups x 4 modes = 256 partitions: every warp of the tail walks several pairs of partitions."""
+    shapes = (("1v1", 2, 1), ("2v2", 2, 2), ("3v3", 2, 3), ("5v5", 2, 5))
+    n = 400_009
+    cfg = pkg.synth.make_config(n_groups=64, modes=shapes, order=RATING, capacity=n)
+    ids, rating, mode, ts = small_pool(pkg, 64, n, n_modes=4, lo=0, hi=5001)
+    for W in (0, 6):
+        with pkg.Engine(cfg) as eng:
+            eng.set_option("max_spread", W)
+            assert eng.enqueue(ids, rating, mode, ts).all()
+            lob, mem, seq, st = eng.tick()
+            check(eng, oracle.run_windowed(cfg, W, ids, rating, mode), lob, mem, seq, st)
+
+
+@pytest.mark.gpu
 def test_window_rejected_in_arrival_order(pkg):
     cfg = pkg.synth.make_config(n_groups=4, order=ARRIVAL, capacity=1000)
     with pkg.Engine(cfg) as eng:
