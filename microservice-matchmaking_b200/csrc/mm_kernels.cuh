@@ -7,12 +7,15 @@
 //    each partition into lobbies of L"
 // which on the GPU is ONE stable counting sort over a small key domain:
 //   bin(player) = mode * stride + lut[clamp(rating)]          (K bins, K ~ 5k * modes)
-// followed by a per-(mode, group)-segment cut.  Kernels:
-//   k_hist     row histograms   M[row][bin]      (reads rating+mode, 5 B/player)
-//   k_colscan  column prefix + bin bases + per-segment lobby arithmetic (tiny)
-//   k_place    stable rank inside the row -> final lobby-major slot; scatters
-//              player_id straight to member_ids (reads 13 B/player, writes 8 B)
-//   k_epilogue residual players -> compacted pool (enqueue order kept) + lobby headers
+// followed by a per-(mode, group)-partition cut.  One cooperative launch, k_tick<512>, runs the four phases
+// (each also exists as a stand-alone kernel):
+//   k_hist3    row histograms M[row][bin] from the resident 16-bit bin column (2 B/player, TMA ring)
+//   k_colscan  column prefix of M + the tail: per bin, how many players are matched (a prefix of the bin) and the
+//              member slot of the first one — policy S0 (reference behaviour) or S1 (rating window, extension)
+//   k_place2   stable rank inside the row -> final lobby-major slot; scatters player_id straight to
+//              member_ids (reads 10 B/player, writes 8 B); players past their bin's prefix: one bit in left_bits
+//   k_epilogue leftover players -> compacted pool (enqueue order kept, work split by rank) + lobby headers
+// k_hist / k_place<0|1> are the round's first versions, kept as on-device cross-checks (rank_impl 0/1).
 // Integer/HBM-bound work: no tensor cores (BASELINE.json north_star).
 #pragma once
 #include <cuda_runtime.h>
