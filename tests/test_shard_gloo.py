@@ -22,7 +22,7 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, order, n, out_q):
+def _worker(rank, world, port, order, n, out_q, max_spread=-1):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -35,6 +35,8 @@ def _worker(rank, world, port, order, n, out_q):
     # the Generic stage's routing (generic/worker.ex:46-69): each rank keeps its groups' players
     mine = shard.route(cfg, rating, world) == rank
     eng = OracleEngine(cfg)
+    if max_spread >= 0:
+        eng.set_option("max_spread", max_spread)
     assert eng.enqueue(ids[mine], rating[mine], mode[mine]).all()
     lob, mem, seq, st = eng.tick()
     gathered = [None] * world
@@ -65,6 +67,31 @@ def test_sharded_equals_single_engine(pkg, oracle, world, order):
     ids, rating, _, _ = pkg.synth.gen_pool(5, n, bell=True)
     mode = rng.integers(0, 2, n).astype(np.uint8)
     ref = oracle.run_literal(cfg, ids, rating, mode)
+    assert np.array_equal(mlob, ref.lobbies)
+    assert np.array_equal(mmem, ref.member_ids)
+    assert np.array_equal(np.sort(mres), np.sort(ref.residual_ids))
+
+
+def test_sharded_rating_window_needs_no_exchange(pkg, oracle):
+    """EXTENSION: the S1 window is defined inside a (mode, group) partition, so it never crosses a shard boundary:
+    sharded ticks with max_spread merge to the single-engine result without any collective."""
+    n, world, W = 20_000, 2, 4
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, 1, n, q, W)) for r in range(world)]
+    for p in procs:
+        p.start()
+    mlob, mmem, mres = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    cfg = pkg.synth.make_config(n_groups=8, order=1, capacity=n)
+    rng = np.random.default_rng(3)
+    ids, rating, _, _ = pkg.synth.gen_pool(5, n, bell=True)
+    mode = rng.integers(0, 2, n).astype(np.uint8)
+    ref = oracle.run_windowed(cfg, W, ids, rating, mode)
+    assert ref.n_residual > 100 and ref.n_lobbies > 100
     assert np.array_equal(mlob, ref.lobbies)
     assert np.array_equal(mmem, ref.member_ids)
     assert np.array_equal(np.sort(mres), np.sort(ref.residual_ids))
