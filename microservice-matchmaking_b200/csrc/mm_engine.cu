@@ -672,7 +672,6 @@ int mm_create(const mm_config* cfg, mm_engine** out) {
       ok = allow_max_smem(e, k_hist3<512>) == cudaSuccess && allow_max_smem(e, k_hist3<1024>) == cudaSuccess;
     }
     if (ok && e->place2_stages) {
-      const int sz = (int)place2_smem(e, e->place2_stages);
       ok = allow_max_smem(e, k_place2<512>) == cudaSuccess &&
            allow_max_smem(e, k_place2<1024>) == cudaSuccess;
       e->rank_impl = 3;
@@ -792,7 +791,6 @@ int mm_set_option(mm_engine* e, const char* name, int64_t value) {
   if (!std::strcmp(name, "persist_mb")) return set_persist(e, value);
   if (!std::strcmp(name, "place2_stages")) {
     if (value < 1 || value > (int64_t)kMaxStages || place2_smem(e, (uint32_t)value) + 1024 > e->smem_optin) return MM_E_ARG;
-    const int sz = (int)place2_smem(e, (uint32_t)value);
     CK(allow_max_smem(e, k_place2<512>));
     CK(allow_max_smem(e, k_place2<1024>));
     e->place2_stages = (uint32_t)value;
