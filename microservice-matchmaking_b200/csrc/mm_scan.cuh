@@ -1,0 +1,246 @@
+// mm_scan.cuh — phase 2 of the tick: column scan of the histogram matrix + the tail (matched prefix per bin, policies S0 / S1)
+#pragma once
+#include "mm_common.cuh"
+
+namespace mm {
+
+// ---------------------------------------------------------------------------------------
+// k_colscan: exclusive prefix down every column of M.  A column CTA is 32 bins wide
+// (lanes = consecutive bins, coalesced) and 16 row-slices deep (warps): every thread sums
+// its slice of rows, the slices are scanned through shared memory, then the slice is
+// rewritten as running prefixes — one round trip of latency instead of R.
+// The LAST CTA of the grid runs concurrently as the "tail": bin totals (accumulated by
+// k_hist with global reductions) -> sorted position of every bin -> how many players of every
+// bin are matched under the tick's policy (always a PREFIX of the bin in enqueue order) ->
+//   outbase[v] = member slot of bin v's first player (exclusive scan of the matched counts)
+//   binlim[v]  = outbase[v] + matched players of bin v; a player at or past it stays queued.
+// ---------------------------------------------------------------------------------------
+constexpr uint32_t kMaxSegs = MM_MAX_GROUPS * MM_MAX_MODES;
+constexpr int kScanBlock = 512;
+constexpr uint32_t kColScratchWords = (kScanBlock / 32) * 33;      // column CTA scratch
+constexpr uint32_t kTailScratchWords = 64 + 4 + 4 * kMaxSegs + 4;  // tail CTA scratch, fixed part
+
+// one 32-bin column group: exclusive prefix down the rows of M (scratch: kColScratchWords)
+__device__ __forceinline__ void colscan_cols_body(uint32_t* scratch, uint32_t group, uint32_t R, uint32_t Kp,
+                                                  uint32_t* __restrict__ M) {
+  uint32_t(*s_part)[33] = reinterpret_cast<uint32_t(*)[33]>(scratch);
+  const uint32_t tid = threadIdx.x, x = tid & 31, y = tid >> 5;
+  constexpr uint32_t NY = kScanBlock / 32;
+  const uint32_t b = group * 32 + x;
+  const uint32_t rp = (R + NY - 1) / NY;
+  const uint32_t r0 = y * rp < R ? y * rp : R, r1 = (r0 + rp < R) ? r0 + rp : R;
+  constexpr int kU = 8;  // independent loads in flight per thread
+  uint32_t sum = 0;
+  if (b < Kp)
+    for (uint32_t r = r0; r < r1; r += kU) {
+      uint32_t v[kU];
+#pragma unroll
+      for (int k = 0; k < kU; ++k) v[k] = (r + k < r1) ? __ldcg(M + (size_t)(r + k) * Kp + b) : 0u;
+#pragma unroll
+      for (int k = 0; k < kU; ++k) sum += v[k];
+    }
+  s_part[y][x] = sum;
+  __syncthreads();
+  uint32_t run = 0;
+  for (uint32_t yy = 0; yy < y; ++yy) run += s_part[yy][x];
+  if (b < Kp)
+    for (uint32_t r = r0; r < r1; r += kU) {
+      uint32_t v[kU];
+#pragma unroll
+      for (int k = 0; k < kU; ++k) v[k] = (r + k < r1) ? __ldcg(M + (size_t)(r + k) * Kp + b) : 0u;
+#pragma unroll
+      for (int k = 0; k < kU; ++k) {
+        if (r + k < r1) M[(size_t)(r + k) * Kp + b] = run;
+        run += v[k];
+      }
+    }
+  __syncthreads();  // scratch may be reused by the next group
+}
+
+// arguments of the tail (shared by k_colscan and the fused k_tick)
+struct TailArgs {
+  uint32_t Kp, K, n_segs;
+  uint32_t layout;                    // bit 0: matched counts in shared memory; bit 1: bin keys too (tail_words)
+  int32_t max_spread;                 // < 0: unlimited (policy S0); >= 0: policy S1, rating order only
+  const uint32_t* tot;                // [Kp] bin totals (k_hist)
+  const uint32_t* seg_bin_lo;         // [n_segs + 1]
+  const uint32_t* seg_L;              // [n_segs]
+  const uint16_t* bin_seg;            // [Kp] bin -> segment
+  const uint16_t* bin_key;            // [Kp] bin -> clamp key (rating order: ascending inside a segment)
+  uint32_t* outbase;                  // [Kp] out: member slot of the bin's first player
+  uint32_t* binlim;                   // [Kp] out: outbase + matched players of the bin
+  SegInfo* seg;                       // [n_segs] out
+  TickCtr* ctr;
+};
+// shared-memory words of the tail for a layout: bases | matched counts (bit 0) | keys (bit 1)
+__host__ __device__ constexpr uint32_t tail_words(uint32_t Kp, uint32_t layout) {
+  return kTailScratchWords + (Kp + 2) + ((layout & 1u) ? (Kp + 2) : 0u) + ((layout & 2u) ? (Kp + 3) / 2 : 0u);
+}
+
+// The tail.  One pipeline for both policies:
+//   bin totals -> bases s_bb -> matched prefix of every bin -> member slot of the bin's first player.
+// S0 (reference behaviour): a (mode, group) partition of n players emits floor(n/L) lobbies, the n mod L
+//   highest-ranked players stay queued: member slot = sorted position - leftovers of earlier partitions,
+//   clipped at the partition's matched end (closed form, only a scan over the partitions).
+// S1 (extension): greedy windowed walk over the partition (oracle: orc_run_windowed).  Players of one bin have
+//   the same key, so the walk runs on the histogram: from position cur in bin v, lobbies are seeded at
+//   cur, cur+L, ... while the seed is still in bin v and its L-th player has key <= key_v + W; whatever is
+//   left of bin v afterwards cannot seed and stays queued.  Two-pointer over the bins of the segment.
+// Very large key domains (layout bit 0 clear) park m_v in global memory and scan it in place of the bases.
+__device__ __forceinline__ void colscan_tail_body(uint32_t* scratch, const TailArgs t) {
+  constexpr uint32_t NW = kScanBlock / 32;
+  uint32_t* s_tmp = scratch;            // [64]
+  uint32_t* s_misc = scratch + 64;      // [4] fullest bin
+  uint32_t* s_a = scratch + 68;         // [kMaxSegs] leftovers of earlier segments / member base
+  uint32_t* s_lob = s_a + kMaxSegs;     // [kMaxSegs] lobbies of earlier segments
+  uint32_t* s_nl = s_lob + kMaxSegs;    // [kMaxSegs] lobbies of the segment
+  uint32_t* s_lo = s_nl + kMaxSegs;     // [kMaxSegs + 1] first bin of the segment
+  uint32_t* s_bb = scratch + kTailScratchWords;  // [Kp + 1] sorted position of the bin's first player
+  const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, Kp = t.Kp, K = t.K, n_segs = t.n_segs;
+  if (tid == 0) s_misc[0] = 0;
+  for (uint32_t sg = tid; sg <= n_segs; sg += kScanBlock) s_lo[sg] = t.seg_bin_lo[sg];
+  __syncthreads();
+  uint32_t lmax = 0;
+  for (uint32_t i = tid; i < Kp; i += kScanBlock) {  // coalesced, independent loads
+    const uint32_t v = __ldcg(&t.tot[i]);
+    s_bb[i] = v;
+    if (i < K && v > lmax) lmax = v;
+  }
+  lmax = __reduce_max_sync(0xFFFFFFFFu, lmax);
+  if ((tid & 31) == 0 && lmax) atomicMax(&s_misc[0], lmax);
+  __syncthreads();
+  const uint32_t total = block_excl_scan<kScanBlock>(s_bb, Kp, s_tmp);
+  if (tid == 0) s_bb[Kp] = total;
+  __syncthreads();
+  const uint32_t alive = s_bb[K], dead = total - alive;
+  uint32_t n_matched, tot_lob;
+
+  if (t.max_spread < 0) {
+    // S0: lobbies_s = n_s / L; the partition's first lobbies_s * L sorted positions are matched.
+    for (uint32_t sg = tid; sg < n_segs; sg += kScanBlock) {
+      const uint32_t ns = s_bb[s_lo[sg + 1]] - s_bb[s_lo[sg]], nl = ns / t.seg_L[sg];
+      s_nl[sg] = nl; s_lob[sg] = nl; s_a[sg] = ns - nl * t.seg_L[sg];
+      t.seg[sg].n = ns; t.seg[sg].n_lobbies = nl;
+    }
+    __syncthreads();
+    const uint32_t n_left = block_excl_scan<kScanBlock>(s_a, n_segs, s_tmp);   // -> leftovers of earlier segments
+    tot_lob = block_excl_scan<kScanBlock>(s_lob, n_segs, s_tmp);               // -> lobbies of earlier segments
+    n_matched = alive - n_left;
+    for (uint32_t sg = warp; sg < n_segs; sg += NW) {  // one warp per partition: no bin -> segment lookups
+      const uint32_t lo = s_lo[sg], hi = s_lo[sg + 1], start = s_bb[lo], shift = s_a[sg];
+      const uint32_t mend = start + s_nl[sg] * t.seg_L[sg];  // end of the partition's matched positions
+      for (uint32_t v = lo + lane; v < hi; v += 32) {
+        const uint32_t b0 = s_bb[v], b1 = s_bb[v + 1];
+        t.outbase[v] = (b0 < mend ? b0 : mend) - shift;
+        t.binlim[v] = (b1 < mend ? b1 : mend) - shift;
+      }
+      if (lane == 0) { t.seg[sg].member_base = start - shift; t.seg[sg].lobby_base = s_lob[sg]; }
+    }
+    for (uint32_t v = K + tid; v < Kp; v += kScanBlock) { t.outbase[v] = n_matched; t.binlim[v] = n_matched; }
+  } else {
+    // S1: greedy windowed walk on the histogram, one thread per partition (see above), then a second scan.
+    const bool m_smem = (t.layout & 1u) != 0, key_smem = (t.layout & 2u) != 0;
+    uint32_t* s_m = m_smem ? s_bb + Kp + 2 : t.binlim;  // [Kp + 1] matched players of the bin
+    uint16_t* s_key = reinterpret_cast<uint16_t*>(s_bb + (m_smem ? 2 : 1) * (Kp + 2));
+    const uint16_t* keys = key_smem ? s_key : t.bin_key;
+    if (key_smem)
+      for (uint32_t v = tid; v < K; v += kScanBlock) s_key[v] = t.bin_key[v];
+    for (uint32_t v = K + tid; v < Kp; v += kScanBlock) s_m[v] = 0;
+    __syncthreads();
+    const int32_t W = t.max_spread;
+    // One warp walks TWO partitions at a time (two independent carry chains in flight).  Per bin, off the chain:
+    //   reach  = sorted position where keys exceed key_v + W (binary search over the partition's keys)
+    //   rsel   = min(reach, b1 - 1 + L): the seeds of bin v are cur, cur + L, ... < min(b1, reach - L + 1), so with
+    //            a = rsel - cur the bin seeds a / L lobbies and p2 = rsel - a mod L is the next unconsumed position
+    // and on the chain only: cur = max(pos, b0); a; a mod L by a reciprocal multiply; p2; select.  Empty bins
+    // fall out of the same arithmetic (cur >= b1), so the 32 bins of a batch are visited by an unrolled loop.
+    for (uint32_t sg0 = warp; sg0 < n_segs; sg0 += 2 * NW) {
+      uint32_t lo[2], hi[2], L[2], Mrec[2], pos[2];
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        const uint32_t sg = sg0 + q * NW;
+        const bool on = sg < n_segs;
+        lo[q] = on ? s_lo[sg] : 0u; hi[q] = on ? s_lo[sg + 1] : 0u; L[q] = on ? t.seg_L[sg] : 1u;
+        Mrec[q] = 0xFFFFFFFFu / L[q];  // umulhi(a, Mrec) is a / L or a / L - 1 for every 32-bit a
+        pos[q] = s_bb[lo[q]];
+        if (on && lane == 0) t.seg[sg].n = s_bb[hi[q]] - s_bb[lo[q]];
+      }
+      const uint32_t span0 = hi[0] - lo[0], span1 = hi[1] - lo[1], span = span0 > span1 ? span0 : span1;
+      for (uint32_t off = 0; off < span; off += 32) {
+        uint32_t b0[2], b1[2], rs[2], mine[2];
+        bool valid[2];
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          const uint32_t v = lo[q] + off + lane;
+          valid[q] = v < hi[q];
+          b0[q] = b1[q] = rs[q] = 0u; mine[q] = 0u;
+          if (valid[q]) {
+            b0[q] = s_bb[v]; b1[q] = s_bb[v + 1];
+            const int32_t lim = (int32_t)keys[v] + W;
+            uint32_t a = v, e = hi[q];  // last bin in [v, hi) with key <= lim
+            while (e - a > 1) { const uint32_t mid = (a + e) >> 1; if ((int32_t)keys[mid] <= lim) a = mid; else e = mid; }
+            const uint32_t reach = s_bb[a + 1], cap = b1[q] - 1 + L[q];
+            rs[q] = reach < cap ? reach : cap;
+          }
+        }
+#pragma unroll 8
+        for (int l = 0; l < 32; ++l) {
+#pragma unroll
+          for (int q = 0; q < 2; ++q) {
+            const uint32_t B0 = __shfl_sync(0xFFFFFFFFu, b0[q], l), B1 = __shfl_sync(0xFFFFFFFFu, b1[q], l);
+            const uint32_t RS = __shfl_sync(0xFFFFFFFFu, rs[q], l);
+            const uint32_t cur = pos[q] > B0 ? pos[q] : B0;
+            const uint32_t a = RS - cur;                      // meaningful when cur < B1 (then RS > cur)
+            uint32_t rem = a - __umulhi(a, Mrec[q]) * L[q];   // a mod L, or a mod L + L
+            rem = rem < rem - L[q] ? rem : rem - L[q];        // unsigned: picks the one below L
+            const uint32_t p2 = RS - rem;                     // next unconsumed position after this bin's lobbies
+            const bool inside = cur < B1, full = p2 >= B1;
+            const uint32_t m = (!inside || full) ? B1 - B0 : p2 - B0;  // matched players of the bin (a prefix)
+            pos[q] = !inside ? pos[q] : (full ? p2 : B1);     // the rest of a partly matched bin stays queued
+            if ((int)lane == l) mine[q] = m;
+          }
+        }
+#pragma unroll
+        for (int q = 0; q < 2; ++q)
+          if (valid[q]) s_m[lo[q] + off + lane] = mine[q];
+      }
+    }
+    __syncthreads();
+    if (!m_smem) {  // very large key domain: the counts were parked in global memory; scan them in place of the bases
+      for (uint32_t v = tid; v < Kp; v += kScanBlock) s_bb[v] = s_m[v];
+      s_m = s_bb;
+      __syncthreads();
+    }
+    // member slots = exclusive scan of the matched counts (members of successive partitions are contiguous)
+    n_matched = block_excl_scan<kScanBlock>(s_m, Kp, s_tmp);
+    if (tid == 0) s_m[Kp] = n_matched;
+    __syncthreads();
+    for (uint32_t v = tid; v < Kp; v += kScanBlock) {
+      t.outbase[v] = s_m[v];
+      t.binlim[v] = s_m[v + 1];  // = outbase + matched players of the bin
+    }
+    for (uint32_t sg = tid; sg < n_segs; sg += kScanBlock) {
+      const uint32_t mb = s_m[s_lo[sg]], nl = (s_m[s_lo[sg + 1]] - mb) / t.seg_L[sg];
+      s_lob[sg] = nl;
+      t.seg[sg].n_lobbies = nl; t.seg[sg].member_base = mb;
+    }
+    __syncthreads();
+    tot_lob = block_excl_scan<kScanBlock>(s_lob, n_segs, s_tmp);
+    for (uint32_t sg = tid; sg < n_segs; sg += kScanBlock) t.seg[sg].lobby_base = s_lob[sg];
+  }
+  if (tid == 0) {
+    t.ctr->n_lobbies = tot_lob; t.ctr->n_matched = n_matched; t.ctr->n_alive = alive; t.ctr->n_dead = dead;
+    // expected players of the fullest bin per tile of one row (players spread evenly over rows)
+    const uint64_t npool = (uint64_t)alive + dead;
+    t.ctr->heavy = ((uint64_t)s_misc[0] * kTile > 4ull * (npool ? npool : 1)) ? 1u : 0u;
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(kScanBlock) k_colscan(uint32_t R, uint32_t* __restrict__ M, const TailArgs t) {
+  extern __shared__ __align__(16) uint32_t scratch[];  // max(kColScratchWords, tail_words(Kp, layout)) words
+  if (blockIdx.x + 1 < gridDim.x) colscan_cols_body(scratch, blockIdx.x, R, t.Kp, M);
+  else colscan_tail_body(scratch, t);
+}
+
+}  // namespace mm
