@@ -169,6 +169,13 @@ int mm_tick(mm_engine* e, uint64_t now, mm_lobby_hdr* lobbies, uint32_t lobby_ca
             uint64_t* member_ids, uint64_t member_cap, uint32_t* emit_seq,
             mm_tick_stats* stats);
 
+/* With mm_set_option("async_results", 1) mm_tick returns as soon as the tick is done and its host copies are
+ * queued: the caller's buffers are valid only after mm_results_wait (or the next mm_tick / mm_tick_device, which wait
+ * first).  mm_enqueue / mm_remove / mm_in_queue may run meanwhile — the next batch's host-to-device transfer overlaps
+ * the previous tick's device-to-host transfer.  What replaces it: nothing (the reference publishes lobby by lobby,
+ * search/worker.ex:250-261); it is the batched hand-off of SURVEY §8f-1.  No-op when nothing is pending.            */
+int mm_results_wait(mm_engine* e);
+
 /* Same tick, results stay in HBM; pointers valid until the next tick/destroy.      */
 int mm_tick_device(mm_engine* e, uint64_t now, mm_tick_stats* stats);
 int mm_results_device(mm_engine* e, const mm_lobby_hdr** d_lobbies,
@@ -196,6 +203,7 @@ int mm_set_stream(mm_engine* e, void* cuda_stream);
  *                   `value` rating points — greedy walk over the rating-sorted partition, a player whose window cannot
  *                   be filled stays queued (oracle: orc_run_windowed).  < 0 (default) = reference behaviour (S0).
  *                   MM_ORDER_RATING only (MM_E_ARG otherwise).  Takes effect from the next tick.
+ *   "async_results" 1 = mm_tick does not wait for its device-to-host copies (see mm_results_wait); default 0
  *   "rows_per_sm", "block", "place2_stages", "persist_mb"      occupancy / cache experiments
  *   "place_debug"   timing experiments that switch parts of the tick off — results are then INVALID        */
 int mm_set_option(mm_engine* e, const char* name, int64_t value);

@@ -85,6 +85,7 @@ PROTOTYPES = {
     "mm_pool_size": (C.c_int, [_vp, _P(C.c_uint32)]),
     "mm_active_size": (C.c_int, [_vp, _P(C.c_uint32)]),
     "mm_tick": (C.c_int, [_vp, C.c_uint64, _vp, C.c_uint32, _vp, C.c_uint64, _vp, _P(TickStats)]),
+    "mm_results_wait": (C.c_int, [_vp]),
     "mm_tick_device": (C.c_int, [_vp, C.c_uint64, _P(TickStats)]),
     "mm_results_device": (C.c_int, [_vp, _P(_vp), _P(_vp)]),
     "mm_pool_read": (C.c_int, [_vp, C.c_uint32, _vp, _vp, _vp, _vp, _vp, _P(C.c_uint32)]),

@@ -43,6 +43,8 @@ struct mm_engine {
   bool own_stream = true;
   cudaStream_t copy_stream = nullptr;  // H2D of ingest chunks, overlapped with the claim kernels
   cudaEvent_t ev_copy = nullptr;
+  cudaStream_t d2h_stream = nullptr;   // async_results: a tick's host copies, overlapped with the next ingest
+  bool async_results = false, results_pending = false;
   cudaEvent_t ev[5]{};  // tick start | after hist | after colscan | after place | after epilogue
   char last_err[512] = {0};
 
@@ -566,6 +568,15 @@ int tick_commit(mm_engine* e, uint32_t n, mm_tick_stats* stats) {
   return MM_OK;
 }
 
+// async_results: the previous tick's host copies must land before its device buffers are overwritten
+int wait_results(mm_engine* e) {
+  if (e->results_pending) {
+    CK(cudaStreamSynchronize(e->d2h_stream));
+    e->results_pending = false;
+  }
+  return MM_OK;
+}
+
 }  // namespace
 
 // =======================================================================================
@@ -635,6 +646,7 @@ int mm_create(const mm_config* cfg, mm_engine** out) {
   e->smem_optin = prop.sharedMemPerBlockOptin;
   e->smem_sm = prop.sharedMemPerMultiprocessor;
   if (cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) != cudaSuccess) return bail(MM_E_CUDA);
+  if (cudaStreamCreateWithFlags(&e->d2h_stream, cudaStreamNonBlocking) != cudaSuccess) return bail(MM_E_CUDA);
   if (cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
       cudaEventCreateWithFlags(&e->ev_copy, cudaEventDisableTiming) != cudaSuccess)
     return bail(MM_E_CUDA);
@@ -740,6 +752,7 @@ int mm_destroy(mm_engine* e) {
   for (auto& ev : e->ev)
     if (ev) cudaEventDestroy(ev);
   if (e->stream && e->own_stream) cudaStreamDestroy(e->stream);
+  if (e->d2h_stream) { cudaStreamSynchronize(e->d2h_stream); cudaStreamDestroy(e->d2h_stream); }
   if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
   if (e->ev_copy) cudaEventDestroy(e->ev_copy);
   cudaGetLastError();
@@ -774,6 +787,12 @@ int mm_set_option(mm_engine* e, const char* name, int64_t value) {
     return MM_OK;
   }
   if (!std::strcmp(name, "dense")) { e->dense_ok = (int)value; return MM_OK; }
+  if (!std::strcmp(name, "async_results")) {
+    int rcw = wait_results(e);
+    if (rcw) return rcw;
+    e->async_results = value != 0;
+    return MM_OK;
+  }
   if (!std::strcmp(name, "max_spread")) {
     // EXTENSION (policy S1): a lobby spans at most `value` rating points; < 0 restores the reference behaviour.
     // Defined on the rating-sorted partition, so MM_ORDER_RATING only (oracle: orc_run_windowed).
@@ -904,11 +923,19 @@ int mm_active_size(mm_engine* e, uint32_t* n) {
   return MM_OK;
 }
 
+int mm_results_wait(mm_engine* e) {
+  if (!e) return MM_E_ARG;
+  std::lock_guard<std::mutex> lk(e->mu);
+  CK(cudaSetDevice(e->device));
+  return wait_results(e);
+}
+
 int mm_tick_device(mm_engine* e, uint64_t now, mm_tick_stats* stats) {
   (void)now;  // strict-parity mode has no time-expanded window
   if (!e) return MM_E_ARG;
   std::lock_guard<std::mutex> lk(e->mu);
   CK(cudaSetDevice(e->device));
+  { int rcw = wait_results(e); if (rcw) return rcw; }
   const uint32_t n = e->pool[e->cur].n;
   e->last_fused = use_fused(e);
   if (e->last_fused) {
@@ -939,6 +966,7 @@ int mm_tick(mm_engine* e, uint64_t now, mm_lobby_hdr* lobbies, uint32_t lobby_ca
   const uint32_t n = e->pool[e->cur].n;
   uint32_t chunk = 0;
   int rc;
+  if ((rc = wait_results(e))) return rc;
   // worst-case output sizes known up front -> the fused single launch is safe
   e->last_fused = use_fused(e) && (!lobbies || (uint64_t)lobby_cap >= n / e->min_L) && (!member_ids || member_cap >= n);
   if (e->last_fused) {
@@ -962,12 +990,16 @@ int mm_tick(mm_engine* e, uint64_t now, mm_lobby_hdr* lobbies, uint32_t lobby_ca
   if ((rc = tick_commit(e, n, stats))) return rc;
 copy_out:
   const TickCtr& c = *e->h_ctr;
+  // the tick is complete here (tick_commit synchronised the engine stream); with async_results the copies run on
+  // their own stream and the call returns: the caller may ingest the next batch meanwhile (PCIe is full duplex)
+  cudaStream_t cs = e->async_results ? e->d2h_stream : e->stream;
   if (lobbies && c.n_lobbies)
-    CK(cudaMemcpyAsync(lobbies, e->d_hdr, (size_t)c.n_lobbies * sizeof(mm_lobby_hdr), cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaMemcpyAsync(lobbies, e->d_hdr, (size_t)c.n_lobbies * sizeof(mm_lobby_hdr), cudaMemcpyDeviceToHost, cs));
   if (member_ids && c.n_matched)
-    CK(cudaMemcpyAsync(member_ids, e->d_members, (size_t)c.n_matched * 8, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaMemcpyAsync(member_ids, e->d_members, (size_t)c.n_matched * 8, cudaMemcpyDeviceToHost, cs));
   if (emit_seq && c.n_lobbies)
-    CK(cudaMemcpyAsync(emit_seq, e->d_emit_seq, (size_t)c.n_lobbies * 4, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaMemcpyAsync(emit_seq, e->d_emit_seq, (size_t)c.n_lobbies * 4, cudaMemcpyDeviceToHost, cs));
+  if (e->async_results) { e->results_pending = true; return MM_OK; }
   CK(cudaStreamSynchronize(e->stream));
   return MM_OK;
 }

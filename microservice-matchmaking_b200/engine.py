@@ -169,8 +169,13 @@ class Engine:
                 continue
             self._check(rc, "mm_tick")
             break
+        self.results_wait()  # no-op unless the "async_results" option is on
         nl, nm = st.n_lobbies, st.n_matched
         return lob[:nl], mem[:nm], (seq[:nl] if seq is not None else None), st
+
+    def results_wait(self):
+        """Block until the host buffers of the last mm_tick are filled ("async_results" mode)."""
+        self._check(self.lib.mm_results_wait(self.h), "mm_results_wait")
 
     def tick_device(self, now=0):
         st = abi.TickStats()

@@ -459,3 +459,36 @@ def test_large_lobbies_and_many_groups(pkg, oracle):
         lob, mem, seq, st = eng.tick()
         assert_tick_matches(eng, oracle.run_literal(cfg, ids, rating, mode), lob, mem, seq, st)
         assert set(np.unique(lob["n_members"])) <= {100, 32}
+
+
+def test_async_results_complete_under_the_next_ingest(pkg, oracle):
+    """mm_set_option("async_results", 1): mm_tick returns with its host copies queued; the next batch is ingested
+    meanwhile; the buffers are valid after mm_results_wait and equal the blocking tick's."""
+    import torch
+    n = 400_000
+    cfg = pkg.synth.make_config(n_groups=8, order=RATING, capacity=2 * n, active_capacity=4 * n)
+    a = make_pool(pkg, 71, n)
+    b_ids, b_rating, _, b_ts = pkg.synth.gen_pool(72, n, first=10 ** 9)
+    b_mode = (np.arange(n) % 2).astype(np.uint8)
+    lob_h = torch.empty(n, dtype=torch.int64).pin_memory()
+    mem_h = torch.empty(n, dtype=torch.int64).pin_memory()
+    seq_h = torch.empty(n, dtype=torch.int32).pin_memory()
+    with pkg.Engine(cfg) as eng:
+        eng.set_option("async_results", 1)
+        assert eng.enqueue(*a).all()
+        st = eng.tick_raw(lob_h.data_ptr(), n, mem_h.data_ptr(), n, seq_h.data_ptr())
+        assert eng.enqueue(b_ids, b_rating, b_mode, b_ts).all()  # overlaps the copies of the tick above
+        eng.results_wait()
+        ref = oracle.run_closed_form(cfg, a[0], a[1], a[2])
+        assert (st.n_lobbies, st.n_matched) == (ref.n_lobbies, ref.n_matched)
+        lob = lob_h.numpy()[:st.n_lobbies].view(ref.lobbies.dtype)
+        assert np.array_equal(lob, ref.lobbies)
+        assert np.array_equal(mem_h.numpy()[:st.n_matched].view(np.uint64), ref.member_ids)
+        assert np.array_equal(seq_h.numpy()[:st.n_lobbies].view(np.uint32), ref.emit_seq)
+        # the second tick sees the leftovers of the first + batch B, and waits for nothing that is not there
+        keep = np.isin(a[0], ref.residual_ids)
+        q = [np.concatenate([x[keep], y]) for x, y in zip(a[:3], (b_ids, b_rating, b_mode))]
+        lob2, mem2, seq2, st2 = eng.tick()
+        assert_tick_matches(eng, oracle.run_closed_form(cfg, *q), lob2, mem2, seq2, st2)
+        eng.results_wait()  # no-op
+        eng.set_option("async_results", 0)
