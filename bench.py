@@ -306,15 +306,20 @@ def main():
             tl2 = torch.tensor([tot_pipe], device="cuda", dtype=torch.float64)
             dist.all_reduce(tl2)
             tot_pipe = float(tl2.item())
-        e2e = {"value": tot_pipe / e2e_s, "unit": "lobbies/s",
+        pipelined = {"value": tot_pipe / e2e_s, "ms_per_step": 1e3 * e2e_s, "steps": S,
+                     "call": "per step: mm_enqueue(pinned host columns) + mm_tick(host lobbies / member_ids) with "
+                             "mm_set_option(async_results): a tick's device-to-host copies complete under the next "
+                             "step's ingest; mm_results_wait after the last step, inside the timed region"}
+        sequential = {"value": total_lobbies_per_step / seq_s, "ms_per_step": 1e3 * seq_s, "steps": len(times),
+                      "enqueue_ms": 1e3 * seq_enq_s, "tick_and_d2h_ms": 1e3 * (seq_s - seq_enq_s),
+                      "call": "blocking mm_enqueue(pinned host columns) + blocking mm_tick(host lobbies / member_ids), "
+                              "one step at a time"}
+        best = pipelined if pipelined["value"] >= sequential["value"] else sequential  # both include every copy
+        e2e = {"value": best["value"], "unit": "lobbies/s",
                "h2d_bytes_per_step": n * (8 + 4 + 1 + 4), "d2h_bytes_per_step": n + st2.n_matched * 8 + st2.n_lobbies * 8,
-               "ms_per_step": 1e3 * e2e_s, "steps": S,
-               "call": "per step: mm_enqueue(pinned host columns) + mm_tick(host lobbies / member_ids) with "
-                       "mm_set_option(async_results): a tick's device-to-host copies complete under the next step's "
-                       "ingest; mm_results_wait after the last step, inside the timed region",
-               "sequential": {"value": total_lobbies_per_step / seq_s, "ms_per_step": 1e3 * seq_s,
-                              "enqueue_ms": 1e3 * seq_enq_s, "tick_and_d2h_ms": 1e3 * (seq_s - seq_enq_s),
-                              "call": "blocking mm_enqueue + blocking mm_tick, one step at a time"}}
+               "ms_per_step": best["ms_per_step"], "steps": best["steps"], "call": best["call"],
+               "mode": "pipelined" if best is pipelined else "sequential",
+               "pipelined": pipelined, "sequential": sequential}
     eng.close()
     clocks = sampler.stop()  # sampled across the device-timed ticks and the e2e steps
 
