@@ -25,7 +25,17 @@ CASES = {
     "reference_groups_rating": (pkg.synth.REFERENCE_GROUPS, pkg.synth.MODES_DEFAULT, 1, 3000, 12, True, 0.02, 0.05),
     "config1_1k_one_group_1v1": (1, (("1v1", 2, 1),), 0, 1000, 1, False, 0.0, 0.0),
     "g8_rating_three_modes": (8, (("1v1", 2, 1), ("5v5", 2, 5), ("3v3v3", 3, 3)), 1, 5000, 13, False, 0.0, 0.03),
+    # EXTENSION (policy S1, rating window — see WINDOW below): produced by orc_run_windowed
+    "g8_rating_window6": (8, (("1v1", 2, 1), ("5v5", 2, 5)), 1, 5000, 14, False, 0.0, 0.03),
+    "reference_groups_window25": (pkg.synth.REFERENCE_GROUPS, pkg.synth.MODES_DEFAULT, 1, 3000, 15, True, 0.02, 0.05),
 }
+WINDOW = {"g8_rating_window6": 6, "reference_groups_window25": 25}  # max lobby spread; absent = reference policy S0
+
+
+def run_oracle(name, cfg, ids, rating, mode, alive):
+    if name in WINDOW:
+        return oracle.run_windowed(cfg, WINDOW[name], ids, rating, mode, alive)
+    return oracle.run_literal(cfg, ids, rating, mode, alive)
 
 
 def build(name):
@@ -46,8 +56,9 @@ def build(name):
 if __name__ == "__main__":
     for name in CASES:
         cfg, ids, rating, mode, alive = build(name)
-        r = oracle.run_literal(cfg, ids, rating, mode, alive)
+        r = run_oracle(name, cfg, ids, rating, mode, alive)
+        rank = r.emission_rank if r.emission_rank is not None else np.zeros(0, np.uint32)
         np.savez_compressed(os.path.join(HERE, name + ".npz"), ids=ids, rating=rating, mode=mode, alive=alive,
                             lobbies=r.lobbies, member_ids=r.member_ids, emit_seq=r.emit_seq,
-                            emission_rank=r.emission_rank, residual_ids=r.residual_ids)
+                            emission_rank=rank, residual_ids=r.residual_ids)
         print(name, r.n_lobbies, "lobbies", r.n_matched, "matched", r.n_residual, "residual", r.n_dead, "dead")

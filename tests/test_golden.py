@@ -20,6 +20,12 @@ def test_oracle_reproduces_golden(oracle, name):
     g = load(name)
     for k, v in (("ids", ids), ("rating", rating), ("mode", mode), ("alive", alive)):
         assert np.array_equal(g[k], v), f"generator drifted: {k}"
+    if name in mk.WINDOW:  # extension: policy S1
+        r = oracle.run_windowed(cfg, mk.WINDOW[name], ids, rating, mode, alive)
+        assert np.array_equal(r.lobbies, g["lobbies"]) and np.array_equal(r.member_ids, g["member_ids"])
+        assert np.array_equal(r.emit_seq, g["emit_seq"]) and np.array_equal(r.residual_ids, g["residual_ids"])
+        assert r.n_residual > 100 and r.n_lobbies > 100  # the window really bites in these fixtures
+        return
     for fn in (oracle.run_literal, oracle.run_closed_form):
         r = fn(cfg, ids, rating, mode, alive)
         assert np.array_equal(r.lobbies, g["lobbies"]) and np.array_equal(r.member_ids, g["member_ids"])
@@ -33,6 +39,7 @@ def test_engine_reproduces_golden(pkg, name):
     cfg, ids, rating, mode, alive = mk.build(name)
     g = load(name)
     with pkg.Engine(cfg) as eng:
+        eng.set_option("max_spread", mk.WINDOW.get(name, -1))
         assert eng.enqueue(ids, rating, mode).all()
         eng.remove(ids[alive == 0])
         lob, mem, seq, st = eng.tick()
