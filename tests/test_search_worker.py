@@ -160,3 +160,40 @@ def test_player_handle_is_stable_and_in_range():
     h = sw.player_handle("c0a8012e-1c9b-4b7e-9d2f-5f1d3a2b4c6d")
     assert h == sw.player_handle("c0a8012e-1c9b-4b7e-9d2f-5f1d3a2b4c6d") and 0 <= h < 2 ** 64 - 2
     assert len({sw.player_handle(f"p{i}") for i in range(10000)}) == 10000
+
+
+def test_malformed_and_overflowing_deliveries(pkg):
+    """nack: no id / no game mode / no rating / pool full; float ratings between the integer ranges take the default
+    group (generic/worker.ex:46-53); batches are flushed at max_batch without waiting for the tick."""
+    cfg = pkg.synth.make_config(groups=pkg.synth.REFERENCE_GROUPS, order=0, capacity=4)
+    eng = OracleEngine(cfg)
+    broker = FakeBroker()
+    pool = sw.SearchPool(eng, ["1v1", "5v5"], pkg.synth.REFERENCE_GROUP_NAMES, max_batch=2)
+    for g in pkg.synth.REFERENCE_GROUP_NAMES:
+        sw.SearchWorker.start_link(broker, pool, {"group_name": g, "channel_name": f"search.{g}"})
+    q = sw.generate_queue_name("gold")
+    ex = sw.generate_exchange_name("gold")
+    broker.publish(ex, q, json.dumps({"rating": 2100, "game-mode": "1v1"}))                 # no id
+    broker.publish(ex, q, json.dumps({"id": "x1", "rating": 2100}))                        # no game mode
+    broker.publish(ex, q, json.dumps({"id": "x2", "game-mode": "1v1"}))                    # no rating
+    assert broker.deliver_all() == 3 and len(broker.nacked) == 3 and not broker.acked
+    broker.publish(ex, q, json.dumps({"id": "f1", "rating": 1499.5, "game-mode": "5v5"}))  # default group (diamond)
+    broker.publish(ex, q, json.dumps({"id": "f2", "detail": {"rating": 2100}, "game-mode": "5v5"}))
+    broker.deliver_all()
+    assert len(broker.acked) == 2 and pool.stats["enqueued"] == 2  # max_batch = 2: flushed before any tick
+    groups = {pkg.synth.REFERENCE_GROUP_NAMES[oracle_group(cfg, r)] for r in eng.pool_read()["rating"].tolist()}
+    assert groups == {"diamond", "gold"}
+    for i in range(4):                                                                       # capacity is 4
+        broker.publish(ex, q, json.dumps({"id": f"c{i}", "rating": 2100 + i, "game-mode": "5v5"}))
+    broker.deliver_all()
+    pool.flush()
+    assert pool.stats["enqueued"] == 4 and pool.stats["invalid"] == 2 and len(broker.nacked) == 5
+    assert pool.tick() == 0 and pool.in_queue("c0") and not pool.in_queue("c3")
+    assert pool.remove_user("nobody") == ("ok", "removed")  # ActiveUser.remove_user/1 is idempotent
+    ok, st = next(iter(pool.workers.values())).status()
+    assert ok == "ok" and st["pool"]["message_count"] == 4
+
+
+def oracle_group(cfg, rating):
+    from oracle import oracle as orc
+    return orc.find_rating_group(cfg, rating)
