@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define MM_ABI_VERSION 1u
+#define MM_ABI_VERSION 2u
 
 #define MM_MAX_GROUPS 64u   /* rating groups (reference default: 7, config.exs:27-36) */
 #define MM_MAX_MODES 8u     /* game modes ("1v1", "5v5", ...)                         */
@@ -54,6 +54,9 @@ typedef enum mm_order_mode { MM_ORDER_ARRIVAL = 0, MM_ORDER_RATING = 1 } mm_orde
 
 /* mm_config.flags */
 #define MM_F_NO_DEDUPE 1u /* skip the "already in the queue" check (middleware/worker.ex:65-70) */
+#define MM_F_DENSE_IDS 2u /* player ids are dense host handles 0 .. active_capacity-1 (the host owns the
+                             UUID <-> handle table): the active set is a direct-mapped array instead of a hash
+                             table, and the packed entry points (mm_enqueue_packed / mm_tick_packed) apply.        */
 
 typedef struct mm_mode_desc {
   uint16_t teams;     /* T: number of teams ("1v1" -> 2, "5v5" -> 2)   */
@@ -74,7 +77,7 @@ typedef struct mm_config {
   mm_mode_desc modes[MM_MAX_MODES];
   uint32_t order_mode;      /* mm_order_mode */
   uint32_t capacity;        /* max players resident in the pool           */
-  uint32_t active_capacity; /* max ids in the active set (0 = 2*capacity) */
+  uint32_t active_capacity; /* max ids in the active set (0 = 2*capacity); MM_F_DENSE_IDS: handle range */
   int32_t device;           /* CUDA device ordinal                        */
   uint32_t flags;
 } mm_config;
@@ -129,8 +132,11 @@ int mm_group_of(const mm_config* cfg, int32_t rating);
  * request to the group queue (generic/worker.ex:55-69).  Players are appended in
  * call order = enqueue order.  accepted[i]: 1 = queued, 0 = "already in the queue"
  * (also for a repeat inside the same batch: first occurrence wins), 2 = invalid
- * mode / rating without a default group, 3 = pool or active set full.
- * enq_ts may be NULL (stored as 0).                                                 */
+ * mode / id / rating without a default group, 3 = pool full (the LAST players of the
+ * batch that do not fit).  A batch the active set cannot hold at all (more than
+ * active_capacity ids resident) is refused as a whole with MM_E_CAP — nothing is
+ * enqueued, the caller nacks / retries after mm_remove.  enq_ts may be NULL (stored 0).
+ * Every offered player (accepted or not) consumes one enqueue sequence number.     */
 int mm_enqueue(mm_engine* e, uint32_t n, const uint64_t* id, const int32_t* rating,
                const uint8_t* mode, const uint32_t* enq_ts, uint8_t* accepted);
 /* Same, all five pointers are DEVICE pointers (accepted may be NULL).              */
@@ -138,11 +144,19 @@ int mm_enqueue_device(mm_engine* e, uint32_t n, const uint64_t* id, const int32_
                       const uint8_t* mode, const uint32_t* enq_ts, uint8_t* accepted,
                       uint32_t* n_accepted);
 
+/* Packed ingest for MM_F_DENSE_IDS engines — 6 bytes per player over PCIe instead of 17:
+ * handle = the host's dense slot of the player (what the device stores as the id),
+ * key = mode << 13 | rating with rating in 0 .. 8191 (other ratings: use mm_enqueue).
+ * Same semantics and accepted codes as mm_enqueue.                                  */
+int mm_enqueue_packed(mm_engine* e, uint32_t n, const uint32_t* handle, const uint16_t* key,
+                      const uint32_t* enq_ts, uint8_t* accepted);
+
 /* Replaces ActiveUser.remove_user/1 (models/active_user.ex:57-66; callers
  * game-lobby/worker.ex:80,96).  A removed id that is still queued is dropped by the
  * next tick exactly as remove_inactive_players/1 filters it
  * (search/worker.ex:267-280).  Unknown ids are ignored, like Mnesia.delete.         */
 int mm_remove(mm_engine* e, uint32_t n, const uint64_t* id, uint32_t* n_removed);
+int mm_remove_packed(mm_engine* e, uint32_t n, const uint32_t* handle, uint32_t* n_removed);
 
 /* Replaces ActiveUser.in_queue?/1 (models/active_user.ex:33-44), batched.          */
 int mm_in_queue(mm_engine* e, uint32_t n, const uint64_t* id, uint8_t* out);
@@ -160,14 +174,21 @@ int mm_active_size(mm_engine* e, uint32_t* n_ids);
  *
  * mm_tick copies results to host buffers: lobbies[0..n_lobbies) ordered by
  * (mode, group, emission order inside the (mode, group) partition) and
- * member_ids[0..n_matched).  emit_seq (may be NULL) receives, per lobby, the pool
- * position (enqueue rank among the players resident at tick start) of the member
- * whose arrival completed it: sorting lobbies by emit_seq reproduces the serialized
- * reference's emission order in ORDER_ARRIVAL.
+ * member_ids[0..n_matched).  emit_seq (may be NULL) receives, per lobby, the enqueue
+ * sequence number (mod 2^32; the i-th player offered to the k-th mm_enqueue call has
+ * number (players offered by earlier calls) + i) of the member whose arrival
+ * completed it: sorting lobbies by emit_seq reproduces the serialized reference's
+ * emission order in ORDER_ARRIVAL.
  * MM_E_CAP if lobby_cap / member_cap are too small (nothing is consumed).           */
 int mm_tick(mm_engine* e, uint64_t now, mm_lobby_hdr* lobbies, uint32_t lobby_cap,
             uint64_t* member_ids, uint64_t member_cap, uint32_t* emit_seq,
             mm_tick_stats* stats);
+
+/* Same tick, members returned as 32-bit host handles (MM_F_DENSE_IDS engines): 4 bytes per
+ * matched player over PCIe instead of 8.                                            */
+int mm_tick_packed(mm_engine* e, uint64_t now, mm_lobby_hdr* lobbies, uint32_t lobby_cap,
+                   uint32_t* member_handles, uint64_t member_cap, uint32_t* emit_seq,
+                   mm_tick_stats* stats);
 
 /* With mm_set_option("async_results", 1) mm_tick returns as soon as the tick is done and its host copies are
  * queued: the caller's buffers are valid only after mm_results_wait (or the next mm_tick / mm_tick_device, which wait
@@ -181,7 +202,7 @@ int mm_tick_device(mm_engine* e, uint64_t now, mm_tick_stats* stats);
 int mm_results_device(mm_engine* e, const mm_lobby_hdr** d_lobbies,
                       const uint64_t** d_member_ids);
 
-/* Copy the queued players (enqueue order, dead ones skipped) to host buffers; any
+/* Copy the queued players (global enqueue order, dead ones skipped) to host buffers; any
  * pointer may be NULL.  Test/diagnostic aid and the body of Search.Worker.status/0's
  * queue-depth report (search/worker.ex:326-334).                                    */
 int mm_pool_read(mm_engine* e, uint32_t cap, uint64_t* id, int32_t* rating, uint8_t* mode,
@@ -195,17 +216,15 @@ int mm_restore(mm_engine* e);
 /* Use an externally owned CUDA stream (cudaStream_t passed as void*).              */
 int mm_set_stream(mm_engine* e, void* cuda_stream);
 
-/* Tuning / debugging knobs (name -> value); unknown name or bad value = MM_E_ARG.
+/* Options (name -> value); unknown name or bad value = MM_E_ARG.
  *   "tick_impl"     1 = whole tick in one cooperative launch (default when it fits), 0 = four launches
- *   "rank_impl"     3 = TMA-fed tile kernel (default), 1 / 0 = first list / warp-serial kernels (cross-checks)
- *   "dense"         small-key-domain ranking: 2 = private byte counters (default), 1 = vote matrix, 0 = lists
+ *   "rank_impl"     3 = per tile: ballot counting sort staged in shared memory for partitions of <= 255 bins, hashed
+ *                   lists otherwise (default); 2 = hashed lists for every tile (cross-check of the two rankings)
  *   "max_spread"    EXTENSION beyond the reference (strategist policy S1): a lobby may span at most
  *                   `value` rating points — greedy walk over the rating-sorted partition, a player whose window cannot
  *                   be filled stays queued (oracle: orc_run_windowed).  < 0 (default) = reference behaviour (S0).
  *                   MM_ORDER_RATING only (MM_E_ARG otherwise).  Takes effect from the next tick.
- *   "async_results" 1 = mm_tick does not wait for its device-to-host copies (see mm_results_wait); default 0
- *   "rows_per_sm", "block", "place2_stages", "persist_mb"      occupancy / cache experiments
- *   "place_debug"   timing experiments that switch parts of the tick off — results are then INVALID        */
+ *   "async_results" 1 = mm_tick does not wait for its device-to-host copies (see mm_results_wait); default 0   */
 int mm_set_option(mm_engine* e, const char* name, int64_t value);
 
 const char* mm_strerror(int status);

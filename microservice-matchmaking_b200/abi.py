@@ -5,7 +5,7 @@ the test-side oracle wrapper (oracle/oracle.py), which shares `mm_config`.
 """
 import ctypes as C
 
-MM_ABI_VERSION = 1
+MM_ABI_VERSION = 2
 MM_MAX_GROUPS = 64
 MM_MAX_MODES = 8
 MM_MODE_DEAD = 0xFF
@@ -21,6 +21,7 @@ MM_ORDER_ARRIVAL = 0
 MM_ORDER_RATING = 1
 
 MM_F_NO_DEDUPE = 1
+MM_F_DENSE_IDS = 2
 
 
 class ModeDesc(C.Structure):
@@ -80,11 +81,14 @@ PROTOTYPES = {
     "mm_group_of": (C.c_int, [_P(Config), C.c_int32]),
     "mm_enqueue": (C.c_int, [_vp, C.c_uint32, _vp, _vp, _vp, _vp, _vp]),
     "mm_enqueue_device": (C.c_int, [_vp, C.c_uint32, _vp, _vp, _vp, _vp, _vp, _P(C.c_uint32)]),
+    "mm_enqueue_packed": (C.c_int, [_vp, C.c_uint32, _vp, _vp, _vp, _vp]),
     "mm_remove": (C.c_int, [_vp, C.c_uint32, _vp, _P(C.c_uint32)]),
+    "mm_remove_packed": (C.c_int, [_vp, C.c_uint32, _vp, _P(C.c_uint32)]),
     "mm_in_queue": (C.c_int, [_vp, C.c_uint32, _vp, _vp]),
     "mm_pool_size": (C.c_int, [_vp, _P(C.c_uint32)]),
     "mm_active_size": (C.c_int, [_vp, _P(C.c_uint32)]),
     "mm_tick": (C.c_int, [_vp, C.c_uint64, _vp, C.c_uint32, _vp, C.c_uint64, _vp, _P(TickStats)]),
+    "mm_tick_packed": (C.c_int, [_vp, C.c_uint64, _vp, C.c_uint32, _vp, C.c_uint64, _vp, _P(TickStats)]),
     "mm_results_wait": (C.c_int, [_vp]),
     "mm_tick_device": (C.c_int, [_vp, C.c_uint64, _P(TickStats)]),
     "mm_results_device": (C.c_int, [_vp, _P(_vp), _P(_vp)]),

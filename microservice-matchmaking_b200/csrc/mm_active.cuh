@@ -1,4 +1,4 @@
-// mm_active.cuh — active set (GPU hash table) and pool ingest kernels
+// mm_active.cuh — active set (GPU hash table / direct-mapped handle table) and pool ingest kernels
 #pragma once
 #include "mm_common.cuh"
 
@@ -6,34 +6,53 @@ namespace mm {
 
 // =======================================================================================
 // Active set (replaces the Mnesia table of models/active_user.ex) + pool ingest.
-// Open addressing, linear probing.  keys: EMPTY / TOMB / id.  vals: FREE (all ones) when
-// the key is not committed, PENDING|batch_index while an enqueue batch is being resolved,
-// (pool_generation << 32 | pool_slot) once the player is queued.
+// Hashed mode: open addressing, linear probing; keys EMPTY / TOMB / id.  Direct mode (dense 32-bit host handles):
+// the handle indexes the value array.  Values: FREE (all ones) when the id is not committed, PENDING|batch_index
+// while an enqueue batch is being resolved, (pool_generation << 32 | pool_slot) once the player is queued.
+// Generations are 31-bit (kGenMask), so a committed value is always below PENDING.
+//
+// Ingest of one chunk of a batch = claim -> [count, scan, cut: only when the batch could overflow the pool]
+// -> route -> alloc -> append.  The pool is segmented by (mode, group) partition: `route` counts every ingest
+// block's winners per partition, `alloc` turns the counts into per-(partition, block) bases, extends the partition
+// chunk lists from the bump allocator and advances the fills, `append` writes every winner to
+// fill[partition] + its stable rank among the batch's winners of that partition — enqueue order is kept inside
+// the partition, which is all the serialized reference defines (one queue per group, search/worker.ex:46-66).
 // =======================================================================================
+constexpr uint32_t kIngestItems = 1024;  // batch entries per ingest block: 256 threads x 4, warp-striped
+constexpr uint16_t kNoPart = 0xFFFFu;
 
 // E1: validate + claim.  The lowest batch index wins a repeated id (atomicMin), which
 // is what a serialized in_queue?/add_user sequence (middleware/worker.ex:65-70) yields.
 __global__ void k_enq_claim(uint32_t base, uint32_t n, const uint64_t* __restrict__ id, const int32_t* __restrict__ rating,
                             const uint8_t* __restrict__ mode, const uint8_t* __restrict__ grp_lut, int32_t key_lo,
-                            uint32_t KR, uint32_t n_modes, ActiveView act, uint64_t* __restrict__ hslot,
-                            uint8_t* __restrict__ code) {
+                            uint32_t KR, uint32_t n_modes, uint32_t n_groups, ActiveView act,
+                            uint64_t* __restrict__ hslot, uint8_t* __restrict__ code, uint16_t* __restrict__ part) {
   const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;  // this launch covers batch indices [base, base + n)
   if (t >= n) return;
   const uint32_t i = base + t;
   const uint64_t pid = id[i];
   const int32_t hi = key_lo + (int32_t)KR - 1;
   const int32_t r = rating[i] < key_lo ? key_lo : (rating[i] > hi ? hi : rating[i]);
-  if (mode[i] >= n_modes || pid >= kTombKey || grp_lut[r - key_lo] == 0xFF) { code[i] = 2; hslot[i] = ~0ull; return; }
-  if (!act.mask) { code[i] = 1; hslot[i] = ~0ull; return; }
+  const uint32_t grp = grp_lut[r - key_lo];
+  const bool bad_id = act.dcap ? pid >= act.dcap : pid >= kTombKey;
+  if (mode[i] >= n_modes || bad_id || grp == 0xFF) { code[i] = 2; hslot[i] = ~0ull; part[i] = kNoPart; return; }
+  part[i] = (uint16_t)(mode[i] * n_groups + grp);
+  if (!act.on()) { code[i] = 1; hslot[i] = ~0ull; return; }
+  if (act.dcap) {
+    const unsigned long long old = atomicMin(act.val(pid), kPending | i);
+    code[i] = (old < kPending) ? 0 : 1;
+    hslot[i] = pid;
+    return;
+  }
   uint64_t h = hash64(pid) & act.mask;
   for (uint64_t probe = 0; probe <= act.mask; ++probe) {
-    unsigned long long k = act.keys[h];
+    unsigned long long k = *act.key(h);
     if (k == kEmptyKey) {
-      k = atomicCAS(&act.keys[h], kEmptyKey, pid);
+      k = atomicCAS(act.key(h), kEmptyKey, pid);
       if (k == kEmptyKey) k = pid;
     }
     if (k == pid) {
-      const unsigned long long old = atomicMin(&act.vals[h], kPending | i);
+      const unsigned long long old = atomicMin(act.val(h), kPending | i);
       code[i] = (old < kPending) ? 0 : 1;  // committed entry -> "already in the queue"
       hslot[i] = h;
       return;
@@ -43,10 +62,9 @@ __global__ void k_enq_claim(uint32_t base, uint32_t n, const uint64_t* __restric
   code[i] = 3; hslot[i] = ~0ull;  // table full
 }
 
-// E2: winners = entries whose PENDING index is their own; per-block winner counts.
-// E2 / E3 run per ingest chunk — batch indices [base, base + n) — so that they overlap the
-// host-to-device copy of the next chunk; the lowest batch index wins a repeated id, and a chunk's
-// winners are final once every lower index has claimed.
+// ---- only when n_pool + batch could exceed the capacity: exact "the last ones do not fit" cut --------------------
+// winners = entries whose PENDING index is their own; per-block winner counts.  A chunk's winners are final once
+// every lower batch index has claimed.
 __global__ void k_enq_count(uint32_t base, uint32_t n, ActiveView act, const uint64_t* __restrict__ hslot,
                             uint8_t* __restrict__ code, uint32_t* __restrict__ blocksum) {
   __shared__ uint32_t s_cnt;
@@ -56,7 +74,7 @@ __global__ void k_enq_count(uint32_t base, uint32_t n, ActiveView act, const uin
   const uint32_t i = base + t;
   bool win = false;
   if (t < n && code[i] == 1) {
-    win = !act.mask || act.vals[hslot[i]] == (kPending | i);
+    win = !act.on() || *act.val(hslot[i]) == (kPending | i);
     if (!win) code[i] = 0;  // a lower batch index holds the id
   }
   const uint32_t b = __ballot_sync(0xFFFFFFFFu, win);
@@ -64,9 +82,7 @@ __global__ void k_enq_count(uint32_t base, uint32_t n, ActiveView act, const uin
   __syncthreads();
   if (threadIdx.x == 0) blocksum[blockIdx.x] = s_cnt;
 }
-
-// exclusive scan of blocksum (single CTA; nblocks is at most a few 10k), continued from the
-// running total of the earlier chunks of the batch (*total), which it then advances
+// exclusive scan of blocksum (single CTA), continued from the running total of the earlier chunks (*total)
 __global__ void __launch_bounds__(1024) k_scan_small(uint32_t nb, uint32_t* __restrict__ v, uint32_t* __restrict__ total) {
   __shared__ uint32_t s_sum[1024];
   const uint32_t tid = threadIdx.x;
@@ -88,15 +104,10 @@ __global__ void __launch_bounds__(1024) k_scan_small(uint32_t nb, uint32_t* __re
   __syncthreads();  // everyone has read *total
   if (tid == 1023) *total = before + s_sum[1023];
 }
-
-// E3: append winners to the pool in batch order (= enqueue order) and commit their
-// active-set entries.  Players past the pool capacity are rolled back with code 3.
-__global__ void k_enq_append(uint32_t base, uint32_t n, const uint64_t* __restrict__ id, const int32_t* __restrict__ rating,
-                             const uint8_t* __restrict__ mode, const uint32_t* __restrict__ ts,
-                             const uint8_t* __restrict__ mode_tsize, ActiveView act, const uint64_t* __restrict__ hslot,
-                             uint8_t* __restrict__ code, const uint32_t* __restrict__ blockoff, PoolView pool,
-                             uint32_t n_pool, uint32_t capacity, uint32_t gen, uint32_t* __restrict__ n_rejected_cap,
-                             BinMap bm) {
+// winners whose rank among the batch's winners does not fit the pool are rolled back with code 3
+__global__ void k_enq_cut(uint32_t base, uint32_t n, ActiveView act, const uint64_t* __restrict__ hslot,
+                          uint8_t* __restrict__ code, const uint32_t* __restrict__ blockoff, uint32_t room,
+                          uint32_t* __restrict__ n_rejected_cap) {
   __shared__ uint32_t s_warp[32];
   const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
   const uint32_t i = base + t;
@@ -108,98 +119,231 @@ __global__ void k_enq_append(uint32_t base, uint32_t n, const uint64_t* __restri
   uint32_t woff = 0;
   for (uint32_t w = 0; w < warp; ++w) woff += s_warp[w];
   if (!win) return;
-  const uint32_t slot = n_pool + blockoff[blockIdx.x] + woff + __popc(b & ((1u << lane) - 1u));
-  if (slot >= capacity) {
+  const uint32_t grank = blockoff[blockIdx.x] + woff + __popc(b & ((1u << lane) - 1u));
+  if (grank >= room) {
     code[i] = 3;
-    if (act.mask) { act.vals[hslot[i]] = kFreeVal; act.keys[hslot[i]] = kTombKey; }
+    if (act.on()) {
+      *act.val(hslot[i]) = kFreeVal;
+      if (!act.dcap) *act.key(hslot[i]) = kTombKey;
+    }
     atomicAdd(n_rejected_cap, 1u);
-    return;
   }
-  pool.id[slot] = id[i]; pool.rating[slot] = rating[i]; pool.mode[slot] = mode[i];
-  pool.tsize[slot] = mode_tsize[mode[i]]; pool.ts[slot] = ts ? ts[i] : 0u;
-  pool.bin[slot] = (uint16_t)bin_of(bm, bm.lut, rating[i], mode[i]);  // the tick's sort key, derived once at ingest
-  if (act.mask) act.vals[hslot[i]] = ((unsigned long long)gen << 32) | slot;
+}
+
+// E2: winners per (ingest block, partition).  blockhist is [n_segs][nblk].
+__global__ void __launch_bounds__(256) k_enq_route(uint32_t base, uint32_t n, ActiveView act,
+                                                   const uint64_t* __restrict__ hslot, uint8_t* __restrict__ code,
+                                                   const uint16_t* __restrict__ part, uint32_t n_segs, uint32_t nblk,
+                                                   uint32_t* __restrict__ blockhist) {
+  __shared__ uint32_t s_hist[kMaxSegs];
+  const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (uint32_t p = tid; p < n_segs; p += 256) s_hist[p] = 0;
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const uint32_t t = blockIdx.x * kIngestItems + warp * 128 + j * 32 + lane;
+    if (t < n) {
+      const uint32_t i = base + t;
+      if (code[i] == 1) {
+        const bool win = !act.on() || *act.val(hslot[i]) == (kPending | i);
+        if (win) atomicAdd(&s_hist[part[i]], 1u);
+        else code[i] = 0;  // a lower batch index holds the id: "already in the queue"
+      }
+    }
+  }
+  __syncthreads();
+  for (uint32_t p = tid; p < n_segs; p += 256) blockhist[(size_t)p * nblk + blockIdx.x] = s_hist[p];
+}
+
+// E3 (one CTA): blockhist -> per-(partition, block) append bases; new chunks from the bump allocator; fills advance.
+// counters[0] += players accepted by this chunk.
+__global__ void __launch_bounds__(512) k_enq_alloc(uint32_t n_segs, uint32_t nblk, uint32_t* __restrict__ blockhist,
+                                                   PoolMeta meta, uint32_t* __restrict__ counters) {
+  __shared__ uint32_t s_old[kMaxSegs], s_new[kMaxSegs], s_need[kMaxSegs], s_tmp[64];
+  const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (uint32_t p = warp; p < n_segs; p += 16) {  // one warp per partition: shuffle scan over the blocks, 32 at a time
+    const uint32_t fill = meta.fill[p];
+    uint32_t carry = fill;
+    uint32_t* hrow = blockhist + (size_t)p * nblk;
+    for (uint32_t b0 = 0; b0 < nblk; b0 += 32) {
+      const uint32_t b = b0 + lane;
+      const uint32_t v = b < nblk ? hrow[b] : 0u;
+      uint32_t incl = v;
+#pragma unroll
+      for (int off = 1; off < 32; off <<= 1) {
+        const uint32_t u = __shfl_up_sync(0xFFFFFFFFu, incl, off);
+        if (lane >= (uint32_t)off) incl += u;
+      }
+      if (b < nblk) hrow[b] = carry + incl - v;
+      carry += __shfl_sync(0xFFFFFFFFu, incl, 31);
+    }
+    if (lane == 0) {
+      s_old[p] = fill; s_new[p] = carry;
+      s_need[p] = (carry + kTile - 1) / kTile - (fill + kTile - 1) / kTile;
+    }
+  }
+  __syncthreads();
+  uint32_t added = 0;
+  for (uint32_t p = tid; p < n_segs; p += 512) added += s_new[p] - s_old[p];
+  added = __reduce_add_sync(0xFFFFFFFFu, added);
+  if (lane == 0 && added) atomicAdd(&counters[0], added);
+  const uint32_t total = block_excl_scan<512>(s_need, n_segs, s_tmp);  // -> first new chunk of the partition (relative)
+  const uint32_t bump = *meta.bump;
+  for (uint32_t p = warp; p < n_segs; p += 16) {
+    const uint32_t have = (s_old[p] + kTile - 1) / kTile, want = (s_new[p] + kTile - 1) / kTile;
+    for (uint32_t k = lane; k < want - have; k += 32) meta.chunk_tab[(size_t)p * meta.max_ch + have + k] = bump + s_need[p] + k;
+    if (lane == 0) meta.fill[p] = s_new[p];
+  }
+  __syncthreads();
+  if (tid == 0) *meta.bump = bump + total;
+}
+
+// E4: append winners to their partition in batch order (= enqueue order) and commit their active-set entries.
+// Stable rank inside the block: peers of the same partition inside a warp by ballots over the partition index bits,
+// per-warp counters in shared memory, prefix over the block's 8 warps.
+__global__ void __launch_bounds__(256) k_enq_append(uint32_t base, uint32_t n, const uint64_t* __restrict__ id,
+                                                    const int32_t* __restrict__ rating, const uint8_t* __restrict__ mode,
+                                                    const uint32_t* __restrict__ ts, const uint8_t* __restrict__ mode_tsize,
+                                                    ActiveView act, const uint64_t* __restrict__ hslot,
+                                                    const uint8_t* __restrict__ code, const uint16_t* __restrict__ part,
+                                                    uint32_t n_segs, uint32_t nblk, const uint32_t* __restrict__ blockbase,
+                                                    PoolView pool, PoolMeta meta, uint32_t gen, uint32_t seq_base, BinMap bm) {
+  extern __shared__ __align__(16) uint32_t s_dyn[];  // wc[8][n_segs + 1] u16 | bbase[n_segs] u32
+  uint16_t* wc = reinterpret_cast<uint16_t*>(s_dyn);
+  const uint32_t S1 = n_segs + 1;                     // digit n_segs = not a winner
+  uint32_t* bbase = s_dyn + (8 * S1 + 1) / 2;
+  const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t lt_mask = (1u << lane) - 1u;
+  for (uint32_t k = tid; k < 8 * S1; k += 256) wc[k] = 0;
+  for (uint32_t p = tid; p < n_segs; p += 256) bbase[p] = blockbase[(size_t)p * nblk + blockIdx.x];
+  __syncthreads();
+  const uint32_t nbits = 32u - __clz(n_segs);
+  uint32_t dg[4], rk[4], idx[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const uint32_t t = blockIdx.x * kIngestItems + warp * 128 + j * 32 + lane;
+    idx[j] = base + t;
+    dg[j] = (t < n && code[idx[j]] == 1) ? (uint32_t)part[idx[j]] : n_segs;
+    uint32_t peers = 0xFFFFFFFFu;
+    for (uint32_t bit = 0; bit < nbits; ++bit) {
+      const bool on = (dg[j] >> bit) & 1u;
+      const uint32_t bal = __ballot_sync(0xFFFFFFFFu, on);
+      peers &= on ? bal : ~bal;
+    }
+    const uint32_t leader = __ffs(peers) - 1;
+    uint32_t old = 0;
+    uint16_t* c = wc + warp * S1 + dg[j];
+    if (lane == leader) { old = *c; *c = (uint16_t)(old + __popc(peers)); }
+    __syncwarp();
+    old = __shfl_sync(0xFFFFFFFFu, old, leader);
+    rk[j] = old + __popc(peers & lt_mask);
+  }
+  __syncthreads();
+  for (uint32_t p = tid; p < n_segs; p += 256) {  // prefix over the 8 warps
+    uint32_t run = 0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) { const uint32_t v = wc[w * S1 + p]; wc[w * S1 + p] = (uint16_t)run; run += v; }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    if (dg[j] >= n_segs) continue;
+    const uint32_t p = dg[j], i = idx[j];
+    const uint32_t pos = bbase[p] + wc[warp * S1 + p] + rk[j];
+    const uint32_t slot = meta.chunk_tab[(size_t)p * meta.max_ch + pos / kTile] * kTile + pos % kTile;
+    pool.id[slot] = id[i]; pool.rating[slot] = rating[i]; pool.mode[slot] = mode[i];
+    pool.tsize[slot] = mode_tsize[mode[i]]; pool.ts[slot] = ts ? ts[i] : 0u;
+    pool.bin[slot] = (uint16_t)bin_of(bm, bm.lut, rating[i], mode[i]);  // the tick's sort key, derived once at ingest
+    pool.seq[slot] = seq_base + i;
+    if (act.on()) *act.val(hslot[i]) = ((unsigned long long)gen << 32) | slot;
+  }
 }
 
 // ActiveUser.remove_user/1 (models/active_user.ex:57-66), batched.  A player still
 // queued is tombstoned in the pool (mode byte = DEAD) so the next tick drops it the way
 // remove_inactive_players/1 (search/worker.ex:267-280) filters it.
-__global__ void k_remove(uint32_t n, const uint64_t* __restrict__ id, ActiveView act, PoolView pool, uint32_t n_pool,
+__global__ void k_remove(uint32_t n, const uint64_t* __restrict__ id, ActiveView act, PoolView pool, uint32_t n_slots,
                          uint32_t gen, uint32_t dead_bin, uint32_t* __restrict__ n_removed) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n || !act.mask) return;
+  if (i >= n || !act.on()) return;
   const uint64_t pid = id[i];
-  if (pid >= kTombKey) return;
-  uint64_t h = hash64(pid) & act.mask;
-  for (uint64_t probe = 0; probe <= act.mask; ++probe) {
-    const unsigned long long k = act.keys[h];
-    if (k == kEmptyKey) return;
-    if (k == pid) {
-      const unsigned long long v = act.vals[h];
-      if (atomicCAS(&act.keys[h], (unsigned long long)pid, kTombKey) != pid) return;  // a twin in this batch won
-      act.vals[h] = kFreeVal;
-      const uint32_t slot = (uint32_t)v, g = (uint32_t)(v >> 32);
-      if (v < kPending && g == gen && slot < n_pool && pool.id[slot] == pid) {
-        pool.mode[slot] = MM_MODE_DEAD;
-        pool.bin[slot] = (uint16_t)dead_bin;
-      }
-      atomicAdd(n_removed, 1u);
-      return;
-    }
-    h = (h + 1) & act.mask;
+  const uint64_t h = act_find(act, pid);
+  if (h == ~0ull) return;
+  unsigned long long v;
+  if (act.dcap) {
+    v = atomicExch(act.val(h), kFreeVal);
+    if (v == kFreeVal) return;  // not active (or a twin in this batch won)
+  } else {
+    v = *act.val(h);
+    if (atomicCAS(act.key(h), (unsigned long long)pid, kTombKey) != pid) return;  // a twin in this batch won
+    *act.val(h) = kFreeVal;
   }
+  const uint32_t slot = (uint32_t)v, g = (uint32_t)(v >> 32);
+  if (v < kPending && g == gen && slot < n_slots && pool.id[slot] == pid) {
+    pool.mode[slot] = MM_MODE_DEAD;
+    pool.bin[slot] = (uint16_t)dead_bin;
+  }
+  atomicAdd(n_removed, 1u);
 }
 
 // ActiveUser.in_queue?/1 (models/active_user.ex:33-44), batched.
 __global__ void k_lookup(uint32_t n, const uint64_t* __restrict__ id, ActiveView act, uint8_t* __restrict__ out) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  const uint64_t pid = id[i];
   uint8_t found = 0;
-  if (act.mask && pid < kTombKey) {
-    uint64_t h = hash64(pid) & act.mask;
-    for (uint64_t probe = 0; probe <= act.mask; ++probe) {
-      const unsigned long long k = act.keys[h];
-      if (k == kEmptyKey) break;
-      if (k == pid) { found = 1; break; }
-      h = (h + 1) & act.mask;
-    }
+  if (act.on()) {
+    const uint64_t h = act_find(act, id[i]);
+    if (h != ~0ull) found = act.dcap ? (*act.val(h) != kFreeVal) : 1;
   }
   out[i] = found;
 }
 
-// Rebuild without tombstones: re-insert every committed entry of the old table.
+// Rebuild without tombstones: re-insert every committed entry of the old table (hashed mode).
 __global__ void k_rehash(ActiveView oldt, ActiveView newt) {
   for (uint64_t s = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; s <= oldt.mask; s += (uint64_t)gridDim.x * blockDim.x) {
-    const unsigned long long k = oldt.keys[s];
+    const unsigned long long k = *oldt.key(s);
     if (k >= kTombKey) continue;
     uint64_t h = hash64(k) & newt.mask;
     for (;;) {
-      if (atomicCAS(&newt.keys[h], kEmptyKey, k) == kEmptyKey) { newt.vals[h] = oldt.vals[s]; break; }
+      if (atomicCAS(newt.key(h), kEmptyKey, k) == kEmptyKey) { *newt.val(h) = *oldt.val(s); break; }
       h = (h + 1) & newt.mask;
     }
   }
 }
 
-// After mm_restore: point every queued player's entry at its slot again.
-__global__ void k_restamp(PoolView pool, uint32_t n_pool, ActiveView act, uint32_t gen) {
-  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n_pool || !act.mask) return;
-  if (pool.mode[i] == MM_MODE_DEAD) return;
-  const uint64_t pid = pool.id[i];
-  uint64_t h = hash64(pid) & act.mask;
-  for (uint64_t probe = 0; probe <= act.mask; ++probe) {
-    const unsigned long long k = act.keys[h];
-    if (k == kEmptyKey) return;
-    if (k == pid) { act.vals[h] = ((unsigned long long)gen << 32) | i; return; }
-    h = (h + 1) & act.mask;
+// After mm_restore / a generation wrap: point every queued player's entry at its slot again.
+// grid = (chunks in use, partitions): block (k, p) handles the partition's k-th chunk.
+__global__ void k_restamp(PoolView pool, PoolMeta meta, ActiveView act, uint32_t gen) {
+  const uint32_t p = blockIdx.y, k = blockIdx.x;
+  const uint32_t fill = meta.fill[p];
+  if ((uint64_t)k * kTile >= fill || !act.on()) return;
+  const uint32_t cnt = fill - k * kTile < kTile ? fill - k * kTile : kTile;
+  const uint32_t c = meta.chunk_tab[(size_t)p * meta.max_ch + k];
+  for (uint32_t o = threadIdx.x; o < cnt; o += blockDim.x) {
+    const uint32_t slot = c * kTile + o;
+    if (pool.mode[slot] == MM_MODE_DEAD) continue;
+    const uint64_t h = act_find(act, pool.id[slot]);
+    if (h != ~0ull) *act.val(h) = ((unsigned long long)gen << 32) | slot;
   }
 }
 
-// empty active set: every slot {EMPTY key, FREE value}
+// empty hashed active set: every slot {EMPTY key, FREE value}
 __global__ void k_fill_kv(ulonglong2* p, uint64_t n, unsigned long long k, unsigned long long v) {
   for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
     p[i] = make_ulonglong2(k, v);
+}
+
+// ---- packed host formats (mm_enqueue_packed / mm_tick_packed): 6 B per player up, 4 B per player down ----------
+// key = mode << 13 | rating (0 .. 8191); the 32-bit host handle is the player id on the device
+__global__ void k_unpack(uint32_t n, const uint32_t* __restrict__ handle, const uint16_t* __restrict__ key,
+                         uint64_t* __restrict__ id, int32_t* __restrict__ rating, uint8_t* __restrict__ mode) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint32_t k = key[i];
+  id[i] = handle[i]; rating[i] = (int32_t)(k & 0x1FFFu); mode[i] = (uint8_t)(k >> 13);
+}
+__global__ void k_narrow(uint32_t n, const uint64_t* __restrict__ src, uint32_t* __restrict__ dst) {
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) dst[i] = (uint32_t)src[i];
 }
 
 }  // namespace mm

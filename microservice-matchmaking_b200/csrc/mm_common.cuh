@@ -7,21 +7,22 @@
 
 namespace mm {
 
-constexpr int kBlock = 1024;          // threads per CTA for hist / place
-constexpr int kJ = 4;                 // batches per round in k_place
-constexpr uint32_t kRound = kBlock * kJ;
-constexpr uint32_t kNone = 0x1FFFu;   // list terminator (13-bit node ids)
+constexpr int kBlock = 512;           // threads per CTA of every tick phase (two CTAs share an SM)
+constexpr uint32_t kTile = 2048;      // players per pool chunk = per TMA tile (a tile never mixes partitions)
 constexpr uint32_t kMaxRows = 2048;   // rows (CTAs) of the histogram matrix
-constexpr uint32_t kTile = 2048;      // players per TMA tile in k_place2
 constexpr uint32_t kMaxStages = 4;    // depth of the (bin, id) shared-memory ring
 constexpr uint32_t kTileBytes = kTile * (8 + 2);
-constexpr uint32_t kDenseStride = 66;  // u16 per bin row of the dense group-size matrix (64 batches + pad)
-constexpr uint32_t kDenseMaxBins = 256;
+constexpr uint32_t kMaxSegs = MM_MAX_GROUPS * MM_MAX_MODES;  // (mode, group) partitions
+constexpr uint32_t kFastBins = 255;   // partitions with <= 255 bins rank with warp ballots (8-bit digit + "dead")
 constexpr uint64_t kEmptyKey = 0xFFFFFFFFFFFFFFFFull;
 constexpr uint64_t kTombKey = 0xFFFFFFFFFFFFFFFEull;
 constexpr uint64_t kFreeVal = 0xFFFFFFFFFFFFFFFFull;
 constexpr uint64_t kPending = 0x8000000000000000ull;
+constexpr uint32_t kGenMask = 0x7FFFFFFFu;  // pool generations live in 31 bits: committed values stay below kPending
 
+// The resident pool: SoA columns over fixed-size chunks of kTile players.  Every (mode, group) partition — the
+// reference's per-group queue (search/worker.ex:46-66) x the game_mode selector of LobbyState
+// (models/lobby_state.ex:72-79) — owns an ordered list of chunks; inside a partition players sit in enqueue order.
 struct PoolView {
   uint64_t* id;
   int32_t* rating;
@@ -29,6 +30,13 @@ struct PoolView {
   uint8_t* tsize;
   uint32_t* ts;
   uint16_t* bin;  // derived at ingest: mode * stride + lut[clamp(rating)]; K = removed while queued
+  uint32_t* seq;  // enqueue sequence number (mod 2^32): global arrival order across partitions
+};
+struct PoolMeta {
+  uint32_t* fill;       // [n_segs] players of the partition (dead ones included)
+  uint32_t* chunk_tab;  // [n_segs][max_ch] physical chunk of the partition's k-th chunk
+  uint32_t* bump;       // chunks handed out so far
+  uint32_t max_ch;
 };
 
 struct BinMap {
@@ -39,42 +47,64 @@ struct BinMap {
   uint32_t K;           // live bins; bin K = removed-while-queued players
 };
 
-struct SegInfo {        // one (mode, group) partition
+struct SegInfo {        // one (mode, group) partition, written by the scan tail
   uint32_t n;           // alive players
   uint32_t n_lobbies;
   uint32_t member_base; // first slot in member_ids
   uint32_t lobby_base;  // first lobby index
+  uint32_t left_base;   // leftover players of earlier partitions (rank base of the compaction)
+  uint32_t new_chunk;   // first chunk of the partition in the compacted pool
+  uint32_t n_left;      // players of the partition that stay queued
+  uint32_t reserved;
 };
 
 struct TickCtr {
   uint32_t gbar;  // grid barrier of the fused tick kernel
   uint32_t n_lobbies, n_matched, n_alive, n_dead, n_resid;
-  uint32_t reserved0;
-  uint32_t heavy;  // some bin expects > 4 players per tile: use warp-aggregated ranking
+  uint32_t n_tiles;
+  uint32_t heavy;  // some bin expects > 8 players per tile: the list ranking uses warp-aggregated nodes
   unsigned long long t[8];  // fused kernel: %globaltimer (ns) at phase boundaries, CTA 0; [6],[7]: max over CTAs
 };
 
-// Active set slot = {key, value} adjacent in one 16-byte pair: the claim's CAS on the key and atomicMin on the
-// value, the winner check and the commit all touch the same 32-byte sector (one DRAM access instead of four).
-struct Strided64 {
-  unsigned long long* p;
-  __device__ __forceinline__ unsigned long long& operator[](uint64_t h) const { return p[2 * h]; }
+// Tile geometry of a tick, rebuilt by every CTA from the partition fills: the pool's tiles in (partition, chunk) order
+// form the VIRTUAL tile sequence 0 .. NT-1; row r (= CTA r) owns tiles [r * tpr, (r + 1) * tpr).  Virtual position
+// = tile * kTile + offset indexes left_bits / src_idx; only the pool loads translate a tile to its physical chunk.
+struct Geo {
+  uint32_t T0[kMaxSegs + 1];  // first virtual tile of the partition
+  uint32_t NT, tpr, n_segs, pad;
 };
+
+// Active set = {key, value} pairs (hashed: open addressing on the u64 player id) or a direct-mapped value array
+// (dense 32-bit host handles).  value: FREE | PENDING|batch index | (pool generation << 32 | slot).
 struct ActiveView {
-  Strided64 keys;  // keys[h] = kv[2h]
-  Strided64 vals;  // vals[h] = kv[2h + 1]
-  uint64_t mask;   // capacity - 1, 0 = no active set
+  unsigned long long* kv;  // hashed: [cap] x {key, value} (one 16-byte pair = one sector); direct: value[dcap]
+  uint64_t mask;           // hashed: capacity - 1
+  uint64_t dcap;           // direct: handle capacity (mask = 0)
+  __device__ __forceinline__ bool on() const { return mask != 0 || dcap != 0; }
+  __device__ __forceinline__ unsigned long long* key(uint64_t h) const { return kv + 2 * h; }
+  __device__ __forceinline__ unsigned long long* val(uint64_t h) const { return dcap ? kv + h : kv + 2 * h + 1; }
 };
 
 __device__ __forceinline__ uint64_t hash64(uint64_t x) {
   x ^= x >> 33; x *= 0xFF51AFD7ED558CCDull; x ^= x >> 33; x *= 0xC4CEB9FE1A85EC53ull; x ^= x >> 33;
   return x;
 }
+// slot of a resident id, ~0 when absent
+__device__ __forceinline__ uint64_t act_find(const ActiveView& a, uint64_t pid) {
+  if (a.dcap) return pid < a.dcap ? pid : ~0ull;
+  if (pid >= kTombKey) return ~0ull;
+  uint64_t h = hash64(pid) & a.mask;
+  for (uint64_t probe = 0; probe <= a.mask; ++probe) {
+    const unsigned long long k = *a.key(h);
+    if (k == pid) return h;
+    if (k == kEmptyKey) return ~0ull;
+    h = (h + 1) & a.mask;
+  }
+  return ~0ull;
+}
 
-// L2 cache-policy hints.  The placement kernel scatters 8-byte ids into member_ids: the
-// 4 writes that complete a 32-byte sector arrive at unrelated times, so member_ids has to
-// stay L2-resident until the kernel ends (evict_last) while the input columns stream
-// through once (evict_first, no L1 allocation).
+// L2 cache-policy hints: the input columns stream through once (evict_first); the histogram pass keeps the 2-byte bin
+// column in L2 for the placement pass (evict_last).
 __device__ __forceinline__ uint64_t policy_evict_first() {
   uint64_t p;
   asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
@@ -85,22 +115,7 @@ __device__ __forceinline__ uint64_t policy_evict_last() {
   asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
   return p;
 }
-__device__ __forceinline__ int32_t ld_stream_s32(const int32_t* a, uint64_t pol) {
-  int32_t v;
-  asm volatile("ld.global.L1::no_allocate.L2::cache_hint.s32 %0, [%1], %2;" : "=r"(v) : "l"(a), "l"(pol));
-  return v;
-}
-__device__ __forceinline__ uint32_t ld_stream_u8(const uint8_t* a, uint64_t pol) {
-  uint32_t v;
-  asm volatile("ld.global.L1::no_allocate.L2::cache_hint.u8 %0, [%1], %2;" : "=r"(v) : "l"(a), "l"(pol));
-  return v;
-}
-__device__ __forceinline__ uint64_t ld_stream_u64(const uint64_t* a, uint64_t pol) {
-  uint64_t v;
-  asm volatile("ld.global.L1::no_allocate.L2::cache_hint.u64 %0, [%1], %2;" : "=l"(v) : "l"(a), "l"(pol));
-  return v;
-}
-__device__ __forceinline__ void st_keep_u64(uint64_t* a, uint64_t v, uint64_t pol) {
+__device__ __forceinline__ void st_hint_u64(uint64_t* a, uint64_t v, uint64_t pol) {
   asm volatile("st.global.L2::cache_hint.u64 [%0], %1, %2;" ::"l"(a), "l"(v), "l"(pol) : "memory");
 }
 
@@ -129,6 +144,10 @@ __device__ __forceinline__ void mbar_inval(uint64_t* bar) {
 }
 // order earlier generic-proxy accesses to shared memory before later async-proxy (TMA) writes
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+// barrier among the first `nthreads` threads of the CTA only (named barrier 1)
+__device__ __forceinline__ void bar_sync_named(uint32_t nthreads) {
+  asm volatile("bar.sync 1, %0;" ::"r"(nthreads) : "memory");
+}
 // Grid-wide barrier for the fused tick kernel (cooperative launch: all CTAs are co-resident).
 __device__ __forceinline__ void grid_barrier(unsigned int* bar, unsigned int target) {
   __syncthreads();
@@ -144,7 +163,7 @@ __device__ __forceinline__ void grid_barrier(unsigned int* bar, unsigned int tar
   }
   __syncthreads();
 }
-// global -> shared bulk copy (SASS: UBLKCP), completion counted on `bar`, L2 evict-first
+// global -> shared bulk copy (SASS: UBLKCP), completion counted on `bar`, with an L2 cache-policy hint
 __device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar, uint64_t pol) {
   asm volatile(
       "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
@@ -186,6 +205,45 @@ __device__ __forceinline__ uint32_t block_excl_scan(uint32_t* a, uint32_t n, uin
   const uint32_t total = s_tmp[32];
   __syncthreads();
   return total;
+}
+
+// Every CTA derives the tick's tile geometry from the partition fills (n_segs <= 512 values: one block scan).
+template <int BLOCK>
+__device__ __forceinline__ void geo_build(Geo& g, const uint32_t* __restrict__ fill, uint32_t n_segs, uint32_t R,
+                                          uint32_t* s_tmp) {
+  for (uint32_t p = threadIdx.x; p < n_segs; p += BLOCK) g.T0[p] = (__ldcg(&fill[p]) + kTile - 1) / kTile;
+  __syncthreads();
+  const uint32_t NT = block_excl_scan<BLOCK>(g.T0, n_segs, s_tmp);
+  if (threadIdx.x == 0) {
+    g.T0[n_segs] = NT;
+    g.NT = NT;
+    g.tpr = NT ? (NT + R - 1) / R : 1u;
+    g.n_segs = n_segs;
+  }
+  __syncthreads();
+}
+// partition owning virtual tile s (s < NT): the last p with T0[p] <= s (empty partitions share their successor's T0)
+__device__ __forceinline__ uint32_t geo_seg_of(const Geo& g, uint32_t s) {
+  uint32_t a = 0, e = g.n_segs;
+  while (e - a > 1) { const uint32_t mid = (a + e) >> 1; if (g.T0[mid] <= s) a = mid; else e = mid; }
+  return a;
+}
+struct TileDesc { uint32_t phys, nvalid, seg; };
+__device__ __forceinline__ TileDesc geo_tile(const Geo& g, const PoolMeta& m, uint32_t s) {
+  TileDesc d;
+  d.seg = geo_seg_of(g, s);
+  const uint32_t k = s - g.T0[d.seg];
+  d.phys = __ldcg(&m.chunk_tab[(size_t)d.seg * m.max_ch + k]);
+  const uint32_t left = __ldcg(&m.fill[d.seg]) - k * kTile;
+  d.nvalid = left < kTile ? left : kTile;
+  return d;
+}
+// rows [rlo, rhi] holding tiles of partition p; false when the partition is empty
+__device__ __forceinline__ bool geo_rows_of(const Geo& g, uint32_t p, uint32_t& rlo, uint32_t& rhi) {
+  const uint32_t a = g.T0[p], b = g.T0[p + 1];
+  if (b == a) return false;
+  rlo = a / g.tpr; rhi = (b - 1) / g.tpr;
+  return true;
 }
 
 __device__ __forceinline__ uint32_t bin_of(const BinMap& bm, const uint16_t* s_lut, int32_t rating, uint32_t mode) {

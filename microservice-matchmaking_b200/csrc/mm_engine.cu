@@ -3,9 +3,10 @@
 // Host side of the drop-in for the reference search stage
 // (matchmaking/lib/search/worker.ex + models/{active_user,lobby_state}.ex).  The pool
 // is a GPU-resident SoA (player_id u64 / rating i32 / game-mode u8 / team-size u8 /
-// enqueue-time u32) kept in enqueue order; all matching work runs in the kernels of
-// mm_kernels.cuh.  There is no CPU path: every entry point either launches CUDA work
-// or fails with MM_E_CUDA.
+// enqueue-time u32 + derived sort key u16 + enqueue sequence u32), segmented by
+// (mode, rating group) partition into chunk lists, enqueue order kept inside a partition;
+// all matching work runs in the kernels of mm_kernels.cuh.  There is no CPU path: every
+// entry point either launches CUDA work or fails with MM_E_CUDA.
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -23,11 +24,12 @@ namespace {
 
 struct Pool {
   PoolView v{};
-  uint32_t n = 0;
+  PoolMeta m{};
+  uint32_t n = 0;  // host mirror of the sum of the partition fills (dead players included)
 };
 
 struct Table {
-  unsigned long long* kv = nullptr;  // hcap x {key, value}
+  unsigned long long* kv = nullptr;  // hashed: hcap x {key, value}; direct: dcap values
 };
 
 }  // namespace
@@ -38,10 +40,9 @@ struct mm_engine {
   int device = 0;
   int n_sms = 0;
   size_t smem_optin = 0, smem_sm = 0;
-  int block = 1024;  // threads per row CTA (512 when two rows share an SM)
   cudaStream_t stream = nullptr;
   bool own_stream = true;
-  cudaStream_t copy_stream = nullptr;  // H2D of ingest chunks, overlapped with the claim kernels
+  cudaStream_t copy_stream = nullptr;  // H2D of ingest chunks, overlapped with the ingest kernels
   cudaEvent_t ev_copy = nullptr;
   cudaStream_t d2h_stream = nullptr;   // async_results: a tick's host copies, overlapped with the next ingest
   bool async_results = false, results_pending = false;
@@ -61,39 +62,39 @@ struct mm_engine {
 
   // pool (double buffered) + snapshot
   uint32_t capacity = 0;
+  uint32_t n_chunks = 0;  // physical chunks per pool buffer
   Pool pool[2];
   int cur = 0;
   uint32_t gen = 1;
+  uint32_t seq_next = 0;  // enqueue sequence number of the next batch's first entry
   Pool snap;
-  uint32_t snap_gen = 0;
+  uint32_t snap_gen = 0, snap_seq = 0;
   bool has_snap = false;
 
   // active set
-  bool use_active = true;
-  uint64_t hcap = 0;
+  bool use_active = true, dense_ids = false;
+  uint64_t hcap = 0;  // hashed: slots (power of two); direct: handle capacity
   Table tab[2];
   int tcur = 0;
   uint64_t n_active = 0, n_tomb = 0;
 
   // tick scratch
   uint32_t R = 0;
-  int rows_per_sm = 1;
-  int rank_impl = 1;
-  int place_debug = 0;
-  size_t persist_bytes = 0;
-  uint32_t place2_stages = 0;  // 0 = k_place2 does not fit in shared memory
-  uint32_t hist3_stages = 4;   // ring depth of the bin-column histogram
-  int fused_ok = 0;  // k_tick<512> can be launched cooperatively with 2 CTAs per SM
+  int rows_per_sm = 2;
+  int rank_impl = 3;           // 3 = ballot tile sort for partitions of <= 255 bins + lists otherwise; 2 = lists only
+  uint32_t place_stages = 0;
+  uint32_t hist_stages = 4;
+  int fused_ok = 0;  // k_tick<512> can be launched cooperatively with R CTAs
   int tick_impl = 1; // 1 = one fused cooperative launch when possible, 0 = four launches
   size_t tick_smem = 0;
-  int dense_ok = 2;            // small-K ranking: 0 = off, 1 = MATCH-based matrix, 2 = private byte counters when possible
   uint32_t* d_M = nullptr;
   uint32_t *d_tot = nullptr, *d_outbase = nullptr, *d_binlim = nullptr;
   uint16_t* d_bin_key = nullptr;
   int32_t max_spread = -1;  // < 0: policy S0 (reference behaviour); >= 0: policy S1 (extension)
   SegInfo* d_seg = nullptr;
-  uint32_t* d_left_bits = nullptr;  // one bit per pool slot: stays queued after the tick
+  uint32_t* d_left_bits = nullptr;  // one bit per virtual pool position: stays queued after the tick
   uint64_t* d_members = nullptr;
+  uint32_t* d_members32 = nullptr;  // mm_tick_packed: member handles narrowed for the host copy
   uint32_t* d_src_idx = nullptr;
   mm_lobby_hdr* d_hdr = nullptr;
   uint32_t* d_emit_seq = nullptr;
@@ -107,8 +108,10 @@ struct mm_engine {
   uint64_t *d_in_id = nullptr, *d_hslot = nullptr;
   int32_t* d_in_rating = nullptr;
   uint8_t *d_in_mode = nullptr, *d_code = nullptr;
-  uint32_t *d_in_ts = nullptr, *d_blocksum = nullptr, *d_small = nullptr;  // d_small: [0]=total [1]=rejected [2]=removed
-  uint32_t* h_small = nullptr;                                             // pinned
+  uint16_t *d_part = nullptr, *d_in_key = nullptr;
+  uint32_t *d_in_ts = nullptr, *d_in_handle = nullptr, *d_blocksum = nullptr, *d_blockhist = nullptr;
+  uint32_t* d_small = nullptr;  // [0] accepted  [1] rejected: pool full  [2] removed  [3] running winner total (cut)
+  uint32_t* h_small = nullptr;  // pinned
 
   // last tick
   mm_tick_stats last{};
@@ -116,6 +119,8 @@ struct mm_engine {
 };
 
 namespace {
+
+constexpr uint32_t kEnqChunk = 1u << 20;  // batch entries per pipelined ingest chunk
 
 int fail(mm_engine* e, cudaError_t err, const char* what) {
   if (e) std::snprintf(e->last_err, sizeof(e->last_err), "%s: %s", what, cudaGetErrorString(err));
@@ -139,29 +144,64 @@ cudaError_t allow_max_smem(const mm_engine* e, F* func) {
                               (int)(e->smem_optin - fa.sharedSizeBytes));
 }
 
-int alloc_pool(mm_engine* e, Pool& p, uint32_t cap) {
-  const size_t c = (size_t)cap + 3 * kRound;  // TMA tiles are read whole: pad past the last row
+size_t pool_slots(const mm_engine* e) { return (size_t)e->n_chunks * kTile; }
+
+int alloc_pool(mm_engine* e, Pool& p) {
+  const size_t c = pool_slots(e);
   CK(cudaMalloc(&p.v.id, c * 8));
   CK(cudaMalloc(&p.v.rating, c * 4));
   CK(cudaMalloc(&p.v.mode, c));
   CK(cudaMalloc(&p.v.tsize, c));
   CK(cudaMalloc(&p.v.ts, c * 4));
   CK(cudaMalloc(&p.v.bin, c * 2));
+  CK(cudaMalloc(&p.v.seq, c * 4));
+  p.m.max_ch = e->n_chunks;
+  CK(cudaMalloc(&p.m.fill, (size_t)e->n_segs * 4));
+  CK(cudaMalloc(&p.m.chunk_tab, (size_t)e->n_segs * e->n_chunks * 4));
+  CK(cudaMalloc(&p.m.bump, 4));
+  CK(cudaMemset(p.m.fill, 0, (size_t)e->n_segs * 4));
+  CK(cudaMemset(p.m.bump, 0, 4));
+  // chunks are read whole by the TMA tiles: keep the bin column defined (and "dead") past the fills
+  CK(cudaMemset(p.v.bin, 0xFF, c * 2));
   p.n = 0;
   return MM_OK;
 }
 void free_pool(Pool& p) {
   cudaFree(p.v.id); cudaFree(p.v.rating); cudaFree(p.v.mode); cudaFree(p.v.tsize); cudaFree(p.v.ts); cudaFree(p.v.bin);
+  cudaFree(p.v.seq); cudaFree(p.m.fill); cudaFree(p.m.chunk_tab); cudaFree(p.m.bump);
   p = Pool{};
+}
+int copy_pool(mm_engine* e, Pool& dst, const Pool& src) {
+  const size_t c = pool_slots(e);
+  CK(cudaMemcpyAsync(dst.v.id, src.v.id, c * 8, cudaMemcpyDeviceToDevice, e->stream));
+  CK(cudaMemcpyAsync(dst.v.rating, src.v.rating, c * 4, cudaMemcpyDeviceToDevice, e->stream));
+  CK(cudaMemcpyAsync(dst.v.mode, src.v.mode, c, cudaMemcpyDeviceToDevice, e->stream));
+  CK(cudaMemcpyAsync(dst.v.tsize, src.v.tsize, c, cudaMemcpyDeviceToDevice, e->stream));
+  CK(cudaMemcpyAsync(dst.v.ts, src.v.ts, c * 4, cudaMemcpyDeviceToDevice, e->stream));
+  CK(cudaMemcpyAsync(dst.v.bin, src.v.bin, c * 2, cudaMemcpyDeviceToDevice, e->stream));
+  CK(cudaMemcpyAsync(dst.v.seq, src.v.seq, c * 4, cudaMemcpyDeviceToDevice, e->stream));
+  CK(cudaMemcpyAsync(dst.m.fill, src.m.fill, (size_t)e->n_segs * 4, cudaMemcpyDeviceToDevice, e->stream));
+  CK(cudaMemcpyAsync(dst.m.chunk_tab, src.m.chunk_tab, (size_t)e->n_segs * e->n_chunks * 4, cudaMemcpyDeviceToDevice, e->stream));
+  CK(cudaMemcpyAsync(dst.m.bump, src.m.bump, 4, cudaMemcpyDeviceToDevice, e->stream));
+  dst.n = src.n;
+  return MM_OK;
 }
 
 ActiveView act_view(mm_engine* e) {
   ActiveView a{};
-  if (e->use_active) { a.keys.p = e->tab[e->tcur].kv; a.vals.p = e->tab[e->tcur].kv + 1; a.mask = e->hcap - 1; }
+  if (e->use_active) {
+    a.kv = e->tab[e->tcur].kv;
+    if (e->dense_ids) a.dcap = e->hcap;
+    else a.mask = e->hcap - 1;
+  }
   return a;
 }
 
 int clear_table(mm_engine* e, Table& t) {
+  if (e->dense_ids) {
+    CK(cudaMemsetAsync(t.kv, 0xFF, e->hcap * 8, e->stream));  // FREE = all ones
+    return MM_OK;
+  }
   k_fill_kv<<<1024, 256, 0, e->stream>>>(reinterpret_cast<ulonglong2*>(t.kv), e->hcap, kEmptyKey, kFreeVal);
   CK(cudaGetLastError());
   return MM_OK;
@@ -180,6 +220,7 @@ int check_config(const mm_config* c) {
   if (c->default_group >= (int32_t)c->n_groups || c->default_group < -1) return MM_E_ARG;
   if (c->order_mode > MM_ORDER_RATING) return MM_E_ARG;
   if (c->capacity == 0 || c->capacity > 0x7FFF0000u) return MM_E_ARG;
+  if (c->flags & ~(MM_F_NO_DEDUPE | MM_F_DENSE_IDS)) return MM_E_ARG;
   for (uint32_t g = 0; g < c->n_groups; ++g) {
     if (c->group_lo[g] > c->group_hi[g]) return MM_E_ARG;
     if (c->group_lo[g] < -(1 << 30) || c->group_hi[g] > (1 << 30)) return MM_E_ARG;
@@ -191,22 +232,6 @@ int check_config(const mm_config* c) {
   return MM_OK;
 }
 
-size_t place_smem(const mm_engine* e, int impl) {
-  size_t words = e->Kp + (impl == 1 ? (size_t)e->Kp + kRound : 0);
-  return words * 4 + (size_t)e->KR * 2 + 16;
-}
-bool place2_dense(const mm_engine* e) { return e->Kp <= kDenseMaxBins; }
-// private byte counters c8[Kp][512] + lane bases + bases: only for very few bins and 512-thread CTAs
-bool place2_dense2(const mm_engine* e) { return e->Kp <= 96; }
-size_t place2_dense_bytes(const mm_engine* e) {
-  size_t a = place2_dense(e) ? (size_t)e->Kp * kDenseStride * 2 * 2 + (size_t)e->Kp * 4 : 0;
-  size_t b = place2_dense2(e) ? (size_t)e->Kp * (512 + 16) + (size_t)e->Kp * 68 + (size_t)e->Kp * 4 + 32 : 0;
-  return std::max(a, b);
-}
-size_t place2_smem(const mm_engine* e, uint32_t stages) {
-  return (size_t)stages * kTileBytes + 64 + ((size_t)e->Kp + kHeadSlots + kTile) * 4 + (size_t)kTile * 2 +
-         place2_dense_bytes(e) + 16;
-}
 // Shared-memory layout of the scan tail: everything on chip up to ~100 KB (so that it never exceeds the placement
 // phase's footprint in the fused kernel), else keys from global memory, else matched counts parked in global too.
 uint32_t tail_layout(const mm_engine* e) {
@@ -217,8 +242,6 @@ uint32_t tail_layout(const mm_engine* e) {
 size_t colscan_smem(const mm_engine* e) {
   return (size_t)std::max<uint32_t>(kColScratchWords, tail_words(e->Kp, tail_layout(e))) * 4;
 }
-size_t hist3_smem(const mm_engine* e, uint32_t stages) { return (size_t)stages * kBTileBytes + 64 + (size_t)e->Kp * 4 + 16; }
-size_t hist_smem(const mm_engine* e) { return (size_t)e->Kp * 4 + (size_t)e->KR * 2 + 16; }
 
 // Build the key -> bin LUT and the (mode, group) segment table (see mm_kernels.cuh).
 int build_tables(mm_engine* e) {
@@ -255,6 +278,7 @@ int build_tables(mm_engine* e) {
   }
   e->K = c.n_modes * e->stride;
   e->Kp = e->K + 1;
+  if (e->Kp > 65535u) return MM_E_ARG;  // the resident sort key is 16 bits
   e->n_segs = c.n_modes * G;
   std::vector<uint32_t> seg_lo(e->n_segs + 1), seg_L(e->n_segs);
   e->min_L = 0xFFFFFFFFu;
@@ -299,7 +323,7 @@ int alloc_tick_scratch(mm_engine* e) {
   e->R = (uint32_t)e->n_sms * (uint32_t)e->rows_per_sm;
   if (e->R > kMaxRows) e->R = kMaxRows;
   if (e->d_M) { cudaFree(e->d_M); cudaFree(e->d_rescnt); }
-  CK(cudaMalloc(&e->d_M, (size_t)e->R * e->Kp * 4));
+  CK(cudaMalloc(&e->d_M, (size_t)(e->R + 1) * e->Kp * 4));
   CK(cudaMalloc(&e->d_rescnt, (size_t)(e->R + 1) * 4));
   return MM_OK;
 }
@@ -307,7 +331,8 @@ int alloc_tick_scratch(mm_engine* e) {
 int ensure_enq_scratch(mm_engine* e, uint32_t n) {
   if (n <= e->enq_cap) return MM_OK;
   cudaFree(e->d_in_id); cudaFree(e->d_hslot); cudaFree(e->d_in_rating); cudaFree(e->d_in_mode);
-  cudaFree(e->d_code); cudaFree(e->d_in_ts); cudaFree(e->d_blocksum);
+  cudaFree(e->d_code); cudaFree(e->d_in_ts); cudaFree(e->d_blocksum); cudaFree(e->d_part); cudaFree(e->d_in_key);
+  cudaFree(e->d_in_handle);
   e->enq_cap = 0;
   const size_t c = (size_t)n + 64;
   CK(cudaMalloc(&e->d_in_id, c * 8));
@@ -315,18 +340,22 @@ int ensure_enq_scratch(mm_engine* e, uint32_t n) {
   CK(cudaMalloc(&e->d_in_rating, c * 4));
   CK(cudaMalloc(&e->d_in_mode, c));
   CK(cudaMalloc(&e->d_code, c));
+  CK(cudaMalloc(&e->d_part, c * 2));
+  CK(cudaMalloc(&e->d_in_key, c * 2));
+  CK(cudaMalloc(&e->d_in_handle, c * 4));
   CK(cudaMalloc(&e->d_in_ts, c * 4));
-  CK(cudaMalloc(&e->d_blocksum, (c / 256 + 2) * 4));
+  CK(cudaMalloc(&e->d_blocksum, (std::min<size_t>(c, kEnqChunk) / 256 + 2) * 4));
   e->enq_cap = n;
   return MM_OK;
 }
 
-// Drop tombstones: re-insert the committed entries into the spare table.
+// Drop tombstones: re-insert the committed entries into the spare table (hashed mode).
 int rehash(mm_engine* e) {
   Table& nt = e->tab[e->tcur ^ 1];
   int rc = clear_table(e, nt);
   if (rc) return rc;
-  ActiveView oldv = act_view(e), newv{{nt.kv}, {nt.kv + 1}, e->hcap - 1};
+  ActiveView oldv = act_view(e), newv{};
+  newv.kv = nt.kv; newv.mask = e->hcap - 1;
   k_rehash<<<2048, 256, 0, e->stream>>>(oldv, newv);
   CK(cudaGetLastError());
   CK(cudaStreamSynchronize(e->stream));
@@ -339,33 +368,38 @@ int rehash(mm_engine* e) {
 int enq_prepare(mm_engine* e, uint32_t n) {
   int rc = ensure_enq_scratch(e, n);
   if (rc) return rc;
-  if (e->use_active && (e->n_active + e->n_tomb + n) * 4 > e->hcap * 3) {
-    if ((e->n_active + n) * 4 > e->hcap * 3) return MM_E_CAP;  // active set full
+  if (e->use_active && !e->dense_ids && (e->n_active + e->n_tomb + n) * 4 > e->hcap * 3) {
+    if ((e->n_active + n) * 4 > e->hcap * 3) {
+      std::snprintf(e->last_err, sizeof(e->last_err), "active set full: %llu ids resident, batch of %u, capacity %llu",
+                    (unsigned long long)e->n_active, n, (unsigned long long)(e->hcap * 3 / 4));
+      return MM_E_CAP;
+    }
     if ((rc = rehash(e))) return rc;
   }
   CK(cudaMemsetAsync(e->d_small, 0, 16, e->stream));
   return MM_OK;
 }
 
-// E1 on batch indices [base, base + cnt): validate + claim in the active set
-int enq_claim(mm_engine* e, uint32_t base, uint32_t cnt, const uint64_t* id, const int32_t* rating, const uint8_t* mode) {
-  k_enq_claim<<<(cnt + 255) / 256, 256, 0, e->stream>>>(base, cnt, id, rating, mode, e->d_grp_lut, e->key_lo, e->KR,
-                                                         e->cfg.n_modes, act_view(e), e->d_hslot, e->d_code);
-  CK(cudaGetLastError());
-  return MM_OK;
-}
-
-// E2 + E3 on batch indices [base, base + cnt): winners, stable append to the pool (after the winners of the
-// earlier chunks: the running total lives in d_small[0]), commit
-int enq_append(mm_engine* e, uint32_t base, uint32_t cnt, const uint64_t* id, const int32_t* rating, const uint8_t* mode,
-               const uint32_t* ts) {
-  const uint32_t nb = (cnt + 255) / 256;
+// one ingest chunk = batch indices [base, base + cnt): claim, (exact capacity cut), route, alloc, append
+int enq_chunk(mm_engine* e, uint32_t base, uint32_t cnt, const uint64_t* id, const int32_t* rating, const uint8_t* mode,
+              const uint32_t* ts, bool may_overflow) {
   Pool& p = e->pool[e->cur];
   ActiveView av = act_view(e);
-  k_enq_count<<<nb, 256, 0, e->stream>>>(base, cnt, av, e->d_hslot, e->d_code, e->d_blocksum);
-  k_scan_small<<<1, 1024, 0, e->stream>>>(nb, e->d_blocksum, e->d_small);
-  k_enq_append<<<nb, 256, 0, e->stream>>>(base, cnt, id, rating, mode, ts, e->d_mode_tsize, av, e->d_hslot, e->d_code,
-                                          e->d_blocksum, p.v, p.n, e->capacity, e->gen, e->d_small + 1, bin_map(e));
+  const uint32_t nb = (cnt + 255) / 256, nblk = (cnt + kIngestItems - 1) / kIngestItems;
+  k_enq_claim<<<nb, 256, 0, e->stream>>>(base, cnt, id, rating, mode, e->d_grp_lut, e->key_lo, e->KR, e->cfg.n_modes,
+                                         e->cfg.n_groups, av, e->d_hslot, e->d_code, e->d_part);
+  if (may_overflow) {  // the batch might not fit: the winners past the pool capacity are rolled back (code 3)
+    const uint32_t room = e->capacity > p.n ? e->capacity - p.n : 0u;
+    k_enq_count<<<nb, 256, 0, e->stream>>>(base, cnt, av, e->d_hslot, e->d_code, e->d_blocksum);
+    k_scan_small<<<1, 1024, 0, e->stream>>>(nb, e->d_blocksum, e->d_small + 3);
+    k_enq_cut<<<nb, 256, 0, e->stream>>>(base, cnt, av, e->d_hslot, e->d_code, e->d_blocksum, room, e->d_small + 1);
+  }
+  k_enq_route<<<nblk, 256, 0, e->stream>>>(base, cnt, av, e->d_hslot, e->d_code, e->d_part, e->n_segs, nblk, e->d_blockhist);
+  k_enq_alloc<<<1, 512, 0, e->stream>>>(e->n_segs, nblk, e->d_blockhist, p.m, e->d_small);
+  const size_t smem = ((size_t)(8 * (e->n_segs + 1) + 1) / 2 + e->n_segs) * 4;
+  k_enq_append<<<nblk, 256, smem, e->stream>>>(base, cnt, id, rating, mode, ts, e->d_mode_tsize, av, e->d_hslot, e->d_code,
+                                               e->d_part, e->n_segs, nblk, e->d_blockhist, p.v, p.m, e->gen, e->seq_next,
+                                               bin_map(e));
   CK(cudaGetLastError());
   return MM_OK;
 }
@@ -376,122 +410,82 @@ int enq_finish(mm_engine* e, uint32_t n, uint8_t* accepted_dev, uint32_t* n_acce
   CK(cudaMemcpyAsync(e->h_small, e->d_small, 16, cudaMemcpyDeviceToHost, e->stream));
   if (accepted_dev) CK(cudaMemcpyAsync(accepted_dev, e->d_code, n, cudaMemcpyDeviceToDevice, e->stream));
   CK(cudaStreamSynchronize(e->stream));
-  const uint32_t won = e->h_small[0], rej = e->h_small[1];
-  const uint32_t acc = won - rej;
+  const uint32_t acc = e->h_small[0], rej = e->h_small[1];
   p.n += acc;
-  if (e->use_active) { e->n_active += acc; e->n_tomb += rej; }
+  e->seq_next += n;
+  if (e->use_active) { e->n_active += acc; if (!e->dense_ids) e->n_tomb += rej; }
   if (n_accepted) *n_accepted = acc;
   return MM_OK;
 }
 
-int enqueue_device_locked(mm_engine* e, uint32_t n, const uint64_t* id, const int32_t* rating, const uint8_t* mode,
-                          const uint32_t* ts, uint8_t* accepted, uint32_t* n_accepted) {
-  if (n_accepted) *n_accepted = 0;
-  if (n == 0) return MM_OK;
+// Device columns of a whole batch -> pool.  `upload` (may be null) queues the H2D copies of one chunk on the copy
+// stream: the previous chunk's kernels run on the engine stream meanwhile, so the device side of the ingest hides
+// behind the PCIe transfer except for the last chunk.
+template <class Upload>
+int enqueue_batch(mm_engine* e, uint32_t n, const uint64_t* id, const int32_t* rating, const uint8_t* mode,
+                  const uint32_t* ts, Upload upload) {
   int rc = enq_prepare(e, n);
   if (rc) return rc;
-  if ((rc = enq_claim(e, 0, n, id, rating, mode))) return rc;
-  if ((rc = enq_append(e, 0, n, id, rating, mode, ts))) return rc;
-  return enq_finish(e, n, accepted, n_accepted);
-}
-
-// Pin member_ids in a persisting L2 carve-out: the 8-byte scatter of k_place completes
-// 32-byte sectors at unrelated times, so the lines must survive in L2 until the kernel ends
-// (measured: -50 us and -79 MB of DRAM fill reads on the 10M-player tick).
-int set_persist(mm_engine* e, int64_t mb) {
-  CK(cudaStreamSynchronize(e->stream));
-  cudaStreamAttrValue attr{};
-  if (mb > 0) {
-    int max_persist = 0, max_win = 0;
-    CK(cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, e->device));
-    CK(cudaDeviceGetAttribute(&max_win, cudaDevAttrMaxAccessPolicyWindowSize, e->device));
-    const size_t want = std::min<size_t>((size_t)mb << 20, (size_t)max_persist);
-    if (want == 0) return MM_OK;
-    CK(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want));
-    const size_t win = std::min<size_t>({(size_t)e->capacity * 8, (size_t)max_win});
-    attr.accessPolicyWindow.base_ptr = e->d_members;
-    attr.accessPolicyWindow.num_bytes = win;
-    attr.accessPolicyWindow.hitRatio = win ? std::min(1.0f, (float)want / (float)win) : 0.f;
-    attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
-    attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
-    e->persist_bytes = want;
-  } else {
-    attr.accessPolicyWindow.num_bytes = 0;
-    e->persist_bytes = 0;
+  const bool may_overflow = (uint64_t)e->pool[e->cur].n + n > e->capacity;
+  for (uint32_t base = 0; base < n; base += kEnqChunk) {
+    const uint32_t cnt = std::min(kEnqChunk, n - base);
+    if ((rc = upload(base, cnt))) return rc;
+    if ((rc = enq_chunk(e, base, cnt, id, rating, mode, ts, may_overflow))) return rc;
   }
-  CK(cudaStreamSetAttribute(e->stream, cudaStreamAttributeAccessPolicyWindow, &attr));
   return MM_OK;
 }
 
-uint32_t dense_mode(const mm_engine* e) {
-  if (!e->dense_ok) return 0u;
-  if (place2_dense2(e) && e->block == 512 && e->dense_ok != 1) return 2u;  // dense_ok: 1 = MATCH variant only
-  return place2_dense(e) ? 1u : 0u;
-}
-
-TailArgs tail_args(const mm_engine* e) {
+TailArgs tail_args(mm_engine* e) {
   TailArgs t{};
   t.Kp = e->Kp; t.K = e->K; t.n_segs = e->n_segs; t.max_spread = e->max_spread; t.layout = tail_layout(e);
   t.tot = e->d_tot; t.seg_bin_lo = e->d_seg_bin_lo; t.seg_L = e->d_seg_L; t.bin_seg = e->d_bin_seg;
   t.bin_key = e->d_bin_key; t.outbase = e->d_outbase; t.binlim = e->d_binlim; t.seg = e->d_seg; t.ctr = e->d_ctr;
+  t.fill = e->pool[e->cur].m.fill;
+  t.dst = e->pool[e->cur ^ 1].m;
   return t;
 }
-
-// launches k_hist + k_colscan and returns the counters (phase A of a tick)
-int tick_phase_a(mm_engine* e, uint32_t n, uint32_t* chunk_out) {
+PlaceArgs place_args(mm_engine* e, bool want_seq) {
   const Pool& p = e->pool[e->cur];
-  uint32_t chunk = (n + e->R - 1) / e->R;
-  chunk = std::max<uint32_t>(((chunk + kRound - 1) / kRound) * kRound, kRound);
-  *chunk_out = chunk;
+  PlaceArgs a{};
+  a.bins16 = p.v.bin; a.ids = p.v.id; a.meta = p.m;
+  a.K = e->K; a.Kp = e->Kp; a.R = e->R; a.stages = e->place_stages; a.fast_ok = e->rank_impl == 3;
+  a.seg_bin_lo = e->d_seg_bin_lo; a.bin_seg = e->d_bin_seg; a.M = e->d_M; a.tot = e->d_tot;
+  a.outbase = e->d_outbase; a.binlim = e->d_binlim; a.members = e->d_members;
+  a.src_idx = want_seq ? e->d_src_idx : nullptr;
+  a.left_bits = e->d_left_bits; a.rescnt = e->d_rescnt; a.ctr = e->d_ctr;
+  return a;
+}
+uint32_t next_gen(const mm_engine* e) { return e->gen >= kGenMask ? 1u : e->gen + 1; }
+EpiArgs epi_args(mm_engine* e, bool want_seq) {
+  EpiArgs a{};
+  a.src = e->pool[e->cur].v; a.dst = e->pool[e->cur ^ 1].v;
+  a.src_meta = e->pool[e->cur].m; a.dst_meta = e->pool[e->cur ^ 1].m;
+  a.R = e->R; a.new_gen = next_gen(e); a.n_segs = e->n_segs; a.n_groups = e->cfg.n_groups; a.Kp = e->Kp;
+  a.rescnt = e->d_rescnt; a.left_bits = e->d_left_bits; a.act = act_view(e); a.seg = e->d_seg; a.seg_L = e->d_seg_L;
+  a.hdr = e->d_hdr; a.src_idx = want_seq ? e->d_src_idx : nullptr; a.emit_seq = want_seq ? e->d_emit_seq : nullptr;
+  a.tot = e->d_tot; a.ctr = e->d_ctr;
+  return a;
+}
+
+// launches k_hist + k_colscan (phase A of a tick): the counters are final afterwards
+int tick_phase_a(mm_engine* e) {
+  const Pool& p = e->pool[e->cur];
   CK(cudaMemsetAsync(e->d_ctr, 0, sizeof(TickCtr), e->stream));
   CK(cudaEventRecord(e->ev[0], e->stream));
-  if (e->rank_impl == 3) {
-    if (e->block == 512)
-      k_hist3<512><<<e->R, 512, hist3_smem(e, e->hist3_stages), e->stream>>>(p.v.bin, n, chunk, e->Kp, e->hist3_stages, e->d_M,
-                                                                              e->d_tot);
-    else
-      k_hist3<1024><<<e->R, 1024, hist3_smem(e, e->hist3_stages), e->stream>>>(p.v.bin, n, chunk, e->Kp, e->hist3_stages,
-                                                                                e->d_M, e->d_tot);
-  } else if (e->block == 512) {
-    k_hist<512><<<e->R, 512, hist_smem(e), e->stream>>>(p.v, n, chunk, bin_map(e), e->Kp, e->d_M, e->d_tot, nullptr);
-  } else {
-    k_hist<1024><<<e->R, 1024, hist_smem(e), e->stream>>>(p.v, n, chunk, bin_map(e), e->Kp, e->d_M, e->d_tot, nullptr);
-  }
+  k_hist<512><<<e->R, 512, hist_smem_bytes(e->Kp, e->hist_stages), e->stream>>>(
+      p.v.bin, p.m, e->n_segs, e->R, e->Kp, e->K, e->hist_stages, e->d_seg_bin_lo, e->d_M, e->d_tot);
   CK(cudaEventRecord(e->ev[1], e->stream));
-  k_colscan<<<(e->Kp + 31) / 32 + 1, kScanBlock, colscan_smem(e), e->stream>>>(e->R, e->d_M, tail_args(e));
+  k_colscan<<<(e->K + 31) / 32 + 1, kScanBlock, colscan_smem(e), e->stream>>>(e->R, e->d_M, tail_args(e));
   CK(cudaGetLastError());
   return MM_OK;
 }
 
-int tick_phase_b(mm_engine* e, uint32_t n, uint32_t chunk, bool want_seq) {
-  const Pool& p = e->pool[e->cur];
-  Pool& q = e->pool[e->cur ^ 1];
-  uint32_t* src_idx = want_seq ? e->d_src_idx : nullptr;
+int tick_phase_b(mm_engine* e, bool want_seq) {
   CK(cudaEventRecord(e->ev[2], e->stream));
-#define MM_PLACE(IMPL)                                                                                               \
-  k_place<IMPL><<<e->R, kBlock, place_smem(e, IMPL), e->stream>>>(                                                    \
-      p.v, n, chunk, bin_map(e), e->Kp, e->R, e->d_M, e->d_tot, e->d_outbase, e->d_binlim, e->d_members, src_idx,     \
-      e->d_left_bits, e->d_rescnt, e->d_ctr)
-#define MM_PLACE2(BLK)                                                                                               \
-  k_place2<BLK><<<e->R, BLK, place2_smem(e, e->place2_stages), e->stream>>>(                                          \
-      p.v.bin, p.v.id, n, chunk, e->K, e->Kp, e->R, e->place2_stages, dense_mode(e), e->d_M, e->d_tot,                \
-      e->d_outbase, e->d_binlim, e->d_members, src_idx, e->d_left_bits, e->d_rescnt, e->d_ctr,                        \
-      (uint32_t)e->place_debug)
-  if (e->rank_impl == 3) {
-    if (e->block == 512) MM_PLACE2(512);
-    else MM_PLACE2(1024);
-  } else if (e->rank_impl == 0) {
-    MM_PLACE(0);
-  } else {
-    MM_PLACE(1);
-  }
-#undef MM_PLACE2
-#undef MM_PLACE
+  k_place<512><<<e->R, 512, place_smem_bytes(e->Kp, e->place_stages), e->stream>>>(place_args(e, want_seq),
+                                                                                   e->pool[e->cur].m.fill, e->n_segs);
   CK(cudaEventRecord(e->ev[3], e->stream));
-  k_epilogue<<<std::max(1, e->n_sms), 1024, 0, e->stream>>>(p.v, q.v, n, chunk, e->R, e->d_rescnt, e->d_left_bits, act_view(e),
-                                                           e->gen + 1, e->d_seg, e->d_seg_L, e->n_segs, e->cfg.n_groups,
-                                                           e->d_hdr, src_idx, want_seq ? e->d_emit_seq : nullptr, e->d_tot,
-                                                           e->Kp, e->d_ctr);
+  k_epilogue<512><<<std::max(1, e->n_sms), 512, 0, e->stream>>>(epi_args(e, want_seq));
   CK(cudaGetLastError());
   CK(cudaEventRecord(e->ev[4], e->stream));
   CK(cudaMemcpyAsync(e->h_ctr, e->d_ctr, sizeof(TickCtr), cudaMemcpyDeviceToHost, e->stream));
@@ -499,26 +493,18 @@ int tick_phase_b(mm_engine* e, uint32_t n, uint32_t chunk, bool want_seq) {
   return MM_OK;
 }
 
-bool use_fused(const mm_engine* e) {
-  return e->tick_impl == 1 && e->fused_ok && e->rank_impl == 3 && e->block == 512 && e->rows_per_sm == 2;
-}
+bool use_fused(const mm_engine* e) { return e->tick_impl == 1 && e->fused_ok; }
 
 // the whole tick in one cooperative launch (k_tick)
-int tick_fused(mm_engine* e, uint32_t n, bool want_seq) {
-  const Pool& p = e->pool[e->cur];
-  Pool& q = e->pool[e->cur ^ 1];
-  uint32_t chunk = (n + e->R - 1) / e->R;
-  chunk = std::max<uint32_t>(((chunk + kRound - 1) / kRound) * kRound, kRound);
+int tick_fused(mm_engine* e, bool want_seq) {
   TickArgs a{};
-  a.src = p.v; a.dst = q.v; a.left_bits = e->d_left_bits;
-  a.n = n; a.chunk = chunk; a.R = e->R; a.n_groups = e->cfg.n_groups;
-  a.hist_stages = e->hist3_stages; a.place_stages = e->place2_stages;
-  a.dense = dense_mode(e);
-  a.new_gen = e->gen + 1; a.dbg = (uint32_t)e->place_debug;
-  a.M = e->d_M; a.tot = e->d_tot; a.tail = tail_args(e);
-  a.members = e->d_members; a.src_idx = want_seq ? e->d_src_idx : nullptr; a.hdr = e->d_hdr;
-  a.emit_seq = want_seq ? e->d_emit_seq : nullptr; a.rescnt = e->d_rescnt;
-  a.act = act_view(e);
+  a.src = e->pool[e->cur].v;
+  a.hist_stages = e->hist_stages;
+  a.M = e->d_M;
+  a.tot = e->d_tot;
+  a.tail = tail_args(e);
+  a.place = place_args(e, want_seq);
+  a.epi = epi_args(e, want_seq);
   CK(cudaMemsetAsync(e->d_ctr, 0, sizeof(TickCtr), e->stream));
   CK(cudaEventRecord(e->ev[0], e->stream));
   void* params[] = {&a};
@@ -543,26 +529,19 @@ int tick_commit(mm_engine* e, uint32_t n, mm_tick_stats* stats) {
     st.scan_us = (float)(c.t[2] - c.t[1]) * 1e-3f;
     st.place_us = (float)(c.t[3] - c.t[2]) * 1e-3f;
     st.epilogue_us = (float)(c.t[6] - c.t[3]) * 1e-3f;  // until the last CTA is done
-    // debug: lobby headers done (max over CTAs) after barrier 3, in 10 ns units
-    st.reserved = (uint32_t)((c.t[7] - c.t[3]) / 10);
-    e->cur ^= 1;
-    e->pool[e->cur].n = c.n_resid;
-    e->gen += 1;
-    e->last = st;
-    if (stats) *stats = st;
-    return MM_OK;
+  } else {
+    CK(cudaEventElapsedTime(&ms, e->ev[0], e->ev[1]));
+    st.hist_us = ms * 1000.f;
+    CK(cudaEventElapsedTime(&ms, e->ev[1], e->ev[2]));
+    st.scan_us = ms * 1000.f;
+    CK(cudaEventElapsedTime(&ms, e->ev[2], e->ev[3]));
+    st.place_us = ms * 1000.f;
+    CK(cudaEventElapsedTime(&ms, e->ev[3], e->ev[4]));
+    st.epilogue_us = ms * 1000.f;
   }
-  CK(cudaEventElapsedTime(&ms, e->ev[0], e->ev[1]));
-  st.hist_us = ms * 1000.f;
-  CK(cudaEventElapsedTime(&ms, e->ev[1], e->ev[2]));
-  st.scan_us = ms * 1000.f;
-  CK(cudaEventElapsedTime(&ms, e->ev[2], e->ev[3]));
-  st.place_us = ms * 1000.f;
-  CK(cudaEventElapsedTime(&ms, e->ev[3], e->ev[4]));
-  st.epilogue_us = ms * 1000.f;
+  e->gen = next_gen(e);
   e->cur ^= 1;
   e->pool[e->cur].n = c.n_resid;
-  e->gen += 1;
   e->last = st;
   if (stats) *stats = st;
   return MM_OK;
@@ -574,6 +553,55 @@ int wait_results(mm_engine* e) {
     CK(cudaStreamSynchronize(e->d2h_stream));
     e->results_pending = false;
   }
+  return MM_OK;
+}
+
+// mm_tick / mm_tick_packed: run the tick and copy lobbies + members (u64 ids or u32 handles) to host buffers
+int tick_to_host(mm_engine* e, mm_lobby_hdr* lobbies, uint32_t lobby_cap, uint64_t* member_ids, uint32_t* member_handles,
+                 uint64_t member_cap, uint32_t* emit_seq, mm_tick_stats* stats) {
+  const uint32_t n = e->pool[e->cur].n;
+  const bool want_members = member_ids || member_handles;
+  int rc;
+  if ((rc = wait_results(e))) return rc;
+  // worst-case output sizes known up front -> the fused single launch is safe
+  e->last_fused = use_fused(e) && (!lobbies || (uint64_t)lobby_cap >= n / e->min_L) && (!want_members || member_cap >= n);
+  if (e->last_fused) {
+    if ((rc = tick_fused(e, emit_seq != nullptr))) return rc;
+  } else {
+    if ((rc = tick_phase_a(e))) return rc;
+    // the counts are final after phase A: check the caller's capacities before consuming
+    CK(cudaMemcpyAsync(e->h_ctr, e->d_ctr, sizeof(TickCtr), cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    if ((lobbies && e->h_ctr->n_lobbies > lobby_cap) || (want_members && e->h_ctr->n_matched > member_cap)) {
+      std::snprintf(e->last_err, sizeof(e->last_err), "need lobby_cap >= %u, member_cap >= %u", e->h_ctr->n_lobbies,
+                    e->h_ctr->n_matched);
+      CK(cudaMemsetAsync(e->d_tot, 0, (e->Kp + 1) * 4, e->stream));  // the epilogue that re-zeroes it will not run
+      CK(cudaStreamSynchronize(e->stream));
+      return MM_E_CAP;
+    }
+    if ((rc = tick_phase_b(e, emit_seq != nullptr))) return rc;
+  }
+  if ((rc = tick_commit(e, n, stats))) return rc;
+  const TickCtr& c = *e->h_ctr;
+  if (member_handles && c.n_matched) {
+    if (!e->d_members32) CK(cudaMalloc(&e->d_members32, ((size_t)e->capacity + 64) * 4));
+    k_narrow<<<std::max(1, 4 * e->n_sms), 256, 0, e->stream>>>(c.n_matched, e->d_members, e->d_members32);
+    CK(cudaGetLastError());
+    if (e->async_results) CK(cudaStreamSynchronize(e->stream));  // the copy stream must see the narrowed handles
+  }
+  // the tick is complete here (tick_commit synchronised the engine stream); with async_results the copies run on
+  // their own stream and the call returns: the caller may ingest the next batch meanwhile (PCIe is full duplex)
+  cudaStream_t cs = e->async_results ? e->d2h_stream : e->stream;
+  if (lobbies && c.n_lobbies)
+    CK(cudaMemcpyAsync(lobbies, e->d_hdr, (size_t)c.n_lobbies * sizeof(mm_lobby_hdr), cudaMemcpyDeviceToHost, cs));
+  if (member_ids && c.n_matched)
+    CK(cudaMemcpyAsync(member_ids, e->d_members, (size_t)c.n_matched * 8, cudaMemcpyDeviceToHost, cs));
+  if (member_handles && c.n_matched)
+    CK(cudaMemcpyAsync(member_handles, e->d_members32, (size_t)c.n_matched * 4, cudaMemcpyDeviceToHost, cs));
+  if (emit_seq && c.n_lobbies)
+    CK(cudaMemcpyAsync(emit_seq, e->d_emit_seq, (size_t)c.n_lobbies * 4, cudaMemcpyDeviceToHost, cs));
+  if (e->async_results) { e->results_pending = true; return MM_OK; }
+  CK(cudaStreamSynchronize(e->stream));
   return MM_OK;
 }
 
@@ -638,6 +666,7 @@ int mm_create(const mm_config* cfg, mm_engine** out) {
   e->device = cfg->device;
   e->capacity = cfg->capacity;
   e->use_active = !(cfg->flags & MM_F_NO_DEDUPE);
+  e->dense_ids = e->use_active && (cfg->flags & MM_F_DENSE_IDS);
   auto bail = [&](int code) { mm_destroy(e); return code; };
   if (cudaSetDevice(e->device) != cudaSuccess) return bail(MM_E_CUDA);
   cudaDeviceProp prop{};
@@ -653,52 +682,39 @@ int mm_create(const mm_config* cfg, mm_engine** out) {
   for (auto& ev : e->ev)
     if (cudaEventCreate(&ev) != cudaSuccess) return bail(MM_E_CUDA);
   if ((rc = build_tables(e))) return bail(rc);
-  // the placement kernel keeps one slot counter (and one list head) per bin in shared memory
-  if (place_smem(e, 1) > e->smem_optin) e->rank_impl = 0;
-  if (place_smem(e, 0) > e->smem_optin) {
-    std::snprintf(e->last_err, sizeof(e->last_err), "key domain too large for shared memory: %u bins", e->Kp);
-    return bail(MM_E_ARG);
-  }
   {
-    // NOTE: function attributes are process-global.  Every kernel gets the device's opt-in maximum so that
-    // an engine with a small key domain never lowers the limit another engine of this process relies on.
-    if (allow_max_smem(e, k_colscan) != cudaSuccess)
-      return bail(fail(e, cudaGetLastError(), "allow_max_smem(e, k_colscan)"));
-    bool ok = allow_max_smem(e, k_hist<1024>) == cudaSuccess &&
-              allow_max_smem(e, k_place<0>) == cudaSuccess;
-    if (ok && e->rank_impl == 1)
-      ok = allow_max_smem(e, k_place<1>) == cudaSuccess;
-    ok = ok && allow_max_smem(e, k_hist<512>) == cudaSuccess;
-    // The TMA-fed kernel wants >= 2 ring stages next to its per-bin state; when two such CTAs
-    // (512 threads each) fit in one SM, rows = 2 x SMs so barrier phases of one overlap the other.
-    if (e->rank_impl == 1 && e->Kp <= 65535u) {
-      for (uint32_t st = 3; st >= 2 && !e->place2_stages; --st)
-        if (2 * (place2_smem(e, st) + 1024 + 256) <= e->smem_sm) { e->place2_stages = st; e->rows_per_sm = 2; e->block = 512; }
-      for (uint32_t st = kMaxStages; st >= 2 && !e->place2_stages; --st)
-        if (place2_smem(e, st) + 1024 <= e->smem_optin) { e->place2_stages = st; e->rows_per_sm = 1; e->block = 1024; }
+    // Two 512-thread CTAs per SM when the placement phase's per-bin state allows it (one CTA's barrier phases
+    // overlap the other's work), else one.  Function attributes are process-global:
+    // every kernel gets the device's opt-in maximum.
+    const size_t static_smem = sizeof(Geo) + 512;
+    for (uint32_t st = 3; st >= 2 && !e->place_stages; --st)
+      if (2 * (place_smem_bytes(e->Kp, st) + static_smem + 1024) <= e->smem_sm) { e->place_stages = st; e->rows_per_sm = 2; }
+    for (uint32_t st = kMaxStages; st >= 1 && !e->place_stages; --st)  // huge key domains: down to a single stage
+      if (place_smem_bytes(e->Kp, st) + static_smem + 1024 <= e->smem_optin) { e->place_stages = st; e->rows_per_sm = 1; }
+    if (!e->place_stages || colscan_smem(e) + static_smem + 1024 > e->smem_optin) {
+      std::snprintf(e->last_err, sizeof(e->last_err), "key domain too large for shared memory: %u bins", e->Kp);
+      return bail(MM_E_ARG);
     }
-    if (ok && e->place2_stages) {
-      while (e->hist3_stages > 2 && ((size_t)e->rows_per_sm * (hist3_smem(e, e->hist3_stages) + 1280) > e->smem_sm ||
-                                     hist3_smem(e, e->hist3_stages) + 1024 > e->smem_optin))
-        --e->hist3_stages;
-      ok = allow_max_smem(e, k_hist3<512>) == cudaSuccess && allow_max_smem(e, k_hist3<1024>) == cudaSuccess;
-    }
-    if (ok && e->place2_stages) {
-      ok = allow_max_smem(e, k_place2<512>) == cudaSuccess &&
-           allow_max_smem(e, k_place2<1024>) == cudaSuccess;
-      e->rank_impl = 3;
-    }
+    bool ok = allow_max_smem(e, k_colscan) == cudaSuccess && allow_max_smem(e, k_hist<512>) == cudaSuccess &&
+              allow_max_smem(e, k_place<512>) == cudaSuccess && allow_max_smem(e, k_tick<512>) == cudaSuccess;
     if (!ok) return bail(fail(e, cudaGetLastError(), "cudaFuncSetAttribute"));
   }
-  if ((rc = alloc_pool(e, e->pool[0], e->capacity)) || (rc = alloc_pool(e, e->pool[1], e->capacity))) return bail(rc);
-  if (cudaMalloc(&e->d_left_bits, (((size_t)e->capacity + 3 * kRound) / 32 + 64) * 4) != cudaSuccess) return bail(MM_E_CUDA);
+  e->n_chunks = (e->capacity + kTile - 1) / kTile + e->n_segs + 2;
+  if ((uint64_t)e->n_chunks * e->n_segs * 4 > (8ull << 30)) return bail(MM_E_CAP);
+  if ((rc = alloc_pool(e, e->pool[0])) || (rc = alloc_pool(e, e->pool[1]))) return bail(rc);
+  if (cudaMalloc(&e->d_left_bits, (pool_slots(e) / 32 + 64) * 4) != cudaSuccess) return bail(MM_E_CUDA);
   if (e->use_active) {
-    uint64_t want = cfg->active_capacity ? cfg->active_capacity : 2ull * cfg->capacity;
-    uint64_t h = 1024;
-    while (h * 3 < want * 4 + 64) h <<= 1;  // load factor <= 0.75 at active_capacity
-    e->hcap = h;
-    for (auto& t : e->tab) {
-      if (cudaMalloc(&t.kv, h * 16) != cudaSuccess) return bail(MM_E_CUDA);
+    const uint64_t want = cfg->active_capacity ? cfg->active_capacity : 2ull * cfg->capacity;
+    if (e->dense_ids) {
+      e->hcap = want;  // handles 0 .. active_capacity - 1
+      for (auto& t : e->tab) t.kv = nullptr;
+      if (cudaMalloc(&e->tab[0].kv, e->hcap * 8) != cudaSuccess) return bail(MM_E_CUDA);
+    } else {
+      uint64_t h = 1024;
+      while (h * 3 < want * 4 + 64) h <<= 1;  // load factor <= 0.75 at active_capacity
+      e->hcap = h;
+      for (auto& t : e->tab)
+        if (cudaMalloc(&t.kv, h * 16) != cudaSuccess) return bail(MM_E_CUDA);
     }
     if ((rc = clear_table(e, e->tab[0]))) return bail(rc);
   }
@@ -710,18 +726,18 @@ int mm_create(const mm_config* cfg, mm_engine** out) {
       !A((void**)&e->d_members, cap * 8) || !A((void**)&e->d_src_idx, cap * 4) ||
       !A((void**)&e->d_hdr, (size_t)e->max_lobbies * sizeof(mm_lobby_hdr)) ||
       !A((void**)&e->d_emit_seq, (size_t)e->max_lobbies * 4) || !A((void**)&e->d_ctr, sizeof(TickCtr)) ||
-      !A((void**)&e->d_small, 64))
+      !A((void**)&e->d_small, 64) ||
+      !A((void**)&e->d_blockhist, (size_t)e->n_segs * (kEnqChunk / kIngestItems + 1) * 4))
     return bail(fail(e, cudaGetLastError(), "cudaMalloc"));
   if (cudaMallocHost(&e->h_ctr, sizeof(TickCtr)) != cudaSuccess || cudaMallocHost(&e->h_small, 64) != cudaSuccess)
     return bail(MM_E_CUDA);
   if ((rc = alloc_tick_scratch(e))) return bail(rc);
-  if (e->rank_impl == 3 && e->block == 512 && e->rows_per_sm == 2) {
-    size_t sz = std::max(hist3_smem(e, e->hist3_stages), place2_smem(e, e->place2_stages));
+  {
+    size_t sz = std::max(hist_smem_bytes(e->Kp, e->hist_stages), place_smem_bytes(e->Kp, e->place_stages));
     sz = std::max<size_t>(sz, std::max<size_t>((size_t)kEpiScratchWords * 4, colscan_smem(e)));
     int coop = 0, nb = 0;
     cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, e->device);
-    if (coop && allow_max_smem(e, k_tick<512>) == cudaSuccess &&
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_tick<512>, 512, sz) == cudaSuccess &&
+    if (coop && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_tick<512>, 512, sz) == cudaSuccess &&
         (uint32_t)nb * (uint32_t)e->n_sms >= e->R) {
       e->fused_ok = 1;
       e->tick_smem = sz;
@@ -729,7 +745,6 @@ int mm_create(const mm_config* cfg, mm_engine** out) {
     cudaGetLastError();
   }
   if (cudaMemsetAsync(e->d_tot, 0, (e->Kp + 1) * 4, e->stream) != cudaSuccess) return bail(MM_E_CUDA);
-  if ((rc = set_persist(e, 1024))) return bail(rc);  // clamped to the device's persisting-L2 maximum
   if (cudaStreamSynchronize(e->stream) != cudaSuccess) return bail(MM_E_CUDA);
   *out = e;
   return MM_OK;
@@ -739,20 +754,22 @@ int mm_destroy(mm_engine* e) {
   if (!e) return MM_OK;
   cudaSetDevice(e->device);
   if (e->stream) cudaStreamSynchronize(e->stream);
+  if (e->d2h_stream) cudaStreamSynchronize(e->d2h_stream);
   free_pool(e->pool[0]); free_pool(e->pool[1]); free_pool(e->snap); cudaFree(e->d_left_bits);
   for (auto& t : e->tab) cudaFree(t.kv);
   cudaFree(e->d_lut); cudaFree(e->d_grp_lut); cudaFree(e->d_mode_tsize); cudaFree(e->d_seg_bin_lo); cudaFree(e->d_seg_L);
   cudaFree(e->d_M); cudaFree(e->d_tot); cudaFree(e->d_outbase); cudaFree(e->d_binlim); cudaFree(e->d_bin_seg);
-  cudaFree(e->d_bin_key); cudaFree(e->d_seg); cudaFree(e->d_members); cudaFree(e->d_src_idx); cudaFree(e->d_hdr);
-  cudaFree(e->d_emit_seq); cudaFree(e->d_rescnt); cudaFree(e->d_ctr); cudaFree(e->d_small);
+  cudaFree(e->d_bin_key); cudaFree(e->d_seg); cudaFree(e->d_members); cudaFree(e->d_members32); cudaFree(e->d_src_idx);
+  cudaFree(e->d_hdr); cudaFree(e->d_emit_seq); cudaFree(e->d_rescnt); cudaFree(e->d_ctr); cudaFree(e->d_small);
   cudaFree(e->d_in_id); cudaFree(e->d_hslot); cudaFree(e->d_in_rating); cudaFree(e->d_in_mode); cudaFree(e->d_code);
-  cudaFree(e->d_in_ts); cudaFree(e->d_blocksum);
+  cudaFree(e->d_in_ts); cudaFree(e->d_blocksum); cudaFree(e->d_blockhist); cudaFree(e->d_part); cudaFree(e->d_in_key);
+  cudaFree(e->d_in_handle);
   if (e->h_ctr) cudaFreeHost(e->h_ctr);
   if (e->h_small) cudaFreeHost(e->h_small);
   for (auto& ev : e->ev)
     if (ev) cudaEventDestroy(ev);
   if (e->stream && e->own_stream) cudaStreamDestroy(e->stream);
-  if (e->d2h_stream) { cudaStreamSynchronize(e->d2h_stream); cudaStreamDestroy(e->d2h_stream); }
+  if (e->d2h_stream) cudaStreamDestroy(e->d2h_stream);
   if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
   if (e->ev_copy) cudaEventDestroy(e->ev_copy);
   cudaGetLastError();
@@ -768,7 +785,7 @@ int mm_set_stream(mm_engine* e, void* s) {
   if (e->own_stream && e->stream) cudaStreamDestroy(e->stream);
   e->stream = (cudaStream_t)s;
   e->own_stream = false;
-  return set_persist(e, e->persist_bytes ? (int64_t)(e->persist_bytes >> 20) : 0);
+  return MM_OK;
 }
 
 int mm_set_option(mm_engine* e, const char* name, int64_t value) {
@@ -776,17 +793,10 @@ int mm_set_option(mm_engine* e, const char* name, int64_t value) {
   std::lock_guard<std::mutex> lk(e->mu);
   CK(cudaSetDevice(e->device));
   if (!std::strcmp(name, "rank_impl")) {
-    if (value != 0 && value != 1 && value != 3) return MM_E_ARG;
-    if (value == 1 && place_smem(e, 1) > e->smem_optin) return MM_E_ARG;
-    if (value == 1) {
-      const int s1 = (int)place_smem(e, 1);
-      CK(allow_max_smem(e, k_place<1>));
-    }
-    if (value == 3 && !e->place2_stages) return MM_E_ARG;
+    if (value != 2 && value != 3) return MM_E_ARG;
     e->rank_impl = (int)value;
     return MM_OK;
   }
-  if (!std::strcmp(name, "dense")) { e->dense_ok = (int)value; return MM_OK; }
   if (!std::strcmp(name, "async_results")) {
     int rcw = wait_results(e);
     if (rcw) return rcw;
@@ -802,39 +812,19 @@ int mm_set_option(mm_engine* e, const char* name, int64_t value) {
     return MM_OK;
   }
   if (!std::strcmp(name, "tick_impl")) { e->tick_impl = value != 0; return MM_OK; }
-  if (!std::strcmp(name, "place_debug")) {  // timing experiments only: results are NOT valid
-    if (value < 0 || value > 63) return MM_E_ARG;
-    e->place_debug = (int)value;
-    return MM_OK;
-  }
-  if (!std::strcmp(name, "persist_mb")) return set_persist(e, value);
-  if (!std::strcmp(name, "place2_stages")) {
-    if (value < 1 || value > (int64_t)kMaxStages || place2_smem(e, (uint32_t)value) + 1024 > e->smem_optin) return MM_E_ARG;
-    CK(allow_max_smem(e, k_place2<512>));
-    CK(allow_max_smem(e, k_place2<1024>));
-    e->place2_stages = (uint32_t)value;
-    return MM_OK;
-  }
-  if (!std::strcmp(name, "block")) {  // threads per row CTA
-    if (value != 512 && value != 1024) return MM_E_ARG;
-    e->block = (int)value;
-    return MM_OK;
-  }
-  if (!std::strcmp(name, "rows_per_sm")) {
-    if (value < 1 || value > 8) return MM_E_ARG;
-    CK(cudaStreamSynchronize(e->stream));
-    e->rows_per_sm = (int)value;
-    return alloc_tick_scratch(e);
-  }
   return MM_E_ARG;
 }
 
 int mm_enqueue_device(mm_engine* e, uint32_t n, const uint64_t* id, const int32_t* rating, const uint8_t* mode,
                       const uint32_t* enq_ts, uint8_t* accepted, uint32_t* n_accepted) {
+  if (n_accepted) *n_accepted = 0;
   if (!e || (n && (!id || !rating || !mode))) return MM_E_ARG;
+  if (n == 0) return MM_OK;
   std::lock_guard<std::mutex> lk(e->mu);
   CK(cudaSetDevice(e->device));
-  return enqueue_device_locked(e, n, id, rating, mode, enq_ts, accepted, n_accepted);
+  int rc = enqueue_batch(e, n, id, rating, mode, enq_ts, [](uint32_t, uint32_t) { return (int)MM_OK; });
+  if (rc) return rc;
+  return enq_finish(e, n, accepted, n_accepted);
 }
 
 int mm_enqueue(mm_engine* e, uint32_t n, const uint64_t* id, const int32_t* rating, const uint8_t* mode,
@@ -843,14 +833,9 @@ int mm_enqueue(mm_engine* e, uint32_t n, const uint64_t* id, const int32_t* rati
   if (n == 0) return MM_OK;
   std::lock_guard<std::mutex> lk(e->mu);
   CK(cudaSetDevice(e->device));
-  int rc = enq_prepare(e, n);
+  int rc = ensure_enq_scratch(e, n);
   if (rc) return rc;
-  // Pipelined ingest: the host columns go up in chunks on the copy stream while the previous chunk's
-  // claim / dedupe / append kernels run on the engine stream — the whole device side of the ingest hides
-  // behind the PCIe transfer except for the last chunk.
-  const uint32_t chunk = 1u << 20;
-  for (uint32_t base = 0; base < n; base += chunk) {
-    const uint32_t cnt = std::min(chunk, n - base);
+  auto upload = [&](uint32_t base, uint32_t cnt) -> int {
     CK(cudaMemcpyAsync(e->d_in_id + base, id + base, (size_t)cnt * 8, cudaMemcpyHostToDevice, e->copy_stream));
     CK(cudaMemcpyAsync(e->d_in_rating + base, rating + base, (size_t)cnt * 4, cudaMemcpyHostToDevice, e->copy_stream));
     CK(cudaMemcpyAsync(e->d_in_mode + base, mode + base, (size_t)cnt, cudaMemcpyHostToDevice, e->copy_stream));
@@ -858,9 +843,41 @@ int mm_enqueue(mm_engine* e, uint32_t n, const uint64_t* id, const int32_t* rati
       CK(cudaMemcpyAsync(e->d_in_ts + base, enq_ts + base, (size_t)cnt * 4, cudaMemcpyHostToDevice, e->copy_stream));
     CK(cudaEventRecord(e->ev_copy, e->copy_stream));
     CK(cudaStreamWaitEvent(e->stream, e->ev_copy, 0));
-    if ((rc = enq_claim(e, base, cnt, e->d_in_id, e->d_in_rating, e->d_in_mode))) return rc;
-    if ((rc = enq_append(e, base, cnt, e->d_in_id, e->d_in_rating, e->d_in_mode, enq_ts ? e->d_in_ts : nullptr))) return rc;
+    return MM_OK;
+  };
+  rc = enqueue_batch(e, n, e->d_in_id, e->d_in_rating, e->d_in_mode, enq_ts ? e->d_in_ts : nullptr, upload);
+  if (rc) { cudaStreamSynchronize(e->copy_stream); return rc; }
+  rc = enq_finish(e, n, nullptr, nullptr);
+  if (rc) return rc;
+  if (accepted) {
+    CK(cudaMemcpyAsync(accepted, e->d_code, n, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
   }
+  return MM_OK;
+}
+
+int mm_enqueue_packed(mm_engine* e, uint32_t n, const uint32_t* handle, const uint16_t* key, const uint32_t* enq_ts,
+                      uint8_t* accepted) {
+  if (!e || (n && (!handle || !key))) return MM_E_ARG;
+  if (n == 0) return MM_OK;
+  std::lock_guard<std::mutex> lk(e->mu);
+  CK(cudaSetDevice(e->device));
+  int rc = ensure_enq_scratch(e, n);
+  if (rc) return rc;
+  auto upload = [&](uint32_t base, uint32_t cnt) -> int {  // 6 B per player over PCIe, unpacked on the device
+    CK(cudaMemcpyAsync(e->d_in_handle + base, handle + base, (size_t)cnt * 4, cudaMemcpyHostToDevice, e->copy_stream));
+    CK(cudaMemcpyAsync(e->d_in_key + base, key + base, (size_t)cnt * 2, cudaMemcpyHostToDevice, e->copy_stream));
+    if (enq_ts)
+      CK(cudaMemcpyAsync(e->d_in_ts + base, enq_ts + base, (size_t)cnt * 4, cudaMemcpyHostToDevice, e->copy_stream));
+    CK(cudaEventRecord(e->ev_copy, e->copy_stream));
+    CK(cudaStreamWaitEvent(e->stream, e->ev_copy, 0));
+    k_unpack<<<(cnt + 255) / 256, 256, 0, e->stream>>>(cnt, e->d_in_handle + base, e->d_in_key + base, e->d_in_id + base,
+                                                       e->d_in_rating + base, e->d_in_mode + base);
+    CK(cudaGetLastError());
+    return MM_OK;
+  };
+  rc = enqueue_batch(e, n, e->d_in_id, e->d_in_rating, e->d_in_mode, enq_ts ? e->d_in_ts : nullptr, upload);
+  if (rc) { cudaStreamSynchronize(e->copy_stream); return rc; }
   rc = enq_finish(e, n, nullptr, nullptr);
   if (rc) return rc;
   if (accepted) {
@@ -882,15 +899,23 @@ int mm_remove(mm_engine* e, uint32_t n, const uint64_t* id, uint32_t* n_removed)
   const Pool& p = e->pool[e->cur];
   CK(cudaMemcpyAsync(e->d_in_id, id, (size_t)n * 8, cudaMemcpyHostToDevice, e->stream));
   CK(cudaMemsetAsync(e->d_small, 0, 16, e->stream));
-  k_remove<<<(n + 255) / 256, 256, 0, e->stream>>>(n, e->d_in_id, act_view(e), p.v, p.n, e->gen, e->K, e->d_small + 2);
+  k_remove<<<(n + 255) / 256, 256, 0, e->stream>>>(n, e->d_in_id, act_view(e), p.v, (uint32_t)pool_slots(e), e->gen, e->K,
+                                                   e->d_small + 2);
   CK(cudaGetLastError());
   CK(cudaMemcpyAsync(e->h_small, e->d_small, 16, cudaMemcpyDeviceToHost, e->stream));
   CK(cudaStreamSynchronize(e->stream));
   const uint32_t rem = e->h_small[2];
   e->n_active -= std::min<uint64_t>(rem, e->n_active);
-  e->n_tomb += rem;
+  if (!e->dense_ids) e->n_tomb += rem;
   if (n_removed) *n_removed = rem;
   return MM_OK;
+}
+
+int mm_remove_packed(mm_engine* e, uint32_t n, const uint32_t* handle, uint32_t* n_removed) {
+  if (n_removed) *n_removed = 0;
+  if (!e || (n && !handle)) return MM_E_ARG;
+  std::vector<uint64_t> wide(handle, handle + n);
+  return mm_remove(e, n, wide.data(), n_removed);
 }
 
 int mm_in_queue(mm_engine* e, uint32_t n, const uint64_t* id, uint8_t* out) {
@@ -938,15 +963,13 @@ int mm_tick_device(mm_engine* e, uint64_t now, mm_tick_stats* stats) {
   { int rcw = wait_results(e); if (rcw) return rcw; }
   const uint32_t n = e->pool[e->cur].n;
   e->last_fused = use_fused(e);
+  int rc;
   if (e->last_fused) {
-    int rc = tick_fused(e, n, false);
-    if (rc) return rc;
-    return tick_commit(e, n, stats);
+    if ((rc = tick_fused(e, false))) return rc;
+  } else {
+    if ((rc = tick_phase_a(e))) return rc;
+    if ((rc = tick_phase_b(e, false))) return rc;
   }
-  uint32_t chunk = 0;
-  int rc = tick_phase_a(e, n, &chunk);
-  if (rc) return rc;
-  if ((rc = tick_phase_b(e, n, chunk, false))) return rc;
   return tick_commit(e, n, stats);
 }
 
@@ -963,45 +986,16 @@ int mm_tick(mm_engine* e, uint64_t now, mm_lobby_hdr* lobbies, uint32_t lobby_ca
   if (!e) return MM_E_ARG;
   std::lock_guard<std::mutex> lk(e->mu);
   CK(cudaSetDevice(e->device));
-  const uint32_t n = e->pool[e->cur].n;
-  uint32_t chunk = 0;
-  int rc;
-  if ((rc = wait_results(e))) return rc;
-  // worst-case output sizes known up front -> the fused single launch is safe
-  e->last_fused = use_fused(e) && (!lobbies || (uint64_t)lobby_cap >= n / e->min_L) && (!member_ids || member_cap >= n);
-  if (e->last_fused) {
-    if ((rc = tick_fused(e, n, emit_seq != nullptr))) return rc;
-    if ((rc = tick_commit(e, n, stats))) return rc;
-    goto copy_out;
-  }
-  rc = tick_phase_a(e, n, &chunk);
-  if (rc) return rc;
-  // the counts are final after phase A: check the caller's capacities before consuming
-  CK(cudaMemcpyAsync(e->h_ctr, e->d_ctr, sizeof(TickCtr), cudaMemcpyDeviceToHost, e->stream));
-  CK(cudaStreamSynchronize(e->stream));
-  if ((lobbies && e->h_ctr->n_lobbies > lobby_cap) || (member_ids && e->h_ctr->n_matched > member_cap)) {
-    std::snprintf(e->last_err, sizeof(e->last_err), "need lobby_cap >= %u, member_cap >= %u", e->h_ctr->n_lobbies,
-                  e->h_ctr->n_matched);
-    CK(cudaMemsetAsync(e->d_tot, 0, (e->Kp + 1) * 4, e->stream));  // the epilogue that re-zeroes it will not run
-    CK(cudaStreamSynchronize(e->stream));
-    return MM_E_CAP;
-  }
-  if ((rc = tick_phase_b(e, n, chunk, emit_seq != nullptr))) return rc;
-  if ((rc = tick_commit(e, n, stats))) return rc;
-copy_out:
-  const TickCtr& c = *e->h_ctr;
-  // the tick is complete here (tick_commit synchronised the engine stream); with async_results the copies run on
-  // their own stream and the call returns: the caller may ingest the next batch meanwhile (PCIe is full duplex)
-  cudaStream_t cs = e->async_results ? e->d2h_stream : e->stream;
-  if (lobbies && c.n_lobbies)
-    CK(cudaMemcpyAsync(lobbies, e->d_hdr, (size_t)c.n_lobbies * sizeof(mm_lobby_hdr), cudaMemcpyDeviceToHost, cs));
-  if (member_ids && c.n_matched)
-    CK(cudaMemcpyAsync(member_ids, e->d_members, (size_t)c.n_matched * 8, cudaMemcpyDeviceToHost, cs));
-  if (emit_seq && c.n_lobbies)
-    CK(cudaMemcpyAsync(emit_seq, e->d_emit_seq, (size_t)c.n_lobbies * 4, cudaMemcpyDeviceToHost, cs));
-  if (e->async_results) { e->results_pending = true; return MM_OK; }
-  CK(cudaStreamSynchronize(e->stream));
-  return MM_OK;
+  return tick_to_host(e, lobbies, lobby_cap, member_ids, nullptr, member_cap, emit_seq, stats);
+}
+
+int mm_tick_packed(mm_engine* e, uint64_t now, mm_lobby_hdr* lobbies, uint32_t lobby_cap, uint32_t* member_handles,
+                   uint64_t member_cap, uint32_t* emit_seq, mm_tick_stats* stats) {
+  (void)now;
+  if (!e) return MM_E_ARG;
+  std::lock_guard<std::mutex> lk(e->mu);
+  CK(cudaSetDevice(e->device));
+  return tick_to_host(e, lobbies, lobby_cap, nullptr, member_handles, member_cap, emit_seq, stats);
 }
 
 int mm_pool_read(mm_engine* e, uint32_t cap, uint64_t* id, int32_t* rating, uint8_t* mode, uint8_t* team_size,
@@ -1010,23 +1004,39 @@ int mm_pool_read(mm_engine* e, uint32_t cap, uint64_t* id, int32_t* rating, uint
   std::lock_guard<std::mutex> lk(e->mu);
   CK(cudaSetDevice(e->device));
   const Pool& p = e->pool[e->cur];
-  const uint32_t n = p.n;
+  uint32_t bump = 0;
+  std::vector<uint32_t> fill(e->n_segs);
+  CK(cudaMemcpyAsync(&bump, p.m.bump, 4, cudaMemcpyDeviceToHost, e->stream));
+  CK(cudaMemcpyAsync(fill.data(), p.m.fill, (size_t)e->n_segs * 4, cudaMemcpyDeviceToHost, e->stream));
+  CK(cudaStreamSynchronize(e->stream));
+  const size_t n = (size_t)bump * kTile;  // chunks come from a bump allocator: the ones in use are [0, bump)
   std::vector<uint64_t> hid(n);
   std::vector<int32_t> hr(n);
   std::vector<uint8_t> hm(n), hs(n);
-  std::vector<uint32_t> ht(n);
+  std::vector<uint32_t> ht(n), hq(n), tab((size_t)e->n_segs * e->n_chunks);
   if (n) {
-    CK(cudaMemcpyAsync(hid.data(), p.v.id, (size_t)n * 8, cudaMemcpyDeviceToHost, e->stream));
-    CK(cudaMemcpyAsync(hr.data(), p.v.rating, (size_t)n * 4, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaMemcpyAsync(hid.data(), p.v.id, n * 8, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaMemcpyAsync(hr.data(), p.v.rating, n * 4, cudaMemcpyDeviceToHost, e->stream));
     CK(cudaMemcpyAsync(hm.data(), p.v.mode, n, cudaMemcpyDeviceToHost, e->stream));
     CK(cudaMemcpyAsync(hs.data(), p.v.tsize, n, cudaMemcpyDeviceToHost, e->stream));
-    CK(cudaMemcpyAsync(ht.data(), p.v.ts, (size_t)n * 4, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaMemcpyAsync(ht.data(), p.v.ts, n * 4, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaMemcpyAsync(hq.data(), p.v.seq, n * 4, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaMemcpyAsync(tab.data(), p.m.chunk_tab, tab.size() * 4, cudaMemcpyDeviceToHost, e->stream));
     CK(cudaStreamSynchronize(e->stream));
   }
+  // queued players in GLOBAL enqueue order: sort the partitions' lists by sequence number (distance below seq_next)
+  std::vector<std::pair<uint32_t, uint32_t>> order;  // (seq - seq_next mod 2^32, slot)
+  for (uint32_t sg = 0; sg < e->n_segs; ++sg)
+    for (uint32_t k = 0; k < fill[sg]; ++k) {
+      const uint32_t slot = tab[(size_t)sg * e->n_chunks + k / kTile] * kTile + k % kTile;
+      if (hm[slot] == MM_MODE_DEAD) continue;  // removed while queued; the next tick drops it
+      order.emplace_back(hq[slot] - e->seq_next, slot);
+    }
+  std::sort(order.begin(), order.end());
+  if (order.size() > cap) return MM_E_CAP;
   uint32_t k = 0;
-  for (uint32_t i = 0; i < n; ++i) {
-    if (hm[i] == MM_MODE_DEAD) continue;  // removed while queued; the next tick drops it
-    if (k >= cap) return MM_E_CAP;
+  for (const auto& o : order) {
+    const uint32_t i = o.second;
     if (id) id[k] = hid[i];
     if (rating) rating[k] = hr[i];
     if (mode) mode[k] = hm[i];
@@ -1043,19 +1053,13 @@ int mm_snapshot(mm_engine* e) {
   std::lock_guard<std::mutex> lk(e->mu);
   CK(cudaSetDevice(e->device));
   if (!e->snap.v.id) {
-    int rc = alloc_pool(e, e->snap, e->capacity);
+    int rc = alloc_pool(e, e->snap);
     if (rc) return rc;
   }
-  const Pool& p = e->pool[e->cur];
-  const size_t n = p.n;
-  CK(cudaMemcpyAsync(e->snap.v.id, p.v.id, n * 8, cudaMemcpyDeviceToDevice, e->stream));
-  CK(cudaMemcpyAsync(e->snap.v.rating, p.v.rating, n * 4, cudaMemcpyDeviceToDevice, e->stream));
-  CK(cudaMemcpyAsync(e->snap.v.mode, p.v.mode, n, cudaMemcpyDeviceToDevice, e->stream));
-  CK(cudaMemcpyAsync(e->snap.v.tsize, p.v.tsize, n, cudaMemcpyDeviceToDevice, e->stream));
-  CK(cudaMemcpyAsync(e->snap.v.ts, p.v.ts, n * 4, cudaMemcpyDeviceToDevice, e->stream));
-  CK(cudaMemcpyAsync(e->snap.v.bin, p.v.bin, n * 2, cudaMemcpyDeviceToDevice, e->stream));
+  int rc = copy_pool(e, e->snap, e->pool[e->cur]);
+  if (rc) return rc;
   CK(cudaStreamSynchronize(e->stream));
-  e->snap.n = p.n;
+  e->snap_seq = e->seq_next;
   e->has_snap = true;
   return MM_OK;
 }
@@ -1066,17 +1070,12 @@ int mm_restore(mm_engine* e) {
   if (!e->has_snap) return MM_E_STATE;
   CK(cudaSetDevice(e->device));
   Pool& p = e->pool[e->cur];
-  const size_t n = e->snap.n;
-  CK(cudaMemcpyAsync(p.v.id, e->snap.v.id, n * 8, cudaMemcpyDeviceToDevice, e->stream));
-  CK(cudaMemcpyAsync(p.v.rating, e->snap.v.rating, n * 4, cudaMemcpyDeviceToDevice, e->stream));
-  CK(cudaMemcpyAsync(p.v.mode, e->snap.v.mode, n, cudaMemcpyDeviceToDevice, e->stream));
-  CK(cudaMemcpyAsync(p.v.tsize, e->snap.v.tsize, n, cudaMemcpyDeviceToDevice, e->stream));
-  CK(cudaMemcpyAsync(p.v.ts, e->snap.v.ts, n * 4, cudaMemcpyDeviceToDevice, e->stream));
-  CK(cudaMemcpyAsync(p.v.bin, e->snap.v.bin, n * 2, cudaMemcpyDeviceToDevice, e->stream));
-  p.n = e->snap.n;
-  e->gen += 1;
+  int rc = copy_pool(e, p, e->snap);
+  if (rc) return rc;
+  e->seq_next = e->snap_seq;
+  e->gen = next_gen(e);
   if (e->use_active && p.n) {
-    k_restamp<<<(p.n + 255) / 256, 256, 0, e->stream>>>(p.v, p.n, act_view(e), e->gen);
+    k_restamp<<<dim3(e->n_chunks, e->n_segs), 256, 0, e->stream>>>(p.v, p.m, act_view(e), e->gen);
     CK(cudaGetLastError());
   }
   CK(cudaStreamSynchronize(e->stream));

@@ -17,27 +17,61 @@ namespace mm {
 // left resident.
 // ---------------------------------------------------------------------------------------
 constexpr uint32_t kLeftList = 2048;  // leftover players handled per step of the compaction
-constexpr uint32_t kEpiScratchWords = (kMaxRows + 1) + 64 + (kMaxSegs + 1) + 2 * kMaxSegs + kLeftList;
+constexpr uint32_t kEpiScratchWords = (kMaxRows + 1) + 64 + (kMaxSegs + 1) + 4 * kMaxSegs + kLeftList;
+
+struct EpiArgs {
+  PoolView src, dst;
+  PoolMeta src_meta, dst_meta;  // dst_meta was filled in by the scan tail
+  uint32_t R, new_gen, n_segs, n_groups, Kp;
+  const uint32_t* rescnt;
+  const uint32_t* left_bits;
+  ActiveView act;
+  const SegInfo* seg;
+  const uint32_t* seg_L;
+  mm_lobby_hdr* hdr;
+  const uint32_t* src_idx;
+  uint32_t* emit_seq;
+  uint32_t* tot;
+  TickCtr* ctr;
+};
 
 template <int BLOCK>
-__device__ __forceinline__ void epilogue_body(uint32_t* scratch, PoolView src, PoolView dst, uint32_t n, uint32_t chunk,
-                                              uint32_t R, const uint32_t* __restrict__ rescnt,
-                                              const uint32_t* __restrict__ left_bits, ActiveView act, uint32_t new_gen,
-                                              const SegInfo* __restrict__ seg, const uint32_t* __restrict__ seg_L,
-                                              uint32_t n_segs, uint32_t n_groups, mm_lobby_hdr* __restrict__ hdr,
-                                              const uint32_t* __restrict__ src_idx, uint32_t* __restrict__ emit_seq,
-                                              uint32_t* __restrict__ tot, uint32_t Kp, TickCtr* ctr,
+__device__ __forceinline__ void epilogue_body(uint32_t* scratch, const Geo& g, const EpiArgs a,
                                               unsigned long long* t_mid = nullptr) {
+  const PoolView& src = a.src;
+  const PoolView& dst = a.dst;
+  const uint32_t R = a.R, n_segs = a.n_segs, n_groups = a.n_groups, Kp = a.Kp;
+  const uint32_t* __restrict__ rescnt = a.rescnt;
+  const uint32_t* __restrict__ left_bits = a.left_bits;
+  const ActiveView act = a.act;
+  const SegInfo* __restrict__ seg = a.seg;
+  const uint32_t* __restrict__ seg_L = a.seg_L;
+  mm_lobby_hdr* __restrict__ hdr = a.hdr;
+  const uint32_t* __restrict__ src_idx = a.src_idx;
+  uint32_t* __restrict__ emit_seq = a.emit_seq;
+  uint32_t* __restrict__ tot = a.tot;
+  TickCtr* ctr = a.ctr;
+  const uint32_t new_gen = a.new_gen;
+  const uint32_t n = g.NT * kTile;            // virtual positions of this tick
+  const uint32_t chunk = g.tpr * kTile;       // virtual positions per row
   constexpr uint32_t NW = BLOCK / 32;
+  const PoolMeta sm = a.src_meta;
+  auto phys_of = [&](uint32_t v, uint32_t& p) -> uint32_t {  // virtual position of the old pool -> physical slot, partition
+    p = geo_seg_of(g, v / kTile);
+    return __ldcg(&sm.chunk_tab[(size_t)p * sm.max_ch + (v / kTile - g.T0[p])]) * kTile + v % kTile;
+  };
   uint32_t* s_off = scratch;                   // [kMaxRows + 1]
   uint32_t* s_tmp = s_off + kMaxRows + 1;      // [64]
   uint32_t* s_lbase = s_tmp + 64;              // [kMaxSegs + 1]
   uint32_t* s_mbase = s_lbase + kMaxSegs + 1;  // [kMaxSegs]
   uint32_t* s_L = s_mbase + kMaxSegs;          // [kMaxSegs]
-  uint32_t* s_list = s_L + kMaxSegs;           // [kLeftList]
+  uint32_t* s_leftb = s_L + kMaxSegs;          // [kMaxSegs] rank of the partition's first leftover player
+  uint32_t* s_newch = s_leftb + kMaxSegs;      // [kMaxSegs] the partition's first chunk in the compacted pool
+  uint32_t* s_list = s_newch + kMaxSegs;       // [kLeftList]
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   for (uint32_t s = tid; s < n_segs; s += BLOCK) {
     s_lbase[s] = __ldcg(&seg[s].lobby_base); s_mbase[s] = __ldcg(&seg[s].member_base); s_L[s] = seg_L[s];
+    s_leftb[s] = __ldcg(&seg[s].left_base); s_newch[s] = __ldcg(&seg[s].new_chunk);
   }
   for (uint32_t r = tid; r < R; r += BLOCK) s_off[r] = __ldcg(&rescnt[r]);
   __syncthreads();
@@ -63,18 +97,17 @@ __device__ __forceinline__ void epilogue_body(uint32_t* scratch, PoolView src, P
     auto flush = [&](uint32_t count, bool last) {
       __syncthreads();
       for (uint32_t e = tid; e < count; e += BLOCK) {
-        const uint32_t i = s_list[e], t = tbase + e;
+        const uint32_t v = s_list[e], r = tbase + e;  // virtual position in the old pool, global leftover rank
+        uint32_t p;  // a player never leaves its partition
+        const uint32_t i = phys_of(v, p);
+        const uint32_t loc = r - s_leftb[p];
+        const uint32_t t = (s_newch[p] + loc / kTile) * kTile + loc % kTile;
         const uint64_t pid = src.id[i];
         dst.id[t] = pid; dst.rating[t] = src.rating[i]; dst.mode[t] = src.mode[i];
-        dst.tsize[t] = src.tsize[i]; dst.ts[t] = src.ts[i]; dst.bin[t] = src.bin[i];
-        if (act.mask) {
-          uint64_t h = hash64(pid) & act.mask;
-          for (uint64_t probe = 0; probe <= act.mask; ++probe) {
-            const unsigned long long k2 = act.keys[h];
-            if (k2 == pid) { act.vals[h] = ((unsigned long long)new_gen << 32) | t; break; }
-            if (k2 == kEmptyKey) break;
-            h = (h + 1) & act.mask;
-          }
+        dst.tsize[t] = src.tsize[i]; dst.ts[t] = src.ts[i]; dst.bin[t] = src.bin[i]; dst.seq[t] = src.seq[i];
+        if (act.on()) {
+          const uint64_t h = act_find(act, pid);
+          if (h != ~0ull) *act.val(h) = ((unsigned long long)new_gen << 32) | t;
         }
       }
       tbase += count;
@@ -152,20 +185,20 @@ __device__ __forceinline__ void epilogue_body(uint32_t* scratch, PoolView src, P
     h.mode = (uint8_t)(a / n_groups);
     h.group = (uint8_t)(a % n_groups);
     hdr[c] = h;
-    if (emit_seq) emit_seq[c] = __ldcg(&src_idx[h.first_member + L - 1]);
+    if (emit_seq) {  // enqueue sequence number of the member whose arrival completed the lobby
+      uint32_t p;
+      emit_seq[c] = src.seq[phys_of(__ldcg(&src_idx[h.first_member + L - 1]), p)];
+    }
   }
 }
 
-__global__ void __launch_bounds__(1024) k_epilogue(PoolView src, PoolView dst, uint32_t n, uint32_t chunk, uint32_t R,
-                                                   const uint32_t* __restrict__ rescnt,
-                                                   const uint32_t* __restrict__ left_bits, ActiveView act, uint32_t new_gen,
-                                                   const SegInfo* __restrict__ seg, const uint32_t* __restrict__ seg_L,
-                                                   uint32_t n_segs, uint32_t n_groups, mm_lobby_hdr* __restrict__ hdr,
-                                                   const uint32_t* __restrict__ src_idx, uint32_t* __restrict__ emit_seq,
-                                                   uint32_t* __restrict__ tot, uint32_t Kp, TickCtr* ctr) {
+template <int BLOCK>
+__global__ void __launch_bounds__(BLOCK) k_epilogue(const EpiArgs a) {
   __shared__ uint32_t scratch[kEpiScratchWords];
-  epilogue_body<1024>(scratch, src, dst, n, chunk, R, rescnt, left_bits, act, new_gen, seg, seg_L, n_segs, n_groups, hdr,
-                      src_idx, emit_seq, tot, Kp, ctr);
+  __shared__ Geo geo;
+  __shared__ uint32_t s_gtmp[33];
+  geo_build<BLOCK>(geo, a.src_meta.fill, a.n_segs, a.R, s_gtmp);
+  epilogue_body<BLOCK>(scratch, geo, a);
 }
 
 }  // namespace mm

@@ -15,45 +15,47 @@ namespace mm {
 //   outbase[v] = member slot of bin v's first player (exclusive scan of the matched counts)
 //   binlim[v]  = outbase[v] + matched players of bin v; a player at or past it stays queued.
 // ---------------------------------------------------------------------------------------
-constexpr uint32_t kMaxSegs = MM_MAX_GROUPS * MM_MAX_MODES;
 constexpr int kScanBlock = 512;
 constexpr uint32_t kColScratchWords = (kScanBlock / 32) * 33;      // column CTA scratch
-constexpr uint32_t kTailScratchWords = 64 + 4 + 4 * kMaxSegs + 4;  // tail CTA scratch, fixed part
+constexpr uint32_t kTailScratchWords = 64 + 4 + 6 * kMaxSegs + 8;  // tail CTA scratch, fixed part
 
-// one 32-bin column group: exclusive prefix down the rows of M (scratch: kColScratchWords)
-__device__ __forceinline__ void colscan_cols_body(uint32_t* scratch, uint32_t group, uint32_t R, uint32_t Kp,
-                                                  uint32_t* __restrict__ M) {
+// One 32-bin column group: exclusive prefix down the rows of M (scratch: kColScratchWords).  Bin b belongs to one
+// partition, and only the rows holding that partition's tiles wrote M[.][b] (mm_hist.cuh): the scan of a column is
+// confined to rows [rlo, rhi] of its partition — about R / partitions rows instead of R.
+__device__ __forceinline__ void colscan_cols_body(uint32_t* scratch, const Geo& g, uint32_t group, uint32_t Kp, uint32_t K,
+                                                  const uint16_t* __restrict__ bin_seg, uint32_t* __restrict__ M) {
   uint32_t(*s_part)[33] = reinterpret_cast<uint32_t(*)[33]>(scratch);
   const uint32_t tid = threadIdx.x, x = tid & 31, y = tid >> 5;
   constexpr uint32_t NY = kScanBlock / 32;
   const uint32_t b = group * 32 + x;
-  const uint32_t rp = (R + NY - 1) / NY;
-  const uint32_t r0 = y * rp < R ? y * rp : R, r1 = (r0 + rp < R) ? r0 + rp : R;
-  constexpr int kU = 8;  // independent loads in flight per thread
+  uint32_t rlo = 0, rhi = 0;
+  const bool on = b < K && geo_rows_of(g, bin_seg[b], rlo, rhi);
+  const uint32_t nrows = on ? rhi - rlo + 1 : 0u;
+  const uint32_t rp = (nrows + NY - 1) / NY;
+  const uint32_t r0 = rlo + (y * rp < nrows ? y * rp : nrows), r1 = rlo + ((y + 1) * rp < nrows ? (y + 1) * rp : nrows);
+  constexpr int kU = 4;  // independent loads in flight per thread
   uint32_t sum = 0;
-  if (b < Kp)
-    for (uint32_t r = r0; r < r1; r += kU) {
-      uint32_t v[kU];
+  for (uint32_t r = r0; r < r1; r += kU) {
+    uint32_t v[kU];
 #pragma unroll
-      for (int k = 0; k < kU; ++k) v[k] = (r + k < r1) ? __ldcg(M + (size_t)(r + k) * Kp + b) : 0u;
+    for (int k = 0; k < kU; ++k) v[k] = (r + k < r1) ? __ldcg(M + (size_t)(r + k) * Kp + b) : 0u;
 #pragma unroll
-      for (int k = 0; k < kU; ++k) sum += v[k];
-    }
+    for (int k = 0; k < kU; ++k) sum += v[k];
+  }
   s_part[y][x] = sum;
   __syncthreads();
   uint32_t run = 0;
   for (uint32_t yy = 0; yy < y; ++yy) run += s_part[yy][x];
-  if (b < Kp)
-    for (uint32_t r = r0; r < r1; r += kU) {
-      uint32_t v[kU];
+  for (uint32_t r = r0; r < r1; r += kU) {
+    uint32_t v[kU];
 #pragma unroll
-      for (int k = 0; k < kU; ++k) v[k] = (r + k < r1) ? __ldcg(M + (size_t)(r + k) * Kp + b) : 0u;
+    for (int k = 0; k < kU; ++k) v[k] = (r + k < r1) ? __ldcg(M + (size_t)(r + k) * Kp + b) : 0u;
 #pragma unroll
-      for (int k = 0; k < kU; ++k) {
-        if (r + k < r1) M[(size_t)(r + k) * Kp + b] = run;
-        run += v[k];
-      }
+    for (int k = 0; k < kU; ++k) {
+      if (r + k < r1) M[(size_t)(r + k) * Kp + b] = run;
+      run += v[k];
     }
+  }
   __syncthreads();  // scratch may be reused by the next group
 }
 
@@ -71,6 +73,8 @@ struct TailArgs {
   uint32_t* binlim;                   // [Kp] out: outbase + matched players of the bin
   SegInfo* seg;                       // [n_segs] out
   TickCtr* ctr;
+  const uint32_t* fill;               // [n_segs] partition fills of the pool being matched
+  PoolMeta dst;                       // out: layout of the compacted pool (fill, chunk table, chunks used)
 };
 // shared-memory words of the tail for a layout: bases | matched counts (bit 0) | keys (bit 1)
 __host__ __device__ constexpr uint32_t tail_words(uint32_t Kp, uint32_t layout) {
@@ -95,19 +99,23 @@ __device__ __forceinline__ void colscan_tail_body(uint32_t* scratch, const TailA
   uint32_t* s_lob = s_a + kMaxSegs;     // [kMaxSegs] lobbies of earlier segments
   uint32_t* s_nl = s_lob + kMaxSegs;    // [kMaxSegs] lobbies of the segment
   uint32_t* s_lo = s_nl + kMaxSegs;     // [kMaxSegs + 1] first bin of the segment
+  uint32_t* s_left = s_lo + kMaxSegs + 1;  // [kMaxSegs] players of the segment that stay queued -> rank base
+  uint32_t* s_nch = s_left + kMaxSegs;     // [kMaxSegs] chunks of the segment in the compacted pool -> first chunk
   uint32_t* s_bb = scratch + kTailScratchWords;  // [Kp + 1] sorted position of the bin's first player
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, Kp = t.Kp, K = t.K, n_segs = t.n_segs;
   if (tid == 0) s_misc[0] = 0;
   for (uint32_t sg = tid; sg <= n_segs; sg += kScanBlock) s_lo[sg] = t.seg_bin_lo[sg];
   __syncthreads();
-  uint32_t lmax = 0;
+  uint32_t hv = 0;
   for (uint32_t i = tid; i < Kp; i += kScanBlock) {  // coalesced, independent loads
     const uint32_t v = __ldcg(&t.tot[i]);
     s_bb[i] = v;
-    if (i < K && v > lmax) lmax = v;
+    if (i < K && v > 8) {  // a bin of a list-ranked partition expecting > 8 players per tile of that partition
+      const uint32_t sg = t.bin_seg[i];
+      if (s_lo[sg + 1] - s_lo[sg] > kFastBins && (uint64_t)v * kTile > 8ull * __ldcg(&t.fill[sg])) hv = 1;
+    }
   }
-  lmax = __reduce_max_sync(0xFFFFFFFFu, lmax);
-  if ((tid & 31) == 0 && lmax) atomicMax(&s_misc[0], lmax);
+  if (__any_sync(0xFFFFFFFFu, hv) && (tid & 31) == 0) atomicOr(&s_misc[0], 1u);
   __syncthreads();
   const uint32_t total = block_excl_scan<kScanBlock>(s_bb, Kp, s_tmp);
   if (tid == 0) s_bb[Kp] = total;
@@ -120,6 +128,7 @@ __device__ __forceinline__ void colscan_tail_body(uint32_t* scratch, const TailA
     for (uint32_t sg = tid; sg < n_segs; sg += kScanBlock) {
       const uint32_t ns = s_bb[s_lo[sg + 1]] - s_bb[s_lo[sg]], nl = ns / t.seg_L[sg];
       s_nl[sg] = nl; s_lob[sg] = nl; s_a[sg] = ns - nl * t.seg_L[sg];
+      s_left[sg] = s_a[sg];
       t.seg[sg].n = ns; t.seg[sg].n_lobbies = nl;
     }
     __syncthreads();
@@ -163,7 +172,7 @@ __device__ __forceinline__ void colscan_tail_body(uint32_t* scratch, const TailA
         lo[q] = on ? s_lo[sg] : 0u; hi[q] = on ? s_lo[sg + 1] : 0u; L[q] = on ? t.seg_L[sg] : 1u;
         Mrec[q] = 0xFFFFFFFFu / L[q];  // umulhi(a, Mrec) is a / L or a / L - 1 for every 32-bit a
         pos[q] = s_bb[lo[q]];
-        if (on && lane == 0) t.seg[sg].n = s_bb[hi[q]] - s_bb[lo[q]];
+        if (on && lane == 0) { s_nl[sg] = s_bb[hi[q]] - s_bb[lo[q]]; t.seg[sg].n = s_nl[sg]; }
       }
       const uint32_t span0 = hi[0] - lo[0], span1 = hi[1] - lo[1], span = span0 > span1 ? span0 : span1;
       for (uint32_t off = 0; off < span; off += 32) {
@@ -222,25 +231,48 @@ __device__ __forceinline__ void colscan_tail_body(uint32_t* scratch, const TailA
     for (uint32_t sg = tid; sg < n_segs; sg += kScanBlock) {
       const uint32_t mb = s_m[s_lo[sg]], nl = (s_m[s_lo[sg + 1]] - mb) / t.seg_L[sg];
       s_lob[sg] = nl;
+      s_left[sg] = s_nl[sg] - (s_m[s_lo[sg + 1]] - mb);  // s_nl: players of the segment (S1 does not use it otherwise)
       t.seg[sg].n_lobbies = nl; t.seg[sg].member_base = mb;
     }
     __syncthreads();
     tot_lob = block_excl_scan<kScanBlock>(s_lob, n_segs, s_tmp);
     for (uint32_t sg = tid; sg < n_segs; sg += kScanBlock) t.seg[sg].lobby_base = s_lob[sg];
   }
+  // Layout of the compacted pool (the epilogue moves the players that stay queued): partition sg keeps n_left
+  // players in ceil(n_left / kTile) fresh chunks, handed out in partition order from chunk 0.
+  __syncthreads();
+  for (uint32_t sg = tid; sg < n_segs; sg += kScanBlock) {
+    const uint32_t nlft = s_left[sg];
+    s_nch[sg] = (nlft + kTile - 1) / kTile;
+    t.seg[sg].n_left = nlft;
+    t.dst.fill[sg] = nlft;
+  }
+  __syncthreads();
+  block_excl_scan<kScanBlock>(s_left, n_segs, s_tmp);
+  const uint32_t new_chunks = block_excl_scan<kScanBlock>(s_nch, n_segs, s_tmp);
+  for (uint32_t sg = tid; sg < n_segs; sg += kScanBlock) { t.seg[sg].left_base = s_left[sg]; t.seg[sg].new_chunk = s_nch[sg]; }
+  for (uint32_t sg = warp; sg < n_segs; sg += NW) {
+    const uint32_t c0 = s_nch[sg], c1 = sg + 1 < n_segs ? s_nch[sg + 1] : new_chunks;
+    for (uint32_t k = lane; k < c1 - c0; k += 32) t.dst.chunk_tab[(size_t)sg * t.dst.max_ch + k] = c0 + k;
+  }
   if (tid == 0) {
+    *t.dst.bump = new_chunks;
     t.ctr->n_lobbies = tot_lob; t.ctr->n_matched = n_matched; t.ctr->n_alive = alive; t.ctr->n_dead = dead;
-    // expected players of the fullest bin per tile of one row (players spread evenly over rows)
-    const uint64_t npool = (uint64_t)alive + dead;
-    t.ctr->heavy = ((uint64_t)s_misc[0] * kTile > 4ull * (npool ? npool : 1)) ? 1u : 0u;
+    t.ctr->heavy = s_misc[0];
   }
   __syncthreads();
 }
 
 __global__ void __launch_bounds__(kScanBlock) k_colscan(uint32_t R, uint32_t* __restrict__ M, const TailArgs t) {
   extern __shared__ __align__(16) uint32_t scratch[];  // max(kColScratchWords, tail_words(Kp, layout)) words
-  if (blockIdx.x + 1 < gridDim.x) colscan_cols_body(scratch, blockIdx.x, R, t.Kp, M);
-  else colscan_tail_body(scratch, t);
+  __shared__ Geo geo;
+  __shared__ uint32_t s_gtmp[33];
+  if (blockIdx.x + 1 < gridDim.x) {
+    geo_build<kScanBlock>(geo, t.fill, t.n_segs, R, s_gtmp);
+    colscan_cols_body(scratch, geo, blockIdx.x, t.Kp, t.K, t.bin_seg, M);
+  } else {
+    colscan_tail_body(scratch, t);
+  }
 }
 
 }  // namespace mm

@@ -101,12 +101,56 @@ class Engine:
         self._check(self.lib.mm_enqueue(self.h, n, p_ids, p_rating, p_mode, p_ts or None, p_accepted or None),
                     "mm_enqueue")
 
-    def tick_raw(self, p_lobbies, lobby_cap, p_members, member_cap, p_emit_seq=0, now=0):
-        """mm_tick on raw HOST addresses. -> TickStats"""
+    def tick_raw(self, p_lobbies, lobby_cap, p_members, member_cap, p_emit_seq=0, now=0, packed=False):
+        """mm_tick (u64 ids) / mm_tick_packed (u32 handles) on raw HOST addresses. -> TickStats"""
         st = abi.TickStats()
-        self._check(self.lib.mm_tick(self.h, now, p_lobbies, lobby_cap, p_members, member_cap, p_emit_seq or None,
-                                     C.byref(st)), "mm_tick")
+        fn = self.lib.mm_tick_packed if packed else self.lib.mm_tick
+        self._check(fn(self.h, now, p_lobbies, lobby_cap, p_members, member_cap, p_emit_seq or None, C.byref(st)),
+                    "mm_tick_packed" if packed else "mm_tick")
         return st
+
+    # -- packed host formats (MM_F_DENSE_IDS engines): u32 handle + u16 (mode << 13 | rating) --------------
+    @staticmethod
+    def pack_key(rating, mode):
+        rating = np.asarray(rating)
+        assert rating.min(initial=0) >= 0 and rating.max(initial=0) <= 8191, "packed keys carry ratings 0..8191"
+        return (np.asarray(mode, np.uint16) << 13 | rating.astype(np.uint16)).astype(np.uint16)
+
+    def enqueue_packed(self, handles, keys, enq_ts=None):
+        """-> accepted u8[n] (codes as enqueue)."""
+        handles = np.ascontiguousarray(handles, np.uint32)
+        keys = np.ascontiguousarray(keys, np.uint16)
+        n = len(handles)
+        assert len(keys) == n
+        if enq_ts is not None:
+            enq_ts = np.ascontiguousarray(enq_ts, np.uint32)
+        acc = np.empty(n, np.uint8)
+        self._check(self.lib.mm_enqueue_packed(self.h, n, _p(handles), _p(keys), _p(enq_ts), _p(acc)), "mm_enqueue_packed")
+        return acc
+
+    def enqueue_packed_raw(self, n, p_handles, p_keys, p_ts=0, p_accepted=0):
+        self._check(self.lib.mm_enqueue_packed(self.h, n, p_handles, p_keys, p_ts or None, p_accepted or None),
+                    "mm_enqueue_packed")
+
+    def remove_packed(self, handles):
+        handles = np.ascontiguousarray(handles, np.uint32)
+        nr = C.c_uint32(0)
+        self._check(self.lib.mm_remove_packed(self.h, len(handles), _p(handles), C.byref(nr)), "mm_remove_packed")
+        return nr.value
+
+    def tick_packed(self, now=0, lobby_cap=None, member_cap=None, want_emit_seq=True):
+        """Host-buffer tick, members as u32 handles -> (lobbies, member_handles u32, emit_seq|None, TickStats)."""
+        n = self.pool_size()
+        member_cap = max(n, 1) if member_cap is None else member_cap
+        lobby_cap = max(n // 2, 1) if lobby_cap is None else lobby_cap
+        lob = np.empty(lobby_cap, LOBBY_DTYPE)
+        mem = np.empty(member_cap, np.uint32)
+        seq = np.empty(lobby_cap, np.uint32) if want_emit_seq else None
+        st = abi.TickStats()
+        self._check(self.lib.mm_tick_packed(self.h, now, _p(lob), lobby_cap, _p(mem), member_cap, _p(seq), C.byref(st)),
+                    "mm_tick_packed")
+        self.results_wait()
+        return lob[:st.n_lobbies], mem[:st.n_matched], (seq[:st.n_lobbies] if seq is not None else None), st
 
     def enqueue_device(self, n, d_ids, d_rating, d_mode, d_ts=0, d_accepted=0):
         """Device-pointer ingest (ints = raw device addresses). -> n_accepted"""

@@ -102,12 +102,12 @@ def test_every_lobby_respects_the_window(pkg, oracle):
 
 
 # ------------------------------------------------------------------------------- GPU: parity
-def check(eng, ref, lob, mem, seq, st):
+def check(eng, ref, lob, mem, seq, st, seq_of=None):
     assert (st.n_lobbies, st.n_matched, st.n_residual, st.n_dead) == (ref.n_lobbies, ref.n_matched, ref.n_residual, ref.n_dead)
     assert np.array_equal(lob, ref.lobbies)
     assert np.array_equal(mem, ref.member_ids)
     if seq is not None:
-        assert np.array_equal(seq, ref.emit_seq)
+        assert np.array_equal(seq, ref.emit_seq if seq_of is None else np.asarray(seq_of, np.uint32)[ref.emit_seq])
     assert np.array_equal(eng.pool_read()["id"], ref.residual_ids)
 
 
@@ -130,16 +130,16 @@ def test_window_parity_random_pools(pkg, oracle, n, W, tick_impl):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("W", [0, 1, 4])
-def test_window_parity_few_bins_private_counter_ranking(pkg, oracle, W):
-    """A 41-value rating domain: Kp <= 96, so the blocked-tile (dense 2) ranking and its leftovers
-    compaction run in RATING order with a large share of the pool staying queued."""
+def test_window_parity_few_bins_both_rankings(pkg, oracle, W):
+    """A 41-value rating domain: partitions of ~20 bins, so the ballot tile sort and its staged write-back run in
+    RATING order with a large share of the pool staying queued; the hashed lists (heavy bins) must agree."""
     n = 300_007
     cfg = pkg.synth.make_config(groups=((0, 19), (20, 39)), modes=(("1v1", 2, 1), ("3v3", 2, 3)), order=RATING,
                                 capacity=n, default_group=1)
     ids, rating, mode, ts = small_pool(pkg, 5, n, lo=-3, hi=44)
-    for dense in (2, 1, 0):
+    for rank_impl in (3, 2):
         with pkg.Engine(cfg) as eng:
-            eng.set_option("dense", dense)
+            eng.set_option("rank_impl", rank_impl)
             eng.set_option("max_spread", W)
             assert eng.enqueue(ids, rating, mode, ts).all()
             lob, mem, seq, st = eng.tick()
@@ -170,21 +170,23 @@ def test_window_multi_tick_accumulation(pkg, oracle):
     with pkg.Engine(cfg) as eng:
         eng.set_option("max_spread", W)
         q_ids = np.zeros(0, np.uint64); q_r = np.zeros(0, np.int32); q_m = np.zeros(0, np.uint8)
+        q_seq = np.zeros(0, np.uint32)
         for t in range(5):
             ids, rating, mode, ts = small_pool(pkg, 1000 + t, 60_000, lo=0, hi=5001)
             ids = ids + np.uint64(t) * np.uint64(1 << 40)
             assert eng.enqueue(ids, rating, mode, ts).all()
             q_ids = np.concatenate([q_ids, ids]); q_r = np.concatenate([q_r, rating]); q_m = np.concatenate([q_m, mode])
+            q_seq = np.concatenate([q_seq, (t * 60_000 + np.arange(60_000)).astype(np.uint32)])
             lob, mem, seq, st = eng.tick()
             ref = oracle.run_windowed(cfg, W, q_ids, q_r, q_m)
-            check(eng, ref, lob, mem, seq, st)
+            check(eng, ref, lob, mem, seq, st, seq_of=q_seq)
             keep = np.isin(q_ids, ref.residual_ids)
-            q_ids, q_r, q_m = q_ids[keep], q_r[keep], q_m[keep]
+            q_ids, q_r, q_m, q_seq = q_ids[keep], q_r[keep], q_m[keep], q_seq[keep]
             assert eng.in_queue(q_ids[:100]).all()
         # switching the policy off matches the rest with the reference rule
         eng.set_option("max_spread", -1)
         lob, mem, seq, st = eng.tick()
-        check(eng, oracle.run_literal(cfg, q_ids, q_r, q_m), lob, mem, seq, st)
+        check(eng, oracle.run_literal(cfg, q_ids, q_r, q_m), lob, mem, seq, st, seq_of=q_seq)
 
 
 @pytest.mark.gpu
@@ -192,7 +194,7 @@ def test_window_multi_tick_accumulation(pkg, oracle):
 @pytest.mark.parametrize("W", [-1, 30])
 def test_large_key_domains_use_the_fallback_tail_layouts(pkg, oracle, n_modes, W):
     """5 x 5003 bins: the scan tail reads the bin keys from global memory; 8 x 5003 bins: it also parks the matched
-    counts there (and the placement falls back to the first list / warp-serial kernels).  Both policies."""
+    counts there (and the placement runs one CTA per SM with a shallower ring).  Both policies."""
     shapes = (("1v1", 2, 1), ("2v2", 2, 2), ("3v3", 2, 3), ("5v5", 2, 5), ("solo4", 4, 1), ("duo3", 3, 2), ("6v6", 2, 6),
               ("solo3", 3, 1))[:n_modes]
     n = 120_011
