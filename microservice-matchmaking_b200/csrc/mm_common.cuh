@@ -238,6 +238,22 @@ __device__ __forceinline__ TileDesc geo_tile(const Geo& g, const PoolMeta& m, ui
   d.nvalid = left < kTile ? left : kTile;
   return d;
 }
+// The descriptors of a row's tiles, computed by the whole CTA in parallel (each is a binary search + two global
+// loads: far too slow for the one thread that feeds the TMA ring).  Covers tiles [base, base + kDescCap) of the row.
+constexpr uint32_t kDescCap = 64;
+struct DescCache {
+  uint32_t phys[kDescCap];
+  uint32_t nvsg[kDescCap];  // nvalid | seg << 16
+};
+template <int BLOCK>
+__device__ __forceinline__ void desc_fill(DescCache& c, const Geo& g, const PoolMeta& m, uint32_t s_first, uint32_t s_end) {
+  for (uint32_t k = threadIdx.x; k < kDescCap; k += BLOCK)
+    if (s_first + k < s_end) {
+      const TileDesc d = geo_tile(g, m, s_first + k);
+      c.phys[k] = d.phys;
+      c.nvsg[k] = d.nvalid | (d.seg << 16);
+    }
+}
 // rows [rlo, rhi] holding tiles of partition p; false when the partition is empty
 __device__ __forceinline__ bool geo_rows_of(const Geo& g, uint32_t p, uint32_t& rlo, uint32_t& rhi) {
   const uint32_t a = g.T0[p], b = g.T0[p + 1];

@@ -11,7 +11,7 @@ namespace mm {
 // column per tile, L2 evict-last: the placement pass re-reads the column from L2); shared-memory atomics
 // build the row histogram.  Only the bins of the partitions the row touches are written to M — a row's tiles
 // are consecutive in (partition, chunk) order, so that is one contiguous bin range.
-// Shared memory: ring[stages][kTile] u16 | mbarriers | nvalid[kMaxStages] | hist[Kp].
+// Shared memory: ring[stages][kTile] u16 | mbarriers | nvalid[kMaxStages] | hist[Kp] | tile descriptors.
 // ---------------------------------------------------------------------------------------
 template <int BLOCK>
 __device__ __forceinline__ void hist_body(unsigned char* smem_raw, const Geo& g, const uint16_t* __restrict__ bins16,
@@ -23,6 +23,7 @@ __device__ __forceinline__ void hist_body(unsigned char* smem_raw, const Geo& g,
   uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + (size_t)stages * kBytes);        // [kMaxStages]
   uint32_t* s_nv = reinterpret_cast<uint32_t*>(smem_raw + (size_t)stages * kBytes + 32);   // [kMaxStages]
   uint32_t* hist = reinterpret_cast<uint32_t*>(smem_raw + (size_t)stages * kBytes + 64);   // [Kp]
+  DescCache& dc = *reinterpret_cast<DescCache*>(hist + ((Kp + 3) & ~3u));
   const uint32_t tid = threadIdx.x, row = blockIdx.x;
   const uint64_t pol = policy_evict_last();
   const uint32_t s0 = row * g.tpr < g.NT ? row * g.tpr : g.NT;
@@ -33,18 +34,28 @@ __device__ __forceinline__ void hist_body(unsigned char* smem_raw, const Geo& g,
     mbar_fence_init();
   }
   fence_proxy_async();
+  desc_fill<BLOCK>(dc, g, meta, s0, s1);
   __syncthreads();
+  uint32_t dbase = 0;  // first row tile covered by the descriptor cache
+  auto issue = [&](uint32_t stage, uint32_t t) {  // thread 0: the tile's bulk copy
+    uint32_t phys, nv;
+    if (t - dbase < kDescCap) { phys = dc.phys[t - dbase]; nv = dc.nvsg[t - dbase] & 0xFFFFu; }
+    else { const TileDesc d = geo_tile(g, meta, s0 + t); phys = d.phys; nv = d.nvalid; }  // ahead of the cache
+    s_nv[stage] = nv;
+    mbar_expect_tx(&full[stage], kBytes);
+    tma_load_1d(ring + (size_t)stage * kTile, bins16 + (size_t)phys * kTile, kBytes, &full[stage], pol);
+  };
   if (tid == 0)
-    for (uint32_t t = 0; t < stages && t < n_tiles; ++t) {
-      const TileDesc d = geo_tile(g, meta, s0 + t);
-      s_nv[t] = d.nvalid;
-      mbar_expect_tx(&full[t], kBytes);
-      tma_load_1d(ring + (size_t)t * kTile, bins16 + (size_t)d.phys * kTile, kBytes, &full[t], pol);
-    }
+    for (uint32_t t = 0; t < stages && t < n_tiles; ++t) issue(t, t);
   for (uint32_t i = tid; i < Kp; i += BLOCK) hist[i] = 0;
   __syncthreads();
   uint32_t st = 0, parity = 0;
   for (uint32_t t = 0; t < n_tiles; ++t) {
+    if (t == dbase + kDescCap) {  // (uniform) next batch of descriptors; thread 0 is not issuing right now
+      dbase = t;
+      desc_fill<BLOCK>(dc, g, meta, s0 + t, s1);
+      __syncthreads();
+    }
     const uint16_t* tb = ring + (size_t)st * kTile;
     mbar_wait(&full[st], parity);
     const uint32_t valid = s_nv[st];
@@ -62,12 +73,7 @@ __device__ __forceinline__ void hist_body(unsigned char* smem_raw, const Geo& g,
       }
     }
     __syncthreads();
-    if (tid == 0 && t + stages < n_tiles) {
-      const TileDesc d = geo_tile(g, meta, s0 + t + stages);
-      s_nv[st] = d.nvalid;
-      mbar_expect_tx(&full[st], kBytes);
-      tma_load_1d(ring + (size_t)st * kTile, bins16 + (size_t)d.phys * kTile, kBytes, &full[st], pol);
-    }
+    if (tid == 0 && t + stages < n_tiles) issue(st, t + stages);
     if (++st == stages) { st = 0; parity ^= 1u; }
   }
   if (n_tiles) {
@@ -86,7 +92,7 @@ __device__ __forceinline__ void hist_body(unsigned char* smem_raw, const Geo& g,
 }
 
 __host__ __device__ constexpr size_t hist_smem_bytes(uint32_t Kp, uint32_t stages) {
-  return (size_t)stages * kTile * 2 + 64 + (size_t)Kp * 4 + 16;
+  return (size_t)stages * kTile * 2 + 64 + (size_t)((Kp + 3) & ~3u) * 4 + sizeof(DescCache) + 16;
 }
 
 }  // namespace mm

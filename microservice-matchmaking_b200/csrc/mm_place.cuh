@@ -30,10 +30,10 @@ namespace mm {
 //                union { LIST: head[kHeadSlots] node[kTile] nbin[kTile] ; FAST: wcnt[16][256] u16, sslot[kTile] }.
 // ---------------------------------------------------------------------------------------
 constexpr uint32_t kHeadSlots = 4096;
-constexpr uint32_t kPlaceUnionBytes = kHeadSlots * 4 + kTile * 4 + kTile * 2;  // LIST: 28 KB >= FAST: 8 + 8 KB
+constexpr uint32_t kPlaceUnionBytes = kHeadSlots * 4 + kTile * 4 + kTile * 2;  // LIST: 28 KB >= FAST: 16 + 8 + 1 KB
 
 __host__ __device__ constexpr size_t place_smem_bytes(uint32_t Kp, uint32_t stages) {
-  return (size_t)stages * kTileBytes + 128 + (size_t)Kp * 4 + kPlaceUnionBytes + 16;
+  return (size_t)stages * kTileBytes + 128 + (size_t)((Kp + 3) & ~3u) * 4 + kPlaceUnionBytes + sizeof(DescCache) + 16;
 }
 
 struct PlaceArgs {
@@ -65,18 +65,21 @@ __device__ __forceinline__ void place_body(unsigned char* smem_raw, const Geo& g
   uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + (size_t)stages * kTileBytes);      // [kMaxStages]
   uint32_t* s_nv = reinterpret_cast<uint32_t*>(smem_raw + (size_t)stages * kTileBytes + 32); // [kMaxStages] valid players
   uint32_t* s_sg = s_nv + kMaxStages;                                                        // [kMaxStages] partition
-  uint32_t* s_misc = s_sg + kMaxStages;                                                      // [8]
+  uint32_t* s_b0 = s_sg + kMaxStages;                                                        // [kMaxStages] its first bin
+  uint32_t* s_b1 = s_b0 + kMaxStages;                                                        // [kMaxStages] its end bin
+  uint32_t* s_misc = s_b1 + kMaxStages;                                                      // [8]
   uint32_t* cnt = reinterpret_cast<uint32_t*>(smem_raw + (size_t)stages * kTileBytes + 128); // [Kp]
-  unsigned char* uni = reinterpret_cast<unsigned char*>(cnt + Kp);
+  unsigned char* uni = reinterpret_cast<unsigned char*>(cnt + ((Kp + 3) & ~3u));
+  DescCache& dc = *reinterpret_cast<DescCache*>(uni + kPlaceUnionBytes);
   // LIST
   uint32_t* head = reinterpret_cast<uint32_t*>(uni);           // [kHeadSlots]
   uint32_t* node = head + kHeadSlots;                          // [kTile]
   uint16_t* nbin = reinterpret_cast<uint16_t*>(node + kTile);  // [kTile] heavy path: bin of a group node
   // FAST
-  uint16_t* wcnt = reinterpret_cast<uint16_t*>(uni);           // [NW][256] per-warp digit counters
-  uint32_t* wcnt32 = reinterpret_cast<uint32_t*>(uni);         // the same, two digits per word: [NW][128]
-  uint32_t* sslot = reinterpret_cast<uint32_t*>(uni + NW * 256 * 2);  // [kTile] global slot of the staged id
-  uint32_t* lgd = sslot + kTile;                               // [256] (global slot base - tile-local base) | flag
+  uint32_t* wmask = reinterpret_cast<uint32_t*>(uni);          // [NW][256] per-warp match masks (all-zero between items)
+  uint16_t* wcnt = reinterpret_cast<uint16_t*>(wmask + NW * 256);  // [NW][256] per-warp running digit counters
+  uint32_t* wcnt32 = reinterpret_cast<uint32_t*>(wcnt);        // the same, two digits per word: [NW][128]
+  uint32_t* lgd = wcnt32 + NW * 128;                           // [256] (global slot base - tile-local base) | flag
 
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t lt_mask = (1u << lane) - 1u;
@@ -87,24 +90,31 @@ __device__ __forceinline__ void place_body(unsigned char* smem_raw, const Geo& g
   const uint32_t s1 = s0 + g.tpr < g.NT ? s0 + g.tpr : g.NT;
   const uint32_t n_tiles = s1 - s0;
 
-  auto issue = [&](uint32_t stage, uint32_t s) {  // thread 0: descriptor + the tile's two bulk copies
-    const TileDesc d = geo_tile(g, a.meta, s);
-    s_nv[stage] = d.nvalid;
-    s_sg[stage] = d.seg;
+  uint32_t dbase = 0;  // first row tile covered by the descriptor cache
+  auto issue = [&](uint32_t stage, uint32_t t) {  // thread 0: descriptor + the tile's two bulk copies
+    uint32_t phys, nvsg;
+    if (t - dbase < kDescCap) { phys = dc.phys[t - dbase]; nvsg = dc.nvsg[t - dbase]; }
+    else { const TileDesc d = geo_tile(g, a.meta, s0 + t); phys = d.phys; nvsg = d.nvalid | (d.seg << 16); }
+    s_nv[stage] = nvsg & 0xFFFFu;
+    s_sg[stage] = nvsg >> 16;
+    s_b0[stage] = a.seg_bin_lo[nvsg >> 16];
+    s_b1[stage] = a.seg_bin_lo[(nvsg >> 16) + 1];
     mbar_expect_tx(&full[stage], kTileBytes);
-    tma_load_1d(ring_ids + (size_t)stage * kTile, a.ids + (size_t)d.phys * kTile, kTile * 8, &full[stage], pol_in);
-    tma_load_1d(ring_bins + (size_t)stage * kTile, a.bins16 + (size_t)d.phys * kTile, kTile * 2, &full[stage], pol_in);
+    tma_load_1d(ring_ids + (size_t)stage * kTile, a.ids + (size_t)phys * kTile, kTile * 8, &full[stage], pol_in);
+    tma_load_1d(ring_bins + (size_t)stage * kTile, a.bins16 + (size_t)phys * kTile, kTile * 2, &full[stage], pol_in);
   };
 
   if (tid == 0) {
     for (uint32_t s = 0; s < stages; ++s) mbar_init(&full[s], 1);
     mbar_fence_init();
     s_misc[0] = 0;  // players of the row that stay queued
+    s_misc[2] = 0;  // FAST: the current tile has players past their bin's matched prefix
   }
   fence_proxy_async();
+  desc_fill<BLOCK>(dc, g, a.meta, s0, s1);
   __syncthreads();
   if (tid == 0)
-    for (uint32_t t = 0; t < stages && t < n_tiles; ++t) issue(t, s0 + t);
+    for (uint32_t t = 0; t < stages && t < n_tiles; ++t) issue(t, t);
   if (n_tiles) {
     // slot counters of the bins this row can meet: cnt[b] = slot of the (row, bin) cell's first player; bit 31
     // flags a cell that reaches past the bin's matched prefix (only those players look at binlim).
@@ -123,7 +133,7 @@ __device__ __forceinline__ void place_body(unsigned char* smem_raw, const Geo& g
       cnt[i] = v;
     }
   }
-  for (uint32_t i = tid; i < kHeadSlots; i += BLOCK) head[i] = 0;  // = wcnt all-zero as well (it is smaller)
+  for (uint32_t i = tid; i < kHeadSlots + NW * 128; i += BLOCK) head[i] = 0;  // LIST heads = FAST mask table; + FAST counters
   const bool heavy = __ldcg(&a.ctr->heavy) != 0;
   __syncthreads();
 
@@ -131,51 +141,57 @@ __device__ __forceinline__ void place_body(unsigned char* smem_raw, const Geo& g
   uint32_t nleft = 0;  // lane 0: players of this warp's positions that stay queued
   uint32_t uni_st = 0;  // (uniform) who dirtied the union region: 0 nobody (all-zero), 1 LIST, 2 FAST
   for (uint32_t t = 0; t < n_tiles; ++t) {
+    if (t == dbase + kDescCap) {  // (uniform) next batch of descriptors; thread 0 is not issuing right now
+      dbase = t;
+      desc_fill<BLOCK>(dc, g, a.meta, s0 + t, s1);
+      __syncthreads();
+    }
     const uint32_t vbase = (s0 + t) * kTile;  // virtual position of the tile's first player
     uint16_t* tb = ring_bins + (size_t)st * kTile;
     uint64_t* ti = ring_ids + (size_t)st * kTile;
     mbar_wait(&full[st], parity);
-    const uint32_t valid = s_nv[st], sg = s_sg[st];
-    const uint32_t bin0 = a.seg_bin_lo[sg], nb = a.seg_bin_lo[sg + 1] - bin0;
+    const uint32_t valid = s_nv[st];
+    const uint32_t bin0 = s_b0[st], nb = s_b1[st] - bin0;
     const bool fast = a.fast_ok && nb <= kFastBins;
     uint32_t lmask = 0;  // bit j: my j-th player stays queued
 
     if (fast) {
       // ---------------- FAST: 8-bit counting sort of the tile in shared memory ----------------
-      if (uni_st == 1)  // the LIST path left head[] entries in the counter matrix (B1 below orders the stores)
+      if (uni_st == 1) {  // the LIST path left head[] entries in the mask / counter tables (B1 below orders the stores)
+        for (uint32_t i = tid; i < NW * 256; i += BLOCK) wmask[i] = 0;
         for (uint32_t i = tid; i < NW * 128; i += BLOCK) wcnt32[i] = 0;
+      }
       uni_st = 2;
-      const uint32_t nbits = 32u - __clz(nb);  // digits 0 .. nb-1 live, nb = dead / past the tile's end
       uint32_t dg[J], rk[J];
       uint64_t idv[J];
 #pragma unroll
       for (int j = 0; j < J; ++j) {  // warp-striped: position = warp * 128 + j * 32 + lane
         const uint32_t pos = warp * (32 * J) + j * 32 + lane;
-        const uint32_t b = tb[pos];
+        const uint32_t d = (uint32_t)tb[pos] - bin0;  // digits 0 .. nb-1 live, nb = dead / past the tile's end
         idv[j] = ti[pos];
-        const uint32_t d = b - bin0;
         dg[j] = (pos < valid && d < nb) ? d : nb;
       }
       __syncthreads();  // B1: every id / bin of the stage is in registers (the stage becomes the sort buffer);
-                        //     the counter matrix is all-zero
+                        //     the counter table is all-zero, the mask table always is between items
+      {
+        // Peers of the same digit among the warp's 32 players: every lane ORs its bit into the warp's mask table
+        // (shared-memory RED), reads the word back — that IS the match mask — and the lowest peer resets the word
+        // and bumps the warp's running digit counter.  3 shared-memory instructions per 32 players instead of 8
+        // ballots + selects (MATCH.ANY costs 64 cycles per warp instruction on B200).
+        uint32_t* wm = wmask + warp * 256;
+        uint16_t* wc = wcnt + warp * 256;
+        const uint32_t lbit = 1u << lane;
 #pragma unroll
-      for (int j = 0; j < J; ++j) {
-        uint32_t peers = 0xFFFFFFFFu;
-#pragma unroll
-        for (uint32_t bit = 0; bit < 8; ++bit) {
-          if (bit < nbits) {
-            const bool on = (dg[j] >> bit) & 1u;
-            const uint32_t bal = __ballot_sync(0xFFFFFFFFu, on);
-            peers &= on ? bal : ~bal;
-          }
+        for (int j = 0; j < J; ++j) {
+          atomicOr(&wm[dg[j]], lbit);
+          __syncwarp();
+          const uint32_t peers = wm[dg[j]];
+          const uint32_t base = wc[dg[j]];
+          __syncwarp();
+          if ((peers & lt_mask) == 0) { wm[dg[j]] = 0; wc[dg[j]] = (uint16_t)(base + __popc(peers)); }
+          __syncwarp();
+          rk[j] = base + __popc(peers & lt_mask);
         }
-        const uint32_t leader = __ffs(peers) - 1;
-        uint32_t old = 0;
-        uint16_t* c = wcnt + warp * 256 + dg[j];
-        if (lane == leader) { old = *c; *c = (uint16_t)(old + __popc(peers)); }
-        __syncwarp();
-        old = __shfl_sync(0xFFFFFFFFu, old, leader);
-        rk[j] = old + __popc(peers & lt_mask);
       }
       __syncthreads();  // B2: per-warp digit counts complete
       if (tid < 128) {
@@ -197,8 +213,10 @@ __device__ __forceinline__ void place_body(unsigned char* smem_raw, const Geo& g
         for (uint32_t w = 0; w < warp; ++w) wbase += s_misc[4 + w];
         const uint32_t l0 = wbase + incl - both, l1 = l0 + lo;  // tile-local sorted position of the digits' first players
         const uint32_t d0 = 2 * tid, d1 = d0 + 1;
-        if (d0 < nb) { const uint32_t base = cnt[bin0 + d0]; cnt[bin0 + d0] = base + lo; lgd[d0] = (((base & 0x7FFFFFFFu) - l0) & 0x7FFFFFFFu) | (base & 0x80000000u); }
-        if (d1 < nb) { const uint32_t base = cnt[bin0 + d1]; cnt[bin0 + d1] = base + hi; lgd[d1] = (((base & 0x7FFFFFFFu) - l1) & 0x7FFFFFFFu) | (base & 0x80000000u); }
+        uint32_t fl = 0;
+        if (d0 < nb) { const uint32_t base = cnt[bin0 + d0]; cnt[bin0 + d0] = base + lo; lgd[d0] = (((base & 0x7FFFFFFFu) - l0) & 0x7FFFFFFFu) | (base & 0x80000000u); if (lo) fl |= base; }
+        if (d1 < nb) { const uint32_t base = cnt[bin0 + d1]; cnt[bin0 + d1] = base + hi; lgd[d1] = (((base & 0x7FFFFFFFu) - l1) & 0x7FFFFFFFu) | (base & 0x80000000u); if (hi) fl |= base; }
+        if (fl >> 31) s_misc[2] = 1;   // some player of this tile sits in a cell that reaches past its bin's matched prefix
         if (d0 == nb) s_misc[1] = l0;  // live players of the tile (the dead digit sorts last)
         if (d1 == nb) s_misc[1] = l1;
         uint32_t run = l0 | (l1 << 16);
@@ -206,27 +224,33 @@ __device__ __forceinline__ void place_body(unsigned char* smem_raw, const Geo& g
         for (int w = 0; w < NW; ++w) { wcnt32[w * 128 + tid] = run; run += v[w]; }
       }
       __syncthreads();  // B3: wcnt[w][d] = tile-local sorted position of warp w's first player of digit d
+      uint8_t* sdig = reinterpret_cast<uint8_t*>(tb);  // [kTile] digit of the staged id, 255 = stays queued
+      const bool anyf = s_misc[2] != 0;  // (uniform)
 #pragma unroll
       for (int j = 0; j < J; ++j) {
         if (dg[j] < nb) {
           const uint32_t lpos = wcnt[warp * 256 + dg[j]] + rk[j];
-          const uint32_t e = lgd[dg[j]];
-          const uint32_t slot = (e + lpos) & 0x7FFFFFFFu;
           bool matched = true;
-          if (e >> 31) matched = slot < __ldcg(&a.binlim[bin0 + dg[j]]);
+          if (anyf || a.src_idx) {
+            const uint32_t e = lgd[dg[j]];
+            const uint32_t slot = (e + lpos) & 0x7FFFFFFFu;
+            if (e >> 31) matched = slot < __ldcg(&a.binlim[bin0 + dg[j]]);
+            if (matched && a.src_idx) a.src_idx[slot] = vbase + warp * (32 * J) + j * 32 + lane;
+          }
           ti[lpos] = idv[j];
-          sslot[lpos] = matched ? slot : 0xFFFFFFFFu;
+          sdig[lpos] = matched ? (uint8_t)dg[j] : (uint8_t)255;
           if (!matched) lmask |= 1u << j;
-          else if (a.src_idx) a.src_idx[slot] = vbase + warp * (32 * J) + j * 32 + lane;
         }
       }
       {  // left_bits: the warp owns 128 consecutive positions = 4 words; lane j stores word j
         uint32_t mine = 0, all = 0;
+        if (anyf) {
 #pragma unroll
-        for (int j = 0; j < J; ++j) {
-          const uint32_t wv = __ballot_sync(0xFFFFFFFFu, (lmask >> j) & 1u);
-          if (lane == (uint32_t)j) mine = wv;
-          all += __popc(wv);
+          for (int j = 0; j < J; ++j) {
+            const uint32_t wv = __ballot_sync(0xFFFFFFFFu, (lmask >> j) & 1u);
+            if (lane == (uint32_t)j) mine = wv;
+            all += __popc(wv);
+          }
         }
         if (lane < (uint32_t)J) a.left_bits[(vbase >> 5) + warp * J + lane] = mine;
         if (lane == 0) nleft += all;
@@ -234,16 +258,21 @@ __device__ __forceinline__ void place_body(unsigned char* smem_raw, const Geo& g
       __syncthreads();  // B4: the tile is staged in sorted order
       {
         const uint32_t n_live = s_misc[1];
-        for (uint32_t k = tid; k < n_live; k += BLOCK) {
-          const uint32_t slot = sslot[k];
-          if (slot != 0xFFFFFFFFu) a.members[slot] = ti[k];
+#pragma unroll
+        for (int i = 0; i < J; ++i) {
+          const uint32_t k = i * BLOCK + tid;
+          if (k < n_live) {
+            const uint32_t d = sdig[k];
+            if (d != 255u) a.members[(lgd[d] + k) & 0x7FFFFFFFu] = ti[k];
+          }
         }
-        for (uint32_t i = tid; i < NW * 128; i += BLOCK) wcnt32[i] = 0;  // all-zero again for the next tile
+        reinterpret_cast<uint4*>(wcnt32)[tid] = make_uint4(0, 0, 0, 0);  // counter table all-zero again (8 KB = 512 x 16 B)
+        if (tid == 0) s_misc[2] = 0;
       }
       fence_proxy_async();  // the stage was written by threads and is about to be refilled by the async proxy
     } else {
       // ---------------- LIST: hashed per-bin lists, ids scattered from registers ----------------
-      if (uni_st == 2) {  // the FAST path left staged slots in the head table
+      if (uni_st == 2) {  // the FAST path left counters / slot bases in the head table
         for (uint32_t i = tid; i < kHeadSlots; i += BLOCK) head[i] = 0;
         __syncthreads();
       }
@@ -363,7 +392,7 @@ __device__ __forceinline__ void place_body(unsigned char* smem_raw, const Geo& g
       }
     }
     __syncthreads();  // everyone is done with stage st and with this tile's ranking state
-    if (tid == 0 && t + stages < n_tiles) issue(st, s0 + t + stages);
+    if (tid == 0 && t + stages < n_tiles) issue(st, t + stages);
     if (++st == stages) { st = 0; parity ^= 1u; }
   }
 

@@ -17,7 +17,7 @@ namespace mm {
 // ---------------------------------------------------------------------------------------
 constexpr int kScanBlock = 512;
 constexpr uint32_t kColScratchWords = (kScanBlock / 32) * 33;      // column CTA scratch
-constexpr uint32_t kTailScratchWords = 64 + 4 + 6 * kMaxSegs + 8;  // tail CTA scratch, fixed part
+constexpr uint32_t kTailScratchWords = 64 + 4 + 5 * kMaxSegs + 8;  // tail CTA scratch, fixed part
 
 // One 32-bin column group: exclusive prefix down the rows of M (scratch: kColScratchWords).  Bin b belongs to one
 // partition, and only the rows holding that partition's tiles wrote M[.][b] (mm_hist.cuh): the scan of a column is
@@ -94,62 +94,42 @@ __host__ __device__ constexpr uint32_t tail_words(uint32_t Kp, uint32_t layout) 
 __device__ __forceinline__ void colscan_tail_body(uint32_t* scratch, const TailArgs t) {
   constexpr uint32_t NW = kScanBlock / 32;
   uint32_t* s_tmp = scratch;            // [64]
-  uint32_t* s_misc = scratch + 64;      // [4] fullest bin
-  uint32_t* s_a = scratch + 68;         // [kMaxSegs] leftovers of earlier segments / member base
-  uint32_t* s_lob = s_a + kMaxSegs;     // [kMaxSegs] lobbies of earlier segments
-  uint32_t* s_nl = s_lob + kMaxSegs;    // [kMaxSegs] lobbies of the segment
-  uint32_t* s_lo = s_nl + kMaxSegs;     // [kMaxSegs + 1] first bin of the segment
-  uint32_t* s_left = s_lo + kMaxSegs + 1;  // [kMaxSegs] players of the segment that stay queued -> rank base
-  uint32_t* s_nch = s_left + kMaxSegs;     // [kMaxSegs] chunks of the segment in the compacted pool -> first chunk
+  uint32_t* s_misc = scratch + 64;      // [4] heavy flag | n_matched | lobbies | chunks of the compacted pool
+  uint32_t* s_a = scratch + 68;         // [kMaxSegs] leftovers of earlier segments
+  uint32_t* s_ns = s_a + kMaxSegs;      // [kMaxSegs] alive players of the segment
+  uint32_t* s_mt = s_ns + kMaxSegs;     // [kMaxSegs] matched players of the segment
+  uint32_t* s_lo = s_mt + kMaxSegs;     // [kMaxSegs + 1] first bin of the segment
+  uint32_t* s_nch = s_lo + kMaxSegs + 1;   // [kMaxSegs + 1] first chunk of the segment in the compacted pool
   uint32_t* s_bb = scratch + kTailScratchWords;  // [Kp + 1] sorted position of the bin's first player
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, Kp = t.Kp, K = t.K, n_segs = t.n_segs;
   if (tid == 0) s_misc[0] = 0;
   for (uint32_t sg = tid; sg <= n_segs; sg += kScanBlock) s_lo[sg] = t.seg_bin_lo[sg];
+  for (uint32_t i = tid; i < Kp; i += kScanBlock) s_bb[i] = __ldcg(&t.tot[i]);  // coalesced, independent loads
   __syncthreads();
-  uint32_t hv = 0;
-  for (uint32_t i = tid; i < Kp; i += kScanBlock) {  // coalesced, independent loads
-    const uint32_t v = __ldcg(&t.tot[i]);
-    s_bb[i] = v;
-    if (i < K && v > 8) {  // a bin of a list-ranked partition expecting > 8 players per tile of that partition
-      const uint32_t sg = t.bin_seg[i];
-      if (s_lo[sg + 1] - s_lo[sg] > kFastBins && (uint64_t)v * kTile > 8ull * __ldcg(&t.fill[sg])) hv = 1;
-    }
+  // list-ranked partitions only: does some bin expect > 8 players per tile of its partition?
+  for (uint32_t sg = warp; sg < n_segs; sg += NW) {
+    if (s_lo[sg + 1] - s_lo[sg] <= kFastBins) continue;
+    uint32_t mx = 0;
+    for (uint32_t v = s_lo[sg] + lane; v < s_lo[sg + 1]; v += 32) mx = s_bb[v] > mx ? s_bb[v] : mx;
+    mx = __reduce_max_sync(0xFFFFFFFFu, mx);
+    if (lane == 0 && (uint64_t)mx * kTile > 8ull * __ldcg(&t.fill[sg])) s_misc[0] = 1;
   }
-  if (__any_sync(0xFFFFFFFFu, hv) && (tid & 31) == 0) atomicOr(&s_misc[0], 1u);
   __syncthreads();
   const uint32_t total = block_excl_scan<kScanBlock>(s_bb, Kp, s_tmp);
   if (tid == 0) s_bb[Kp] = total;
   __syncthreads();
   const uint32_t alive = s_bb[K], dead = total - alive;
-  uint32_t n_matched, tot_lob;
+  const bool windowed = t.max_spread >= 0;
+  const bool m_smem = (t.layout & 1u) != 0, key_smem = (t.layout & 2u) != 0;
+  uint32_t* s_m = m_smem ? s_bb + Kp + 2 : t.binlim;  // S1: [Kp + 1] matched players of the bin
 
-  if (t.max_spread < 0) {
+  if (!windowed) {
     // S0: lobbies_s = n_s / L; the partition's first lobbies_s * L sorted positions are matched.
     for (uint32_t sg = tid; sg < n_segs; sg += kScanBlock) {
-      const uint32_t ns = s_bb[s_lo[sg + 1]] - s_bb[s_lo[sg]], nl = ns / t.seg_L[sg];
-      s_nl[sg] = nl; s_lob[sg] = nl; s_a[sg] = ns - nl * t.seg_L[sg];
-      s_left[sg] = s_a[sg];
-      t.seg[sg].n = ns; t.seg[sg].n_lobbies = nl;
+      const uint32_t ns = s_bb[s_lo[sg + 1]] - s_bb[s_lo[sg]], L = t.seg_L[sg];
+      s_ns[sg] = ns; s_mt[sg] = ns / L * L;
     }
-    __syncthreads();
-    const uint32_t n_left = block_excl_scan<kScanBlock>(s_a, n_segs, s_tmp);   // -> leftovers of earlier segments
-    tot_lob = block_excl_scan<kScanBlock>(s_lob, n_segs, s_tmp);               // -> lobbies of earlier segments
-    n_matched = alive - n_left;
-    for (uint32_t sg = warp; sg < n_segs; sg += NW) {  // one warp per partition: no bin -> segment lookups
-      const uint32_t lo = s_lo[sg], hi = s_lo[sg + 1], start = s_bb[lo], shift = s_a[sg];
-      const uint32_t mend = start + s_nl[sg] * t.seg_L[sg];  // end of the partition's matched positions
-      for (uint32_t v = lo + lane; v < hi; v += 32) {
-        const uint32_t b0 = s_bb[v], b1 = s_bb[v + 1];
-        t.outbase[v] = (b0 < mend ? b0 : mend) - shift;
-        t.binlim[v] = (b1 < mend ? b1 : mend) - shift;
-      }
-      if (lane == 0) { t.seg[sg].member_base = start - shift; t.seg[sg].lobby_base = s_lob[sg]; }
-    }
-    for (uint32_t v = K + tid; v < Kp; v += kScanBlock) { t.outbase[v] = n_matched; t.binlim[v] = n_matched; }
   } else {
-    // S1: greedy windowed walk on the histogram, one thread per partition (see above), then a second scan.
-    const bool m_smem = (t.layout & 1u) != 0, key_smem = (t.layout & 2u) != 0;
-    uint32_t* s_m = m_smem ? s_bb + Kp + 2 : t.binlim;  // [Kp + 1] matched players of the bin
     uint16_t* s_key = reinterpret_cast<uint16_t*>(s_bb + (m_smem ? 2 : 1) * (Kp + 2));
     const uint16_t* keys = key_smem ? s_key : t.bin_key;
     if (key_smem)
@@ -172,7 +152,7 @@ __device__ __forceinline__ void colscan_tail_body(uint32_t* scratch, const TailA
         lo[q] = on ? s_lo[sg] : 0u; hi[q] = on ? s_lo[sg + 1] : 0u; L[q] = on ? t.seg_L[sg] : 1u;
         Mrec[q] = 0xFFFFFFFFu / L[q];  // umulhi(a, Mrec) is a / L or a / L - 1 for every 32-bit a
         pos[q] = s_bb[lo[q]];
-        if (on && lane == 0) { s_nl[sg] = s_bb[hi[q]] - s_bb[lo[q]]; t.seg[sg].n = s_nl[sg]; }
+        if (on && lane == 0) s_ns[sg] = s_bb[hi[q]] - s_bb[lo[q]];
       }
       const uint32_t span0 = hi[0] - lo[0], span1 = hi[1] - lo[1], span = span0 > span1 ? span0 : span1;
       for (uint32_t off = 0; off < span; off += 32) {
@@ -221,44 +201,71 @@ __device__ __forceinline__ void colscan_tail_body(uint32_t* scratch, const TailA
       __syncthreads();
     }
     // member slots = exclusive scan of the matched counts (members of successive partitions are contiguous)
-    n_matched = block_excl_scan<kScanBlock>(s_m, Kp, s_tmp);
-    if (tid == 0) s_m[Kp] = n_matched;
+    const uint32_t nm = block_excl_scan<kScanBlock>(s_m, Kp, s_tmp);
+    if (tid == 0) s_m[Kp] = nm;
     __syncthreads();
     for (uint32_t v = tid; v < Kp; v += kScanBlock) {
       t.outbase[v] = s_m[v];
       t.binlim[v] = s_m[v + 1];  // = outbase + matched players of the bin
     }
-    for (uint32_t sg = tid; sg < n_segs; sg += kScanBlock) {
-      const uint32_t mb = s_m[s_lo[sg]], nl = (s_m[s_lo[sg + 1]] - mb) / t.seg_L[sg];
-      s_lob[sg] = nl;
-      s_left[sg] = s_nl[sg] - (s_m[s_lo[sg + 1]] - mb);  // s_nl: players of the segment (S1 does not use it otherwise)
-      t.seg[sg].n_lobbies = nl; t.seg[sg].member_base = mb;
+    for (uint32_t sg = tid; sg < n_segs; sg += kScanBlock) s_mt[sg] = s_m[s_lo[sg + 1]] - s_m[s_lo[sg]];
+  }
+  __syncthreads();
+  // Partition table, by ONE warp (<= 512 partitions, 32 per step with carries; no block-wide scans): member / lobby
+  // bases, and the layout of the compacted pool — partition sg keeps n_left players in ceil(n_left / kTile) fresh
+  // chunks handed out in partition order from chunk 0 (the epilogue moves the players).
+  if (warp == 0) {
+    uint32_t c_mem = 0, c_lob = 0, c_left = 0, c_ch = 0;
+    for (uint32_t base = 0; base < n_segs; base += 32) {
+      const uint32_t sg = base + lane;
+      const bool on = sg < n_segs;
+      const uint32_t ns = on ? s_ns[sg] : 0u, mt = on ? s_mt[sg] : 0u, L = on ? t.seg_L[sg] : 1u;
+      const uint32_t nl = mt / L, nleft = ns - mt, nch = (nleft + kTile - 1) / kTile;
+      uint32_t i_mem = mt, i_lob = nl, i_left = nleft, i_ch = nch;
+#pragma unroll
+      for (int off = 1; off < 32; off <<= 1) {
+        const uint32_t a = __shfl_up_sync(0xFFFFFFFFu, i_mem, off), b = __shfl_up_sync(0xFFFFFFFFu, i_lob, off);
+        const uint32_t c = __shfl_up_sync(0xFFFFFFFFu, i_left, off), d = __shfl_up_sync(0xFFFFFFFFu, i_ch, off);
+        if (lane >= (uint32_t)off) { i_mem += a; i_lob += b; i_left += c; i_ch += d; }
+      }
+      if (on) {
+        SegInfo si;
+        si.n = ns; si.n_lobbies = nl; si.member_base = c_mem + i_mem - mt; si.lobby_base = c_lob + i_lob - nl;
+        si.left_base = c_left + i_left - nleft; si.new_chunk = c_ch + i_ch - nch; si.n_left = nleft; si.reserved = 0;
+        t.seg[sg] = si;
+        t.dst.fill[sg] = nleft;
+        s_a[sg] = si.left_base;
+        s_nch[sg] = si.new_chunk;
+      }
+      c_mem += __shfl_sync(0xFFFFFFFFu, i_mem, 31); c_lob += __shfl_sync(0xFFFFFFFFu, i_lob, 31);
+      c_left += __shfl_sync(0xFFFFFFFFu, i_left, 31); c_ch += __shfl_sync(0xFFFFFFFFu, i_ch, 31);
     }
-    __syncthreads();
-    tot_lob = block_excl_scan<kScanBlock>(s_lob, n_segs, s_tmp);
-    for (uint32_t sg = tid; sg < n_segs; sg += kScanBlock) t.seg[sg].lobby_base = s_lob[sg];
-  }
-  // Layout of the compacted pool (the epilogue moves the players that stay queued): partition sg keeps n_left
-  // players in ceil(n_left / kTile) fresh chunks, handed out in partition order from chunk 0.
-  __syncthreads();
-  for (uint32_t sg = tid; sg < n_segs; sg += kScanBlock) {
-    const uint32_t nlft = s_left[sg];
-    s_nch[sg] = (nlft + kTile - 1) / kTile;
-    t.seg[sg].n_left = nlft;
-    t.dst.fill[sg] = nlft;
+    if (lane == 0) {
+      s_nch[n_segs] = c_ch;
+      s_misc[1] = c_mem; s_misc[2] = c_lob;
+      *t.dst.bump = c_ch;
+      t.ctr->n_lobbies = c_lob; t.ctr->n_matched = c_mem; t.ctr->n_alive = alive; t.ctr->n_dead = dead;
+      t.ctr->heavy = s_misc[0];
+    }
   }
   __syncthreads();
-  block_excl_scan<kScanBlock>(s_left, n_segs, s_tmp);
-  const uint32_t new_chunks = block_excl_scan<kScanBlock>(s_nch, n_segs, s_tmp);
-  for (uint32_t sg = tid; sg < n_segs; sg += kScanBlock) { t.seg[sg].left_base = s_left[sg]; t.seg[sg].new_chunk = s_nch[sg]; }
-  for (uint32_t sg = warp; sg < n_segs; sg += NW) {
-    const uint32_t c0 = s_nch[sg], c1 = sg + 1 < n_segs ? s_nch[sg + 1] : new_chunks;
+  const uint32_t n_matched = s_misc[1];
+  if (!windowed) {
+    // S0: member slot = sorted position - leftovers of earlier partitions, clipped at the partition's matched end
+    for (uint32_t sg = warp; sg < n_segs; sg += NW) {  // one warp per partition: no bin -> segment lookups
+      const uint32_t lo = s_lo[sg], hi = s_lo[sg + 1], start = s_bb[lo], shift = s_a[sg];
+      const uint32_t mend = start + s_mt[sg];  // end of the partition's matched positions
+      for (uint32_t v = lo + lane; v < hi; v += 32) {
+        const uint32_t b0 = s_bb[v], b1 = s_bb[v + 1];
+        t.outbase[v] = (b0 < mend ? b0 : mend) - shift;
+        t.binlim[v] = (b1 < mend ? b1 : mend) - shift;
+      }
+    }
+    for (uint32_t v = K + tid; v < Kp; v += kScanBlock) { t.outbase[v] = n_matched; t.binlim[v] = n_matched; }
+  }
+  for (uint32_t sg = warp; sg < n_segs; sg += NW) {  // chunk lists of the compacted pool
+    const uint32_t c0 = s_nch[sg], c1 = s_nch[sg + 1];
     for (uint32_t k = lane; k < c1 - c0; k += 32) t.dst.chunk_tab[(size_t)sg * t.dst.max_ch + k] = c0 + k;
-  }
-  if (tid == 0) {
-    *t.dst.bump = new_chunks;
-    t.ctr->n_lobbies = tot_lob; t.ctr->n_matched = n_matched; t.ctr->n_alive = alive; t.ctr->n_dead = dead;
-    t.ctr->heavy = s_misc[0];
   }
   __syncthreads();
 }
