@@ -83,7 +83,6 @@ struct mm_engine {
   int rows_per_sm = 2;
   int rank_impl = 3;           // 3 = ballot tile sort for partitions of <= 255 bins + lists otherwise; 2 = lists only
   uint32_t place_stages = 0;
-  uint32_t hist_stages = 4;
   int fused_ok = 0;  // k_tick<512> can be launched cooperatively with R CTAs
   int tick_impl = 1; // 1 = one fused cooperative launch when possible, 0 = four launches
   size_t tick_smem = 0;
@@ -472,8 +471,8 @@ int tick_phase_a(mm_engine* e) {
   const Pool& p = e->pool[e->cur];
   CK(cudaMemsetAsync(e->d_ctr, 0, sizeof(TickCtr), e->stream));
   CK(cudaEventRecord(e->ev[0], e->stream));
-  k_hist<512><<<e->R, 512, hist_smem_bytes(e->Kp, e->hist_stages), e->stream>>>(
-      p.v.bin, p.m, e->n_segs, e->R, e->Kp, e->K, e->hist_stages, e->d_seg_bin_lo, e->d_M, e->d_tot);
+  k_hist<512><<<e->R, 512, hist_smem_bytes(e->Kp), e->stream>>>(
+      p.v.bin, p.m, e->n_segs, e->R, e->Kp, e->K, e->d_seg_bin_lo, e->d_M, e->d_tot);
   CK(cudaEventRecord(e->ev[1], e->stream));
   k_colscan<<<(e->K + 31) / 32 + 1, kScanBlock, colscan_smem(e), e->stream>>>(e->R, e->d_M, tail_args(e));
   CK(cudaGetLastError());
@@ -499,7 +498,6 @@ bool use_fused(const mm_engine* e) { return e->tick_impl == 1 && e->fused_ok; }
 int tick_fused(mm_engine* e, bool want_seq) {
   TickArgs a{};
   a.src = e->pool[e->cur].v;
-  a.hist_stages = e->hist_stages;
   a.M = e->d_M;
   a.tot = e->d_tot;
   a.tail = tail_args(e);
@@ -733,7 +731,7 @@ int mm_create(const mm_config* cfg, mm_engine** out) {
     return bail(MM_E_CUDA);
   if ((rc = alloc_tick_scratch(e))) return bail(rc);
   {
-    size_t sz = std::max(hist_smem_bytes(e->Kp, e->hist_stages), place_smem_bytes(e->Kp, e->place_stages));
+    size_t sz = std::max(hist_smem_bytes(e->Kp), place_smem_bytes(e->Kp, e->place_stages));
     sz = std::max<size_t>(sz, std::max<size_t>((size_t)kEpiScratchWords * 4, colscan_smem(e)));
     int coop = 0, nb = 0;
     cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, e->device);

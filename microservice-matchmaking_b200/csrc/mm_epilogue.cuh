@@ -82,6 +82,24 @@ __device__ __forceinline__ void epilogue_body(uint32_t* scratch, const Geo& g, c
     if (blockIdx.x == 0) ctr->n_resid = total;
   }
   __syncthreads();
+  // Lobby headers first: fire-and-forget stores that drain while the compaction below waits on its dependent
+  // gather / hash-probe chains.
+  const uint32_t total_lob = __ldcg(&ctr->n_lobbies);
+  for (uint32_t c = blockIdx.x * BLOCK + tid; c < total_lob; c += gridDim.x * BLOCK) {
+    uint32_t a = 0, e = n_segs;  // last segment with lobby_base <= c
+    while (e - a > 1) { const uint32_t mid = (a + e) >> 1; if (s_lbase[mid] <= c) a = mid; else e = mid; }
+    const uint32_t L = s_L[a];
+    mm_lobby_hdr h;
+    h.first_member = s_mbase[a] + (c - s_lbase[a]) * L;
+    h.n_members = (uint16_t)L;
+    h.mode = (uint8_t)(a / n_groups);
+    h.group = (uint8_t)(a % n_groups);
+    hdr[c] = h;
+    if (emit_seq) {  // enqueue sequence number of the member whose arrival completed the lobby
+      uint32_t p;
+      emit_seq[c] = src.seq[phys_of(__ldcg(&src_idx[h.first_member + L - 1]), p)];
+    }
+  }
   // Work is split by leftover RANK, not by row: under policy S0 the leftovers are the latest arrivals of every
   // partition and sit in the last rows of the pool.  CTA b moves the players with global rank [r0, r1); it walks
   // the bit words of the rows holding them (popcount prefix from the start of the row), enumerates the pool
@@ -131,10 +149,13 @@ __device__ __forceinline__ void epilogue_body(uint32_t* scratch, const Geo& g, c
       row_beg = beg;
       const uint32_t lo_l = (r0 > off ? r0 : off) - off, hi_l = (r1 < off + cnt ? r1 : off + cnt) - off;  // row-local ranks
       uint32_t run_l = 0;  // row-local rank of the step's first leftover player
-      for (uint32_t w0 = 0; w0 < nwords && run_l < hi_l; w0 += BLOCK) {  // BLOCK words = 32 * BLOCK players per step
-        const uint32_t wi = w0 + tid;
-        const uint32_t w = wi < nwords ? __ldcg(&bits[wi]) : 0u;
-        const uint32_t c = __popc(w);
+      // 4 bit words (128 players) per thread and step: a row of 17 tiles is one step of a 512-thread CTA.  nwords is a
+      // multiple of 64 (whole tiles) and `bits` is 16-byte aligned (rows start on tile boundaries).
+      for (uint32_t w0 = 0; w0 < nwords && run_l < hi_l; w0 += 4 * BLOCK) {
+        const uint32_t wi = w0 + 4 * tid;
+        const uint4 w4 = wi < nwords ? __ldcg(reinterpret_cast<const uint4*>(bits + wi)) : make_uint4(0, 0, 0, 0);
+        const uint32_t wv[4] = {w4.x, w4.y, w4.z, w4.w};
+        const uint32_t c = __popc(w4.x) + __popc(w4.y) + __popc(w4.z) + __popc(w4.w);
         uint32_t incl = c;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -145,19 +166,23 @@ __device__ __forceinline__ void epilogue_body(uint32_t* scratch, const Geo& g, c
         __syncthreads();
         uint32_t wbase = 0, wtot = 0;
         for (uint32_t k = 0; k < NW; ++k) { const uint32_t v = s_tmp[k]; if (k < warp) wbase += v; wtot += v; }
-        const uint32_t lpre = run_l + wbase + incl - c;  // row-local rank of this word's first leftover player
+        const uint32_t lpre = run_l + wbase + incl - c;  // row-local rank of this thread's first leftover player
         uint32_t q = lo_l > run_l ? lo_l : run_l;
         const uint32_t q_end = hi_l < run_l + wtot ? hi_l : run_l + wtot;
         while (q < q_end) {  // (uniform) ranks [q, q_end) of this step are mine
           if (fill == kLeftList) { flush(fill, false); fill = 0; }
           const uint32_t room = kLeftList - fill, take = q_end - q < room ? q_end - q : room;
           if (c && lpre < q + take && lpre + c > q) {
-            uint32_t ww = w, r = lpre;
-            while (ww) {
-              const uint32_t bpos = __ffs(ww) - 1;
-              ww &= ww - 1;
-              if (r >= q && r < q + take) s_list[fill + (r - q)] = row_beg + (wi << 5) + bpos;
-              ++r;
+            uint32_t r = lpre;
+#pragma unroll
+            for (int k4 = 0; k4 < 4; ++k4) {
+              uint32_t ww = wv[k4];
+              while (ww) {
+                const uint32_t bpos = __ffs(ww) - 1;
+                ww &= ww - 1;
+                if (r >= q && r < q + take) s_list[fill + (r - q)] = row_beg + ((wi + k4) << 5) + bpos;
+                ++r;
+              }
             }
           }
           fill += take;
@@ -173,22 +198,6 @@ __device__ __forceinline__ void epilogue_body(uint32_t* scratch, const Geo& g, c
     unsigned long long tm;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tm));
     atomicMax(t_mid, tm);
-  }
-  const uint32_t total_lob = __ldcg(&ctr->n_lobbies);
-  for (uint32_t c = blockIdx.x * BLOCK + tid; c < total_lob; c += gridDim.x * BLOCK) {
-    uint32_t a = 0, e = n_segs;  // last segment with lobby_base <= c
-    while (e - a > 1) { const uint32_t mid = (a + e) >> 1; if (s_lbase[mid] <= c) a = mid; else e = mid; }
-    const uint32_t L = s_L[a];
-    mm_lobby_hdr h;
-    h.first_member = s_mbase[a] + (c - s_lbase[a]) * L;
-    h.n_members = (uint16_t)L;
-    h.mode = (uint8_t)(a / n_groups);
-    h.group = (uint8_t)(a % n_groups);
-    hdr[c] = h;
-    if (emit_seq) {  // enqueue sequence number of the member whose arrival completed the lobby
-      uint32_t p;
-      emit_seq[c] = src.seq[phys_of(__ldcg(&src_idx[h.first_member + L - 1]), p)];
-    }
   }
 }
 

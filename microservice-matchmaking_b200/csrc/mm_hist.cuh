@@ -11,18 +11,20 @@ namespace mm {
 // column per tile, L2 evict-last: the placement pass re-reads the column from L2); shared-memory atomics
 // build the row histogram.  Only the bins of the partitions the row touches are written to M — a row's tiles
 // are consecutive in (partition, chunk) order, so that is one contiguous bin range.
-// Shared memory: ring[stages][kTile] u16 | mbarriers | nvalid[kMaxStages] | hist[Kp] | tile descriptors.
+// Shared memory: ring[8][kTile] u16 | mbarriers | nvalid[8] | hist[Kp] | tile descriptors.
 // ---------------------------------------------------------------------------------------
+constexpr uint32_t kHistStages = 8;  // ring depth: two half-turns of 4 tiles (8 192 players each)
+
 template <int BLOCK>
 __device__ __forceinline__ void hist_body(unsigned char* smem_raw, const Geo& g, const uint16_t* __restrict__ bins16,
-                                          const PoolMeta meta, uint32_t Kp, uint32_t K, uint32_t stages,
+                                          const PoolMeta meta, uint32_t Kp, uint32_t K,
                                           const uint32_t* __restrict__ seg_bin_lo, uint32_t* __restrict__ M,
                                           uint32_t* __restrict__ tot) {
-  constexpr uint32_t kBytes = kTile * 2;
-  uint16_t* ring = reinterpret_cast<uint16_t*>(smem_raw);                                  // [stages][kTile]
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + (size_t)stages * kBytes);        // [kMaxStages]
-  uint32_t* s_nv = reinterpret_cast<uint32_t*>(smem_raw + (size_t)stages * kBytes + 32);   // [kMaxStages]
-  uint32_t* hist = reinterpret_cast<uint32_t*>(smem_raw + (size_t)stages * kBytes + 64);   // [Kp]
+  constexpr uint32_t kBytes = kTile * 2, S = kHistStages, H = S / 2;
+  uint16_t* ring = reinterpret_cast<uint16_t*>(smem_raw);                            // [S][kTile]
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + (size_t)S * kBytes);       // [S]
+  uint32_t* s_nv = reinterpret_cast<uint32_t*>(smem_raw + (size_t)S * kBytes + 64);  // [S]
+  uint32_t* hist = reinterpret_cast<uint32_t*>(smem_raw + (size_t)S * kBytes + 128); // [Kp]
   DescCache& dc = *reinterpret_cast<DescCache*>(hist + ((Kp + 3) & ~3u));
   const uint32_t tid = threadIdx.x, row = blockIdx.x;
   const uint64_t pol = policy_evict_last();
@@ -30,7 +32,7 @@ __device__ __forceinline__ void hist_body(unsigned char* smem_raw, const Geo& g,
   const uint32_t s1 = s0 + g.tpr < g.NT ? s0 + g.tpr : g.NT;
   const uint32_t n_tiles = s1 - s0;
   if (tid == 0) {
-    for (uint32_t s = 0; s < stages; ++s) mbar_init(&full[s], 1);
+    for (uint32_t s = 0; s < S; ++s) mbar_init(&full[s], 1);
     mbar_fence_init();
   }
   fence_proxy_async();
@@ -46,35 +48,40 @@ __device__ __forceinline__ void hist_body(unsigned char* smem_raw, const Geo& g,
     tma_load_1d(ring + (size_t)stage * kTile, bins16 + (size_t)phys * kTile, kBytes, &full[stage], pol);
   };
   if (tid == 0)
-    for (uint32_t t = 0; t < stages && t < n_tiles; ++t) issue(t, t);
+    for (uint32_t t = 0; t < S && t < n_tiles; ++t) issue(t, t);
   for (uint32_t i = tid; i < Kp; i += BLOCK) hist[i] = 0;
   __syncthreads();
-  uint32_t st = 0, parity = 0;
-  for (uint32_t t = 0; t < n_tiles; ++t) {
-    if (t == dbase + kDescCap) {  // (uniform) next batch of descriptors; thread 0 is not issuing right now
-      dbase = t;
-      desc_fill<BLOCK>(dc, g, meta, s0 + t, s1);
+  // The ring is consumed half a turn at a time (4 tiles = up to 8 192 players between two CTA barriers) while the
+  // other half's copies are in flight: the pass is latency-bound at this size, fewer and fatter steps win.
+  for (uint32_t i = 0; i * H < n_tiles; ++i) {
+    const uint32_t t0 = i * H, sb = (i & 1u) * H, parity = (i >> 1) & 1u;
+    if (t0 >= dbase + kDescCap) {  // (uniform) next batch of descriptors; thread 0 is not issuing right now
+      dbase = t0;
+      desc_fill<BLOCK>(dc, g, meta, s0 + t0, s1);
       __syncthreads();
     }
-    const uint16_t* tb = ring + (size_t)st * kTile;
-    mbar_wait(&full[st], parity);
-    const uint32_t valid = s_nv[st];
+    const uint32_t nt = n_tiles - t0 < H ? n_tiles - t0 : H;
+    for (uint32_t k = 0; k < nt; ++k) {
+      const uint16_t* tb = ring + (size_t)(sb + k) * kTile;
+      mbar_wait(&full[sb + k], parity);
+      const uint32_t valid = s_nv[sb + k];
 #pragma unroll
-    for (uint32_t q = tid; q < kTile / 8; q += BLOCK) {  // 8 bins (128 bits) per thread per step
-      const uint32_t o = q * 8;
-      if (o + 8 <= valid) {
-        const uint4 v = *reinterpret_cast<const uint4*>(tb + o);
-        atomicAdd(&hist[v.x & 0xFFFFu], 1u); atomicAdd(&hist[v.x >> 16], 1u);
-        atomicAdd(&hist[v.y & 0xFFFFu], 1u); atomicAdd(&hist[v.y >> 16], 1u);
-        atomicAdd(&hist[v.z & 0xFFFFu], 1u); atomicAdd(&hist[v.z >> 16], 1u);
-        atomicAdd(&hist[v.w & 0xFFFFu], 1u); atomicAdd(&hist[v.w >> 16], 1u);
-      } else {
-        for (uint32_t k = o; k < valid; ++k) atomicAdd(&hist[tb[k]], 1u);
+      for (uint32_t q = tid; q < kTile / 8; q += BLOCK) {  // 8 bins (128 bits) per thread per step
+        const uint32_t o = q * 8;
+        if (o + 8 <= valid) {
+          const uint4 v = *reinterpret_cast<const uint4*>(tb + o);
+          atomicAdd(&hist[v.x & 0xFFFFu], 1u); atomicAdd(&hist[v.x >> 16], 1u);
+          atomicAdd(&hist[v.y & 0xFFFFu], 1u); atomicAdd(&hist[v.y >> 16], 1u);
+          atomicAdd(&hist[v.z & 0xFFFFu], 1u); atomicAdd(&hist[v.z >> 16], 1u);
+          atomicAdd(&hist[v.w & 0xFFFFu], 1u); atomicAdd(&hist[v.w >> 16], 1u);
+        } else {
+          for (uint32_t e = o; e < valid; ++e) atomicAdd(&hist[tb[e]], 1u);
+        }
       }
     }
     __syncthreads();
-    if (tid == 0 && t + stages < n_tiles) issue(st, t + stages);
-    if (++st == stages) { st = 0; parity ^= 1u; }
+    if (tid == 0)
+      for (uint32_t k = 0; k < H && t0 + S + k < n_tiles; ++k) issue(sb + k, t0 + S + k);
   }
   if (n_tiles) {
     const uint32_t p_first = geo_seg_of(g, s0), p_last = geo_seg_of(g, s1 - 1);
@@ -88,11 +95,11 @@ __device__ __forceinline__ void hist_body(unsigned char* smem_raw, const Geo& g,
     if (tid == 0 && hist[K]) atomicAdd(&tot[K], hist[K]);  // players removed while queued
   }
   if (tid == 0)
-    for (uint32_t s = 0; s < stages; ++s) mbar_inval(&full[s]);
+    for (uint32_t s = 0; s < kHistStages; ++s) mbar_inval(&full[s]);
 }
 
-__host__ __device__ constexpr size_t hist_smem_bytes(uint32_t Kp, uint32_t stages) {
-  return (size_t)stages * kTile * 2 + 64 + (size_t)((Kp + 3) & ~3u) * 4 + sizeof(DescCache) + 16;
+__host__ __device__ constexpr size_t hist_smem_bytes(uint32_t Kp) {
+  return (size_t)kHistStages * kTile * 2 + 128 + (size_t)((Kp + 3) & ~3u) * 4 + sizeof(DescCache) + 16;
 }
 
 }  // namespace mm

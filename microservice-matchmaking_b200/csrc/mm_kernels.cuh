@@ -34,12 +34,12 @@ namespace mm {
 template <int BLOCK>
 __global__ void __launch_bounds__(BLOCK, 2)
     k_hist(const uint16_t* __restrict__ bins16, const PoolMeta meta, uint32_t n_segs, uint32_t R, uint32_t Kp, uint32_t K,
-           uint32_t stages, const uint32_t* __restrict__ seg_bin_lo, uint32_t* __restrict__ M, uint32_t* __restrict__ tot) {
+           const uint32_t* __restrict__ seg_bin_lo, uint32_t* __restrict__ M, uint32_t* __restrict__ tot) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ Geo geo;
   __shared__ uint32_t s_gtmp[33];
   geo_build<BLOCK>(geo, meta.fill, n_segs, R, s_gtmp);
-  hist_body<BLOCK>(smem_raw, geo, bins16, meta, Kp, K, stages, seg_bin_lo, M, tot);
+  hist_body<BLOCK>(smem_raw, geo, bins16, meta, Kp, K, seg_bin_lo, M, tot);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -53,7 +53,6 @@ __global__ void __launch_bounds__(BLOCK, 2)
 // ---------------------------------------------------------------------------------------
 struct TickArgs {
   PoolView src;
-  uint32_t hist_stages;
   uint32_t* M;
   uint32_t* tot;   // = tail.tot (written by the histogram, re-zeroed by the epilogue)
   TailArgs tail;   // Kp, K, n_segs, tot, segment tables, outbase / binlim, counters, src fill, dst meta
@@ -80,7 +79,7 @@ __global__ void __launch_bounds__(BLOCK, 2) k_tick(const TickArgs a) {
   };
   stamp(0);
   geo_build<BLOCK>(geo, a.place.meta.fill, a.tail.n_segs, G, s_gtmp);
-  hist_body<BLOCK>(smem_raw, geo, a.src.bin, a.place.meta, Kp, K, a.hist_stages, a.tail.seg_bin_lo, a.M, a.tot);
+  hist_body<BLOCK>(smem_raw, geo, a.src.bin, a.place.meta, Kp, K, a.tail.seg_bin_lo, a.M, a.tot);
   grid_barrier(&ctr->gbar, G);
   stamp(1);
   if (blockIdx.x == G - 1) {

@@ -30,7 +30,8 @@ namespace mm {
 //                union { LIST: head[kHeadSlots] node[kTile] nbin[kTile] ; FAST: wcnt[16][256] u16, sslot[kTile] }.
 // ---------------------------------------------------------------------------------------
 constexpr uint32_t kHeadSlots = 4096;
-constexpr uint32_t kPlaceUnionBytes = kHeadSlots * 4 + kTile * 4 + kTile * 2;  // LIST: 28 KB >= FAST: 16 + 8 + 1 KB
+constexpr uint32_t NW16 = 16;  // warps per 512-thread CTA
+constexpr uint32_t kPlaceUnionBytes = NW16 * 256 * 4 + NW16 * 256 * 2 + 1024 + kTile * 4;  // FAST: 16 + 8 + 1 + 8 KB >= LIST: 28 KB
 
 __host__ __device__ constexpr size_t place_smem_bytes(uint32_t Kp, uint32_t stages) {
   return (size_t)stages * kTileBytes + 128 + (size_t)((Kp + 3) & ~3u) * 4 + kPlaceUnionBytes + sizeof(DescCache) + 16;
@@ -80,6 +81,7 @@ __device__ __forceinline__ void place_body(unsigned char* smem_raw, const Geo& g
   uint16_t* wcnt = reinterpret_cast<uint16_t*>(wmask + NW * 256);  // [NW][256] per-warp running digit counters
   uint32_t* wcnt32 = reinterpret_cast<uint32_t*>(wcnt);        // the same, two digits per word: [NW][128]
   uint32_t* lgd = wcnt32 + NW * 128;                           // [256] (global slot base - tile-local base) | flag
+  uint32_t* spd = lgd + 256;                                   // [kTile] sorted position -> tile position | digit << 11
 
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t lt_mask = (1u << lane) - 1u;
@@ -157,26 +159,23 @@ __device__ __forceinline__ void place_body(unsigned char* smem_raw, const Geo& g
 
     if (fast) {
       // ---------------- FAST: 8-bit counting sort of the tile in shared memory ----------------
-      if (uni_st == 1) {  // the LIST path left head[] entries in the mask / counter tables (B1 below orders the stores)
+      if (uni_st == 1) {  // the LIST path left head[] entries in the mask / counter tables
         for (uint32_t i = tid; i < NW * 256; i += BLOCK) wmask[i] = 0;
         for (uint32_t i = tid; i < NW * 128; i += BLOCK) wcnt32[i] = 0;
       }
-      uni_st = 2;
       uint32_t dg[J], rk[J];
-      uint64_t idv[J];
 #pragma unroll
       for (int j = 0; j < J; ++j) {  // warp-striped: position = warp * 128 + j * 32 + lane
         const uint32_t pos = warp * (32 * J) + j * 32 + lane;
         const uint32_t d = (uint32_t)tb[pos] - bin0;  // digits 0 .. nb-1 live, nb = dead / past the tile's end
-        idv[j] = ti[pos];
         dg[j] = (pos < valid && d < nb) ? d : nb;
       }
-      __syncthreads();  // B1: every id / bin of the stage is in registers (the stage becomes the sort buffer);
-                        //     the counter table is all-zero, the mask table always is between items
-      {
+      if (uni_st == 1) __syncthreads();  // (uniform) the tables were just re-zeroed
+      uni_st = 2;
+      {   // the counter table is all-zero here (previous tile / prologue), the mask table always is between items
         // Peers of the same digit among the warp's 32 players: every lane ORs its bit into the warp's mask table
-        // (shared-memory RED), reads the word back — that IS the match mask — and the lowest peer resets the word
-        // and bumps the warp's running digit counter.  3 shared-memory instructions per 32 players instead of 8
+        // (shared-memory RED), reads the word back — that IS the match mask — and the peers reset the word
+        // and bump the warp's running digit counter.  3 shared-memory instructions per 32 players instead of 8
         // ballots + selects (MATCH.ANY costs 64 cycles per warp instruction on B200).
         uint32_t* wm = wmask + warp * 256;
         uint16_t* wc = wcnt + warp * 256;
@@ -188,7 +187,8 @@ __device__ __forceinline__ void place_body(unsigned char* smem_raw, const Geo& g
           const uint32_t peers = wm[dg[j]];
           const uint32_t base = wc[dg[j]];
           __syncwarp();
-          if ((peers & lt_mask) == 0) { wm[dg[j]] = 0; wc[dg[j]] = (uint16_t)(base + __popc(peers)); }
+          wm[dg[j]] = 0;                                    // every peer stores the same values: no leader election,
+          wc[dg[j]] = (uint16_t)(base + __popc(peers));     // no divergence
           __syncwarp();
           rk[j] = base + __popc(peers & lt_mask);
         }
@@ -224,7 +224,6 @@ __device__ __forceinline__ void place_body(unsigned char* smem_raw, const Geo& g
         for (int w = 0; w < NW; ++w) { wcnt32[w * 128 + tid] = run; run += v[w]; }
       }
       __syncthreads();  // B3: wcnt[w][d] = tile-local sorted position of warp w's first player of digit d
-      uint8_t* sdig = reinterpret_cast<uint8_t*>(tb);  // [kTile] digit of the staged id, 255 = stays queued
       const bool anyf = s_misc[2] != 0;  // (uniform)
 #pragma unroll
       for (int j = 0; j < J; ++j) {
@@ -237,8 +236,8 @@ __device__ __forceinline__ void place_body(unsigned char* smem_raw, const Geo& g
             if (e >> 31) matched = slot < __ldcg(&a.binlim[bin0 + dg[j]]);
             if (matched && a.src_idx) a.src_idx[slot] = vbase + warp * (32 * J) + j * 32 + lane;
           }
-          ti[lpos] = idv[j];
-          sdig[lpos] = matched ? (uint8_t)dg[j] : (uint8_t)255;
+          // sorted position -> (tile position, digit); 255 = stays queued.  The ids stay where the TMA put them.
+          spd[lpos] = (warp * (32 * J) + j * 32 + lane) | ((matched ? dg[j] : 255u) << 11);
           if (!matched) lmask |= 1u << j;
         }
       }
@@ -255,21 +254,20 @@ __device__ __forceinline__ void place_body(unsigned char* smem_raw, const Geo& g
         if (lane < (uint32_t)J) a.left_bits[(vbase >> 5) + warp * J + lane] = mine;
         if (lane == 0) nleft += all;
       }
-      __syncthreads();  // B4: the tile is staged in sorted order
+      __syncthreads();  // B4: the sorted order of the tile is staged
       {
         const uint32_t n_live = s_misc[1];
 #pragma unroll
         for (int i = 0; i < J; ++i) {
           const uint32_t k = i * BLOCK + tid;
           if (k < n_live) {
-            const uint32_t d = sdig[k];
-            if (d != 255u) a.members[(lgd[d] + k) & 0x7FFFFFFFu] = ti[k];
+            const uint32_t v = spd[k], d = v >> 11;
+            if (d != 255u) a.members[(lgd[d] + k) & 0x7FFFFFFFu] = ti[v & 0x7FFu];
           }
         }
         reinterpret_cast<uint4*>(wcnt32)[tid] = make_uint4(0, 0, 0, 0);  // counter table all-zero again (8 KB = 512 x 16 B)
         if (tid == 0) s_misc[2] = 0;
       }
-      fence_proxy_async();  // the stage was written by threads and is about to be refilled by the async proxy
     } else {
       // ---------------- LIST: hashed per-bin lists, ids scattered from registers ----------------
       if (uni_st == 2) {  // the FAST path left counters / slot bases in the head table
