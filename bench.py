@@ -7,10 +7,14 @@ A step = one pass of the hot path (one search tick) over one synthetic player po
          engine's own stream (mm_tick_stats.device_us); max over ranks.  Between steps
          (untimed) the pool is restored from a device snapshot and L2 is flushed by
          writing a buffer larger than L2.
-  e2e    same metric through the C-ABI with HOST buffers: mm_enqueue (pinned host
-         columns, H2D inside) + mm_tick (lobbies + member ids D2H inside), wall clock over
-         K steps of new players; mm_tick's host copies finish under the next step's
-         ingest ("async_results"); e2e.sequential = the fully blocking variant.
+  e2e    same metric through the C ABI with HOST buffers, every step a NEW batch of players:
+         mm_enqueue_packed (pinned host columns: u32 handle + u16 mode|rating = 6 B/player H2D
+         inside) + mm_enqueue_rejects + mm_tick_packed (lobby headers + u32 member handles D2H
+         inside), wall clock.  `pipelined`: a tick's host copies finish under the next step's
+         ingest (mm_set_option "async_results"); `sequential`: fully blocking calls;
+         `u64_api`: the 17 B/player mm_enqueue + 8 B/player mm_tick entry points, blocking.
+  strong (N > 1 only) BASELINE configs[3]: ONE pool of the workload's size, its rating groups
+         dealt to the ranks (generic/worker.ex:55-69), device-timed like `value`.
   roofline / cpu_baseline: see DESIGN.md §Measurement.
 Launch: `python bench.py --gpus 1 --steps K --warmup W`, or under torchrun for N>1
 (one rank per GPU; ranks own disjoint rating groups — no data-path collective).
@@ -31,8 +35,9 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 PKG = "microservice-matchmaking_b200"
 
-B_ALG_TICK = 22  # SURVEY §8(d) strict-parity mode: read id 8 + rating 4 + mode 1 + team_size 1, write id 8
-B_ALG_PLACE = 21  # the placement kernel: read rating 4 + mode 1 + id 8, write id 8
+B_ALG_TICK = 22      # SURVEY §8(d) strict-parity mode: read id 8 + rating 4 + mode 1 + team_size 1, write id 8
+B_CONSUMED_TICK = 20  # what the tick really moves per player: bin 2 (twice: histogram + placement, the second time
+#                       from L2) + id 8 read, id 8 written; rating/mode -> bin is paid at ingest
 
 
 def peaks():
@@ -136,9 +141,8 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=10_000_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
-                    help="weak (contract default): every rank holds a full-size pool over its own groups; strong "
-                         "(BASELINE configs[3]): ONE pool of the workload's size, rating groups dealt to the ranks")
+    ap.add_argument("--no-strong", action="store_true", help="under torchrun: skip the configs[3] strong-scaling leg")
+    ap.add_argument("--no-numa", action="store_true", help="do not bind the rank to its GPU's NUMA node")
     ap.add_argument("--two-modes", action="store_true", help="configure both default modes (1v1, 5v5), not just the workload's")
     ap.add_argument("--tick-impl", type=int, default=None, help="1 = one fused cooperative launch (default), 0 = four launches")
     ap.add_argument("--max-spread", type=int, default=None,
@@ -159,26 +163,19 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: the search tick has no CPU path "
                          "(use --impl reference for the CPU restatement)")
     torch.cuda.set_device(local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     import __graft_entry__ as ge
     pkg = ge.build()
+    hostutil = importlib.import_module(PKG + ".hostutil")
+    numa = {"bound": False} if args.no_numa else hostutil.bind_to_gpu_numa(local)  # before any pinned allocation
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     abi = pkg.abi
     order = abi.MM_ORDER_RATING if args.order == "rating" else abi.MM_ORDER_ARRIVAL
     w = pkg.synth.WORKLOADS[args.workload]
     n, L = w["n"], (2 if w["mode"] == 0 else 10)
-    cap = n + 65536 + (n if (args.max_spread is not None and args.max_spread >= 0) else 0)  # S1 leaves players queued
-    cfg, mode_idx = pkg.synth.workload_config(args.workload, order, cap, device=local,
-                                              single_mode=not args.two_modes)
-    # rank r's shard of the N x n pool: its own seed stream (weak scaling, disjoint ids)
-    ids, rating, mode, ts = pkg.synth.gen_pool(1, n, first=rank * n, mode=mode_idx)
-    if args.scaling == "strong" and world > 1:
-        # the Generic stage's routing (generic/worker.ex:46-69): this rank keeps the players of its groups
-        shard = importlib.import_module(PKG + ".shard")
-        ids, rating, mode, ts = pkg.synth.gen_pool(1, n, first=0, mode=mode_idx)
-        mine = shard.route(cfg, rating, world) == rank
-        ids, rating, mode, ts = ids[mine], rating[mine], mode[mine], ts[mine]
-        n = int(mine.sum())
+    windowed = args.max_spread is not None and args.max_spread >= 0
+    cap = n + 65536 + (n if windowed else 0)  # S1 leaves players queued
+    cfg, mode_idx = pkg.synth.workload_config(args.workload, order, cap, device=local, single_mode=not args.two_modes)
 
     def barrier():
         torch.cuda.synchronize()
@@ -186,141 +183,186 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    eng = pkg.Engine(cfg)
-    if args.rank_impl is not None:
-        eng.set_option("rank_impl", args.rank_impl)
-    if args.tick_impl is not None:
-        eng.set_option("tick_impl", args.tick_impl)
-    if args.max_spread is not None:
-        eng.set_option("max_spread", args.max_spread)
-    acc = eng.enqueue(ids, rating, mode, ts)
-    assert acc.all()
-    eng.snapshot()
+    def options(eng):
+        if args.rank_impl is not None:
+            eng.set_option("rank_impl", args.rank_impl)
+        if args.tick_impl is not None:
+            eng.set_option("tick_impl", args.tick_impl)
+        if args.max_spread is not None:
+            eng.set_option("max_spread", args.max_spread)
+
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
 
-    def one_step():
-        eng.restore()
-        flush.fill_(1)  # evict the pool from L2
-        torch.cuda.synchronize()
-        return eng.tick_device()
+    def device_timed(cfg_, ids_, rating_, mode_, ts_, steps, warmup):
+        """K ticks of one resident pool (restored from a device snapshot, L2 flushed, both untimed)."""
+        eng = pkg.Engine(cfg_)
+        options(eng)
+        assert eng.enqueue(ids_, rating_, mode_, ts_).all()
+        eng.snapshot()
 
-    for _ in range(args.warmup):
-        st = one_step()
+        def one_step():
+            eng.restore()
+            flush.fill_(1)  # evict the pool from L2
+            torch.cuda.synchronize()
+            return eng.tick_device()
+
+        for _ in range(warmup):
+            st = one_step()
+        barrier()
+        t0 = time.perf_counter()
+        dev_us, phases = [], []
+        for _ in range(steps):
+            st = one_step()
+            dev_us.append(st.device_us)
+            phases.append((st.hist_us, st.scan_us, st.place_us, st.epilogue_us))
+        barrier()
+        wall = time.perf_counter() - t0
+        eng.close()
+        return sum(dev_us) * 1e-6, st, phases, wall
+
+    # ---- weak leg (the contract's line): every rank holds a full-size pool of its own seed stream -------------
+    ids, rating, mode, ts = pkg.synth.gen_pool(1, n, first=rank * n, mode=mode_idx)
     sampler = ClockSampler(local)
-    barrier()
     sampler.start()
-    t_wall = time.perf_counter()
-    dev_us, place_us, phases = [], [], []
-    for _ in range(args.steps):
-        st = one_step()
-        dev_us.append(st.device_us); place_us.append(st.place_us)
-        phases.append((st.hist_us, st.scan_us, st.place_us, st.epilogue_us))
+    tick_s, st, phases, wall_s = device_timed(cfg, ids, rating, mode, ts, args.steps, args.warmup)
     launches_per_tick = st.n_launches
-    barrier()
-    wall_s = time.perf_counter() - t_wall
     lobbies_per_step = st.n_lobbies
-    tick_s = sum(dev_us) * 1e-6  # device time of the K timed ticks on this rank
     if world > 1:
-        t = torch.tensor([tick_s, float(sum(place_us)) * 1e-6], device="cuda", dtype=torch.float64)
+        t = torch.tensor([tick_s], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        tick_s, place_s = t.tolist()
+        tick_s = float(t.item())
         tl = torch.tensor([lobbies_per_step, n], device="cuda", dtype=torch.int64)
         dist.all_reduce(tl)
         total_lobbies_per_step, total_players = int(tl[0].item()), int(tl[1].item())
     else:
-        place_s = sum(place_us) * 1e-6
         total_lobbies_per_step, total_players = lobbies_per_step, n
     value = total_lobbies_per_step * args.steps / tick_s
 
-    # ---- e2e through the C ABI with host buffers ------------------------------------
+    # ---- strong leg (BASELINE configs[3]): ONE pool, rating groups dealt to the ranks --------------------------
+    strong = None
+    if world > 1 and not args.no_strong:
+        shard = importlib.import_module(PKG + ".shard")
+        g_ids, g_rating, g_mode, g_ts = pkg.synth.gen_pool(1, n, first=0, mode=mode_idx)
+        mine = shard.route(cfg, g_rating, world) == rank  # the Generic stage's routing (generic/worker.ex:46-69)
+        n_mine = int(mine.sum())
+        s_steps = max(3, args.steps // 2)
+        s_tick, s_st, s_ph, _ = device_timed(cfg, g_ids[mine], g_rating[mine], g_mode[mine], g_ts[mine], s_steps, args.warmup)
+        t = torch.tensor([s_tick], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        tl = torch.tensor([s_st.n_lobbies, n_mine], device="cuda", dtype=torch.int64)
+        tmax = tl.clone(); tmin = tl.clone()
+        dist.all_reduce(tl); dist.all_reduce(tmax, op=dist.ReduceOp.MAX); dist.all_reduce(tmin, op=dist.ReduceOp.MIN)
+        s_max = float(t.item())
+        strong = {"value": int(tl[0].item()) * s_steps / s_max, "unit": "lobbies/s", "scaling": "strong",
+                  "ms_per_step": 1e3 * s_max / s_steps, "steps": s_steps, "players_total": int(tl[1].item()),
+                  "players_per_gpu_min": int(tmin[1].item()), "players_per_gpu_max": int(tmax[1].item()),
+                  "rating_groups_per_gpu": w["n_groups"] // world, "lobbies_per_step": int(tl[0].item()),
+                  "workload": args.workload + f" as ONE pool sharded by rating group over {world} GPUs (BASELINE configs[3]); "
+                              "strict parity: no player crosses a group, so no boundary exchange is issued",
+                  "timing": "max over ranks of the device-timed ticks (CUDA events on each engine's stream)"}
+        del g_ids, g_rating, g_mode, g_ts
+
+    # ---- e2e through the C ABI with host buffers ------------------------------------------------------------------
     e2e = None
     if not args.no_e2e:
-        eng.close()
-        eng = pkg.Engine(cfg)
-        if args.rank_impl is not None:
-            eng.set_option("rank_impl", args.rank_impl)
-        if args.tick_impl is not None:
-            eng.set_option("tick_impl", args.tick_impl)
-        if args.max_spread is not None:
-            eng.set_option("max_spread", args.max_spread)
-        pin = lambda a: torch.from_numpy(a).pin_memory()
-        h_ids, h_rating, h_mode, h_ts = pin(ids), pin(rating), pin(mode), pin(ts)
-        h_acc = torch.empty(n, dtype=torch.uint8).pin_memory()
+        pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
         lob_cap, mem_cap = n // L + 8192, n + 65536  # pipelined steps also match the previous step's leftovers
         h_lob = torch.empty(lob_cap, dtype=torch.int64).pin_memory()  # 8-byte mm_lobby_hdr
-        h_mem = torch.empty(mem_cap, dtype=torch.int64).pin_memory()
+        S = 2 * args.e2e_steps  # pipelined: the last step's copies are exposed, amortise them over a few more steps
+
+        # -- packed API on a dense-handle engine: 6 B/player up, 4 B/player down
+        cfgp, _ = pkg.synth.workload_config(args.workload, order, cap, device=local, single_mode=not args.two_modes)
+        cfgp.flags |= abi.MM_F_DENSE_IDS
+        cfgp.active_capacity = (S + 3) * n  # handle range: every step brings new players, nobody has left yet
+        h_mem32 = torch.empty(mem_cap, dtype=torch.int32).pin_memory()
+        batches = []
+        for k in range(S + 2):
+            _, r_k, m_k, _ = pkg.synth.gen_pool(1, n, first=(rank + world * k) * n, mode=mode_idx)
+            handles = (np.arange(n, dtype=np.uint64) + np.uint64(k * n)).astype(np.uint32)
+            batches.append((pin(handles), pin(pkg.Engine.pack_key(r_k, m_k))))
+
+        def step_packed(eng, b):
+            eng.enqueue_packed_raw(n, b[0].data_ptr(), b[1].data_ptr())  # no per-player status transfer ...
+            t1 = time.perf_counter()
+            rej_idx, _ = eng.enqueue_rejects()                              # ... the nack list comes back instead
+            assert len(rej_idx) == 0
+            st_ = eng.tick_raw(h_lob.data_ptr(), lob_cap, h_mem32.data_ptr(), mem_cap, packed=True)
+            return st_, t1
+
+        eng = pkg.Engine(cfgp); options(eng)
         times, t_enq = [], []
         for it in range(args.e2e_steps + 1):
             barrier()
             t0 = time.perf_counter()
-            eng.enqueue_raw(n, h_ids.data_ptr(), h_rating.data_ptr(), h_mode.data_ptr(), h_ts.data_ptr(),
-                            h_acc.data_ptr())
-            t1 = time.perf_counter()
-            st2 = eng.tick_raw(h_lob.data_ptr(), lob_cap, h_mem.data_ptr(), mem_cap)
+            st2, t1 = step_packed(eng, batches[0])
             dt = time.perf_counter() - t0
             if it:  # first iteration = warm-up
                 times.append(dt); t_enq.append(t1 - t0)
-            eng.remove(ids)  # what the lobby stage does later (game-lobby/worker.ex:80); untimed
+            eng.remove_packed(batches[0][0].numpy())  # what the lobby stage does later (game-lobby/worker.ex:80); untimed
         assert st2.n_lobbies == lobbies_per_step
-        seq_s = sum(times) / len(times)
-        seq_enq_s = sum(t_enq) / len(t_enq)
+        seq_s, seq_enq_s = sum(times) / len(times), sum(t_enq) / len(t_enq)
         eng.close()
-        # -- pipelined hand-off: mm_tick returns once its host copies are queued ("async_results"); they land while
-        #    the next step's mm_enqueue streams its input up (PCIe is full duplex).  Every step's H2D and D2H is
-        #    inside the timed region; the last step's copies are awaited (mm_results_wait) before the clock stops.
-        #    Each step is a NEW set of players (nobody has removed the previous ones from the active set yet).
-        S = 2 * args.e2e_steps  # the last step's copies are exposed: amortise them over a few more steps
-        cfg2, _ = pkg.synth.workload_config(args.workload, order, cap, device=local, single_mode=not args.two_modes)
-        cfg2.active_capacity = (S + 2) * n
-        eng = pkg.Engine(cfg2)
-        if args.rank_impl is not None:
-            eng.set_option("rank_impl", args.rank_impl)
-        if args.tick_impl is not None:
-            eng.set_option("tick_impl", args.tick_impl)
-        if args.max_spread is not None:
-            eng.set_option("max_spread", args.max_spread)
+        eng = pkg.Engine(cfgp); options(eng)
         eng.set_option("async_results", 1)
-        batches = [(h_ids, h_rating, h_mode, h_ts)]
-        for k in range(1, S + 1):
-            b = pkg.synth.gen_pool(1, n, first=(rank + world * k) * n, mode=mode_idx)
-            batches.append(tuple(pin(x) for x in b))
         lob_pipe = 0
-        for k, (bi, br, bm_, bt) in enumerate(batches):
+        for k in range(S + 1):
             if k == 1:  # batch 0 = warm-up
                 eng.results_wait()
                 barrier()
                 t0 = time.perf_counter()
-            eng.enqueue_raw(n, bi.data_ptr(), br.data_ptr(), bm_.data_ptr(), bt.data_ptr(), h_acc.data_ptr())
-            st3 = eng.tick_raw(h_lob.data_ptr(), lob_cap, h_mem.data_ptr(), mem_cap)
+            st3, _ = step_packed(eng, batches[k + 1])
             if k:
                 lob_pipe += st3.n_lobbies
         eng.results_wait()
         e2e_s = (time.perf_counter() - t0) / S
-        assert bool(h_acc.numpy().all())
+        eng.close()
         del batches
         tot_pipe = lob_pipe / S
+
+        # -- the u64 entry points (17 B/player up, 8 B/player down), blocking: what round 1 measured
+        h_ids, h_rating, h_mode, h_ts = pin(ids), pin(rating), pin(mode), pin(ts)
+        h_acc = torch.empty(n, dtype=torch.uint8).pin_memory()
+        h_mem = torch.empty(mem_cap, dtype=torch.int64).pin_memory()
+        eng = pkg.Engine(cfg); options(eng)
+        u_times = []
+        for it in range(3):
+            barrier()
+            t0 = time.perf_counter()
+            eng.enqueue_raw(n, h_ids.data_ptr(), h_rating.data_ptr(), h_mode.data_ptr(), h_ts.data_ptr(), h_acc.data_ptr())
+            st4 = eng.tick_raw(h_lob.data_ptr(), lob_cap, h_mem.data_ptr(), mem_cap)
+            if it:
+                u_times.append(time.perf_counter() - t0)
+            eng.remove(ids)
+        eng.close()
+        u64_s = sum(u_times) / len(u_times)
+
         if world > 1:
-            t = torch.tensor([e2e_s, seq_s], device="cuda", dtype=torch.float64)
+            t = torch.tensor([e2e_s, seq_s, u64_s], device="cuda", dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            e2e_s, seq_s = (float(x) for x in t.tolist())
+            e2e_s, seq_s, u64_s = (float(x) for x in t.tolist())
             tl2 = torch.tensor([tot_pipe], device="cuda", dtype=torch.float64)
             dist.all_reduce(tl2)
             tot_pipe = float(tl2.item())
         pipelined = {"value": tot_pipe / e2e_s, "ms_per_step": 1e3 * e2e_s, "steps": S,
-                     "call": "per step: mm_enqueue(pinned host columns) + mm_tick(host lobbies / member_ids) with "
-                             "mm_set_option(async_results): a tick's device-to-host copies complete under the next "
-                             "step's ingest; mm_results_wait after the last step, inside the timed region"}
+                     "call": "per step: mm_enqueue_packed(pinned host handles + keys) + mm_enqueue_rejects + "
+                             "mm_tick_packed(host lobbies / member handles) with mm_set_option(async_results): a tick's "
+                             "device-to-host copies complete under the next step's ingest; mm_results_wait after the "
+                             "last step, inside the timed region"}
         sequential = {"value": total_lobbies_per_step / seq_s, "ms_per_step": 1e3 * seq_s, "steps": len(times),
                       "enqueue_ms": 1e3 * seq_enq_s, "tick_and_d2h_ms": 1e3 * (seq_s - seq_enq_s),
-                      "call": "blocking mm_enqueue(pinned host columns) + blocking mm_tick(host lobbies / member_ids), "
-                              "one step at a time"}
+                      "call": "blocking mm_enqueue_packed + mm_enqueue_rejects + blocking mm_tick_packed, one step at a time"}
         best = pipelined if pipelined["value"] >= sequential["value"] else sequential  # both include every copy
         e2e = {"value": best["value"], "unit": "lobbies/s",
-               "h2d_bytes_per_step": n * (8 + 4 + 1 + 4), "d2h_bytes_per_step": n + st2.n_matched * 8 + st2.n_lobbies * 8,
+               "h2d_bytes_per_step": n * (4 + 2), "d2h_bytes_per_step": 8 + st2.n_matched * 4 + st2.n_lobbies * 8,
                "ms_per_step": best["ms_per_step"], "steps": best["steps"], "call": best["call"],
                "mode": "pipelined" if best is pipelined else "sequential",
-               "pipelined": pipelined, "sequential": sequential}
-    eng.close()
+               "ids": "dense 32-bit host handles (MM_F_DENSE_IDS; the host owns the UUID <-> handle table, SURVEY §7.3)",
+               "pipelined": pipelined, "sequential": sequential,
+               "u64_api": {"value": total_lobbies_per_step / u64_s, "ms_per_step": 1e3 * u64_s,
+                           "h2d_bytes_per_step": n * (8 + 4 + 1 + 4), "d2h_bytes_per_step": n + st4.n_matched * 8 + st4.n_lobbies * 8,
+                           "call": "blocking mm_enqueue(pinned u64 ids, i32 rating, u8 mode, u32 ts; accepted[] back) + "
+                                   "blocking mm_tick(host lobbies / u64 member ids)"},
+               "numa": numa}
     clocks = sampler.stop()  # sampled across the device-timed ticks and the e2e steps
 
     # ---- CPU baseline (rank 0, N=1 only): the oracle's literal loop on a bounded sample ----
@@ -335,33 +377,31 @@ def main():
 
     if rank == 0:
         peak, peak_src = peaks()
-        place_avg_s = place_s / args.steps
         tick_avg_s = tick_s / args.steps
         fused = launches_per_tick == 1
-        # dominant kernel: the fused k_tick IS the tick (one launch processes the whole pool: N players x 22 B);
-        # with --tick-impl 0 it is k_place2 (13 B read + 8 B written per player)
-        dom_kernel, dom_bytes, dom_s = ("k_tick", B_ALG_TICK, tick_avg_s) if fused else ("k_place2", B_ALG_PLACE, place_avg_s)
-        ach = dom_bytes * n / dom_s / 1e9
+        ach = B_ALG_TICK * n / tick_avg_s / 1e9
         traffic = None
         tp = os.path.join(ROOT, "profiles", "tick_traffic.json")
-        if fused and os.path.exists(tp) and args.workload == "config3_10m_g32_5v5" and args.order == "rating":
+        if os.path.exists(tp) and args.workload == "config3_10m_g32_5v5" and args.order == "rating":
             try:
-                traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+                traffic = json.load(open(tp)).get("dram_bytes_per_launch" if fused else "dram_bytes_split_launches")
             except Exception:
                 pass
         line = {
             "metric": "matches/sec", "value": value, "unit": "lobbies/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * tick_s / args.steps, "higher_is_better": True,
-            "scaling": args.scaling, "vs_baseline": None, "dtype": "int32/u64", "data": "synthetic",
-            "config": {"workload": args.workload, "players_per_gpu": n,
-                       "rating_groups_per_gpu": w["n_groups"] if args.scaling == "weak" else w["n_groups"] // world,
+            "scaling": "weak", "vs_baseline": None, "dtype": "int32/u64", "data": "synthetic",
+            "config": {"workload": args.workload, "players_per_gpu": n, "rating_groups_per_gpu": w["n_groups"],
                        "players_total": total_players,
                        "lobby_size": L, "order": args.order, "ratings": "uniform 0..5000, seed 1",
                        "modes_configured": cfg.n_modes, "launches_per_tick": launches_per_tick,
-                       "policy": ("S0 (reference behaviour)" if args.max_spread is None or args.max_spread < 0 else
+                       "policy": ("S0 (reference behaviour)" if not windowed else
                                   f"S1 extension: max lobby spread {args.max_spread} rating points"),
                        "players_left_queued_per_step": int(st.n_residual),
                        "parallelism": f"rating-group shards x{world}, no collective",
+                       "pool_layout": "resident pool segmented by (mode, rating group) into 2048-player chunks at ingest "
+                                      "(the reference queues per group: search/worker.ex:46-66); the tick sorts by rating "
+                                      "inside every group",
                        "l2": "flushed between steps (256 MiB write); pool 180 MB > L2",
                        "timed_region": "mm_tick_device: the whole tick (k_tick: hist | column scan | placement | "
                                        "epilogue in one cooperative launch), CUDA events on the engine stream; "
@@ -370,16 +410,17 @@ def main():
                                  [round(sum(x) / len(x), 2) for x in zip(*phases)])),
             "players_per_s": total_players * args.steps / tick_s,
             "wall_ms_per_step_incl_restore": 1e3 * wall_s / args.steps,
-            "roofline": {"bound": "hbm", "kernel": dom_kernel, "achieved": ach, "peak": peak, "unit": "GB/s",
+            "roofline": {"bound": "hbm", "kernel": "k_tick" if fused else "k_hist + k_colscan + k_place + k_epilogue",
+                         "achieved": ach, "peak": peak, "unit": "GB/s",
                          "frac": ach / peak, "traffic": traffic, "peak_source": peak_src,
-                         "bytes_per_player": dom_bytes, "players_per_launch": n, "us_per_launch": 1e6 * dom_s,
-                         "frac_of_8000": ach / 8000.0},
-            "place_phase": {"bytes_per_player": B_ALG_PLACE, "us": 1e6 * place_avg_s,
-                            "achieved": B_ALG_PLACE * n / place_avg_s / 1e9, "frac": B_ALG_PLACE * n / place_avg_s / 1e9 / peak},
-            "tick_roofline": {"bytes_per_player": B_ALG_TICK, "achieved": B_ALG_TICK * n * args.steps / tick_s / 1e9,
-                              "frac": B_ALG_TICK * n * args.steps / tick_s / 1e9 / peak, "unit": "GB/s",
-                              "frac_of_8000": B_ALG_TICK * n * args.steps / tick_s / 1e9 / 8000.0},
-            "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches_per_tick * args.steps, "clocks": clocks,
+                         "bytes_per_player": B_ALG_TICK, "players_per_launch": n, "us_per_launch": 1e6 * tick_avg_s,
+                         "frac_of_8000": ach / 8000.0,
+                         "consumed": {"bytes_per_player": B_CONSUMED_TICK, "achieved": B_CONSUMED_TICK * n / tick_avg_s / 1e9,
+                                      "frac": B_CONSUMED_TICK * n / tick_avg_s / 1e9 / peak,
+                                      "note": "the tick reads the 2-byte sort key derived at ingest, not rating + mode + "
+                                              "team_size (6 B): on the bytes it really consumes the fraction is lower"}},
+            "cpu_baseline": cpu, "e2e": e2e, "strong": strong,
+            "gpu_launches": launches_per_tick * args.steps, "clocks": clocks,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

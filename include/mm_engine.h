@@ -151,6 +151,11 @@ int mm_enqueue_device(mm_engine* e, uint32_t n, const uint64_t* id, const int32_
 int mm_enqueue_packed(mm_engine* e, uint32_t n, const uint32_t* handle, const uint16_t* key,
                       const uint32_t* enq_ts, uint8_t* accepted);
 
+/* The ack / nack list of the LAST mm_enqueue* batch without a per-player transfer: the batch indices whose code is
+ * not 1 (unordered) and their codes — pass accepted = NULL to mm_enqueue* and ack everything else
+ * (search/worker.ex:323 acks per delivery).  MM_E_CAP if there are more than cap (n_rejects says how many).   */
+int mm_enqueue_rejects(mm_engine* e, uint32_t cap, uint32_t* index, uint8_t* code, uint32_t* n_rejects);
+
 /* Replaces ActiveUser.remove_user/1 (models/active_user.ex:57-66; callers
  * game-lobby/worker.ex:80,96).  A removed id that is still queued is dropped by the
  * next tick exactly as remove_inactive_players/1 filters it

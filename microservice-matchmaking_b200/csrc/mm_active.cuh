@@ -333,6 +333,23 @@ __global__ void k_fill_kv(ulonglong2* p, uint64_t n, unsigned long long k, unsig
     p[i] = make_ulonglong2(k, v);
 }
 
+// batch indices whose code is not 1 ("queued"), compacted for the host (unordered): the ack / nack list of a batch
+__global__ void k_compact_rejects(uint32_t n, const uint8_t* __restrict__ code, uint32_t cap, uint32_t* __restrict__ idx,
+                                  uint8_t* __restrict__ rcode, uint32_t* __restrict__ count) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool rej = i < n && code[i] != 1;
+  const uint32_t b = __ballot_sync(0xFFFFFFFFu, rej);
+  if (!b) return;
+  const uint32_t lane = threadIdx.x & 31;
+  uint32_t base = 0;
+  if (lane == 0) base = atomicAdd(count, (uint32_t)__popc(b));
+  base = __shfl_sync(0xFFFFFFFFu, base, 0);
+  if (rej) {
+    const uint32_t o = base + __popc(b & ((1u << lane) - 1u));
+    if (o < cap) { idx[o] = i; rcode[o] = code[i]; }
+  }
+}
+
 // ---- packed host formats (mm_enqueue_packed / mm_tick_packed): 6 B per player up, 4 B per player down ----------
 // key = mode << 13 | rating (0 .. 8191); the 32-bit host handle is the player id on the device
 __global__ void k_unpack(uint32_t n, const uint32_t* __restrict__ handle, const uint16_t* __restrict__ key,

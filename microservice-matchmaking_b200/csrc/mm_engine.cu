@@ -111,6 +111,8 @@ struct mm_engine {
   uint32_t *d_in_ts = nullptr, *d_in_handle = nullptr, *d_blocksum = nullptr, *d_blockhist = nullptr;
   uint32_t* d_small = nullptr;  // [0] accepted  [1] rejected: pool full  [2] removed  [3] running winner total (cut)
   uint32_t* h_small = nullptr;  // pinned
+  uint32_t last_batch_n = 0;    // entries of the last ingest batch (their codes are still in d_code)
+  uint32_t* d_rej_idx = nullptr; uint8_t* d_rej_code = nullptr; uint32_t rej_cap = 0;
 
   // last tick
   mm_tick_stats last{};
@@ -412,6 +414,7 @@ int enq_finish(mm_engine* e, uint32_t n, uint8_t* accepted_dev, uint32_t* n_acce
   const uint32_t acc = e->h_small[0], rej = e->h_small[1];
   p.n += acc;
   e->seq_next += n;
+  e->last_batch_n = n;
   if (e->use_active) { e->n_active += acc; if (!e->dense_ids) e->n_tomb += rej; }
   if (n_accepted) *n_accepted = acc;
   return MM_OK;
@@ -761,7 +764,7 @@ int mm_destroy(mm_engine* e) {
   cudaFree(e->d_hdr); cudaFree(e->d_emit_seq); cudaFree(e->d_rescnt); cudaFree(e->d_ctr); cudaFree(e->d_small);
   cudaFree(e->d_in_id); cudaFree(e->d_hslot); cudaFree(e->d_in_rating); cudaFree(e->d_in_mode); cudaFree(e->d_code);
   cudaFree(e->d_in_ts); cudaFree(e->d_blocksum); cudaFree(e->d_blockhist); cudaFree(e->d_part); cudaFree(e->d_in_key);
-  cudaFree(e->d_in_handle);
+  cudaFree(e->d_in_handle); cudaFree(e->d_rej_idx); cudaFree(e->d_rej_code);
   if (e->h_ctr) cudaFreeHost(e->h_ctr);
   if (e->h_small) cudaFreeHost(e->h_small);
   for (auto& ev : e->ev)
@@ -883,6 +886,36 @@ int mm_enqueue_packed(mm_engine* e, uint32_t n, const uint32_t* handle, const ui
     CK(cudaStreamSynchronize(e->stream));
   }
   return MM_OK;
+}
+
+int mm_enqueue_rejects(mm_engine* e, uint32_t cap, uint32_t* index, uint8_t* code, uint32_t* n_rejects) {
+  if (!e || !n_rejects || (cap && (!index || !code))) return MM_E_ARG;
+  std::lock_guard<std::mutex> lk(e->mu);
+  CK(cudaSetDevice(e->device));
+  *n_rejects = 0;
+  const uint32_t n = e->last_batch_n;
+  if (n == 0) return MM_OK;
+  if (cap > e->rej_cap) {
+    cudaFree(e->d_rej_idx); cudaFree(e->d_rej_code);
+    e->rej_cap = 0;
+    CK(cudaMalloc(&e->d_rej_idx, (size_t)cap * 4));
+    CK(cudaMalloc(&e->d_rej_code, (size_t)cap));
+    e->rej_cap = cap;
+  }
+  CK(cudaMemsetAsync(e->d_small + 4, 0, 4, e->stream));
+  k_compact_rejects<<<(n + 255) / 256, 256, 0, e->stream>>>(n, e->d_code, cap, e->d_rej_idx, e->d_rej_code, e->d_small + 4);
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(e->h_small + 4, e->d_small + 4, 4, cudaMemcpyDeviceToHost, e->stream));
+  CK(cudaStreamSynchronize(e->stream));
+  const uint32_t cnt = e->h_small[4];
+  *n_rejects = cnt;
+  const uint32_t m = std::min(cnt, cap);
+  if (m) {
+    CK(cudaMemcpyAsync(index, e->d_rej_idx, (size_t)m * 4, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaMemcpyAsync(code, e->d_rej_code, m, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+  }
+  return cnt > cap ? MM_E_CAP : MM_OK;
 }
 
 int mm_remove(mm_engine* e, uint32_t n, const uint64_t* id, uint32_t* n_removed) {

@@ -132,6 +132,19 @@ class Engine:
         self._check(self.lib.mm_enqueue_packed(self.h, n, p_handles, p_keys, p_ts or None, p_accepted or None),
                     "mm_enqueue_packed")
 
+    def enqueue_rejects(self, cap=4096):
+        """(batch index, code) of the entries of the last enqueue batch that were not queued (unordered)."""
+        while True:
+            idx = np.empty(cap, np.uint32)
+            code = np.empty(cap, np.uint8)
+            n = C.c_uint32(0)
+            rc = self.lib.mm_enqueue_rejects(self.h, cap, _p(idx), _p(code), C.byref(n))
+            if rc == abi.MM_E_CAP:
+                cap = n.value
+                continue
+            self._check(rc, "mm_enqueue_rejects")
+            return idx[:n.value], code[:n.value]
+
     def remove_packed(self, handles):
         handles = np.ascontiguousarray(handles, np.uint32)
         nr = C.c_uint32(0)

@@ -497,3 +497,51 @@ def test_async_results_complete_under_the_next_ingest(pkg, oracle):
         assert_tick_matches(eng, oracle.run_closed_form(cfg, *q), lob2, mem2, seq2, st2, seq_of=qseq)
         eng.results_wait()  # no-op
         eng.set_option("async_results", 0)
+
+
+# ---- packed host formats on a dense-handle engine (MM_F_DENSE_IDS; SURVEY §7.3 "dense slot index") ----------------
+@pytest.mark.parametrize("order", [ARRIVAL, RATING])
+def test_packed_dense_engine_equals_u64_engine_and_oracle(pkg, oracle, order):
+    """mm_enqueue_packed (u32 handle + u16 mode << 13 | rating) / mm_tick_packed (u32 handles) on a direct-mapped
+    active set give the lobbies of the u64 entry points and of the oracle, handle for handle."""
+    n = 300_017
+    cfg = pkg.synth.make_config(n_groups=32, order=order, capacity=n)
+    _, rating, mode, ts = make_pool(pkg, 123, n, oor=0.0)
+    handles = np.random.default_rng(9).permutation(2 * n)[:n].astype(np.uint32)  # sparse, unordered handle use
+    cfgd = pkg.synth.make_config(n_groups=32, order=order, capacity=n, active_capacity=2 * n)
+    cfgd.flags |= pkg.abi.MM_F_DENSE_IDS
+    rng = np.random.default_rng(2)
+    alive = (rng.random(n) > 0.05).astype(np.uint8)
+    ref = oracle.run_closed_form(cfg, handles.astype(np.uint64), rating, mode, alive)
+    with pkg.Engine(cfgd) as eng:
+        acc = eng.enqueue_packed(handles, pkg.Engine.pack_key(rating, mode), ts)
+        assert (acc == 1).all()
+        idx, code = eng.enqueue_rejects()
+        assert len(idx) == 0
+        assert eng.remove_packed(handles[alive == 0]) == int((alive == 0).sum())
+        assert list(eng.in_queue(handles[:64].astype(np.uint64))) == [bool(a) for a in alive[:64]]
+        lob, mem, seq, st = eng.tick_packed()
+        assert mem.dtype == np.uint32
+        assert np.array_equal(lob, ref.lobbies) and np.array_equal(mem.astype(np.uint64), ref.member_ids)
+        assert np.array_equal(seq, ref.emit_seq)
+        assert np.array_equal(eng.pool_read()["id"], ref.residual_ids)
+        # matched players stay active until removed; a second offer is "already in the queue"
+        again = eng.enqueue_packed(handles[:1000], pkg.Engine.pack_key(rating[:1000], mode[:1000]))
+        assert (again[alive[:1000] == 1] == 0).all() and (again[alive[:1000] == 0] == 1).all()
+
+
+def test_packed_rejects_list(pkg):
+    cfg = pkg.synth.make_config(groups=pkg.synth.REFERENCE_GROUPS, order=ARRIVAL, capacity=6, active_capacity=100)
+    cfg.flags |= pkg.abi.MM_F_DENSE_IDS
+    with pkg.Engine(cfg) as eng:
+        handles = np.array([5, 6, 5, 100, 7, 8, 9, 10, 11, 12], np.uint32)  # 5 twice, 100 = out of the handle range
+        mode = np.array([0, 0, 0, 0, 7, 0, 0, 0, 0, 0], np.uint8)           # mode 7 is not configured
+        rating = np.full(10, 1000)
+        acc = eng.enqueue_packed(handles, pkg.Engine.pack_key(rating, mode))
+        assert list(acc) == [1, 1, 0, 2, 2, 1, 1, 1, 1, 3]                     # capacity 6: the last one does not fit
+        idx, code = eng.enqueue_rejects()
+        order = np.argsort(idx)
+        assert list(idx[order]) == [2, 3, 4, 9] and list(code[order]) == [0, 2, 2, 3]
+        assert eng.pool_size() == 6 and eng.active_size() == 6
+        assert list(eng.in_queue(np.array([5, 12, 100], np.uint64))) == [True, False, False]
+        assert eng.remove_packed(np.array([5, 5, 99], np.uint32)) == 1
