@@ -572,6 +572,203 @@ done:
 /* ------------------------------------------------------------------------- */
 /* timed legs                                                                   */
 /* ------------------------------------------------------------------------- */
+/* Persistent session: the reference's state KEPT ACROSS REQUESTS.               */
+/* LobbyState rows survive between batches (models/lobby_state.ex:61-131), the   */
+/* active set is mutated by add_user / remove_user (models/active_user.ex:46-66), */
+/* requests are consumed one at a time in arrival order (search/worker.ex:291-324)*/
+/* — what a single serialized search worker per group does over its lifetime.    */
+/* Pins the one documented deviation of the batched tick: after a  */
+/* member of a SAVED partial lobby leaves, the reference fills the hole in that   */
+/* team first; the tick re-derives teams from pool order.  Lobbies that saw such a */
+/* hole are flagged.                                                              */
+/* ------------------------------------------------------------------------- */
+#define ORC_TOMB (UINT64_MAX - 1)
+typedef struct { uint64_t* slot; uint64_t mask, used, live; } orc_set;
+static int orc_set_init(orc_set* a, uint64_t cap) {
+  uint64_t c = 16;
+  while (c < cap) c <<= 1;
+  a->slot = (uint64_t*)malloc(c * sizeof(uint64_t));
+  if (!a->slot) return -1;
+  memset(a->slot, 0xFF, c * sizeof(uint64_t));
+  a->mask = c - 1; a->used = 0; a->live = 0;
+  return 0;
+}
+static int orc_set_has(const orc_set* a, uint64_t id) {
+  uint64_t h = orc_hash(id) & a->mask;
+  while (a->slot[h] != ORC_EMPTY) { if (a->slot[h] == id) return 1; h = (h + 1) & a->mask; }
+  return 0;
+}
+static int orc_set_add(orc_set* a, uint64_t id);
+static int orc_set_grow(orc_set* a) {
+  orc_set b;
+  if (orc_set_init(&b, (a->live + 8) * 4) < 0) return -1;
+  for (uint64_t i = 0; i <= a->mask; ++i) if (a->slot[i] < ORC_TOMB) orc_set_add(&b, a->slot[i]);
+  free(a->slot); *a = b;
+  return 0;
+}
+static int orc_set_add(orc_set* a, uint64_t id) { /* caller checked !has */
+  if ((a->used + 1) * 2 > a->mask + 1 && orc_set_grow(a) < 0) return -1;
+  uint64_t h = orc_hash(id) & a->mask;
+  while (a->slot[h] != ORC_EMPTY) h = (h + 1) & a->mask;
+  a->slot[h] = id; a->used++; a->live++;
+  return 0;
+}
+static int orc_set_del(orc_set* a, uint64_t id) {
+  uint64_t h = orc_hash(id) & a->mask;
+  while (a->slot[h] != ORC_EMPTY) {
+    if (a->slot[h] == id) { a->slot[h] = ORC_TOMB; a->live--; return 1; }
+    h = (h + 1) & a->mask;
+  }
+  return 0;
+}
+
+typedef struct { uint8_t mode, hole; orc_teams teams; } orc_prow;
+struct orc_session {
+  mm_config cfg;
+  orc_set active;
+  orc_prow** rows; uint32_t* n_rows; uint32_t* cap_rows;   /* per group: LobbyState table */
+  orc_emit* emits; uint32_t n_emits, cap_emits;
+  uint8_t* holes;                                           /* per emitted lobby */
+  uint64_t* members; uint64_t n_members, cap_members;
+  uint32_t seq;                                             /* requests seen so far */
+};
+
+orc_session* orc_session_new(const mm_config* cfg) {
+  if (orc_check_cfg(cfg) != MM_OK) return NULL;
+  orc_session* s = (orc_session*)calloc(1, sizeof(orc_session));
+  if (!s) return NULL;
+  s->cfg = *cfg;
+  s->rows = (orc_prow**)calloc(cfg->n_groups, sizeof(orc_prow*));
+  s->n_rows = (uint32_t*)calloc(cfg->n_groups, sizeof(uint32_t));
+  s->cap_rows = (uint32_t*)calloc(cfg->n_groups, sizeof(uint32_t));
+  if (!s->rows || !s->n_rows || !s->cap_rows || orc_set_init(&s->active, 1024) < 0) { orc_session_free(s); return NULL; }
+  return s;
+}
+void orc_session_free(orc_session* s) {
+  if (!s) return;
+  if (s->rows) for (uint32_t g = 0; g < s->cfg.n_groups; ++g) free(s->rows[g]);
+  free(s->rows); free(s->n_rows); free(s->cap_rows); free(s->active.slot);
+  free(s->emits); free(s->holes); free(s->members); free(s);
+}
+
+/* one request through consume/5 with the LobbyState of its group kept from earlier requests */
+static int orc_session_consume(orc_session* s, uint8_t group, uint64_t player, uint8_t mode) {
+  const mm_config* cfg = &s->cfg;
+  const uint16_t S = cfg->modes[mode].team_size;
+  const uint32_t L = (uint32_t)cfg->modes[mode].teams * S;
+  orc_teams grouped; uint8_t hole = 0;
+  grouped.n_teams = 0; memset(grouped.count, 0, sizeof(grouped.count));
+  orc_prow* tb = s->rows[group];
+  for (uint32_t i = 0; i < s->n_rows[group]; ++i)                    /* get_state: pop a row of this mode */
+    if (tb[i].mode == mode) {
+      orc_teams_copy(&grouped, &tb[i].teams, L); hole = tb[i].hole;
+      tb[i] = tb[s->n_rows[group] - 1]; s->n_rows[group]--;
+      break;
+    }
+  orc_reply data = orc_strategist_s0(cfg, mode, player, &grouped);   /* :296-306 */
+  /* :308-310 requeue: never under S0 (added is always true for a non-full lobby)                  */
+  /* remove_inactive_players/1 (:267-280) against the LIVE active set                              */
+  uint32_t before = orc_players_count(&grouped);
+  for (uint16_t t = 0; t < grouped.n_teams; ++t) {
+    uint16_t k = 0; uint64_t* m = &grouped.member[(uint32_t)t * S];
+    for (uint16_t i = 0; i < grouped.count[t]; ++i) if (orc_set_has(&s->active, m[i])) m[k++] = m[i];
+    grouped.count[t] = k;
+  }
+  const int is_changed = before != orc_players_count(&grouped);
+  if (is_changed) hole = 1;
+  if (data.is_filled && !is_changed) {                               /* :313-319 emit */
+    if (s->n_emits == s->cap_emits) {
+      uint32_t nc = s->cap_emits ? s->cap_emits * 2 : 256;
+      orc_emit* ne = (orc_emit*)realloc(s->emits, (size_t)nc * sizeof(orc_emit));
+      uint8_t* nh = (uint8_t*)realloc(s->holes, nc);
+      if (ne) s->emits = ne;
+      if (nh) s->holes = nh;
+      if (!ne || !nh) return -1;
+      s->cap_emits = nc;
+    }
+    if (s->n_members + L > s->cap_members) {
+      uint64_t nc = s->cap_members ? s->cap_members * 2 : 4096;
+      while (nc < s->n_members + L) nc *= 2;
+      uint64_t* nm = (uint64_t*)realloc(s->members, nc * sizeof(uint64_t));
+      if (!nm) return -1;
+      s->members = nm; s->cap_members = nc;
+    }
+    orc_emit* e = &s->emits[s->n_emits];
+    s->holes[s->n_emits++] = hole;
+    e->mode = mode; e->group = group; e->n_members = (uint16_t)orc_players_count(&grouped); e->emit_seq = s->seq;
+    e->first_member = s->n_members;
+    for (uint16_t t = 0; t < grouped.n_teams; ++t)
+      for (uint16_t i = 0; i < grouped.count[t]; ++i) s->members[s->n_members++] = grouped.member[(uint32_t)t * S + i];
+  } else {                                                            /* :320 save_new_state */
+    if (s->n_rows[group] == s->cap_rows[group]) {
+      uint32_t nc = s->cap_rows[group] ? s->cap_rows[group] * 2 : 4;
+      orc_prow* nr = (orc_prow*)realloc(s->rows[group], (size_t)nc * sizeof(orc_prow));
+      if (!nr) return -1;
+      s->rows[group] = nr; s->cap_rows[group] = nc;
+    }
+    orc_prow* r = &s->rows[group][s->n_rows[group]++];
+    r->mode = mode; r->hole = hole; orc_teams_copy(&r->teams, &grouped, L);
+  }
+  return 0;
+}
+
+/* middleware/worker.ex:65-70 (dedupe + add_user) -> generic/worker.ex:46-69 (routing) -> consume/5, per request */
+int orc_session_feed(orc_session* s, uint32_t n, const uint64_t* id, const int32_t* rating, const uint8_t* mode,
+                     uint8_t* accepted) {
+  if (!s) return MM_E_ARG;
+  for (uint32_t i = 0; i < n; ++i, ++s->seq) {
+    const int g = mode[i] < s->cfg.n_modes ? orc_find_rating_group(&s->cfg, (double)rating[i]) : -1;
+    if (g < 0) { if (accepted) accepted[i] = 2; continue; }
+    if (orc_set_has(&s->active, id[i])) { if (accepted) accepted[i] = 0; continue; }  /* "You are already in the queue." */
+    if (orc_set_add(&s->active, id[i]) < 0) return MM_E_CAP;
+    if (accepted) accepted[i] = 1;
+    if (orc_session_consume(s, (uint8_t)g, id[i], mode[i]) < 0) return MM_E_CAP;
+  }
+  return MM_OK;
+}
+/* ActiveUser.remove_user/1 (models/active_user.ex:57-66): the entry goes, saved lobbies are NOT touched */
+int orc_session_remove(orc_session* s, uint32_t n, const uint64_t* id, uint32_t* n_removed) {
+  if (!s) return MM_E_ARG;
+  uint32_t k = 0;
+  for (uint32_t i = 0; i < n; ++i) k += (uint32_t)orc_set_del(&s->active, id[i]);
+  if (n_removed) *n_removed = k;
+  return MM_OK;
+}
+/* lobbies emitted since the last take, canonical order; hole[c] = 1 when the lobby saw a mid-lobby leaver.
+ * residual_ids = members of the saved partial lobbies that are still active (team-major per row; order is not
+ * the enqueue order).  emit_seq = request number (all requests of the session, rejected ones included).        */
+int orc_session_take(orc_session* s, orc_result* out, uint8_t** hole) {
+  if (!s || !out) return MM_E_ARG;
+  memset(out, 0, sizeof(*out));
+  int rc = orc_assemble(&s->cfg, s->emits, s->n_emits, s->members, s->n_members, out);
+  if (rc != MM_OK) return rc;
+  if (hole) {
+    *hole = (uint8_t*)malloc((size_t)s->n_emits + 1);
+    if (!*hole) return MM_E_CAP;
+    for (uint32_t c = 0; c < s->n_emits; ++c) (*hole)[c] = s->holes[out->emission_rank[c]];
+  }
+  uint64_t cap = 0;
+  for (uint32_t g = 0; g < s->cfg.n_groups; ++g) cap += (uint64_t)s->n_rows[g] * ORC_MAX_LOBBY;
+  out->residual_ids = (uint64_t*)malloc((cap + 1) * sizeof(uint64_t));
+  if (!out->residual_ids) return MM_E_CAP;
+  uint32_t k = 0;
+  for (uint32_t g = 0; g < s->cfg.n_groups; ++g)
+    for (uint32_t r = 0; r < s->n_rows[g]; ++r) {
+      const orc_prow* row = &s->rows[g][r];
+      const uint16_t S = s->cfg.modes[row->mode].team_size;
+      for (uint16_t t = 0; t < row->teams.n_teams; ++t)
+        for (uint16_t i = 0; i < row->teams.count[t]; ++i) {
+          const uint64_t m = row->teams.member[(uint32_t)t * S + i];
+          if (orc_set_has(&s->active, m)) out->residual_ids[k++] = m;
+        }
+    }
+  out->n_residual = k;
+  s->n_emits = 0; s->n_members = 0;
+  return MM_OK;
+}
+void orc_free(void* p) { free(p); }
+
+/* ------------------------------------------------------------------------- */
 static double orc_now(void) {
   struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts);
   return (double)ts.tv_sec + 1e-9 * (double)ts.tv_nsec;

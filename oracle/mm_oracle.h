@@ -80,6 +80,19 @@ int orc_run_closed_form(const mm_config* cfg, uint32_t order_mode, uint32_t n,
 int orc_run_windowed(const mm_config* cfg, int32_t max_spread, uint32_t n, const uint64_t* id, const int32_t* rating,
                      const uint8_t* mode, const uint8_t* alive, orc_result* out);
 
+/* Persistent session (ARRIVAL order): LobbyState rows and the active set are KEPT across calls, requests are
+ * consumed one at a time — the reference's own lifetime behaviour (models/lobby_state.ex:61-131,
+ * search/worker.ex:312-321).  orc_session_take returns the lobbies emitted since the last take in canonical order
+ * with hole[c] = 1 for a lobby that saw a member leave while it was being filled (free hole with orc_free).       */
+typedef struct orc_session orc_session;
+orc_session* orc_session_new(const mm_config* cfg);
+void orc_session_free(orc_session* s);
+int orc_session_feed(orc_session* s, uint32_t n, const uint64_t* id, const int32_t* rating, const uint8_t* mode,
+                     uint8_t* accepted);
+int orc_session_remove(orc_session* s, uint32_t n, const uint64_t* id, uint32_t* n_removed);
+int orc_session_take(orc_session* s, orc_result* out, uint8_t** hole);
+void orc_free(void* p);
+
 /* Timed legs for bench.py.  Both run the LITERAL loop and return wall seconds
  * (setup — building the active set, routing by group — is outside the timer, as the
  * middleware / generic stages are outside the search stage).  n_threads==1: one

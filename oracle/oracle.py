@@ -72,6 +72,18 @@ def lib():
         L.orc_time_literal.restype = C.c_double
         L.orc_time_literal.argtypes = [C.POINTER(abi.Config), C.c_uint32, C.c_uint32, vp, vp, vp, C.c_uint32,
                                        C.POINTER(C.c_uint32)]
+        L.orc_session_new.restype = vp
+        L.orc_session_new.argtypes = [C.POINTER(abi.Config)]
+        L.orc_session_free.restype = None
+        L.orc_session_free.argtypes = [vp]
+        L.orc_session_feed.restype = C.c_int
+        L.orc_session_feed.argtypes = [vp, C.c_uint32, vp, vp, vp, vp]
+        L.orc_session_remove.restype = C.c_int
+        L.orc_session_remove.argtypes = [vp, C.c_uint32, vp, C.POINTER(C.c_uint32)]
+        L.orc_session_take.restype = C.c_int
+        L.orc_session_take.argtypes = [vp, C.POINTER(OrcResult), C.POINTER(C.POINTER(C.c_uint8))]
+        L.orc_free.restype = None
+        L.orc_free.argtypes = [vp]
         L.orc_mix64.restype = C.c_uint64
         L.orc_mix64.argtypes = [C.c_uint64]
         L.orc_gen_pool.restype = None
@@ -214,3 +226,55 @@ def closed_form_numpy(cfg, ids, rating, mode, alive=None, order=None):
         resid.append(part[a + nl * L:b])
     resid = np.sort(np.concatenate(resid)) if resid else np.zeros(0, np.int64)
     return (np.concatenate(lm), np.concatenate(lg), np.concatenate(members), ids[resid])
+
+
+class Session:
+    """The reference's state kept ACROSS requests (orc_session_*): LobbyState rows survive between batches, the
+    active set is mutated by feed / remove, requests are consumed one at a time in arrival order."""
+
+    def __init__(self, cfg):
+        self.cfg = cfg
+        self.h = lib().orc_session_new(C.byref(cfg))
+        if not self.h:
+            raise ValueError("orc_session_new failed")
+
+    def close(self):
+        if self.h:
+            lib().orc_session_free(self.h)
+            self.h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def feed(self, ids, rating, mode):
+        ids = np.ascontiguousarray(ids, np.uint64); rating = np.ascontiguousarray(rating, np.int32)
+        mode = np.ascontiguousarray(mode, np.uint8)
+        acc = np.empty(len(ids), np.uint8)
+        rc = lib().orc_session_feed(self.h, len(ids), _ptr(ids), _ptr(rating), _ptr(mode), _ptr(acc))
+        if rc:
+            raise ValueError(f"orc_session_feed returned {rc}")
+        return acc
+
+    def remove(self, ids):
+        ids = np.ascontiguousarray(ids, np.uint64)
+        k = C.c_uint32(0)
+        lib().orc_session_remove(self.h, len(ids), _ptr(ids), C.byref(k))
+        return k.value
+
+    def take(self):
+        """-> (Result of the lobbies emitted since the last take, hole flags u8[n_lobbies])."""
+        r = OrcResult()
+        hp = C.POINTER(C.c_uint8)()
+        rc = lib().orc_session_take(self.h, C.byref(r), C.byref(hp))
+        if rc:
+            raise ValueError(f"orc_session_take returned {rc}")
+        try:
+            res = Result(r, True)
+            hole = np.ctypeslib.as_array(hp, shape=(max(res.n_lobbies, 1),))[:res.n_lobbies].copy()
+            return res, hole
+        finally:
+            lib().orc_free(hp)
+            lib().orc_result_free(C.byref(r))

@@ -545,3 +545,48 @@ def test_packed_rejects_list(pkg):
         assert eng.pool_size() == 6 and eng.active_size() == 6
         assert list(eng.in_queue(np.array([5, 12, 100], np.uint64))) == [True, False, False]
         assert eng.remove_packed(np.array([5, 5, 99], np.uint32)) == 1
+
+
+# ---- rating-group shards on real engines: K engines, one per rank's group range, merged ----------------
+@pytest.mark.parametrize("K,workload", [(2, None), (4, None), (8, "config3_10m_g32_5v5")])
+@pytest.mark.parametrize("order", [RATING, ARRIVAL])
+def test_group_sharded_gpu_engines_merge_to_the_single_engine(pkg, oracle, K, workload, order):
+    """shard.route deals the players to K engines by rating group (generic/worker.ex:46-69), every engine ticks on
+    its own, shard.merge_results == the single engine over the whole pool == the oracle.  K = 8 on BASELINE
+    configs[3] (one 10 M pool, 4 groups per engine)."""
+    import importlib
+    shard = importlib.import_module("microservice-matchmaking_b200.shard")
+    if workload:
+        w = pkg.synth.WORKLOADS[workload]
+        n, G = w["n"], w["n_groups"]
+        cfg = pkg.synth.make_config(n_groups=G, order=order, capacity=n)
+        ids, rating, mode, ts = pkg.synth.gen_pool(1, n, mode=w["mode"])
+    else:
+        n, G = 400_003, 32
+        cfg = pkg.synth.make_config(n_groups=G, order=order, capacity=n)
+        ids, rating, mode, ts = make_pool(pkg, 31 * K, n, bell=True, oor=0.0)
+    owner = shard.route(cfg, rating, K)
+    assert (owner >= 0).all()
+    per_rank, resid = [], []
+    for r in range(K):
+        mine = owner == r
+        cfg_r = pkg.synth.make_config(n_groups=G, order=order, capacity=max(int(mine.sum()), 1))
+        with pkg.Engine(cfg_r) as eng:
+            assert eng.enqueue(ids[mine], rating[mine], mode[mine], ts[mine]).all()
+            lob, mem, seq, st = eng.tick()
+            per_rank.append((lob, mem, None))
+            resid.append(eng.pool_read()["id"])
+            assert set(np.unique(lob["group"])) <= set(shard.groups_of_rank(r, G, K).tolist())
+    mlob, mmem = shard.merge_results(cfg, per_rank)[:2]
+    with pkg.Engine(cfg) as eng:
+        assert eng.enqueue(ids, rating, mode, ts).all()
+        lob1, mem1, _, st1 = eng.tick()
+        resid1 = eng.pool_read()["id"]
+    assert np.array_equal(mlob, lob1) and np.array_equal(mmem, mem1)
+    assert np.array_equal(np.sort(np.concatenate(resid)), np.sort(resid1))
+    if n <= 1_000_000:
+        ref = oracle.run_closed_form(cfg, ids, rating, mode)
+        assert np.array_equal(mlob, ref.lobbies) and np.array_equal(mmem, ref.member_ids)
+    else:
+        lm, lg, members, res = oracle.closed_form_numpy(cfg, ids, rating, mode)
+        assert np.array_equal(members, mmem) and np.array_equal(lg, mlob["group"])
