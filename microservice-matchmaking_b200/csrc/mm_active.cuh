@@ -255,6 +255,7 @@ __global__ void __launch_bounds__(256) k_enq_append(uint32_t base, uint32_t n, c
     pool.tsize[slot] = mode_tsize[mode[i]]; pool.ts[slot] = ts ? ts[i] : 0u;
     pool.bin[slot] = (uint16_t)bin_of(bm, bm.lut, rating[i], mode[i]);  // the tick's sort key, derived once at ingest
     pool.seq[slot] = seq_base + i;
+    atomicAdd(&meta.tot[pool.bin[slot]], 1u);  // bin totals stay current: the tick needs no counting pass for them
     if (act.on()) *act.val(hslot[i]) = ((unsigned long long)gen << 32) | slot;
   }
 }
@@ -263,7 +264,7 @@ __global__ void __launch_bounds__(256) k_enq_append(uint32_t base, uint32_t n, c
 // queued is tombstoned in the pool (mode byte = DEAD) so the next tick drops it the way
 // remove_inactive_players/1 (search/worker.ex:267-280) filters it.
 __global__ void k_remove(uint32_t n, const uint64_t* __restrict__ id, ActiveView act, PoolView pool, uint32_t n_slots,
-                         uint32_t gen, uint32_t dead_bin, uint32_t* __restrict__ n_removed) {
+                         uint32_t gen, uint32_t dead_bin, uint32_t* __restrict__ tot, uint32_t* __restrict__ n_removed) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n || !act.on()) return;
   const uint64_t pid = id[i];
@@ -281,6 +282,8 @@ __global__ void k_remove(uint32_t n, const uint64_t* __restrict__ id, ActiveView
   const uint32_t slot = (uint32_t)v, g = (uint32_t)(v >> 32);
   if (v < kPending && g == gen && slot < n_slots && pool.id[slot] == pid) {
     pool.mode[slot] = MM_MODE_DEAD;
+    atomicSub(&tot[pool.bin[slot]], 1u);
+    atomicAdd(&tot[dead_bin], 1u);
     pool.bin[slot] = (uint16_t)dead_bin;
   }
   atomicAdd(n_removed, 1u);

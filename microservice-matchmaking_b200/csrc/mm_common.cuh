@@ -36,6 +36,7 @@ struct PoolMeta {
   uint32_t* fill;       // [n_segs] players of the partition (dead ones included)
   uint32_t* chunk_tab;  // [n_segs][max_ch] physical chunk of the partition's k-th chunk
   uint32_t* bump;       // chunks handed out so far
+  uint32_t* tot;        // [K + 1] players per bin (K = removed while queued), kept up to date by ingest / remove / tick
   uint32_t max_ch;
 };
 
@@ -71,7 +72,7 @@ struct TickCtr {
 // = tile * kTile + offset indexes left_bits / src_idx; only the pool loads translate a tile to its physical chunk.
 struct Geo {
   uint32_t T0[kMaxSegs + 1];  // first virtual tile of the partition
-  uint32_t NT, tpr, n_segs, pad;
+  uint32_t NT, tpr, n_segs, max_rows;  // max_rows: most rows any partition spans
 };
 
 // Active set = {key, value} pairs (hashed: open addressing on the u64 player id) or a direct-mapped value array
@@ -219,7 +220,16 @@ __device__ __forceinline__ void geo_build(Geo& g, const uint32_t* __restrict__ f
     g.NT = NT;
     g.tpr = NT ? (NT + R - 1) / R : 1u;
     g.n_segs = n_segs;
+    g.max_rows = 0;
   }
+  __syncthreads();
+  uint32_t mr = 0;
+  for (uint32_t p = threadIdx.x; p < n_segs; p += BLOCK) {
+    const uint32_t a = g.T0[p], b = g.T0[p + 1];
+    if (b > a) { const uint32_t r = (b - 1) / g.tpr - a / g.tpr + 1; mr = r > mr ? r : mr; }
+  }
+  mr = __reduce_max_sync(0xFFFFFFFFu, mr);
+  if ((threadIdx.x & 31) == 0 && mr) atomicMax(&g.max_rows, mr);
   __syncthreads();
 }
 // partition owning virtual tile s (s < NT): the last p with T0[p] <= s (empty partitions share their successor's T0)
@@ -253,6 +263,13 @@ __device__ __forceinline__ void desc_fill(DescCache& c, const Geo& g, const Pool
       c.phys[k] = d.phys;
       c.nvsg[k] = d.nvalid | (d.seg << 16);
     }
+}
+// Row prefixes of the histogram matrix: with few rows per partition (R rows over tens of partitions) every row sums
+// the rows before it on the fly; only when a partition spans many rows (one rating group over the whole pool) is the
+// column-scan phase (and its grid barrier) worth it.  Uniform: every CTA derives the same answer from the geometry.
+constexpr uint32_t kInlinePrefixRows = 24;
+__device__ __forceinline__ bool geo_use_colscan(const Geo& g) {
+  return g.NT > (uint64_t)g.tpr * kInlinePrefixRows && g.max_rows > kInlinePrefixRows;
 }
 // rows [rlo, rhi] holding tiles of partition p; false when the partition is empty
 __device__ __forceinline__ bool geo_rows_of(const Geo& g, uint32_t p, uint32_t& rlo, uint32_t& rhi) {

@@ -79,15 +79,16 @@ struct mm_engine {
   uint64_t n_active = 0, n_tomb = 0;
 
   // tick scratch
-  uint32_t R = 0;
+  uint32_t R = 0;        // row CTAs of a tick
+  uint32_t helpers = 0;  // extra CTAs of the fused launch: the tail, then the lobby headers
   int rows_per_sm = 2;
   int rank_impl = 3;           // 3 = ballot tile sort for partitions of <= 255 bins + lists otherwise; 2 = lists only
   uint32_t place_stages = 0;
   int fused_ok = 0;  // k_tick<512> can be launched cooperatively with R CTAs
   int tick_impl = 1; // 1 = one fused cooperative launch when possible, 0 = four launches
   size_t tick_smem = 0;
-  uint32_t* d_M = nullptr;
-  uint32_t *d_tot = nullptr, *d_outbase = nullptr, *d_binlim = nullptr;
+  uint32_t *d_M = nullptr, *d_P = nullptr;  // row histograms, their column prefixes (only for many-row partitions)
+  uint32_t *d_outbase = nullptr, *d_binlim = nullptr;
   uint16_t* d_bin_key = nullptr;
   int32_t max_spread = -1;  // < 0: policy S0 (reference behaviour); >= 0: policy S1 (extension)
   SegInfo* d_seg = nullptr;
@@ -160,6 +161,8 @@ int alloc_pool(mm_engine* e, Pool& p) {
   CK(cudaMalloc(&p.m.fill, (size_t)e->n_segs * 4));
   CK(cudaMalloc(&p.m.chunk_tab, (size_t)e->n_segs * e->n_chunks * 4));
   CK(cudaMalloc(&p.m.bump, 4));
+  CK(cudaMalloc(&p.m.tot, ((size_t)e->Kp + 1) * 4));
+  CK(cudaMemset(p.m.tot, 0, ((size_t)e->Kp + 1) * 4));
   CK(cudaMemset(p.m.fill, 0, (size_t)e->n_segs * 4));
   CK(cudaMemset(p.m.bump, 0, 4));
   // chunks are read whole by the TMA tiles: keep the bin column defined (and "dead") past the fills
@@ -169,7 +172,7 @@ int alloc_pool(mm_engine* e, Pool& p) {
 }
 void free_pool(Pool& p) {
   cudaFree(p.v.id); cudaFree(p.v.rating); cudaFree(p.v.mode); cudaFree(p.v.tsize); cudaFree(p.v.ts); cudaFree(p.v.bin);
-  cudaFree(p.v.seq); cudaFree(p.m.fill); cudaFree(p.m.chunk_tab); cudaFree(p.m.bump);
+  cudaFree(p.v.seq); cudaFree(p.m.fill); cudaFree(p.m.chunk_tab); cudaFree(p.m.bump); cudaFree(p.m.tot);
   p = Pool{};
 }
 int copy_pool(mm_engine* e, Pool& dst, const Pool& src) {
@@ -184,6 +187,7 @@ int copy_pool(mm_engine* e, Pool& dst, const Pool& src) {
   CK(cudaMemcpyAsync(dst.m.fill, src.m.fill, (size_t)e->n_segs * 4, cudaMemcpyDeviceToDevice, e->stream));
   CK(cudaMemcpyAsync(dst.m.chunk_tab, src.m.chunk_tab, (size_t)e->n_segs * e->n_chunks * 4, cudaMemcpyDeviceToDevice, e->stream));
   CK(cudaMemcpyAsync(dst.m.bump, src.m.bump, 4, cudaMemcpyDeviceToDevice, e->stream));
+  CK(cudaMemcpyAsync(dst.m.tot, src.m.tot, ((size_t)e->Kp + 1) * 4, cudaMemcpyDeviceToDevice, e->stream));
   dst.n = src.n;
   return MM_OK;
 }
@@ -321,10 +325,13 @@ BinMap bin_map(const mm_engine* e) {
 }
 
 int alloc_tick_scratch(mm_engine* e) {
-  e->R = (uint32_t)e->n_sms * (uint32_t)e->rows_per_sm;
-  if (e->R > kMaxRows) e->R = kMaxRows;
-  if (e->d_M) { cudaFree(e->d_M); cudaFree(e->d_rescnt); }
+  uint32_t total = (uint32_t)e->n_sms * (uint32_t)e->rows_per_sm;
+  if (total > kMaxRows) total = kMaxRows;
+  e->helpers = total >= 64 ? 4u : (total > 1 ? 1u : 0u);
+  e->R = total - e->helpers;
+  if (e->d_M) { cudaFree(e->d_M); cudaFree(e->d_P); cudaFree(e->d_rescnt); }
   CK(cudaMalloc(&e->d_M, (size_t)(e->R + 1) * e->Kp * 4));
+  CK(cudaMalloc(&e->d_P, (size_t)(e->R + 1) * e->Kp * 4));
   CK(cudaMalloc(&e->d_rescnt, (size_t)(e->R + 1) * 4));
   return MM_OK;
 }
@@ -440,7 +447,7 @@ int enqueue_batch(mm_engine* e, uint32_t n, const uint64_t* id, const int32_t* r
 TailArgs tail_args(mm_engine* e) {
   TailArgs t{};
   t.Kp = e->Kp; t.K = e->K; t.n_segs = e->n_segs; t.max_spread = e->max_spread; t.layout = tail_layout(e);
-  t.tot = e->d_tot; t.seg_bin_lo = e->d_seg_bin_lo; t.seg_L = e->d_seg_L; t.bin_seg = e->d_bin_seg;
+  t.tot = e->pool[e->cur].m.tot; t.seg_bin_lo = e->d_seg_bin_lo; t.seg_L = e->d_seg_L; t.bin_seg = e->d_bin_seg;
   t.bin_key = e->d_bin_key; t.outbase = e->d_outbase; t.binlim = e->d_binlim; t.seg = e->d_seg; t.ctr = e->d_ctr;
   t.fill = e->pool[e->cur].m.fill;
   t.dst = e->pool[e->cur ^ 1].m;
@@ -451,21 +458,22 @@ PlaceArgs place_args(mm_engine* e, bool want_seq) {
   PlaceArgs a{};
   a.bins16 = p.v.bin; a.ids = p.v.id; a.meta = p.m;
   a.K = e->K; a.Kp = e->Kp; a.R = e->R; a.stages = e->place_stages; a.fast_ok = e->rank_impl == 3;
-  a.seg_bin_lo = e->d_seg_bin_lo; a.bin_seg = e->d_bin_seg; a.M = e->d_M; a.tot = e->d_tot;
+  a.seg_bin_lo = e->d_seg_bin_lo; a.bin_seg = e->d_bin_seg; a.M = e->d_M; a.P = e->d_P;
   a.outbase = e->d_outbase; a.binlim = e->d_binlim; a.members = e->d_members;
   a.src_idx = want_seq ? e->d_src_idx : nullptr;
   a.left_bits = e->d_left_bits; a.rescnt = e->d_rescnt; a.ctr = e->d_ctr;
   return a;
 }
 uint32_t next_gen(const mm_engine* e) { return e->gen >= kGenMask ? 1u : e->gen + 1; }
-EpiArgs epi_args(mm_engine* e, bool want_seq) {
+EpiArgs epi_args(mm_engine* e, bool want_seq, bool headers) {
   EpiArgs a{};
   a.src = e->pool[e->cur].v; a.dst = e->pool[e->cur ^ 1].v;
   a.src_meta = e->pool[e->cur].m; a.dst_meta = e->pool[e->cur ^ 1].m;
   a.R = e->R; a.new_gen = next_gen(e); a.n_segs = e->n_segs; a.n_groups = e->cfg.n_groups; a.Kp = e->Kp;
+  a.write_headers = headers ? 1u : 0u;
   a.rescnt = e->d_rescnt; a.left_bits = e->d_left_bits; a.act = act_view(e); a.seg = e->d_seg; a.seg_L = e->d_seg_L;
   a.hdr = e->d_hdr; a.src_idx = want_seq ? e->d_src_idx : nullptr; a.emit_seq = want_seq ? e->d_emit_seq : nullptr;
-  a.tot = e->d_tot; a.ctr = e->d_ctr;
+  a.ctr = e->d_ctr;
   return a;
 }
 
@@ -474,10 +482,9 @@ int tick_phase_a(mm_engine* e) {
   const Pool& p = e->pool[e->cur];
   CK(cudaMemsetAsync(e->d_ctr, 0, sizeof(TickCtr), e->stream));
   CK(cudaEventRecord(e->ev[0], e->stream));
-  k_hist<512><<<e->R, 512, hist_smem_bytes(e->Kp), e->stream>>>(
-      p.v.bin, p.m, e->n_segs, e->R, e->Kp, e->K, e->d_seg_bin_lo, e->d_M, e->d_tot);
+  k_hist<512><<<e->R, 512, hist_smem_bytes(e->Kp), e->stream>>>(p.v.bin, p.m, e->n_segs, e->R, e->Kp, e->d_seg_bin_lo, e->d_M);
   CK(cudaEventRecord(e->ev[1], e->stream));
-  k_colscan<<<(e->K + 31) / 32 + 1, kScanBlock, colscan_smem(e), e->stream>>>(e->R, e->d_M, tail_args(e));
+  k_colscan<<<(e->K + 31) / 32 + 1, kScanBlock, colscan_smem(e), e->stream>>>(e->R, e->d_M, e->d_P, tail_args(e));
   CK(cudaGetLastError());
   return MM_OK;
 }
@@ -487,7 +494,7 @@ int tick_phase_b(mm_engine* e, bool want_seq) {
   k_place<512><<<e->R, 512, place_smem_bytes(e->Kp, e->place_stages), e->stream>>>(place_args(e, want_seq),
                                                                                    e->pool[e->cur].m.fill, e->n_segs);
   CK(cudaEventRecord(e->ev[3], e->stream));
-  k_epilogue<512><<<std::max(1, e->n_sms), 512, 0, e->stream>>>(epi_args(e, want_seq));
+  k_epilogue<512><<<std::max(1, e->n_sms), 512, 0, e->stream>>>(epi_args(e, want_seq, true));
   CK(cudaGetLastError());
   CK(cudaEventRecord(e->ev[4], e->stream));
   CK(cudaMemcpyAsync(e->h_ctr, e->d_ctr, sizeof(TickCtr), cudaMemcpyDeviceToHost, e->stream));
@@ -501,15 +508,16 @@ bool use_fused(const mm_engine* e) { return e->tick_impl == 1 && e->fused_ok; }
 int tick_fused(mm_engine* e, bool want_seq) {
   TickArgs a{};
   a.src = e->pool[e->cur].v;
+  a.R = e->R;
   a.M = e->d_M;
-  a.tot = e->d_tot;
+  a.P = e->d_P;
   a.tail = tail_args(e);
   a.place = place_args(e, want_seq);
-  a.epi = epi_args(e, want_seq);
+  a.epi = epi_args(e, want_seq, want_seq || e->helpers == 0);  // emission order needs the placement's src_idx first
   CK(cudaMemsetAsync(e->d_ctr, 0, sizeof(TickCtr), e->stream));
   CK(cudaEventRecord(e->ev[0], e->stream));
   void* params[] = {&a};
-  CK(cudaLaunchCooperativeKernel((const void*)k_tick<512>, dim3(e->R), dim3(512), params, e->tick_smem, e->stream));
+  CK(cudaLaunchCooperativeKernel((const void*)k_tick<512>, dim3(e->R + e->helpers), dim3(512), params, e->tick_smem, e->stream));
   CK(cudaEventRecord(e->ev[4], e->stream));
   CK(cudaMemcpyAsync(e->h_ctr, e->d_ctr, sizeof(TickCtr), cudaMemcpyDeviceToHost, e->stream));
   CK(cudaStreamSynchronize(e->stream));
@@ -576,8 +584,6 @@ int tick_to_host(mm_engine* e, mm_lobby_hdr* lobbies, uint32_t lobby_cap, uint64
     if ((lobbies && e->h_ctr->n_lobbies > lobby_cap) || (want_members && e->h_ctr->n_matched > member_cap)) {
       std::snprintf(e->last_err, sizeof(e->last_err), "need lobby_cap >= %u, member_cap >= %u", e->h_ctr->n_lobbies,
                     e->h_ctr->n_matched);
-      CK(cudaMemsetAsync(e->d_tot, 0, (e->Kp + 1) * 4, e->stream));  // the epilogue that re-zeroes it will not run
-      CK(cudaStreamSynchronize(e->stream));
       return MM_E_CAP;
     }
     if ((rc = tick_phase_b(e, emit_seq != nullptr))) return rc;
@@ -722,7 +728,7 @@ int mm_create(const mm_config* cfg, mm_engine** out) {
   const size_t cap = (size_t)e->capacity + 64;
   e->max_lobbies = e->capacity / e->min_L + 1;
   auto A = [&](void** p, size_t bytes) { return cudaMalloc(p, bytes) == cudaSuccess; };
-  if (!A((void**)&e->d_tot, (e->Kp + 1) * 4) || !A((void**)&e->d_outbase, (e->Kp + 1) * 4) ||
+  if (!A((void**)&e->d_outbase, (e->Kp + 1) * 4) ||
       !A((void**)&e->d_binlim, (e->Kp + 1) * 4) || !A((void**)&e->d_seg, e->n_segs * sizeof(SegInfo)) ||
       !A((void**)&e->d_members, cap * 8) || !A((void**)&e->d_src_idx, cap * 4) ||
       !A((void**)&e->d_hdr, (size_t)e->max_lobbies * sizeof(mm_lobby_hdr)) ||
@@ -739,13 +745,12 @@ int mm_create(const mm_config* cfg, mm_engine** out) {
     int coop = 0, nb = 0;
     cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, e->device);
     if (coop && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_tick<512>, 512, sz) == cudaSuccess &&
-        (uint32_t)nb * (uint32_t)e->n_sms >= e->R) {
+        (uint32_t)nb * (uint32_t)e->n_sms >= e->R + e->helpers) {
       e->fused_ok = 1;
       e->tick_smem = sz;
     }
     cudaGetLastError();
   }
-  if (cudaMemsetAsync(e->d_tot, 0, (e->Kp + 1) * 4, e->stream) != cudaSuccess) return bail(MM_E_CUDA);
   if (cudaStreamSynchronize(e->stream) != cudaSuccess) return bail(MM_E_CUDA);
   *out = e;
   return MM_OK;
@@ -759,7 +764,7 @@ int mm_destroy(mm_engine* e) {
   free_pool(e->pool[0]); free_pool(e->pool[1]); free_pool(e->snap); cudaFree(e->d_left_bits);
   for (auto& t : e->tab) cudaFree(t.kv);
   cudaFree(e->d_lut); cudaFree(e->d_grp_lut); cudaFree(e->d_mode_tsize); cudaFree(e->d_seg_bin_lo); cudaFree(e->d_seg_L);
-  cudaFree(e->d_M); cudaFree(e->d_tot); cudaFree(e->d_outbase); cudaFree(e->d_binlim); cudaFree(e->d_bin_seg);
+  cudaFree(e->d_M); cudaFree(e->d_P); cudaFree(e->d_outbase); cudaFree(e->d_binlim); cudaFree(e->d_bin_seg);
   cudaFree(e->d_bin_key); cudaFree(e->d_seg); cudaFree(e->d_members); cudaFree(e->d_members32); cudaFree(e->d_src_idx);
   cudaFree(e->d_hdr); cudaFree(e->d_emit_seq); cudaFree(e->d_rescnt); cudaFree(e->d_ctr); cudaFree(e->d_small);
   cudaFree(e->d_in_id); cudaFree(e->d_hslot); cudaFree(e->d_in_rating); cudaFree(e->d_in_mode); cudaFree(e->d_code);
@@ -931,7 +936,7 @@ int mm_remove(mm_engine* e, uint32_t n, const uint64_t* id, uint32_t* n_removed)
   CK(cudaMemcpyAsync(e->d_in_id, id, (size_t)n * 8, cudaMemcpyHostToDevice, e->stream));
   CK(cudaMemsetAsync(e->d_small, 0, 16, e->stream));
   k_remove<<<(n + 255) / 256, 256, 0, e->stream>>>(n, e->d_in_id, act_view(e), p.v, (uint32_t)pool_slots(e), e->gen, e->K,
-                                                   e->d_small + 2);
+                                                   p.m.tot, e->d_small + 2);
   CK(cudaGetLastError());
   CK(cudaMemcpyAsync(e->h_small, e->d_small, 16, cudaMemcpyDeviceToHost, e->stream));
   CK(cudaStreamSynchronize(e->stream));

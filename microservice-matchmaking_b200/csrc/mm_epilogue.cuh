@@ -22,7 +22,7 @@ constexpr uint32_t kEpiScratchWords = (kMaxRows + 1) + 64 + (kMaxSegs + 1) + 4 *
 struct EpiArgs {
   PoolView src, dst;
   PoolMeta src_meta, dst_meta;  // dst_meta was filled in by the scan tail
-  uint32_t R, new_gen, n_segs, n_groups, Kp;
+  uint32_t R, new_gen, n_segs, n_groups, Kp, write_headers;
   const uint32_t* rescnt;
   const uint32_t* left_bits;
   ActiveView act;
@@ -31,25 +31,58 @@ struct EpiArgs {
   mm_lobby_hdr* hdr;
   const uint32_t* src_idx;
   uint32_t* emit_seq;
-  uint32_t* tot;
   TickCtr* ctr;
 };
+
+// Lobby headers from the segment table — lobby c of segment s = members [member_base + k*L, +L); replaces the payload
+// assembly at search/worker.ex:315-319.  Written by `nparts` CTAs (part = 0 .. nparts-1), 8 B per lobby.
+template <int BLOCK>
+__device__ __forceinline__ void headers_body(const Geo& g, const EpiArgs& a, const uint32_t* s_lbase, const uint32_t* s_mbase,
+                                             const uint32_t* s_L, uint32_t part, uint32_t nparts) {
+  const uint32_t tid = threadIdx.x, n_segs = a.n_segs, n_groups = a.n_groups;
+  const PoolMeta sm = a.src_meta;
+  const uint32_t total_lob = __ldcg(&a.ctr->n_lobbies);
+  for (uint32_t sg = 0; sg < n_segs; ++sg) {  // segment by segment: no per-lobby search, ~8 instructions per header
+    const uint32_t l0 = s_lbase[sg], l1 = sg + 1 < n_segs ? s_lbase[sg + 1] : total_lob;
+    const uint32_t L = s_L[sg], mb = s_mbase[sg];
+    mm_lobby_hdr h;
+    h.n_members = (uint16_t)L;
+    h.mode = (uint8_t)(sg / n_groups);
+    h.group = (uint8_t)(sg % n_groups);
+    for (uint32_t c = l0 + part * BLOCK + tid; c < l1; c += nparts * BLOCK) {
+      h.first_member = mb + (c - l0) * L;
+      a.hdr[c] = h;
+      if (a.emit_seq) {  // enqueue sequence number of the member whose arrival completed the lobby
+        const uint32_t v = __ldcg(&a.src_idx[h.first_member + L - 1]), p = geo_seg_of(g, v / kTile);
+        a.emit_seq[c] = a.src.seq[__ldcg(&sm.chunk_tab[(size_t)p * sm.max_ch + (v / kTile - g.T0[p])]) * kTile + v % kTile];
+      }
+    }
+  }
+}
+// segment tables the headers need, into shared memory (helper CTAs of the fused tick)
+template <int BLOCK>
+__device__ __forceinline__ void headers_only(uint32_t* scratch, const Geo& g, const EpiArgs& a, uint32_t part, uint32_t nparts) {
+  uint32_t* s_lbase = scratch;                 // [kMaxSegs + 1]
+  uint32_t* s_mbase = s_lbase + kMaxSegs + 1;  // [kMaxSegs]
+  uint32_t* s_L = s_mbase + kMaxSegs;          // [kMaxSegs]
+  for (uint32_t s = threadIdx.x; s < a.n_segs; s += BLOCK) {
+    s_lbase[s] = __ldcg(&a.seg[s].lobby_base); s_mbase[s] = __ldcg(&a.seg[s].member_base); s_L[s] = a.seg_L[s];
+  }
+  __syncthreads();
+  headers_body<BLOCK>(g, a, s_lbase, s_mbase, s_L, part, nparts);
+}
 
 template <int BLOCK>
 __device__ __forceinline__ void epilogue_body(uint32_t* scratch, const Geo& g, const EpiArgs a,
                                               unsigned long long* t_mid = nullptr) {
   const PoolView& src = a.src;
   const PoolView& dst = a.dst;
-  const uint32_t R = a.R, n_segs = a.n_segs, n_groups = a.n_groups, Kp = a.Kp;
+  const uint32_t R = a.R, n_segs = a.n_segs;
   const uint32_t* __restrict__ rescnt = a.rescnt;
   const uint32_t* __restrict__ left_bits = a.left_bits;
   const ActiveView act = a.act;
   const SegInfo* __restrict__ seg = a.seg;
   const uint32_t* __restrict__ seg_L = a.seg_L;
-  mm_lobby_hdr* __restrict__ hdr = a.hdr;
-  const uint32_t* __restrict__ src_idx = a.src_idx;
-  uint32_t* __restrict__ emit_seq = a.emit_seq;
-  uint32_t* __restrict__ tot = a.tot;
   TickCtr* ctr = a.ctr;
   const uint32_t new_gen = a.new_gen;
   const uint32_t n = g.NT * kTile;            // virtual positions of this tick
@@ -75,31 +108,14 @@ __device__ __forceinline__ void epilogue_body(uint32_t* scratch, const Geo& g, c
   }
   for (uint32_t r = tid; r < R; r += BLOCK) s_off[r] = __ldcg(&rescnt[r]);
   __syncthreads();
-  for (uint32_t i = blockIdx.x * BLOCK + tid; i < Kp; i += gridDim.x * BLOCK) tot[i] = 0;  // ready for the next tick
   const uint32_t total = block_excl_scan<BLOCK>(s_off, R, s_tmp);
   if (tid == 0) {
     s_off[R] = total;
     if (blockIdx.x == 0) ctr->n_resid = total;
   }
   __syncthreads();
-  // Lobby headers first: fire-and-forget stores that drain while the compaction below waits on its dependent
-  // gather / hash-probe chains.
-  const uint32_t total_lob = __ldcg(&ctr->n_lobbies);
-  for (uint32_t c = blockIdx.x * BLOCK + tid; c < total_lob; c += gridDim.x * BLOCK) {
-    uint32_t a = 0, e = n_segs;  // last segment with lobby_base <= c
-    while (e - a > 1) { const uint32_t mid = (a + e) >> 1; if (s_lbase[mid] <= c) a = mid; else e = mid; }
-    const uint32_t L = s_L[a];
-    mm_lobby_hdr h;
-    h.first_member = s_mbase[a] + (c - s_lbase[a]) * L;
-    h.n_members = (uint16_t)L;
-    h.mode = (uint8_t)(a / n_groups);
-    h.group = (uint8_t)(a % n_groups);
-    hdr[c] = h;
-    if (emit_seq) {  // enqueue sequence number of the member whose arrival completed the lobby
-      uint32_t p;
-      emit_seq[c] = src.seq[phys_of(__ldcg(&src_idx[h.first_member + L - 1]), p)];
-    }
-  }
+  if (a.write_headers)  // fire-and-forget stores first: they drain while the compaction waits on its dependent chains
+    headers_body<BLOCK>(g, a, s_lbase, s_mbase, s_L, blockIdx.x, gridDim.x);
   // Work is split by leftover RANK, not by row: under policy S0 the leftovers are the latest arrivals of every
   // partition and sit in the last rows of the pool.  CTA b moves the players with global rank [r0, r1); it walks
   // the bit words of the rows holding them (popcount prefix from the start of the row), enumerates the pool

@@ -17,9 +17,8 @@ constexpr uint32_t kHistStages = 8;  // ring depth: two half-turns of 4 tiles (8
 
 template <int BLOCK>
 __device__ __forceinline__ void hist_body(unsigned char* smem_raw, const Geo& g, const uint16_t* __restrict__ bins16,
-                                          const PoolMeta meta, uint32_t Kp, uint32_t K,
-                                          const uint32_t* __restrict__ seg_bin_lo, uint32_t* __restrict__ M,
-                                          uint32_t* __restrict__ tot) {
+                                          const PoolMeta meta, uint32_t Kp,
+                                          const uint32_t* __restrict__ seg_bin_lo, uint32_t* __restrict__ M) {
   constexpr uint32_t kBytes = kTile * 2, S = kHistStages, H = S / 2;
   uint16_t* ring = reinterpret_cast<uint16_t*>(smem_raw);                            // [S][kTile]
   uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + (size_t)S * kBytes);       // [S]
@@ -87,12 +86,7 @@ __device__ __forceinline__ void hist_body(unsigned char* smem_raw, const Geo& g,
     const uint32_t p_first = geo_seg_of(g, s0), p_last = geo_seg_of(g, s1 - 1);
     const uint32_t blo = seg_bin_lo[p_first], bhi = seg_bin_lo[p_last + 1];
     uint32_t* mrow = M + (size_t)row * Kp;
-    for (uint32_t i = blo + tid; i < bhi; i += BLOCK) {
-      const uint32_t v = hist[i];
-      mrow[i] = v;
-      if (v) atomicAdd(&tot[i], v);  // bin totals (tot[] is zeroed by the previous tick's epilogue)
-    }
-    if (tid == 0 && hist[K]) atomicAdd(&tot[K], hist[K]);  // players removed while queued
+    for (uint32_t i = blo + tid; i < bhi; i += BLOCK) mrow[i] = hist[i];
   }
   if (tid == 0)
     for (uint32_t s = 0; s < kHistStages; ++s) mbar_inval(&full[s]);

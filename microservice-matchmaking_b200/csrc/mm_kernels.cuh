@@ -13,9 +13,9 @@
 // followed by the per-partition lobby cut.  One cooperative launch, k_tick<512>, runs the four phases
 // (each also exists as a stand-alone kernel):
 //   k_hist     row histograms M[row][bin] from the resident 16-bit bin column (2 B/player, TMA ring)
-//   k_colscan  column prefix of M + the tail: per bin, how many players are matched (a prefix of the bin) and the
-//              member slot of the first one — policy S0 (reference behaviour) or S1 (rating window, extension);
-//              layout of the compacted pool
+//   k_colscan  the tail: per bin, how many players are matched (a prefix of the bin) and the member slot of the first
+//              one — policy S0 (reference behaviour) or S1 (rating window, extension) — from the resident bin totals;
+//              layout and bin totals of the compacted pool; column prefix of M only when a partition spans many rows
 //   k_place    stable rank inside the row -> final lobby-major slot; tile-local counting sort staged in shared
 //              memory, ids written to member_ids in whole sectors (reads 10 B/player, writes 8 B); players past
 //              their bin's prefix: one bit in left_bits
@@ -33,29 +33,32 @@ namespace mm {
 
 template <int BLOCK>
 __global__ void __launch_bounds__(BLOCK, 2)
-    k_hist(const uint16_t* __restrict__ bins16, const PoolMeta meta, uint32_t n_segs, uint32_t R, uint32_t Kp, uint32_t K,
-           const uint32_t* __restrict__ seg_bin_lo, uint32_t* __restrict__ M, uint32_t* __restrict__ tot) {
+    k_hist(const uint16_t* __restrict__ bins16, const PoolMeta meta, uint32_t n_segs, uint32_t R, uint32_t Kp,
+           const uint32_t* __restrict__ seg_bin_lo, uint32_t* __restrict__ M) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ Geo geo;
   __shared__ uint32_t s_gtmp[33];
   geo_build<BLOCK>(geo, meta.fill, n_segs, R, s_gtmp);
-  hist_body<BLOCK>(smem_raw, geo, bins16, meta, Kp, K, seg_bin_lo, M, tot);
+  hist_body<BLOCK>(smem_raw, geo, bins16, meta, Kp, seg_bin_lo, M);
 }
 
 // ---------------------------------------------------------------------------------------
 // k_tick<512>: the whole search tick in ONE cooperative launch ("fully matched in one
-// launch", BASELINE.json).  Phases are the bodies above, separated by grid barriers; the
-// CTA's dynamic shared memory is re-used by every phase, the tile geometry is built once:
-//   hist (TMA ring of bin tiles, row histogram)                             | barrier 1
-//   column scan of M (all CTAs) + tail (last CTA: bin bases, segments)      | barrier 2
-//   placement (TMA ring of bin/id tiles, tile sort, sector-complete stores) | barrier 3
-//   epilogue (lobby headers + pool compaction by leftover rank, all CTAs)
+// launch", BASELINE.json).  G CTAs = R row CTAs + a few helper CTAs; the CTA's dynamic shared
+// memory is re-used by every phase, the tile geometry is built once:
+//   rows: histogram of their tiles      || helper 0: the tail (bin totals are resident, kept
+//         (TMA ring of bin tiles)       ||   current by ingest / remove / the previous tick)         | barrier 1
+//   [only when a partition spans many rows: column scan of M by all CTAs                            | barrier 1b]
+//   rows: placement (TMA ring of bin/id tiles, tile sort, sector-complete stores)
+//                                       || helpers: lobby headers                                   | barrier 2
+//   all:  pool compaction by leftover rank (+ headers here when emission order was asked for)
 // ---------------------------------------------------------------------------------------
 struct TickArgs {
   PoolView src;
+  uint32_t R;      // row CTAs; the grid has R + helpers CTAs
   uint32_t* M;
-  uint32_t* tot;   // = tail.tot (written by the histogram, re-zeroed by the epilogue)
-  TailArgs tail;   // Kp, K, n_segs, tot, segment tables, outbase / binlim, counters, src fill, dst meta
+  uint32_t* P;
+  TailArgs tail;   // Kp, K, n_segs, src bin totals, segment tables, outbase / binlim, counters, src fill, dst meta
   PlaceArgs place;
   EpiArgs epi;
 };
@@ -68,8 +71,11 @@ __global__ void __launch_bounds__(BLOCK, 2) k_tick(const TickArgs a) {
   __shared__ uint32_t s_gtmp[33];
   uint32_t* scratch = reinterpret_cast<uint32_t*>(smem_raw);
   const unsigned int G = gridDim.x;
-  const uint32_t Kp = a.tail.Kp, K = a.tail.K;
+  const uint32_t R = a.R, Kp = a.tail.Kp, K = a.tail.K;
+  const bool is_row = blockIdx.x < R;
+  const uint32_t helper = blockIdx.x - R, n_helpers = G - R;  // (helper valid when !is_row)
   TickCtr* ctr = a.tail.ctr;
+  unsigned int bar = 0;
   auto stamp = [&](int k) {
     if (blockIdx.x == 0 && threadIdx.x == 0) {
       unsigned long long t;
@@ -78,11 +84,9 @@ __global__ void __launch_bounds__(BLOCK, 2) k_tick(const TickArgs a) {
     }
   };
   stamp(0);
-  geo_build<BLOCK>(geo, a.place.meta.fill, a.tail.n_segs, G, s_gtmp);
-  hist_body<BLOCK>(smem_raw, geo, a.src.bin, a.place.meta, Kp, K, a.tail.seg_bin_lo, a.M, a.tot);
-  grid_barrier(&ctr->gbar, G);
-  stamp(1);
-  if (blockIdx.x == G - 1) {
+  geo_build<BLOCK>(geo, a.place.meta.fill, a.tail.n_segs, R, s_gtmp);
+  if (is_row) hist_body<BLOCK>(smem_raw, geo, a.src.bin, a.place.meta, Kp, a.tail.seg_bin_lo, a.M);
+  if (blockIdx.x == G - 1) {  // the last CTA: helper 0's job when there are helpers, else after its own row
     colscan_tail_body(scratch, a.tail);
     if (threadIdx.x == 0) {
       unsigned long long t;
@@ -90,11 +94,16 @@ __global__ void __launch_bounds__(BLOCK, 2) k_tick(const TickArgs a) {
       ctr->t[5] = t;
     }
   }
-  for (uint32_t grp = blockIdx.x; grp < (K + 31) / 32; grp += G) colscan_cols_body(scratch, geo, grp, Kp, K, a.tail.bin_seg, a.M);
-  grid_barrier(&ctr->gbar, 2 * G);
+  grid_barrier(&ctr->gbar, (bar += G));
+  stamp(1);
+  if (geo_use_colscan(geo)) {  // (uniform over the grid)
+    for (uint32_t grp = blockIdx.x; grp < (K + 31) / 32; grp += G) colscan_cols_body(scratch, geo, grp, Kp, K, a.tail.bin_seg, a.M, a.P);
+    grid_barrier(&ctr->gbar, (bar += G));
+  }
   stamp(2);
-  place_body<BLOCK>(smem_raw, geo, a.place);
-  grid_barrier(&ctr->gbar, 3 * G);
+  if (is_row) place_body<BLOCK>(smem_raw, geo, a.place);
+  else if (!a.epi.write_headers) headers_only<BLOCK>(scratch, geo, a.epi, helper, n_helpers);
+  grid_barrier(&ctr->gbar, (bar += G));
   stamp(3);
   epilogue_body<BLOCK>(scratch, geo, a.epi, &ctr->t[7]);
   stamp(4);  // CTA 0's view

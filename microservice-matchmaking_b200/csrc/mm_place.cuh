@@ -44,8 +44,8 @@ struct PlaceArgs {
   uint32_t K, Kp, R, stages, fast_ok;
   const uint32_t* seg_bin_lo;
   const uint16_t* bin_seg;
-  const uint32_t* M;
-  const uint32_t* tot;
+  const uint32_t* M;     // [rows][Kp] row histograms (raw counts)
+  const uint32_t* P;     // [rows][Kp] their column prefixes, only when the column-scan phase ran
   const uint32_t* outbase;
   const uint32_t* binlim;
   uint64_t* members;
@@ -122,13 +122,15 @@ __device__ __forceinline__ void place_body(unsigned char* smem_raw, const Geo& g
     // flags a cell that reaches past the bin's matched prefix (only those players look at binlim).
     const uint32_t p_first = geo_seg_of(g, s0), p_last = geo_seg_of(g, s1 - 1);
     const uint32_t blo = a.seg_bin_lo[p_first], bhi = a.seg_bin_lo[p_last + 1];
-    const uint32_t* mrow = a.M + (size_t)row * Kp;
+    const bool scanned = geo_use_colscan(g);  // (uniform) the column-scan phase ran: P holds the row prefixes
     for (uint32_t i = blo + tid; i < bhi; i += BLOCK) {
       uint32_t rlo = 0, rhi = 0, v = 0;
       if (geo_rows_of(g, a.bin_seg[i], rlo, rhi) && row >= rlo && row <= rhi) {
         // __ldcg: these arrays are produced earlier in the same (fused) launch by other SMs
-        const uint32_t pre = __ldcg(&mrow[i]);
-        const uint32_t c = (row < rhi ? __ldcg(&mrow[Kp + i]) : __ldcg(&a.tot[i])) - pre;
+        uint32_t pre = 0;
+        if (scanned) pre = __ldcg(&a.P[(size_t)row * Kp + i]);
+        else for (uint32_t r = rlo; r < row; ++r) pre += __ldcg(&a.M[(size_t)r * Kp + i]);  // few rows per partition
+        const uint32_t c = __ldcg(&a.M[(size_t)row * Kp + i]);
         const uint32_t start = __ldcg(&a.outbase[i]) + pre;
         v = start | ((start + c > __ldcg(&a.binlim[i])) ? 0x80000000u : 0u);
       }

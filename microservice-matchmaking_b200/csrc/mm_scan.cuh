@@ -21,9 +21,12 @@ constexpr uint32_t kTailScratchWords = 64 + 4 + 5 * kMaxSegs + 8;  // tail CTA s
 
 // One 32-bin column group: exclusive prefix down the rows of M (scratch: kColScratchWords).  Bin b belongs to one
 // partition, and only the rows holding that partition's tiles wrote M[.][b] (mm_hist.cuh): the scan of a column is
-// confined to rows [rlo, rhi] of its partition — about R / partitions rows instead of R.
+// confined to rows [rlo, rhi] of its partition — about R / partitions rows instead of R.  The prefixes go to P; M
+// keeps the raw counts (a row's own count is M[row][b]).  Only run when geo_use_colscan(g): otherwise every row sums
+// the few rows before it by itself (mm_place.cuh).
 __device__ __forceinline__ void colscan_cols_body(uint32_t* scratch, const Geo& g, uint32_t group, uint32_t Kp, uint32_t K,
-                                                  const uint16_t* __restrict__ bin_seg, uint32_t* __restrict__ M) {
+                                                  const uint16_t* __restrict__ bin_seg, const uint32_t* __restrict__ M,
+                                                  uint32_t* __restrict__ P) {
   uint32_t(*s_part)[33] = reinterpret_cast<uint32_t(*)[33]>(scratch);
   const uint32_t tid = threadIdx.x, x = tid & 31, y = tid >> 5;
   constexpr uint32_t NY = kScanBlock / 32;
@@ -52,7 +55,7 @@ __device__ __forceinline__ void colscan_cols_body(uint32_t* scratch, const Geo& 
     for (int k = 0; k < kU; ++k) v[k] = (r + k < r1) ? __ldcg(M + (size_t)(r + k) * Kp + b) : 0u;
 #pragma unroll
     for (int k = 0; k < kU; ++k) {
-      if (r + k < r1) M[(size_t)(r + k) * Kp + b] = run;
+      if (r + k < r1) P[(size_t)(r + k) * Kp + b] = run;
       run += v[k];
     }
   }
@@ -64,7 +67,7 @@ struct TailArgs {
   uint32_t Kp, K, n_segs;
   uint32_t layout;                    // bit 0: matched counts in shared memory; bit 1: bin keys too (tail_words)
   int32_t max_spread;                 // < 0: unlimited (policy S0); >= 0: policy S1, rating order only
-  const uint32_t* tot;                // [Kp] bin totals (k_hist)
+  const uint32_t* tot;                // [Kp] bin totals of the pool being matched (kept up to date by ingest / remove / tick)
   const uint32_t* seg_bin_lo;         // [n_segs + 1]
   const uint32_t* seg_L;              // [n_segs]
   const uint16_t* bin_seg;            // [Kp] bin -> segment
@@ -207,6 +210,8 @@ __device__ __forceinline__ void colscan_tail_body(uint32_t* scratch, const TailA
     for (uint32_t v = tid; v < Kp; v += kScanBlock) {
       t.outbase[v] = s_m[v];
       t.binlim[v] = s_m[v + 1];  // = outbase + matched players of the bin
+      // bin totals of the compacted pool: what was there minus the matched prefix; removed players are gone
+      t.dst.tot[v] = v < K ? __ldcg(&t.tot[v]) - (s_m[v + 1] - s_m[v]) : 0u;
     }
     for (uint32_t sg = tid; sg < n_segs; sg += kScanBlock) s_mt[sg] = s_m[s_lo[sg + 1]] - s_m[s_lo[sg]];
   }
@@ -257,11 +262,13 @@ __device__ __forceinline__ void colscan_tail_body(uint32_t* scratch, const TailA
       const uint32_t mend = start + s_mt[sg];  // end of the partition's matched positions
       for (uint32_t v = lo + lane; v < hi; v += 32) {
         const uint32_t b0 = s_bb[v], b1 = s_bb[v + 1];
-        t.outbase[v] = (b0 < mend ? b0 : mend) - shift;
-        t.binlim[v] = (b1 < mend ? b1 : mend) - shift;
+        const uint32_t o = (b0 < mend ? b0 : mend), l = (b1 < mend ? b1 : mend);
+        t.outbase[v] = o - shift;
+        t.binlim[v] = l - shift;
+        t.dst.tot[v] = (b1 - b0) - (l - o);  // bin totals of the compacted pool: the unmatched tail of the bin
       }
     }
-    for (uint32_t v = K + tid; v < Kp; v += kScanBlock) { t.outbase[v] = n_matched; t.binlim[v] = n_matched; }
+    for (uint32_t v = K + tid; v < Kp; v += kScanBlock) { t.outbase[v] = n_matched; t.binlim[v] = n_matched; t.dst.tot[v] = 0; }
   }
   for (uint32_t sg = warp; sg < n_segs; sg += NW) {  // chunk lists of the compacted pool
     const uint32_t c0 = s_nch[sg], c1 = s_nch[sg + 1];
@@ -270,13 +277,14 @@ __device__ __forceinline__ void colscan_tail_body(uint32_t* scratch, const TailA
   __syncthreads();
 }
 
-__global__ void __launch_bounds__(kScanBlock) k_colscan(uint32_t R, uint32_t* __restrict__ M, const TailArgs t) {
+__global__ void __launch_bounds__(kScanBlock) k_colscan(uint32_t R, const uint32_t* __restrict__ M, uint32_t* __restrict__ P,
+                                                        const TailArgs t) {
   extern __shared__ __align__(16) uint32_t scratch[];  // max(kColScratchWords, tail_words(Kp, layout)) words
   __shared__ Geo geo;
   __shared__ uint32_t s_gtmp[33];
   if (blockIdx.x + 1 < gridDim.x) {
     geo_build<kScanBlock>(geo, t.fill, t.n_segs, R, s_gtmp);
-    colscan_cols_body(scratch, geo, blockIdx.x, t.Kp, t.K, t.bin_seg, M);
+    if (geo_use_colscan(geo)) colscan_cols_body(scratch, geo, blockIdx.x, t.Kp, t.K, t.bin_seg, M, P);
   } else {
     colscan_tail_body(scratch, t);
   }

@@ -26,8 +26,8 @@ The AMQP connection is duck-typed (declare_exchange / declare_queue / bind / qos
 basic_consume / basic_publish / basic_ack / basic_nack / queue_status) so the same code
 drives a real client or the in-memory broker used by the tests.
 """
-import hashlib
 import json
+import math
 
 import numpy as np
 
@@ -53,21 +53,64 @@ def generate_exchange_name(suffix):  # worker.ex:50-52
 
 
 def prepare_config(opts):  # worker.ex:54-66
+    """opts["prefetch_count"] overrides the reference's QoS (worker.ex:29: 10).  The batched worker acks a delivery only
+    once its player is resident in the pool (SearchPool.flush), so a prefetch of 10 would cap the ingest at 10
+    players per worker per flush: start_link passes the pool's batch size instead."""
     if not opts.get("group_name"):
         raise RuntimeError("You need to configure group_name in options.")
     queue_name = generate_queue_name(opts["group_name"])
+    qos = dict(QOS_OPTIONS)
+    if opts.get("prefetch_count"):
+        qos["prefetch_count"] = int(opts["prefetch_count"])
     return {
         "queue": dict(name=queue_name, routing_key=queue_name, **QUEUE_OPTIONS),
         "exchange": dict(name=generate_exchange_name(opts["group_name"]), **EXCHANGE_OPTIONS),
-        "qos": dict(QOS_OPTIONS),
+        "qos": qos,
     }
 
 
-def player_handle(player_id):
-    """u64 device handle of a player id (reference ids are UUID strings, active_user.ex:7).
-    The two top values are reserved by the engine's hash table."""
-    h = int.from_bytes(hashlib.blake2b(str(player_id).encode(), digest_size=8).digest(), "little")
-    return h if h < 0xFFFFFFFFFFFFFFFE else h - 2
+class HandleTable:
+    """Host-side player id <-> dense device handle table (SURVEY §7.3 "dense slot index").
+
+    Reference ids are UUID strings (active_user.ex:7); the device stores a small integer.  A table — not a hash of
+    the id — so that two players can never collide into "You are already in the queue." and so that the Elixir and
+    Python hosts need not agree on a hash function; handles are recycled when the player leaves the active set
+    (ActiveUser.remove_user/1).  With an MM_F_DENSE_IDS engine the handle indexes the device's active set directly."""
+
+    def __init__(self, capacity=None):
+        self.capacity = capacity
+        self.handle_of = {}
+        self.id_of = []
+        self.free = []
+
+    def acquire(self, player_id):
+        """-> (handle, is_new).  None when the handle range is exhausted."""
+        h = self.handle_of.get(player_id)
+        if h is not None:
+            return h, False
+        if self.free:
+            h = self.free.pop()
+            self.id_of[h] = player_id
+        else:
+            if self.capacity is not None and len(self.id_of) >= self.capacity:
+                return None, False
+            h = len(self.id_of)
+            self.id_of.append(player_id)
+        self.handle_of[player_id] = h
+        return h, True
+
+    def lookup(self, player_id):
+        return self.handle_of.get(player_id)
+
+    def release(self, player_id):
+        h = self.handle_of.pop(player_id, None)
+        if h is not None:
+            self.id_of[h] = None
+            self.free.append(h)
+        return h
+
+    def __len__(self):
+        return len(self.handle_of)
 
 
 class WindowSchedule:
@@ -97,10 +140,14 @@ class SearchPool:
 
     engine: an object with the `Engine` API (enqueue / tick / remove / in_queue /
     pool_size / set_option); mode_names: index -> "1v1", ...; group_names: index -> "bronze", ...
+    max_batch: deliveries staged before an ingest (also the QoS prefetch every worker asks the broker for: a
+    delivery is acked only once its player is resident, so the broker must be allowed that many unacked messages);
+    flush_every_s: an ingest also happens when the oldest staged delivery has waited this long (and at every tick);
     window: optional WindowSchedule (extension; needs MM_ORDER_RATING); clock: () -> seconds.
     """
 
-    def __init__(self, engine, mode_names, group_names, max_batch=65536, window=None, clock=None):
+    def __init__(self, engine, mode_names, group_names, max_batch=65536, window=None, clock=None, flush_every_s=0.005,
+                 handle_capacity=None):
         import time
         self.window = window
         self.clock = clock or time.monotonic
@@ -111,40 +158,66 @@ class SearchPool:
         self.mode_index = {m: i for i, m in enumerate(self.mode_names)}
         self.group_names = list(group_names)
         self.max_batch = max_batch
+        self.flush_every_s = flush_every_s
+        self.handles = HandleTable(handle_capacity)
         self.players = {}   # handle -> decoded player document (without "game-mode")
         self.workers = {}   # group name -> worker that publishes the group's lobbies
-        self._staged = []   # (handle, rating, mode, player, worker, tag)
-        self.stats = {"enqueued": 0, "duplicates": 0, "invalid": 0, "lobbies": 0}
+        self._staged = []   # (player id, rating, mode, player, worker, tag)
+        self._staged_since = None
+        self.stats = {"enqueued": 0, "duplicates": 0, "invalid": 0, "lobbies": 0, "failed_batches": 0}
 
     # -- models/active_user.ex mirrors ---------------------------------------------------
     def in_queue(self, player_id):  # ActiveUser.in_queue?/1
-        return bool(self.engine.in_queue([player_handle(player_id)])[0])
+        h = self.handles.lookup(player_id)
+        return h is not None and bool(self.engine.in_queue([h])[0])
 
     def remove_user(self, player_id):  # ActiveUser.remove_user/1 -> {:ok, :removed}
         self.flush()
-        h = player_handle(player_id)
-        self.engine.remove([h])
-        self.players.pop(h, None)
-        self.enqueued_at.pop(h, None)
+        h = self.handles.lookup(player_id)
+        if h is not None:
+            self.engine.remove([h])
+            self.handles.release(player_id)
+            self.players.pop(h, None)
+            self.enqueued_at.pop(h, None)
         return ("ok", "removed")
 
     # -- ingest -----------------------------------------------------------------------------
     def stage(self, worker, tag, player, game_mode, rating):
-        self._staged.append((player_handle(player["id"]), int(rating), game_mode, player, worker, tag))
-        if len(self._staged) >= self.max_batch:
+        if not self._staged:
+            self._staged_since = self.clock()
+        self._staged.append((player["id"], int(rating), game_mode, player, worker, tag))
+        if len(self._staged) >= self.max_batch or self.clock() - self._staged_since >= self.flush_every_s:
             self.flush()
 
     def flush(self):
-        """mm_enqueue the staged deliveries; ack each one once its player is resident."""
+        """mm_enqueue the staged deliveries; ack each one once its player is resident.  Never raises: a batch the
+        engine refuses (active set full, CUDA error) is nacked as a whole — the broker redelivers it."""
         staged, self._staged = self._staged, []
         if not staged:
             return 0
-        ids = np.array([s[0] for s in staged], np.uint64)
+        fresh = []
+        ids = np.empty(len(staged), np.uint64)
+        for i, s in enumerate(staged):
+            h, is_new = self.handles.acquire(s[0])
+            if h is None:                      # handle range exhausted: an id the engine rejects as invalid
+                h = 2 ** 64 - 1
+            elif is_new:
+                fresh.append(s[0])
+            ids[i] = h
         rating = np.clip(np.array([s[1] for s in staged], np.int64), -(2 ** 31), 2 ** 31 - 1).astype(np.int32)
-        mode = np.array([self.mode_index.get(s[2], 255) for s in staged], np.uint8)
-        acc = self.engine.enqueue(ids, rating, mode, None)
+        mode = np.array([self.mode_index.get(s[2], 255) if isinstance(s[2], str) else 255 for s in staged], np.uint8)
+        try:
+            acc = self.engine.enqueue(ids, rating, mode, None)
+        except Exception:                       # nothing was enqueued (mm_enqueue refuses a batch as a whole)
+            for pid in fresh:
+                self.handles.release(pid)
+            for (_pid, _r, _m, _player, worker, tag) in staged:
+                worker.nack(worker.channel_name, tag)
+            self.stats["failed_batches"] += 1
+            return 0
         t_resident = self.clock() if self.window else None
-        for code, (h, _r, _m, player, worker, tag) in zip(acc, staged):
+        fresh = set(fresh)
+        for code, h, (pid, _r, _m, player, worker, tag) in zip(acc, ids.tolist(), staged):
             if code == 1:
                 self.players[h] = player
                 if self.window:
@@ -155,6 +228,8 @@ class SearchPool:
                 self.stats["duplicates"] += 1
                 worker.ack(worker.channel_name, tag)
             else:                                           # unknown mode / unroutable rating / full
+                if pid in fresh and self.handles.lookup(pid) == h and h not in self.players:
+                    self.handles.release(pid)
                 self.stats["invalid"] += 1
                 worker.nack(worker.channel_name, tag)
         return len(staged)
@@ -204,7 +279,7 @@ class SearchWorker:
     # worker.ex:68-71 + init/1 :220-237
     @classmethod
     def start_link(cls, connection, pool, opts):
-        config = prepare_config(opts)
+        config = prepare_config(dict(opts, prefetch_count=opts.get("prefetch_count") or pool.max_batch))
         if connection is None:
             return ("error", "noconn")  # worker.ex:225-228
         w = cls(connection, pool, config, opts)
@@ -238,15 +313,23 @@ class SearchWorker:
 
     # worker.ex:291-324 — one delivery
     def consume(self, channel_name, group_name, tag, headers, payload):
-        player_data = json.loads(payload)                         # :292
+        try:
+            player_data = json.loads(payload)                     # :292
+        except (ValueError, TypeError):
+            return self.nack(channel_name, tag)
+        if not isinstance(player_data, dict):                     # "[1, 2]" decodes, but is not a request
+            return self.nack(channel_name, tag)
         game_mode = player_data.pop("game-mode", None)           # :294
         rating = player_data.get("rating")                        # generic/worker.ex:57 reads it top-level
         if rating is None and isinstance(player_data.get("detail"), dict):
             rating = player_data["detail"].get("rating")
-        if "id" not in player_data or game_mode is None or not isinstance(rating, (int, float)):
+        if ("id" not in player_data or not isinstance(player_data["id"], (str, int)) or not isinstance(game_mode, str)
+                or isinstance(rating, bool) or not isinstance(rating, (int, float))
+                or (isinstance(rating, float) and not math.isfinite(rating))):  # json.loads accepts NaN / Infinity
             return self.nack(channel_name, tag)
         if isinstance(rating, float) and rating != int(rating):
             rating = 2 ** 31 - 1  # falls between the integer ranges -> default group (generic/worker.ex:46-53)
+        rating = max(-(2 ** 31), min(2 ** 31 - 1, int(rating)))
         self.pool.stage(self, tag, player_data, game_mode, rating)
 
     # worker.ex:337-368
@@ -258,7 +341,14 @@ class SearchWorker:
             return ("stop", "normal", self)
         if kind == "basic_deliver":
             _, payload, headers = msg
-            self.consume(self.channel_name, self.group_name, headers.get("delivery_tag"), headers, payload)
+            tag = headers.get("delivery_tag")
+            try:  # in the reference a bad payload only kills the process spawned for this delivery (worker.ex:356)
+                self.consume(self.channel_name, self.group_name, tag, headers, payload)
+            except Exception:
+                try:
+                    self.nack(self.channel_name, tag)
+                except Exception:
+                    pass
             return ("noreply", self)
         if kind == "DOWN":  # re-register the consumer (worker.ex:361-368)
             self.meta = {"consumer": self.create_consumer(self.channel_name, self.config["queue"]["name"])}

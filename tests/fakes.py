@@ -65,14 +65,18 @@ class FakeBroker:
             self.queues[q].append((payload, props or {}))
 
     def deliver_all(self):
-        """Push every queued message to its consumers (round-robin), like the broker would."""
+        """Push queued messages to their consumers (round-robin), like the broker would: a channel with
+        `prefetch` unacknowledged deliveries (basic.qos, search/worker.ex:29) gets nothing more until it acks."""
         n = 0
         for q, cons in list(self.consumers.items()):
             i = 0
             while self.queues[q] and cons:
-                payload, props = self.queues[q].popleft()
-                ch, consumer = cons[i % len(cons)]
+                ready = [(ch, c) for ch, c in cons if not ch.prefetch or len(ch.unacked) < ch.prefetch]
+                if not ready:
+                    break  # every consumer of this queue is at its QoS limit
+                ch, consumer = ready[i % len(ready)]
                 i += 1
+                payload, props = self.queues[q].popleft()
                 self._tag += 1
                 ch.unacked[self._tag] = payload
                 consumer.handle_info(("basic_deliver", payload, {"delivery_tag": self._tag, **props}))
@@ -91,6 +95,7 @@ class OracleEngine:
         self.alive = np.zeros(0, np.uint8)
         self.active = set()
         self.max_spread = -1
+        self.dead_pending = 0
 
     def set_option(self, name, value):
         if name != "max_spread":
@@ -119,11 +124,17 @@ class OracleEngine:
         return acc
 
     def remove(self, ids):
+        """Like the GPU engine, the queued entry of a leaver is dropped for good (the engine tombstones it): an id that
+        is removed and enqueued again — e.g. a recycled host handle — is a NEW entry.  (In the serialized reference the
+        stale entry would pass in_queue? again and show up twice; DESIGN.md §2 lists it as a reference defect.)"""
         n = 0
         for p in np.asarray(ids, np.uint64).tolist():
             if p in self.active:
                 self.active.discard(p)
-                self.alive[self.q[0] == p] = 0
+                keep = self.q[0] != p
+                self.dead_pending += int((~keep).sum())
+                self.q = [a[keep] for a in self.q]
+                self.alive = self.alive[keep]
                 n += 1
         return n
 
@@ -142,7 +153,8 @@ class OracleEngine:
         self.q = [a[keep] for a in self.q]
         self.alive = np.ones(len(self.q[0]), np.uint8)
         st = self.abi.TickStats()
-        st.n_lobbies, st.n_matched, st.n_residual, st.n_dead = ref.n_lobbies, ref.n_matched, ref.n_residual, ref.n_dead
+        st.n_lobbies, st.n_matched, st.n_residual, st.n_dead = ref.n_lobbies, ref.n_matched, ref.n_residual, ref.n_dead + self.dead_pending
+        self.dead_pending = 0
         return ref.lobbies, ref.member_ids, ref.emit_seq, st
 
     def pool_read(self):

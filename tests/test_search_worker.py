@@ -16,7 +16,7 @@ def boot(pkg, engine_cls, order=0):
     cfg = pkg.synth.make_config(groups=pkg.synth.REFERENCE_GROUPS, order=order, capacity=10_000)
     eng = engine_cls(cfg)
     broker = FakeBroker()
-    pool = sw.SearchPool(eng, ["1v1", "5v5"], pkg.synth.REFERENCE_GROUP_NAMES)
+    pool = sw.SearchPool(eng, ["1v1", "5v5"], pkg.synth.REFERENCE_GROUP_NAMES, flush_every_s=3600)
     workers = {}
     for g in pkg.synth.REFERENCE_GROUP_NAMES:  # application.ex:26-40: one worker per rating group
         ok, w = sw.SearchWorker.start_link(broker, pool, {"group_name": g, "channel_name": f"search.{g}"})
@@ -40,7 +40,7 @@ def scenario(pkg, engine_cls):
     cfg, eng, broker, pool, workers = boot(pkg, engine_cls)
     assert workers["gold"].config["queue"]["name"] == "matchmaking.queues.gold"  # worker.ex:46-66
     assert workers["gold"].config["exchange"]["name"] == "open-matchmaking.matchmaking.gold.direct"
-    assert workers["gold"].config["qos"] == {"prefetch_count": 10}
+    assert workers["gold"].config["qos"] == {"prefetch_count": pool.max_batch}  # not the reference's 10: see prepare_config
     players = [("u1", 100, "1v1"), ("u2", 2100, "1v1"), ("u3", 150, "1v1"), ("u4", 2200, "1v1"),
                ("u5", 4500, "1v1"), ("u1", 100, "1v1")]  # u1 twice: "already in the queue"
     for pid, r, m in players:
@@ -49,7 +49,7 @@ def scenario(pkg, engine_cls):
     assert not broker.acked  # nothing is acked before the players are resident
     assert pool.tick() == 2
     assert len(broker.acked) == 6 and not broker.nacked
-    assert pool.stats == {"enqueued": 5, "duplicates": 1, "invalid": 0, "lobbies": 2}
+    assert pool.stats == {"enqueued": 5, "duplicates": 1, "invalid": 0, "lobbies": 2, "failed_batches": 0}
     lobbies = [json.loads(p) for p, _ in broker.queues[sw.QUEUE_FORWARD]]
     props = [pr for _, pr in broker.queues[sw.QUEUE_FORWARD]]
     assert all(pr == {"persistent": True, "content_type": "application/json"} for pr in props)  # worker.ex:254-258
@@ -104,7 +104,8 @@ def window_scenario(pkg, engine_cls):
     broker = FakeBroker()
     now = [100.0]
     pool = sw.SearchPool(eng, ["1v1", "5v5"], pkg.synth.REFERENCE_GROUP_NAMES,
-                         window=sw.WindowSchedule(w0=10, growth_per_s=20, w_max=400), clock=lambda: now[0])
+                         window=sw.WindowSchedule(w0=10, growth_per_s=20, w_max=400), clock=lambda: now[0],
+                         flush_every_s=3600)
     for g in pkg.synth.REFERENCE_GROUP_NAMES:
         sw.SearchWorker.start_link(broker, pool, {"group_name": g, "channel_name": f"search.{g}"})
     broker.bind(sw.EXCHANGE_FORWARD, sw.QUEUE_FORWARD, sw.QUEUE_FORWARD)
@@ -124,7 +125,7 @@ def window_scenario(pkg, engine_cls):
     broker.deliver_all()
     now[0] += 100.0
     assert pool.tick() == 0 and pool.last_spread == 10         # e just arrived: the window is tight again
-    assert pool.in_queue("e") and not pool.enqueued_at.keys() - {sw.player_handle("e")}
+    assert pool.in_queue("e") and not pool.enqueued_at.keys() - {pool.handles.lookup("e")}
     pool.remove_user("e")
     assert not pool.enqueued_at
     assert pool.tick() == 0 and pool.last_spread == 10
@@ -156,10 +157,101 @@ def test_handle_info_clauses(pkg):
     assert w.handle_info(("DOWN", None))[0] == "noreply" and "consumer" in w.meta
 
 
-def test_player_handle_is_stable_and_in_range():
-    h = sw.player_handle("c0a8012e-1c9b-4b7e-9d2f-5f1d3a2b4c6d")
-    assert h == sw.player_handle("c0a8012e-1c9b-4b7e-9d2f-5f1d3a2b4c6d") and 0 <= h < 2 ** 64 - 2
-    assert len({sw.player_handle(f"p{i}") for i in range(10000)}) == 10000
+def test_handle_table_is_dense_collision_free_and_recycles():
+    t = sw.HandleTable(capacity=3)
+    a, new_a = t.acquire("c0a8012e-1c9b-4b7e-9d2f-5f1d3a2b4c6d")
+    assert (a, new_a) == (0, True) and t.acquire("c0a8012e-1c9b-4b7e-9d2f-5f1d3a2b4c6d") == (0, False)
+    assert t.acquire("b") == (1, True) and t.acquire("c") == (2, True)
+    assert t.acquire("d") == (None, False)                  # handle range exhausted
+    assert t.release("b") == 1 and t.lookup("b") is None
+    assert t.acquire("d") == (1, True) and len(t) == 3      # the freed handle is reused
+    big = sw.HandleTable()
+    assert len({big.acquire(f"p{i}")[0] for i in range(10000)}) == 10000
+
+
+def test_prefetch_is_enforced_and_ingest_never_stalls(pkg):
+    """with the reference's QoS (prefetch 10) a worker that acks only after the batched ingest gets 10
+    deliveries per flush; with prefetch = the pool's batch size (what start_link asks for) one round delivers all.
+    Either way nothing deadlocks: tick() flushes, acks, and the broker delivers the next window."""
+    for prefetch, rounds_expected in ((10, lambda r: r > 10), (None, lambda r: r == 1)):
+        cfg = pkg.synth.make_config(groups=pkg.synth.REFERENCE_GROUPS, order=0, capacity=10_000)
+        broker = FakeBroker()
+        pool = sw.SearchPool(OracleEngine(cfg), ["1v1", "5v5"], pkg.synth.REFERENCE_GROUP_NAMES, flush_every_s=3600)
+        for g in pkg.synth.REFERENCE_GROUP_NAMES:
+            opts = {"group_name": g, "channel_name": f"search.{g}"}
+            if prefetch:
+                opts["prefetch_count"] = prefetch
+            sw.SearchWorker.start_link(broker, pool, opts)
+        for i in range(600):
+            publish_player(pkg, broker, cfg, f"p{i}", 2100 + (i % 300), "1v1")  # all in "gold": one worker
+        rounds = 0
+        while broker.queues[sw.generate_queue_name("gold")] or pool._staged:
+            delivered = broker.deliver_all()
+            assert delivered <= (prefetch or pool.max_batch)
+            pool.tick()
+            rounds += 1
+            assert rounds < 200
+        assert rounds_expected(rounds) and pool.stats["enqueued"] == 600 and len(broker.acked) == 600
+
+
+def test_time_triggered_flush(pkg):
+    cfg = pkg.synth.make_config(groups=pkg.synth.REFERENCE_GROUPS, order=0, capacity=100)
+    broker, now = FakeBroker(), [0.0]
+    pool = sw.SearchPool(OracleEngine(cfg), ["1v1"], pkg.synth.REFERENCE_GROUP_NAMES, flush_every_s=0.005, clock=lambda: now[0])
+    for g in pkg.synth.REFERENCE_GROUP_NAMES:
+        sw.SearchWorker.start_link(broker, pool, {"group_name": g, "channel_name": f"search.{g}"})
+    publish_player(pkg, broker, cfg, "a", 100, "1v1")
+    broker.deliver_all()
+    assert not broker.acked                     # staged, not resident yet
+    now[0] += 0.010
+    publish_player(pkg, broker, cfg, "b", 120, "1v1")
+    broker.deliver_all()                        # the oldest staged delivery waited 10 ms: ingest now, no tick needed
+    assert len(broker.acked) == 2 and pool.in_queue("a") and pool.in_queue("b")
+
+
+def test_failing_engine_nacks_the_whole_batch(pkg):
+    """A batch mm_enqueue refuses (active set full / CUDA error) must not vanish: every staged delivery is nacked,
+    the handles taken for it are released, and the worker keeps serving."""
+    cfg = pkg.synth.make_config(groups=pkg.synth.REFERENCE_GROUPS, order=0, capacity=100)
+
+    class Failing(OracleEngine):
+        fail = True
+
+        def enqueue(self, *a, **k):
+            if self.fail:
+                raise RuntimeError("mm_enqueue: status -3 — capacity exceeded")
+            return super().enqueue(*a, **k)
+
+    broker, eng = FakeBroker(), Failing(cfg)
+    pool = sw.SearchPool(eng, ["1v1"], pkg.synth.REFERENCE_GROUP_NAMES, flush_every_s=3600)
+    for g in pkg.synth.REFERENCE_GROUP_NAMES:
+        sw.SearchWorker.start_link(broker, pool, {"group_name": g, "channel_name": f"search.{g}"})
+    for i in range(5):
+        publish_player(pkg, broker, cfg, f"p{i}", 100 + i, "1v1")
+    broker.deliver_all()
+    assert pool.flush() == 0 and len(broker.nacked) == 5 and not broker.acked
+    assert pool.stats["failed_batches"] == 1 and len(pool.handles) == 0 and not pool._staged
+    eng.fail = False
+    publish_player(pkg, broker, cfg, "p9", 100, "1v1")
+    broker.deliver_all()
+    assert pool.flush() == 1 and len(broker.acked) == 1 and pool.in_queue("p9")
+
+
+def test_hostile_payloads_are_nacked_not_raised(pkg):
+    """json.loads accepts NaN / Infinity and non-object documents; a list game-mode is unhashable."""
+    cfg, eng, broker, pool, workers = boot(pkg, OracleEngine)
+    q, ex = sw.generate_queue_name("gold"), sw.generate_exchange_name("gold")
+    for doc in ('[1, 2]', '"str"', '{"id": "n1", "rating": NaN, "game-mode": "1v1"}',
+                '{"id": "n2", "rating": Infinity, "game-mode": "1v1"}', '{"id": "n3", "rating": 2100, "game-mode": ["1v1"]}',
+                '{"id": "n4", "rating": true, "game-mode": "1v1"}', '{"id": {"x": 1}, "rating": 2100, "game-mode": "1v1"}',
+                'not json at all', '{"id": "n5", "rating": 1e400, "game-mode": "1v1"}'):
+        broker.publish(ex, q, doc)
+    assert broker.deliver_all() == 9
+    pool.flush()
+    assert len(broker.nacked) == 9 and not broker.acked and pool.stats["enqueued"] == 0
+    broker.publish(ex, q, '{"id": "ok", "rating": 1e3, "game-mode": "1v1"}')  # a float that is an integer is fine
+    broker.deliver_all(); pool.flush()
+    assert len(broker.acked) == 1
 
 
 def test_malformed_and_overflowing_deliveries(pkg):
