@@ -127,6 +127,58 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+def stream_leg(pkg, device, seconds, rate, dt_ms, groups=32, max_spread=-1):
+    """BASELINE configs[4] on one GPU: Poisson arrivals at `rate` players/s into the resident pool through
+    mm_enqueue_packed, one search tick (mm_tick_packed, host results) every dt_ms, real time (the loop is paced with
+    the wall clock).  latency = t(host holds the lobby that contains the player) - t(player arrived)."""
+    import numpy as np
+    abi = pkg.abi
+    dt = dt_ms * 1e-3
+    n_total = int(rate * seconds)
+    rng = np.random.default_rng(1)
+    arrive = np.cumsum(rng.exponential(1.0 / rate, n_total))
+    _, rating, _, _ = pkg.synth.gen_pool(3, n_total)
+    keys = pkg.Engine.pack_key(rating, np.zeros(n_total, np.uint8))
+    handles = np.arange(n_total, dtype=np.uint32)  # the host's dense handle = arrival index
+    cfg = pkg.synth.make_config(n_groups=groups, modes=(("5v5", 2, 5),), order=abi.MM_ORDER_RATING, capacity=1 << 20,
+                                active_capacity=n_total + 1024, device=device)
+    cfg.flags |= abi.MM_F_DENSE_IDS
+    eng = pkg.Engine(cfg)
+    eng.set_option("max_spread", max_spread)
+    eng.enqueue_packed(handles[:10], keys[:10]); eng.tick_packed(want_emit_seq=False); eng.remove_packed(handles[:10])  # warm-up
+    matched_at = np.full(n_total, np.nan)
+    lo, overruns, tick_us, call_us = 10, 0, [], []
+    n_ticks = int(seconds / dt)
+    t0 = time.perf_counter()
+    for k in range(1, n_ticks + 1):
+        deadline = t0 + k * dt
+        while time.perf_counter() < deadline:
+            pass
+        now = time.perf_counter() - t0
+        hi = int(np.searchsorted(arrive, now))  # everyone who has arrived by now
+        if hi > lo:
+            eng.enqueue_packed(handles[lo:hi], keys[lo:hi])
+        lob, mem, _, st = eng.tick_packed(want_emit_seq=False)
+        done = time.perf_counter() - t0
+        matched_at[mem] = done
+        tick_us.append(st.device_us); call_us.append((done - now) * 1e6)
+        overruns += done > (k + 1) * dt
+        lo = max(lo, hi)
+    eng.close()
+    lat = (matched_at - arrive)[10:lo]
+    ok = ~np.isnan(lat)
+    q = lambda p: float(np.percentile(lat[ok], p) * 1e3)
+    return {"workload": "Poisson arrivals into the resident pool, 5v5, %d rating groups, one tick per period" % groups,
+            "rate_per_s": rate, "dt_ms": dt_ms, "seconds": seconds, "max_spread": max_spread,
+            "players_enqueued": int(lo - 10), "matched": int(ok.sum()), "still_queued": int((~ok).sum()),
+            "latency_ms": {"p50": q(50), "p99": q(99), "p99.9": q(99.9), "max": q(100)},
+            "tick_device_us": {"mean": float(np.mean(tick_us)), "p99": float(np.percentile(tick_us, 99))},
+            "enqueue_plus_tick_call_us": {"mean": float(np.mean(call_us)), "p99": float(np.percentile(call_us, 99))},
+            "ticks": n_ticks, "overrun_ticks": int(overruns),
+            "note": "strict parity has no time-expanded window (SURVEY F3): a player waits for L-1 more players of its "
+                    "(mode, group) and the next tick; the pool holds < L players per partition between ticks"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -143,6 +195,9 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-strong", action="store_true", help="under torchrun: skip the configs[3] strong-scaling leg")
     ap.add_argument("--no-numa", action="store_true", help="do not bind the rank to its GPU's NUMA node")
+    ap.add_argument("--stream-seconds", type=float, default=1.0, help="length of the streaming leg (configs[4]); 0 = skip")
+    ap.add_argument("--stream-rate", type=float, default=1e6)
+    ap.add_argument("--stream-dt-ms", type=float, default=1.0)
     ap.add_argument("--two-modes", action="store_true", help="configure both default modes (1v1, 5v5), not just the workload's")
     ap.add_argument("--tick-impl", type=int, default=None, help="1 = one fused cooperative launch (default), 0 = four launches")
     ap.add_argument("--max-spread", type=int, default=None,
@@ -363,6 +418,9 @@ def main():
                            "call": "blocking mm_enqueue(pinned u64 ids, i32 rating, u8 mode, u32 ts; accepted[] back) + "
                                    "blocking mm_tick(host lobbies / u64 member ids)"},
                "numa": numa}
+    stream = None
+    if args.stream_seconds > 0 and not args.no_e2e and rank == 0 and world == 1:
+        stream = stream_leg(pkg, local, args.stream_seconds, args.stream_rate, args.stream_dt_ms)
     clocks = sampler.stop()  # sampled across the device-timed ticks and the e2e steps
 
     # ---- CPU baseline (rank 0, N=1 only): the oracle's literal loop on a bounded sample ----
@@ -419,7 +477,7 @@ def main():
                                       "frac": B_CONSUMED_TICK * n / tick_avg_s / 1e9 / peak,
                                       "note": "the tick reads the 2-byte sort key derived at ingest, not rating + mode + "
                                               "team_size (6 B): on the bytes it really consumes the fraction is lower"}},
-            "cpu_baseline": cpu, "e2e": e2e, "strong": strong,
+            "cpu_baseline": cpu, "e2e": e2e, "strong": strong, "stream": stream,
             "gpu_launches": launches_per_tick * args.steps, "clocks": clocks,
         }
         print(json.dumps(line), flush=True)

@@ -108,6 +108,52 @@ static ERL_NIF_TERM nif_tick(ErlNifEnv* env, int argc, const ERL_NIF_TERM argv[]
   return enif_make_tuple4(env, atom(env, "ok"), enif_make_binary(env, &lob), enif_make_binary(env, &mem), stats);
 }
 
+/* enqueue_packed(ref, handles :: binary(u32[]), keys :: binary(u16[])) -> {:ok, accepted :: binary}   (6 B per player) */
+static ERL_NIF_TERM nif_enqueue_packed(ErlNifEnv* env, int argc, const ERL_NIF_TERM argv[]) {
+  engine_res* r; ErlNifBinary hs, ks;
+  (void)argc;
+  if (!enif_get_resource(env, argv[0], ENGINE_T, (void**)&r) || !enif_inspect_binary(env, argv[1], &hs) ||
+      !enif_inspect_binary(env, argv[2], &ks) || hs.size != 2 * ks.size)
+    return enif_make_badarg(env);
+  size_t n = ks.size / 2;
+  ERL_NIF_TERM out;
+  unsigned char* acc = enif_make_new_binary(env, n, &out);
+  int rc = mm_enqueue_packed(r->e, (uint32_t)n, (const uint32_t*)hs.data, (const uint16_t*)ks.data, NULL, acc);
+  return rc ? err(env, rc) : enif_make_tuple2(env, atom(env, "ok"), out);
+}
+
+static ERL_NIF_TERM nif_remove_packed(ErlNifEnv* env, int argc, const ERL_NIF_TERM argv[]) {
+  engine_res* r; ErlNifBinary hs; uint32_t removed = 0;
+  (void)argc;
+  if (!enif_get_resource(env, argv[0], ENGINE_T, (void**)&r) || !enif_inspect_binary(env, argv[1], &hs))
+    return enif_make_badarg(env);
+  int rc = mm_remove_packed(r->e, (uint32_t)(hs.size / 4), (const uint32_t*)hs.data, &removed);
+  return rc ? err(env, rc) : enif_make_tuple2(env, atom(env, "ok"), enif_make_uint(env, removed));
+}
+
+/* tick_packed(ref, now_ms) -> {:ok, lobbies :: binary(mm_lobby_hdr[]), member_handles :: binary(u32[]), stats :: map} */
+static ERL_NIF_TERM nif_tick_packed(ErlNifEnv* env, int argc, const ERL_NIF_TERM argv[]) {
+  engine_res* r; ErlNifUInt64 now; uint32_t n = 0;
+  (void)argc;
+  if (!enif_get_resource(env, argv[0], ENGINE_T, (void**)&r) || !enif_get_uint64(env, argv[1], &now))
+    return enif_make_badarg(env);
+  if (mm_pool_size(r->e, &n)) return err(env, MM_E_ARG);
+  ErlNifBinary lob, mem;
+  if (!enif_alloc_binary((size_t)n * sizeof(mm_lobby_hdr) + 8, &lob)) return err(env, MM_E_CAP);
+  if (!enif_alloc_binary((size_t)n * 4 + 8, &mem)) { enif_release_binary(&lob); return err(env, MM_E_CAP); }
+  mm_tick_stats st;
+  int rc = mm_tick_packed(r->e, now, (mm_lobby_hdr*)lob.data, n, (uint32_t*)mem.data, n, NULL, &st);
+  if (rc) { enif_release_binary(&lob); enif_release_binary(&mem); return err(env, rc); }
+  enif_realloc_binary(&lob, (size_t)st.n_lobbies * sizeof(mm_lobby_hdr));
+  enif_realloc_binary(&mem, (size_t)st.n_matched * 4);
+  ERL_NIF_TERM stats = enif_make_new_map(env);
+  enif_make_map_put(env, stats, atom(env, "lobbies"), enif_make_uint(env, st.n_lobbies), &stats);
+  enif_make_map_put(env, stats, atom(env, "matched"), enif_make_uint(env, st.n_matched), &stats);
+  enif_make_map_put(env, stats, atom(env, "residual"), enif_make_uint(env, st.n_residual), &stats);
+  enif_make_map_put(env, stats, atom(env, "device_us"), enif_make_double(env, st.device_us), &stats);
+  return enif_make_tuple4(env, atom(env, "ok"), enif_make_binary(env, &lob), enif_make_binary(env, &mem), stats);
+}
+
 static ERL_NIF_TERM nif_status(ErlNifEnv* env, int argc, const ERL_NIF_TERM argv[]) {
   engine_res* r; uint32_t n = 0, a = 0;
   (void)argc;
@@ -135,6 +181,9 @@ static ErlNifFunc funcs[] = {
   {"remove", 2, nif_remove, ERL_NIF_DIRTY_JOB_CPU_BOUND},
   {"in_queue?", 2, nif_in_queue, ERL_NIF_DIRTY_JOB_CPU_BOUND},
   {"tick", 2, nif_tick, ERL_NIF_DIRTY_JOB_CPU_BOUND},
+  {"enqueue_packed", 3, nif_enqueue_packed, ERL_NIF_DIRTY_JOB_CPU_BOUND},
+  {"remove_packed", 2, nif_remove_packed, ERL_NIF_DIRTY_JOB_CPU_BOUND},
+  {"tick_packed", 2, nif_tick_packed, ERL_NIF_DIRTY_JOB_CPU_BOUND},
   {"status", 1, nif_status, 0},
   {"set_max_spread", 2, nif_set_max_spread, 0},
 };

@@ -24,26 +24,31 @@ defmodule Matchmaking.Search.Engine do
     his = pad.(Enum.map(groups, &elem(&1, 1)), @max_groups)
     default = if div(n, 2) + 1 < n, do: div(n, 2) + 1, else: -1   # generic/worker.ex:27
     modes = pad.(Enum.flat_map(@modes, fn {_, t, s} -> [t, s] end), 2 * @max_modes)
-    <<1::little-32, n::little-32>> <>
+    <<2::little-32, n::little-32>> <>                                   # MM_ABI_VERSION
       for(v <- los, into: <<>>, do: <<v::little-signed-32>>) <>
       for(v <- his, into: <<>>, do: <<v::little-signed-32>>) <>
       <<default::little-signed-32, length(@modes)::little-32>> <>
       for(v <- modes, into: <<>>, do: <<v::little-16>>) <>
       <<Keyword.get(opts, :order_mode, 0)::little-32, Keyword.get(opts, :capacity, 1_048_576)::little-32,
         Keyword.get(opts, :active_capacity, 0)::little-32, Keyword.get(opts, :device, 0)::little-signed-32,
-        0::little-32>>
+        (if Keyword.get(opts, :dense_ids, false), do: 2, else: 0)::little-32>>   # MM_F_DENSE_IDS
   end
 
   def mode_index(name), do: Enum.find_index(@modes, fn {n, _, _} -> n == name end)
   def mode_name(index), do: elem(Enum.at(@modes, index), 0)
   def teams_of(index), do: elem(Enum.at(@modes, index), 1)
 
-  @doc "u64 device handle of a player id (UUID string)."
-  def handle(id), do: :binary.decode_unsigned(binary_part(:crypto.hash(:blake2b, id), 0, 8), :little)
+  # Player ids (UUID strings) are mapped to dense device handles by a table in Matchmaking.Search.Pool — not by a
+  # hash: no collisions, no hash function the Elixir and Python hosts would have to agree on.
 
   def new(_config), do: :erlang.nif_error(:nif_not_loaded)
   def enqueue(_ref, _ids, _ratings, _modes), do: :erlang.nif_error(:nif_not_loaded)
   def remove(_ref, _ids), do: :erlang.nif_error(:nif_not_loaded)
+  @doc "Dense-handle engines: handles :: binary(u32[]), keys :: binary(u16[] = mode <<< 13 ||| rating) -> {:ok, codes}"
+  def enqueue_packed(_ref, _handles, _keys), do: :erlang.nif_error(:nif_not_loaded)
+  def remove_packed(_ref, _handles), do: :erlang.nif_error(:nif_not_loaded)
+  @doc "-> {:ok, lobbies :: binary(mm_lobby_hdr[]), member_handles :: binary(u32[]), stats}"
+  def tick_packed(_ref, _now_ms), do: :erlang.nif_error(:nif_not_loaded)
   def in_queue?(_ref, _id), do: :erlang.nif_error(:nif_not_loaded)
   def tick(_ref, _now_ms), do: :erlang.nif_error(:nif_not_loaded)
   def status(_ref), do: :erlang.nif_error(:nif_not_loaded)

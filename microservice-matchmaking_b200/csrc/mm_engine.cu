@@ -453,11 +453,18 @@ TailArgs tail_args(mm_engine* e) {
   t.dst = e->pool[e->cur ^ 1].m;
   return t;
 }
+// Rows (CTAs) a tick uses: small pools do not pay the grid barriers and per-row set-up of the full grid.  About two
+// tiles per row at least; the tile count is bounded from the host-side player count.
+uint32_t tick_rows(const mm_engine* e) {
+  const uint64_t tiles = (uint64_t)e->pool[e->cur].n / kTile + e->n_segs;
+  return (uint32_t)std::min<uint64_t>(e->R, std::max<uint64_t>(1, (tiles + 1) / 2));
+}
+
 PlaceArgs place_args(mm_engine* e, bool want_seq) {
   const Pool& p = e->pool[e->cur];
   PlaceArgs a{};
   a.bins16 = p.v.bin; a.ids = p.v.id; a.meta = p.m;
-  a.K = e->K; a.Kp = e->Kp; a.R = e->R; a.stages = e->place_stages; a.fast_ok = e->rank_impl == 3;
+  a.K = e->K; a.Kp = e->Kp; a.R = tick_rows(e); a.stages = e->place_stages; a.fast_ok = e->rank_impl == 3;
   a.seg_bin_lo = e->d_seg_bin_lo; a.bin_seg = e->d_bin_seg; a.M = e->d_M; a.P = e->d_P;
   a.outbase = e->d_outbase; a.binlim = e->d_binlim; a.members = e->d_members;
   a.src_idx = want_seq ? e->d_src_idx : nullptr;
@@ -469,7 +476,7 @@ EpiArgs epi_args(mm_engine* e, bool want_seq, bool headers) {
   EpiArgs a{};
   a.src = e->pool[e->cur].v; a.dst = e->pool[e->cur ^ 1].v;
   a.src_meta = e->pool[e->cur].m; a.dst_meta = e->pool[e->cur ^ 1].m;
-  a.R = e->R; a.new_gen = next_gen(e); a.n_segs = e->n_segs; a.n_groups = e->cfg.n_groups; a.Kp = e->Kp;
+  a.R = tick_rows(e); a.new_gen = next_gen(e); a.n_segs = e->n_segs; a.n_groups = e->cfg.n_groups; a.Kp = e->Kp;
   a.write_headers = headers ? 1u : 0u;
   a.rescnt = e->d_rescnt; a.left_bits = e->d_left_bits; a.act = act_view(e); a.seg = e->d_seg; a.seg_L = e->d_seg_L;
   a.hdr = e->d_hdr; a.src_idx = want_seq ? e->d_src_idx : nullptr; a.emit_seq = want_seq ? e->d_emit_seq : nullptr;
@@ -482,19 +489,21 @@ int tick_phase_a(mm_engine* e) {
   const Pool& p = e->pool[e->cur];
   CK(cudaMemsetAsync(e->d_ctr, 0, sizeof(TickCtr), e->stream));
   CK(cudaEventRecord(e->ev[0], e->stream));
-  k_hist<512><<<e->R, 512, hist_smem_bytes(e->Kp), e->stream>>>(p.v.bin, p.m, e->n_segs, e->R, e->Kp, e->d_seg_bin_lo, e->d_M);
+  const uint32_t rows = tick_rows(e);
+  k_hist<512><<<rows, 512, hist_smem_bytes(e->Kp), e->stream>>>(p.v.bin, p.m, e->n_segs, rows, e->Kp, e->d_seg_bin_lo, e->d_M);
   CK(cudaEventRecord(e->ev[1], e->stream));
-  k_colscan<<<(e->K + 31) / 32 + 1, kScanBlock, colscan_smem(e), e->stream>>>(e->R, e->d_M, e->d_P, tail_args(e));
+  k_colscan<<<(e->K + 31) / 32 + 1, kScanBlock, colscan_smem(e), e->stream>>>(rows, e->d_M, e->d_P, tail_args(e));
   CK(cudaGetLastError());
   return MM_OK;
 }
 
 int tick_phase_b(mm_engine* e, bool want_seq) {
   CK(cudaEventRecord(e->ev[2], e->stream));
-  k_place<512><<<e->R, 512, place_smem_bytes(e->Kp, e->place_stages), e->stream>>>(place_args(e, want_seq),
-                                                                                   e->pool[e->cur].m.fill, e->n_segs);
+  const uint32_t rows = tick_rows(e);
+  k_place<512><<<rows, 512, place_smem_bytes(e->Kp, e->place_stages), e->stream>>>(place_args(e, want_seq),
+                                                                                  e->pool[e->cur].m.fill, e->n_segs);
   CK(cudaEventRecord(e->ev[3], e->stream));
-  k_epilogue<512><<<std::max(1, e->n_sms), 512, 0, e->stream>>>(epi_args(e, want_seq, true));
+  k_epilogue<512><<<std::max<uint32_t>(1, std::min<uint32_t>((uint32_t)e->n_sms, 2 * rows)), 512, 0, e->stream>>>(epi_args(e, want_seq, true));
   CK(cudaGetLastError());
   CK(cudaEventRecord(e->ev[4], e->stream));
   CK(cudaMemcpyAsync(e->h_ctr, e->d_ctr, sizeof(TickCtr), cudaMemcpyDeviceToHost, e->stream));
@@ -507,17 +516,19 @@ bool use_fused(const mm_engine* e) { return e->tick_impl == 1 && e->fused_ok; }
 // the whole tick in one cooperative launch (k_tick)
 int tick_fused(mm_engine* e, bool want_seq) {
   TickArgs a{};
+  const uint32_t rows = tick_rows(e);
+  const uint32_t helpers = rows >= 64 ? e->helpers : (rows > 1 ? 1u : 0u);
   a.src = e->pool[e->cur].v;
-  a.R = e->R;
+  a.R = rows;
   a.M = e->d_M;
   a.P = e->d_P;
   a.tail = tail_args(e);
   a.place = place_args(e, want_seq);
-  a.epi = epi_args(e, want_seq, want_seq || e->helpers == 0);  // emission order needs the placement's src_idx first
+  a.epi = epi_args(e, want_seq, want_seq || helpers == 0);  // emission order needs the placement's src_idx first
   CK(cudaMemsetAsync(e->d_ctr, 0, sizeof(TickCtr), e->stream));
   CK(cudaEventRecord(e->ev[0], e->stream));
   void* params[] = {&a};
-  CK(cudaLaunchCooperativeKernel((const void*)k_tick<512>, dim3(e->R + e->helpers), dim3(512), params, e->tick_smem, e->stream));
+  CK(cudaLaunchCooperativeKernel((const void*)k_tick<512>, dim3(rows + helpers), dim3(512), params, e->tick_smem, e->stream));
   CK(cudaEventRecord(e->ev[4], e->stream));
   CK(cudaMemcpyAsync(e->h_ctr, e->d_ctr, sizeof(TickCtr), cudaMemcpyDeviceToHost, e->stream));
   CK(cudaStreamSynchronize(e->stream));
