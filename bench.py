@@ -195,6 +195,8 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-strong", action="store_true", help="under torchrun: skip the configs[3] strong-scaling leg")
     ap.add_argument("--no-numa", action="store_true", help="do not bind the rank to its GPU's NUMA node")
+    ap.add_argument("--boundary-w", type=int, default=2,
+                    help="under torchrun: window of the boundary-pass extension leg (0 = skip)")
     ap.add_argument("--stream-seconds", type=float, default=1.0, help="length of the streaming leg (configs[4]); 0 = skip")
     ap.add_argument("--stream-rate", type=float, default=1e6)
     ap.add_argument("--stream-dt-ms", type=float, default=1.0)
@@ -315,6 +317,37 @@ def main():
                   "workload": args.workload + f" as ONE pool sharded by rating group over {world} GPUs (BASELINE configs[3]); "
                               "strict parity: no player crosses a group, so no boundary exchange is issued",
                   "timing": "max over ranks of the device-timed ticks (CUDA events on each engine's stream)"}
+        # -- EXTENSION leg (not reference behaviour): policy S1 (max_spread W) on the same sharded pool + the boundary
+        #    pass: residual players within W of a group boundary owned by another rank travel over NCCL send/recv
+        if args.boundary_w > 0:
+            Wb = args.boundary_w
+            cfg_b, _ = pkg.synth.workload_config(args.workload, abi.MM_ORDER_RATING, n_mine + 65536, device=local,
+                                                 single_mode=not args.two_modes)
+            eng = pkg.Engine(cfg_b)
+            eng.set_option("max_spread", Wb)
+            assert eng.enqueue(g_ids[mine], g_rating[mine], g_mode[mine], g_ts[mine]).all()
+            stb = eng.tick_device()
+            comm = shard.DistComm(device=torch.device("cuda", local))
+            cache = {}
+            barrier()
+            t0 = time.perf_counter()
+            bp = shard.boundary_pass(pkg, cfg_b, Wb, world, rank, eng, comm, cache=cache)
+            barrier()
+            bp_ms = 1e3 * (time.perf_counter() - t0)
+            for band in cache.values():
+                band.close()
+            eng.close()
+            tb = torch.tensor([bp["sent"], bp["received"], bp["matched"], bp["lobbies"], comm.bytes_sent, stb.n_residual],
+                              device="cuda", dtype=torch.int64)
+            dist.all_reduce(tb)
+            strong["boundary_pass"] = {
+                "policy": f"S1 extension, max lobby spread {Wb}", "players_left_queued_by_the_local_ticks": int(tb[5].item()),
+                "players_sent_to_the_lower_neighbour": int(tb[0].item()), "players_received": int(tb[1].item()),
+                "players_matched_across_a_boundary": int(tb[2].item()), "lobbies": int(tb[3].item()),
+                "bytes_over_nccl": int(tb[4].item()), "wall_ms": bp_ms,
+                "note": "torch.distributed send/recv on the NCCL process group (NVLink): candidates up, consumed ids back; "
+                        "host-orchestrated (pool_read + band engines), so the wall time is dominated by host copies, not "
+                        "by the link"}
         del g_ids, g_rating, g_mode, g_ts
 
     # ---- e2e through the C ABI with host buffers ------------------------------------------------------------------

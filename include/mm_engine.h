@@ -163,6 +163,11 @@ int mm_enqueue_rejects(mm_engine* e, uint32_t cap, uint32_t* index, uint8_t* cod
 int mm_remove(mm_engine* e, uint32_t n, const uint64_t* id, uint32_t* n_removed);
 int mm_remove_packed(mm_engine* e, uint32_t n, const uint32_t* handle, uint32_t* n_removed);
 
+/* EXTENSION (cross-group boundary pass): queued players that were matched outside this engine's tick
+ * leave the pool but STAY in the active set — like the members of an emitted lobby, who are "in the queue" until
+ * the lobby stage removes them (game-lobby/worker.ex:80).  Ids that are not queued are ignored.               */
+int mm_take(mm_engine* e, uint32_t n, const uint64_t* id, uint32_t* n_taken);
+
 /* Replaces ActiveUser.in_queue?/1 (models/active_user.ex:33-44), batched.          */
 int mm_in_queue(mm_engine* e, uint32_t n, const uint64_t* id, uint8_t* out);
 

@@ -85,6 +85,7 @@ PROTOTYPES = {
     "mm_enqueue_rejects": (C.c_int, [_vp, C.c_uint32, _vp, _vp, _P(C.c_uint32)]),
     "mm_remove": (C.c_int, [_vp, C.c_uint32, _vp, _P(C.c_uint32)]),
     "mm_remove_packed": (C.c_int, [_vp, C.c_uint32, _vp, _P(C.c_uint32)]),
+    "mm_take": (C.c_int, [_vp, C.c_uint32, _vp, _P(C.c_uint32)]),
     "mm_in_queue": (C.c_int, [_vp, C.c_uint32, _vp, _vp]),
     "mm_pool_size": (C.c_int, [_vp, _P(C.c_uint32)]),
     "mm_active_size": (C.c_int, [_vp, _P(C.c_uint32)]),

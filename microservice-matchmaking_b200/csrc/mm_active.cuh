@@ -289,6 +289,31 @@ __global__ void k_remove(uint32_t n, const uint64_t* __restrict__ id, ActiveView
   atomicAdd(n_removed, 1u);
 }
 
+// mm_take: queued players matched OUTSIDE this engine's tick (the cross-group boundary pass, shard.py) leave the pool
+// but stay in the active set — exactly like members of an emitted lobby, who are "in the queue" until the lobby stage
+// removes them (game-lobby/worker.ex:80).
+__global__ void k_take(uint32_t n, const uint64_t* __restrict__ id, ActiveView act, PoolView pool, uint32_t n_slots,
+                       uint32_t gen, uint32_t dead_bin, uint32_t* __restrict__ tot, uint32_t* __restrict__ n_taken) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n || !act.on()) return;
+  const uint64_t pid = id[i];
+  const uint64_t h = act_find(act, pid);
+  if (h == ~0ull) return;
+  const unsigned long long v = *act.val(h);
+  const uint32_t slot = (uint32_t)v, g = (uint32_t)(v >> 32);
+  if (v < kPending && g == gen && slot < n_slots && pool.id[slot] == pid) {
+    // a twin in the same batch must not count twice: the mode byte is the claim
+    const uint32_t word = slot & ~3u, sh = (slot & 3u) * 8;
+    uint32_t* mw = reinterpret_cast<uint32_t*>(pool.mode + word);
+    const uint32_t old = atomicOr(mw, 0xFFu << sh);
+    if (((old >> sh) & 0xFFu) == MM_MODE_DEAD) return;
+    atomicSub(&tot[pool.bin[slot]], 1u);
+    atomicAdd(&tot[dead_bin], 1u);
+    pool.bin[slot] = (uint16_t)dead_bin;
+    atomicAdd(n_taken, 1u);
+  }
+}
+
 // ActiveUser.in_queue?/1 (models/active_user.ex:33-44), batched.
 __global__ void k_lookup(uint32_t n, const uint64_t* __restrict__ id, ActiveView act, uint8_t* __restrict__ out) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;

@@ -958,6 +958,27 @@ int mm_remove(mm_engine* e, uint32_t n, const uint64_t* id, uint32_t* n_removed)
   return MM_OK;
 }
 
+int mm_take(mm_engine* e, uint32_t n, const uint64_t* id, uint32_t* n_taken) {
+  if (n_taken) *n_taken = 0;
+  if (!e || (n && !id)) return MM_E_ARG;
+  if (!e->use_active) return MM_E_STATE;
+  if (n == 0) return MM_OK;
+  std::lock_guard<std::mutex> lk(e->mu);
+  CK(cudaSetDevice(e->device));
+  int rc = ensure_enq_scratch(e, n);
+  if (rc) return rc;
+  const Pool& p = e->pool[e->cur];
+  CK(cudaMemcpyAsync(e->d_in_id, id, (size_t)n * 8, cudaMemcpyHostToDevice, e->stream));
+  CK(cudaMemsetAsync(e->d_small, 0, 16, e->stream));
+  k_take<<<(n + 255) / 256, 256, 0, e->stream>>>(n, e->d_in_id, act_view(e), p.v, (uint32_t)pool_slots(e), e->gen, e->K,
+                                                 p.m.tot, e->d_small + 2);
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(e->h_small, e->d_small, 16, cudaMemcpyDeviceToHost, e->stream));
+  CK(cudaStreamSynchronize(e->stream));
+  if (n_taken) *n_taken = e->h_small[2];
+  return MM_OK;
+}
+
 int mm_remove_packed(mm_engine* e, uint32_t n, const uint32_t* handle, uint32_t* n_removed) {
   if (n_removed) *n_removed = 0;
   if (!e || (n && !handle)) return MM_E_ARG;

@@ -178,6 +178,13 @@ class Engine:
         self._check(self.lib.mm_remove(self.h, len(ids), _p(ids), C.byref(nr)), "mm_remove")
         return nr.value
 
+    def take(self, ids):
+        """Queued players matched outside this engine's tick leave the pool but stay active (mm_take). -> count"""
+        ids = np.ascontiguousarray(ids, np.uint64)
+        nt = C.c_uint32(0)
+        self._check(self.lib.mm_take(self.h, len(ids), _p(ids), C.byref(nt)), "mm_take")
+        return nt.value
+
     def in_queue(self, ids):
         ids = np.ascontiguousarray(ids, np.uint64)
         out = np.empty(len(ids), np.uint8)

@@ -138,6 +138,14 @@ class OracleEngine:
                 n += 1
         return n
 
+    def take(self, ids):
+        """mm_take: leave the pool, stay in the active set."""
+        ids = np.asarray(ids, np.uint64)
+        hit = np.isin(self.q[0], ids)
+        self.q = [a[~hit] for a in self.q]
+        self.alive = self.alive[~hit]
+        return int(hit.sum())
+
     def in_queue(self, ids):
         return np.array([p in self.active for p in np.asarray(ids, np.uint64).tolist()], bool)
 
