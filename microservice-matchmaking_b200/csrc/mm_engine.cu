@@ -11,6 +11,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <new>
@@ -59,6 +60,7 @@ struct mm_engine {
   uint32_t* d_seg_L = nullptr;
   uint16_t* d_bin_seg = nullptr;  // [Kp] bin -> (mode, group) segment
   uint32_t min_L = 1;
+  uint32_t max_nb = 1;  // most sort keys any one (mode, group) partition has
 
   // pool (double buffered) + snapshot
   uint32_t capacity = 0;
@@ -295,6 +297,8 @@ int build_tables(mm_engine* e) {
     for (uint32_t g = 0; g < G; ++g) { seg_lo[m * G + g] = m * e->stride + first[g]; seg_L[m * G + g] = L; }
   }
   seg_lo[e->n_segs] = e->K;
+  e->max_nb = 1;
+  for (uint32_t sgi = 0; sgi < e->n_segs; ++sgi) e->max_nb = std::max(e->max_nb, seg_lo[sgi + 1] - seg_lo[sgi]);
   std::vector<uint16_t> bin_seg(e->Kp, 0);
   for (uint32_t sgi = 0; sgi < e->n_segs; ++sgi)
     for (uint32_t b = seg_lo[sgi]; b < seg_lo[sgi + 1]; ++b) bin_seg[b] = (uint16_t)sgi;
@@ -464,7 +468,7 @@ PlaceArgs place_args(mm_engine* e, bool want_seq) {
   const Pool& p = e->pool[e->cur];
   PlaceArgs a{};
   a.bins16 = p.v.bin; a.ids = p.v.id; a.meta = p.m;
-  a.K = e->K; a.Kp = e->Kp; a.R = tick_rows(e); a.stages = e->place_stages; a.fast_ok = e->rank_impl == 3;
+  a.K = e->K; a.Kp = e->Kp; a.R = tick_rows(e); a.stages = e->place_stages; a.fast_ok = e->rank_impl == 3; a.max_nb = e->max_nb;
   a.seg_bin_lo = e->d_seg_bin_lo; a.bin_seg = e->d_bin_seg; a.M = e->d_M; a.P = e->d_P;
   a.outbase = e->d_outbase; a.binlim = e->d_binlim; a.members = e->d_members;
   a.src_idx = want_seq ? e->d_src_idx : nullptr;
@@ -490,7 +494,7 @@ int tick_phase_a(mm_engine* e) {
   CK(cudaMemsetAsync(e->d_ctr, 0, sizeof(TickCtr), e->stream));
   CK(cudaEventRecord(e->ev[0], e->stream));
   const uint32_t rows = tick_rows(e);
-  k_hist<512><<<rows, 512, hist_smem_bytes(e->Kp), e->stream>>>(p.v.bin, p.m, e->n_segs, rows, e->Kp, e->d_seg_bin_lo, e->d_M);
+  k_hist<512><<<rows, 512, hist_smem_bytes(e->max_nb), e->stream>>>(p.v.bin, p.m, e->n_segs, rows, e->Kp, e->max_nb, e->d_seg_bin_lo, e->d_M);
   CK(cudaEventRecord(e->ev[1], e->stream));
   k_colscan<<<(e->K + 31) / 32 + 1, kScanBlock, colscan_smem(e), e->stream>>>(rows, e->d_M, e->d_P, tail_args(e));
   CK(cudaGetLastError());
@@ -500,7 +504,7 @@ int tick_phase_a(mm_engine* e) {
 int tick_phase_b(mm_engine* e, bool want_seq) {
   CK(cudaEventRecord(e->ev[2], e->stream));
   const uint32_t rows = tick_rows(e);
-  k_place<512><<<rows, 512, place_smem_bytes(e->Kp, e->place_stages), e->stream>>>(place_args(e, want_seq),
+  k_place<512><<<rows, 512, place_smem_bytes(e->max_nb, e->place_stages), e->stream>>>(place_args(e, want_seq),
                                                                                   e->pool[e->cur].m.fill, e->n_segs);
   CK(cudaEventRecord(e->ev[3], e->stream));
   k_epilogue<512><<<std::max<uint32_t>(1, std::min<uint32_t>((uint32_t)e->n_sms, 2 * rows)), 512, 0, e->stream>>>(epi_args(e, want_seq, true));
@@ -705,10 +709,12 @@ int mm_create(const mm_config* cfg, mm_engine** out) {
     // overlap the other's work), else one.  Function attributes are process-global:
     // every kernel gets the device's opt-in maximum.
     const size_t static_smem = sizeof(Geo) + 512;
-    for (uint32_t st = 3; st >= 2 && !e->place_stages; --st)
-      if (2 * (place_smem_bytes(e->Kp, st) + static_smem + 1024) <= e->smem_sm) { e->place_stages = st; e->rows_per_sm = 2; }
+    uint32_t st_max = 2;  // measured: 2 stages x 2 CTAs per SM beat 3 x 2 by ~1 us (MM_PLACE_STAGES=3 to compare)
+    if (const char* ev = std::getenv("MM_PLACE_STAGES")) st_max = (uint32_t)std::min(3, std::max(2, std::atoi(ev)));  // tuning override
+    for (uint32_t st = st_max; st >= 2 && !e->place_stages; --st)
+      if (2 * (place_smem_bytes(e->max_nb, st) + static_smem + 1024) <= e->smem_sm) { e->place_stages = st; e->rows_per_sm = 2; }
     for (uint32_t st = kMaxStages; st >= 1 && !e->place_stages; --st)  // huge key domains: down to a single stage
-      if (place_smem_bytes(e->Kp, st) + static_smem + 1024 <= e->smem_optin) { e->place_stages = st; e->rows_per_sm = 1; }
+      if (place_smem_bytes(e->max_nb, st) + static_smem + 1024 <= e->smem_optin) { e->place_stages = st; e->rows_per_sm = 1; }
     if (!e->place_stages || colscan_smem(e) + static_smem + 1024 > e->smem_optin) {
       std::snprintf(e->last_err, sizeof(e->last_err), "key domain too large for shared memory: %u bins", e->Kp);
       return bail(MM_E_ARG);
@@ -751,7 +757,7 @@ int mm_create(const mm_config* cfg, mm_engine** out) {
     return bail(MM_E_CUDA);
   if ((rc = alloc_tick_scratch(e))) return bail(rc);
   {
-    size_t sz = std::max(hist_smem_bytes(e->Kp), place_smem_bytes(e->Kp, e->place_stages));
+    size_t sz = std::max(hist_smem_bytes(e->max_nb), place_smem_bytes(e->max_nb, e->place_stages));
     sz = std::max<size_t>(sz, std::max<size_t>((size_t)kEpiScratchWords * 4, colscan_smem(e)));
     int coop = 0, nb = 0;
     cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, e->device);

@@ -33,13 +33,13 @@ namespace mm {
 
 template <int BLOCK>
 __global__ void __launch_bounds__(BLOCK, 2)
-    k_hist(const uint16_t* __restrict__ bins16, const PoolMeta meta, uint32_t n_segs, uint32_t R, uint32_t Kp,
+    k_hist(const uint16_t* __restrict__ bins16, const PoolMeta meta, uint32_t n_segs, uint32_t R, uint32_t Kp, uint32_t max_nb,
            const uint32_t* __restrict__ seg_bin_lo, uint32_t* __restrict__ M) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ Geo geo;
   __shared__ uint32_t s_gtmp[33];
   geo_build<BLOCK>(geo, meta.fill, n_segs, R, s_gtmp);
-  hist_body<BLOCK>(smem_raw, geo, bins16, meta, Kp, seg_bin_lo, M);
+  hist_body<BLOCK>(smem_raw, geo, bins16, meta, Kp, max_nb, seg_bin_lo, M);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -85,7 +85,7 @@ __global__ void __launch_bounds__(BLOCK, 2) k_tick(const TickArgs a) {
   };
   stamp(0);
   geo_build<BLOCK>(geo, a.place.meta.fill, a.tail.n_segs, R, s_gtmp);
-  if (is_row) hist_body<BLOCK>(smem_raw, geo, a.src.bin, a.place.meta, Kp, a.tail.seg_bin_lo, a.M);
+  if (is_row) hist_body<BLOCK>(smem_raw, geo, a.src.bin, a.place.meta, Kp, a.place.max_nb, a.tail.seg_bin_lo, a.M);
   if (blockIdx.x == G - 1) {  // the last CTA: helper 0's job when there are helpers, else after its own row
     colscan_tail_body(scratch, a.tail);
     if (threadIdx.x == 0) {

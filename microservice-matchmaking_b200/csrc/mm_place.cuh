@@ -26,22 +26,24 @@ namespace mm {
 //    smaller tile position; ids are scattered straight from registers.  `heavy` ticks (some bin expects > 8
 //    players per tile) aggregate the nodes per warp first (__match_any_sync) so a list never exceeds 64 nodes.
 //
-// Shared memory: ring_ids[stages][kTile] | ring_bins[stages][kTile] | mbarriers + tile descriptors | cnt[Kp] |
+// Shared memory: ring_ids[stages][kTile] | ring_bins[stages][kTile] | mbarriers + tile descriptors | cnt[keys of one partition] |
 //                union { LIST: head[kHeadSlots] node[kTile] nbin[kTile] ; FAST: wcnt[16][256] u16, sslot[kTile] }.
 // ---------------------------------------------------------------------------------------
 constexpr uint32_t kHeadSlots = 4096;
 constexpr uint32_t NW16 = 16;  // warps per 512-thread CTA
 constexpr uint32_t kPlaceUnionBytes = NW16 * 256 * 4 + NW16 * 256 * 2 + 1024 + kTile * 4;  // FAST: 16 + 8 + 1 + 8 KB >= LIST: 28 KB
 
-__host__ __device__ constexpr size_t place_smem_bytes(uint32_t Kp, uint32_t stages) {
-  return (size_t)stages * kTileBytes + 128 + (size_t)((Kp + 3) & ~3u) * 4 + kPlaceUnionBytes + sizeof(DescCache) + 16;
+// max_nb = most sort keys any one partition has: the slot counters are kept per partition, not for the whole key domain
+__host__ __device__ constexpr uint32_t place_cnt_cap(uint32_t max_nb) { return (max_nb > 1024u ? max_nb : 1024u); }
+__host__ __device__ constexpr size_t place_smem_bytes(uint32_t max_nb, uint32_t stages) {
+  return (size_t)stages * kTileBytes + 128 + (size_t)((place_cnt_cap(max_nb) + 3) & ~3u) * 4 + kPlaceUnionBytes + sizeof(DescCache) + 16;
 }
 
 struct PlaceArgs {
   const uint16_t* bins16;
   const uint64_t* ids;
   PoolMeta meta;
-  uint32_t K, Kp, R, stages, fast_ok;
+  uint32_t K, Kp, R, stages, fast_ok, max_nb;
   const uint32_t* seg_bin_lo;
   const uint16_t* bin_seg;
   const uint32_t* M;     // [rows][Kp] row histograms (raw counts)
@@ -69,8 +71,9 @@ __device__ __forceinline__ void place_body(unsigned char* smem_raw, const Geo& g
   uint32_t* s_b0 = s_sg + kMaxStages;                                                        // [kMaxStages] its first bin
   uint32_t* s_b1 = s_b0 + kMaxStages;                                                        // [kMaxStages] its end bin
   uint32_t* s_misc = s_b1 + kMaxStages;                                                      // [8]
-  uint32_t* cnt = reinterpret_cast<uint32_t*>(smem_raw + (size_t)stages * kTileBytes + 128); // [Kp]
-  unsigned char* uni = reinterpret_cast<unsigned char*>(cnt + ((Kp + 3) & ~3u));
+  uint32_t* cnt = reinterpret_cast<uint32_t*>(smem_raw + (size_t)stages * kTileBytes + 128); // [max_nb] of the current partition
+  const uint32_t cnt_cap = place_cnt_cap(a.max_nb);
+  unsigned char* uni = reinterpret_cast<unsigned char*>(cnt + ((cnt_cap + 3) & ~3u));
   DescCache& dc = *reinterpret_cast<DescCache*>(uni + kPlaceUnionBytes);
   // LIST
   uint32_t* head = reinterpret_cast<uint32_t*>(uni);           // [kHeadSlots]
@@ -117,32 +120,14 @@ __device__ __forceinline__ void place_body(unsigned char* smem_raw, const Geo& g
   __syncthreads();
   if (tid == 0)
     for (uint32_t t = 0; t < stages && t < n_tiles; ++t) issue(t, t);
-  if (n_tiles) {
-    // slot counters of the bins this row can meet: cnt[b] = slot of the (row, bin) cell's first player; bit 31
-    // flags a cell that reaches past the bin's matched prefix (only those players look at binlim).
-    const uint32_t p_first = geo_seg_of(g, s0), p_last = geo_seg_of(g, s1 - 1);
-    const uint32_t blo = a.seg_bin_lo[p_first], bhi = a.seg_bin_lo[p_last + 1];
-    const bool scanned = geo_use_colscan(g);  // (uniform) the column-scan phase ran: P holds the row prefixes
-    for (uint32_t i = blo + tid; i < bhi; i += BLOCK) {
-      uint32_t rlo = 0, rhi = 0, v = 0;
-      if (geo_rows_of(g, a.bin_seg[i], rlo, rhi) && row >= rlo && row <= rhi) {
-        // __ldcg: these arrays are produced earlier in the same (fused) launch by other SMs
-        uint32_t pre = 0;
-        if (scanned) pre = __ldcg(&a.P[(size_t)row * Kp + i]);
-        else for (uint32_t r = rlo; r < row; ++r) pre += __ldcg(&a.M[(size_t)r * Kp + i]);  // few rows per partition
-        const uint32_t c = __ldcg(&a.M[(size_t)row * Kp + i]);
-        const uint32_t start = __ldcg(&a.outbase[i]) + pre;
-        v = start | ((start + c > __ldcg(&a.binlim[i])) ? 0x80000000u : 0u);
-      }
-      cnt[i] = v;
-    }
-  }
   for (uint32_t i = tid; i < kHeadSlots + NW * 128; i += BLOCK) head[i] = 0;  // LIST heads = FAST mask table; + FAST counters
   const bool heavy = __ldcg(&a.ctr->heavy) != 0;
   __syncthreads();
 
   uint32_t st = 0, parity = 0;
   uint32_t nleft = 0;  // lane 0: players of this warp's positions that stay queued
+  uint32_t wb = 0, we = 0;  // [wb, we): bins whose slot counters are loaded
+  const uint32_t row_p_last = n_tiles ? geo_seg_of(g, s1 - 1) : 0u;
   uint32_t uni_st = 0;  // (uniform) who dirtied the union region: 0 nobody (all-zero), 1 LIST, 2 FAST
   for (uint32_t t = 0; t < n_tiles; ++t) {
     if (t == dbase + kDescCap) {  // (uniform) next batch of descriptors; thread 0 is not issuing right now
@@ -156,6 +141,35 @@ __device__ __forceinline__ void place_body(unsigned char* smem_raw, const Geo& g
     mbar_wait(&full[st], parity);
     const uint32_t valid = s_nv[st];
     const uint32_t bin0 = s_b0[st], nb = s_b1[st] - bin0;
+    if (bin0 < wb || bin0 + nb > we) {
+      // (uniform) the row enters a partition whose slot counters are not loaded: load a window of whole partitions
+      // starting with this one (a row's tiles come in partition order; a row usually spans 1-3 partitions, which fit
+      // at once).  cnt[b - wb] = slot of the (row, b) cell's first player; bit 31 flags a cell that reaches past
+      // the bin's matched prefix (only those players look at binlim).
+      wb = bin0; we = bin0 + nb;
+      for (uint32_t p = s_sg[st] + 1; p <= row_p_last; ++p) {
+        const uint32_t e = a.seg_bin_lo[p + 1];
+        if (e - wb > cnt_cap) break;
+        we = e;
+      }
+      const bool scanned = geo_use_colscan(g);  // the column-scan phase ran: P holds the row prefixes
+      __syncthreads();
+      for (uint32_t i = wb + tid; i < we; i += BLOCK) {
+        uint32_t rlo = 0, rhi = 0, v = 0;
+        if (geo_rows_of(g, a.bin_seg[i], rlo, rhi) && row >= rlo && row <= rhi) {
+          // __ldcg: these arrays are produced earlier in the same (fused) launch by other SMs
+          uint32_t pre = 0;
+          if (scanned) pre = __ldcg(&a.P[(size_t)row * Kp + i]);
+          else for (uint32_t r = rlo; r < row; ++r) pre += __ldcg(&a.M[(size_t)r * Kp + i]);  // few rows per partition
+          const uint32_t c = __ldcg(&a.M[(size_t)row * Kp + i]);
+          const uint32_t start = __ldcg(&a.outbase[i]) + pre;
+          v = start | ((start + c > __ldcg(&a.binlim[i])) ? 0x80000000u : 0u);
+        }
+        cnt[i - wb] = v;
+      }
+      __syncthreads();
+    }
+    uint32_t* cntp = cnt + (bin0 - wb);  // counters of this tile's partition
     const bool fast = a.fast_ok && nb <= kFastBins;
     uint32_t lmask = 0;  // bit j: my j-th player stays queued
 
@@ -182,17 +196,39 @@ __device__ __forceinline__ void place_body(unsigned char* smem_raw, const Geo& g
         uint32_t* wm = wmask + warp * 256;
         uint16_t* wc = wcnt + warp * 256;
         const uint32_t lbit = 1u << lane;
+        if (nb > 16) {
 #pragma unroll
-        for (int j = 0; j < J; ++j) {
-          atomicOr(&wm[dg[j]], lbit);
-          __syncwarp();
-          const uint32_t peers = wm[dg[j]];
-          const uint32_t base = wc[dg[j]];
-          __syncwarp();
-          wm[dg[j]] = 0;                                    // every peer stores the same values: no leader election,
-          wc[dg[j]] = (uint16_t)(base + __popc(peers));     // no divergence
-          __syncwarp();
-          rk[j] = base + __popc(peers & lt_mask);
+          for (int j = 0; j < J; ++j) {
+            atomicOr(&wm[dg[j]], lbit);
+            __syncwarp();
+            const uint32_t peers = wm[dg[j]];
+            const uint32_t base = wc[dg[j]];
+            __syncwarp();
+            wm[dg[j]] = 0;                                    // every peer stores the same values: no leader election,
+            wc[dg[j]] = (uint16_t)(base + __popc(peers));     // no divergence
+            __syncwarp();
+            rk[j] = base + __popc(peers & lt_mask);
+          }
+        } else {
+          // a handful of keys (arrival order: ONE per partition): the 32 lanes would serialise on a few mask words,
+          // so the peers come from <= 5 ballots instead
+          const uint32_t nbits = 32u - __clz(nb);
+#pragma unroll
+          for (int j = 0; j < J; ++j) {
+            uint32_t peers = 0xFFFFFFFFu;
+#pragma unroll
+            for (uint32_t bit = 0; bit < 5; ++bit)
+              if (bit < nbits) {
+                const bool on = (dg[j] >> bit) & 1u;
+                const uint32_t bal = __ballot_sync(0xFFFFFFFFu, on);
+                peers &= on ? bal : ~bal;
+              }
+            const uint32_t base = wc[dg[j]];
+            __syncwarp();
+            wc[dg[j]] = (uint16_t)(base + __popc(peers));
+            __syncwarp();
+            rk[j] = base + __popc(peers & lt_mask);
+          }
         }
       }
       __syncthreads();  // B2: per-warp digit counts complete
@@ -216,8 +252,8 @@ __device__ __forceinline__ void place_body(unsigned char* smem_raw, const Geo& g
         const uint32_t l0 = wbase + incl - both, l1 = l0 + lo;  // tile-local sorted position of the digits' first players
         const uint32_t d0 = 2 * tid, d1 = d0 + 1;
         uint32_t fl = 0;
-        if (d0 < nb) { const uint32_t base = cnt[bin0 + d0]; cnt[bin0 + d0] = base + lo; lgd[d0] = (((base & 0x7FFFFFFFu) - l0) & 0x7FFFFFFFu) | (base & 0x80000000u); if (lo) fl |= base; }
-        if (d1 < nb) { const uint32_t base = cnt[bin0 + d1]; cnt[bin0 + d1] = base + hi; lgd[d1] = (((base & 0x7FFFFFFFu) - l1) & 0x7FFFFFFFu) | (base & 0x80000000u); if (hi) fl |= base; }
+        if (d0 < nb) { const uint32_t base = cntp[d0]; cntp[d0] = base + lo; lgd[d0] = (((base & 0x7FFFFFFFu) - l0) & 0x7FFFFFFFu) | (base & 0x80000000u); if (lo) fl |= base; }
+        if (d1 < nb) { const uint32_t base = cntp[d1]; cntp[d1] = base + hi; lgd[d1] = (((base & 0x7FFFFFFFu) - l1) & 0x7FFFFFFFu) | (base & 0x80000000u); if (hi) fl |= base; }
         if (fl >> 31) s_misc[2] = 1;   // some player of this tile sits in a cell that reaches past its bin's matched prefix
         if (d0 == nb) s_misc[1] = l0;  // live players of the tile (the dead digit sorts last)
         if (d1 == nb) s_misc[1] = l1;
@@ -294,7 +330,7 @@ __device__ __forceinline__ void place_body(unsigned char* smem_raw, const Geo& g
           const uint32_t pos = j * BLOCK + tid;
           snap[j] = 0;
           if (bin[j] < K) {
-            snap[j] = cnt[bin[j]];
+            snap[j] = cntp[bin[j] - bin0];
             const uint32_t prev = atomicExch(&head[bin[j] & (kHeadSlots - 1)], (epoch << 12) | pos);
             const uint32_t pn = ((prev >> 12) == epoch) ? (prev & 0xFFFu) : 0xFFFu;
             node[pos] = pn | (bin[j] << 12);
@@ -318,7 +354,7 @@ __device__ __forceinline__ void place_body(unsigned char* smem_raw, const Geo& g
             }
             slot[j] = (snap[j] & 0x7FFFFFFFu) + lower;
             flag[j] = (snap[j] >> 31) != 0;
-            if (lower == 0) cnt[bin[j]] = snap[j] + total;  // the bin's earliest player of the tile
+            if (lower == 0) cntp[bin[j] - bin0] = snap[j] + total;  // the bin's earliest player of the tile
           }
         }
       } else {
@@ -333,7 +369,7 @@ __device__ __forceinline__ void place_body(unsigned char* smem_raw, const Geo& g
           isl[j] = (lane == leader[j]) && (bin[j] < K);
           snap[j] = 0;
           if (isl[j]) {
-            snap[j] = cnt[bin[j]];
+            snap[j] = cntp[bin[j] - bin0];
             const uint32_t prev = atomicExch(&head[bin[j] & (kHeadSlots - 1)], (epoch << 12) | pos);
             const uint32_t pn = ((prev >> 12) == epoch) ? (prev & 0xFFFu) : 0xFFFu;
             node[pos] = pn | ((uint32_t)__popc(mask) << 12);
@@ -357,7 +393,7 @@ __device__ __forceinline__ void place_body(unsigned char* smem_raw, const Geo& g
               cur = nd & 0xFFFu;
             }
             bg = snap[j] + lower;
-            if (lower == 0) cnt[bin[j]] = snap[j] + total;
+            if (lower == 0) cntp[bin[j] - bin0] = snap[j] + total;
           }
           bg = __shfl_sync(0xFFFFFFFFu, bg, leader[j]);
           slot[j] = (bg & 0x7FFFFFFFu) + rankw[j];
