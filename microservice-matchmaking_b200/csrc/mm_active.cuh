@@ -194,6 +194,8 @@ __global__ void __launch_bounds__(512) k_enq_alloc(uint32_t n_segs, uint32_t nbl
     for (uint32_t k = lane; k < want - have; k += 32) meta.chunk_tab[(size_t)p * meta.max_ch + have + k] = bump + s_need[p] + k;
     if (lane == 0) meta.fill[p] = s_new[p];
   }
+  if (meta.chist)  // chunks come from a bump allocator that restarts every tick: a new chunk starts with an empty histogram
+    for (size_t i = (size_t)bump * kChunkHist + tid; i < (size_t)(bump + total) * kChunkHist; i += 512) meta.chist[i] = 0;
   __syncthreads();
   if (tid == 0) *meta.bump = bump + total;
 }
@@ -207,7 +209,8 @@ __global__ void __launch_bounds__(256) k_enq_append(uint32_t base, uint32_t n, c
                                                     ActiveView act, const uint64_t* __restrict__ hslot,
                                                     const uint8_t* __restrict__ code, const uint16_t* __restrict__ part,
                                                     uint32_t n_segs, uint32_t nblk, const uint32_t* __restrict__ blockbase,
-                                                    PoolView pool, PoolMeta meta, uint32_t gen, uint32_t seq_base, BinMap bm) {
+                                                    PoolView pool, PoolMeta meta, uint32_t gen, uint32_t seq_base, BinMap bm,
+                                                    const uint32_t* __restrict__ seg_bin_lo) {
   extern __shared__ __align__(16) uint32_t s_dyn[];  // wc[8][n_segs + 1] u16 | bbase[n_segs] u32
   uint16_t* wc = reinterpret_cast<uint16_t*>(s_dyn);
   const uint32_t S1 = n_segs + 1;                     // digit n_segs = not a winner
@@ -256,6 +259,7 @@ __global__ void __launch_bounds__(256) k_enq_append(uint32_t base, uint32_t n, c
     pool.bin[slot] = (uint16_t)bin_of(bm, bm.lut, rating[i], mode[i]);  // the tick's sort key, derived once at ingest
     pool.seq[slot] = seq_base + i;
     atomicAdd(&meta.tot[pool.bin[slot]], 1u);  // bin totals stay current: the tick needs no counting pass for them
+    if (meta.chist) atomicAdd(&meta.chist[(size_t)(slot / kTile) * kChunkHist + (pool.bin[slot] - seg_bin_lo[p])], 1u);
     if (act.on()) *act.val(hslot[i]) = ((unsigned long long)gen << 32) | slot;
   }
 }
@@ -263,8 +267,19 @@ __global__ void __launch_bounds__(256) k_enq_append(uint32_t base, uint32_t n, c
 // ActiveUser.remove_user/1 (models/active_user.ex:57-66), batched.  A player still
 // queued is tombstoned in the pool (mode byte = DEAD) so the next tick drops it the way
 // remove_inactive_players/1 (search/worker.ex:267-280) filters it.
-__global__ void k_remove(uint32_t n, const uint64_t* __restrict__ id, ActiveView act, PoolView pool, uint32_t n_slots,
-                         uint32_t gen, uint32_t dead_bin, uint32_t* __restrict__ tot, uint32_t* __restrict__ n_removed) {
+// bookkeeping of a queued player that turns "removed": bin totals, chunk histogram, sort key
+__device__ __forceinline__ void pool_mark_dead(PoolView pool, const PoolMeta& meta, uint32_t slot, uint32_t dead_bin,
+                                               const uint16_t* __restrict__ bin_seg, const uint32_t* __restrict__ seg_bin_lo) {
+  const uint32_t b = pool.bin[slot];
+  atomicSub(&meta.tot[b], 1u);
+  atomicAdd(&meta.tot[dead_bin], 1u);
+  if (meta.chist) atomicSub(&meta.chist[(size_t)(slot / kTile) * kChunkHist + (b - seg_bin_lo[bin_seg[b]])], 1u);
+  pool.bin[slot] = (uint16_t)dead_bin;
+}
+
+__global__ void k_remove(uint32_t n, const uint64_t* __restrict__ id, ActiveView act, PoolView pool, PoolMeta meta,
+                         uint32_t n_slots, uint32_t gen, uint32_t dead_bin, const uint16_t* __restrict__ bin_seg,
+                         const uint32_t* __restrict__ seg_bin_lo, uint32_t* __restrict__ n_removed) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n || !act.on()) return;
   const uint64_t pid = id[i];
@@ -282,9 +297,7 @@ __global__ void k_remove(uint32_t n, const uint64_t* __restrict__ id, ActiveView
   const uint32_t slot = (uint32_t)v, g = (uint32_t)(v >> 32);
   if (v < kPending && g == gen && slot < n_slots && pool.id[slot] == pid) {
     pool.mode[slot] = MM_MODE_DEAD;
-    atomicSub(&tot[pool.bin[slot]], 1u);
-    atomicAdd(&tot[dead_bin], 1u);
-    pool.bin[slot] = (uint16_t)dead_bin;
+    pool_mark_dead(pool, meta, slot, dead_bin, bin_seg, seg_bin_lo);
   }
   atomicAdd(n_removed, 1u);
 }
@@ -292,8 +305,9 @@ __global__ void k_remove(uint32_t n, const uint64_t* __restrict__ id, ActiveView
 // mm_take: queued players matched OUTSIDE this engine's tick (the cross-group boundary pass, shard.py) leave the pool
 // but stay in the active set — exactly like members of an emitted lobby, who are "in the queue" until the lobby stage
 // removes them (game-lobby/worker.ex:80).
-__global__ void k_take(uint32_t n, const uint64_t* __restrict__ id, ActiveView act, PoolView pool, uint32_t n_slots,
-                       uint32_t gen, uint32_t dead_bin, uint32_t* __restrict__ tot, uint32_t* __restrict__ n_taken) {
+__global__ void k_take(uint32_t n, const uint64_t* __restrict__ id, ActiveView act, PoolView pool, PoolMeta meta,
+                       uint32_t n_slots, uint32_t gen, uint32_t dead_bin, const uint16_t* __restrict__ bin_seg,
+                       const uint32_t* __restrict__ seg_bin_lo, uint32_t* __restrict__ n_taken) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n || !act.on()) return;
   const uint64_t pid = id[i];
@@ -307,9 +321,7 @@ __global__ void k_take(uint32_t n, const uint64_t* __restrict__ id, ActiveView a
     uint32_t* mw = reinterpret_cast<uint32_t*>(pool.mode + word);
     const uint32_t old = atomicOr(mw, 0xFFu << sh);
     if (((old >> sh) & 0xFFu) == MM_MODE_DEAD) return;
-    atomicSub(&tot[pool.bin[slot]], 1u);
-    atomicAdd(&tot[dead_bin], 1u);
-    pool.bin[slot] = (uint16_t)dead_bin;
+    pool_mark_dead(pool, meta, slot, dead_bin, bin_seg, seg_bin_lo);
     atomicAdd(n_taken, 1u);
   }
 }

@@ -13,6 +13,7 @@ constexpr uint32_t kMaxRows = 2048;   // rows (CTAs) of the histogram matrix
 constexpr uint32_t kMaxStages = 4;    // depth of the (bin, id) shared-memory ring
 constexpr uint32_t kTileBytes = kTile * (8 + 2);
 constexpr uint32_t kMaxSegs = MM_MAX_GROUPS * MM_MAX_MODES;  // (mode, group) partitions
+constexpr uint32_t kChunkHist = 256;  // counters per chunk histogram row
 constexpr uint32_t kFastBins = 255;   // partitions with <= 255 bins rank with warp ballots (8-bit digit + "dead")
 constexpr uint64_t kEmptyKey = 0xFFFFFFFFFFFFFFFFull;
 constexpr uint64_t kTombKey = 0xFFFFFFFFFFFFFFFEull;
@@ -37,6 +38,8 @@ struct PoolMeta {
   uint32_t* chunk_tab;  // [n_segs][max_ch] physical chunk of the partition's k-th chunk
   uint32_t* bump;       // chunks handed out so far
   uint32_t* tot;        // [K + 1] players per bin (K = removed while queued), kept up to date by ingest / remove / tick
+  uint32_t* chist;      // [chunks][kChunkHist] live players of the chunk per key of its partition (key - first key of the
+                        // partition), kept up to date by ingest / remove / tick; null when a partition has > 255 keys
   uint32_t max_ch;
 };
 
@@ -60,11 +63,13 @@ struct SegInfo {        // one (mode, group) partition, written by the scan tail
 };
 
 struct TickCtr {
-  uint32_t gbar;  // grid barrier of the fused tick kernel
+  uint32_t gbar;  // grid barrier of the fused tick kernel (zero at launch: re-armed by the previous tick, see k_tick)
+  uint32_t done;  // CTAs that finished the fused tick
   uint32_t n_lobbies, n_matched, n_alive, n_dead, n_resid;
   uint32_t n_tiles;
   uint32_t heavy;  // some bin expects > 8 players per tile: the list ranking uses warp-aggregated nodes
-  unsigned long long t[8];  // fused kernel: %globaltimer (ns) at phase boundaries, CTA 0; [6],[7]: max over CTAs
+  unsigned long long t[12]; // fused kernel: %globaltimer (ns) at phase boundaries, CTA 0; [6],[7]: max over CTAs;
+                            // [8] last row done with phase 1, [9] min CTA start, [10] last row done placing
 };
 
 // Tile geometry of a tick, rebuilt by every CTA from the partition fills: the pool's tiles in (partition, chunk) order

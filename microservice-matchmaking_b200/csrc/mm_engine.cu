@@ -102,7 +102,9 @@ struct mm_engine {
   uint32_t* d_emit_seq = nullptr;
   uint32_t max_lobbies = 0;
   uint32_t* d_rescnt = nullptr;
-  TickCtr* d_ctr = nullptr;
+  TickCtr* d_ctr2 = nullptr;  // two counter blocks, used alternately (the fused kernel re-arms the other one)
+  TickCtr* d_ctr = nullptr;   // the block of the current / last tick
+  int ctr_idx = 0;
   TickCtr* h_ctr = nullptr;  // pinned
 
   // enqueue scratch (grown on demand)
@@ -164,6 +166,11 @@ int alloc_pool(mm_engine* e, Pool& p) {
   CK(cudaMalloc(&p.m.chunk_tab, (size_t)e->n_segs * e->n_chunks * 4));
   CK(cudaMalloc(&p.m.bump, 4));
   CK(cudaMalloc(&p.m.tot, ((size_t)e->Kp + 1) * 4));
+  p.m.chist = nullptr;
+  if (e->max_nb <= kFastBins) {  // per-chunk key histograms: the tick skips its counting pass over the pool
+    CK(cudaMalloc(&p.m.chist, (size_t)e->n_chunks * kChunkHist * 4));
+    CK(cudaMemset(p.m.chist, 0, (size_t)e->n_chunks * kChunkHist * 4));
+  }
   CK(cudaMemset(p.m.tot, 0, ((size_t)e->Kp + 1) * 4));
   CK(cudaMemset(p.m.fill, 0, (size_t)e->n_segs * 4));
   CK(cudaMemset(p.m.bump, 0, 4));
@@ -174,7 +181,7 @@ int alloc_pool(mm_engine* e, Pool& p) {
 }
 void free_pool(Pool& p) {
   cudaFree(p.v.id); cudaFree(p.v.rating); cudaFree(p.v.mode); cudaFree(p.v.tsize); cudaFree(p.v.ts); cudaFree(p.v.bin);
-  cudaFree(p.v.seq); cudaFree(p.m.fill); cudaFree(p.m.chunk_tab); cudaFree(p.m.bump); cudaFree(p.m.tot);
+  cudaFree(p.v.seq); cudaFree(p.m.fill); cudaFree(p.m.chunk_tab); cudaFree(p.m.bump); cudaFree(p.m.tot); cudaFree(p.m.chist);
   p = Pool{};
 }
 int copy_pool(mm_engine* e, Pool& dst, const Pool& src) {
@@ -190,6 +197,8 @@ int copy_pool(mm_engine* e, Pool& dst, const Pool& src) {
   CK(cudaMemcpyAsync(dst.m.chunk_tab, src.m.chunk_tab, (size_t)e->n_segs * e->n_chunks * 4, cudaMemcpyDeviceToDevice, e->stream));
   CK(cudaMemcpyAsync(dst.m.bump, src.m.bump, 4, cudaMemcpyDeviceToDevice, e->stream));
   CK(cudaMemcpyAsync(dst.m.tot, src.m.tot, ((size_t)e->Kp + 1) * 4, cudaMemcpyDeviceToDevice, e->stream));
+  if (src.m.chist)
+    CK(cudaMemcpyAsync(dst.m.chist, src.m.chist, (size_t)e->n_chunks * kChunkHist * 4, cudaMemcpyDeviceToDevice, e->stream));
   dst.n = src.n;
   return MM_OK;
 }
@@ -411,7 +420,7 @@ int enq_chunk(mm_engine* e, uint32_t base, uint32_t cnt, const uint64_t* id, con
   const size_t smem = ((size_t)(8 * (e->n_segs + 1) + 1) / 2 + e->n_segs) * 4;
   k_enq_append<<<nblk, 256, smem, e->stream>>>(base, cnt, id, rating, mode, ts, e->d_mode_tsize, av, e->d_hslot, e->d_code,
                                                e->d_part, e->n_segs, nblk, e->d_blockhist, p.v, p.m, e->gen, e->seq_next,
-                                               bin_map(e));
+                                               bin_map(e), e->d_seg_bin_lo);
   CK(cudaGetLastError());
   return MM_OK;
 }
@@ -483,6 +492,7 @@ EpiArgs epi_args(mm_engine* e, bool want_seq, bool headers) {
   a.R = tick_rows(e); a.new_gen = next_gen(e); a.n_segs = e->n_segs; a.n_groups = e->cfg.n_groups; a.Kp = e->Kp;
   a.write_headers = headers ? 1u : 0u;
   a.rescnt = e->d_rescnt; a.left_bits = e->d_left_bits; a.act = act_view(e); a.seg = e->d_seg; a.seg_L = e->d_seg_L;
+  a.seg_bin_lo = e->d_seg_bin_lo;
   a.hdr = e->d_hdr; a.src_idx = want_seq ? e->d_src_idx : nullptr; a.emit_seq = want_seq ? e->d_emit_seq : nullptr;
   a.ctr = e->d_ctr;
   return a;
@@ -507,6 +517,8 @@ int tick_phase_b(mm_engine* e, bool want_seq) {
   k_place<512><<<rows, 512, place_smem_bytes(e->max_nb, e->place_stages), e->stream>>>(place_args(e, want_seq),
                                                                                   e->pool[e->cur].m.fill, e->n_segs);
   CK(cudaEventRecord(e->ev[3], e->stream));
+  if (e->pool[e->cur ^ 1].m.chist)  // the compacted pool's chunk histograms start empty (the fused tick's helper CTAs do this)
+    CK(cudaMemsetAsync(e->pool[e->cur ^ 1].m.chist, 0, (size_t)e->n_chunks * kChunkHist * 4, e->stream));
   k_epilogue<512><<<std::max<uint32_t>(1, std::min<uint32_t>((uint32_t)e->n_sms, 2 * rows)), 512, 0, e->stream>>>(epi_args(e, want_seq, true));
   CK(cudaGetLastError());
   CK(cudaEventRecord(e->ev[4], e->stream));
@@ -526,10 +538,12 @@ int tick_fused(mm_engine* e, bool want_seq) {
   a.R = rows;
   a.M = e->d_M;
   a.P = e->d_P;
+  e->ctr_idx ^= 1;
+  e->d_ctr = e->d_ctr2 + e->ctr_idx;  // armed (barrier / stamps zero) by the previous fused tick or by mm_create
   a.tail = tail_args(e);
   a.place = place_args(e, want_seq);
   a.epi = epi_args(e, want_seq, want_seq || helpers == 0);  // emission order needs the placement's src_idx first
-  CK(cudaMemsetAsync(e->d_ctr, 0, sizeof(TickCtr), e->stream));
+  a.next_ctr = e->d_ctr2 + (e->ctr_idx ^ 1);
   CK(cudaEventRecord(e->ev[0], e->stream));
   void* params[] = {&a};
   CK(cudaLaunchCooperativeKernel((const void*)k_tick<512>, dim3(rows + helpers), dim3(512), params, e->tick_smem, e->stream));
@@ -553,6 +567,10 @@ int tick_commit(mm_engine* e, uint32_t n, mm_tick_stats* stats) {
     st.scan_us = (float)(c.t[2] - c.t[1]) * 1e-3f;
     st.place_us = (float)(c.t[3] - c.t[2]) * 1e-3f;
     st.epilogue_us = (float)(c.t[6] - c.t[3]) * 1e-3f;  // until the last CTA is done
+    if (std::getenv("MM_TRACE"))
+      std::fprintf(stderr, "[mm] t0=0 rows_p1_done=%.1f tail_done=%.1f bar1=%.1f place_start=%.1f rows_place_done=%.1f bar2=%.1f end=%.1f us\n",
+                   (c.t[8] - c.t[0]) * 1e-3, (c.t[5] - c.t[0]) * 1e-3, (c.t[1] - c.t[0]) * 1e-3, (c.t[2] - c.t[0]) * 1e-3,
+                   (c.t[10] - c.t[0]) * 1e-3, (c.t[3] - c.t[0]) * 1e-3, (c.t[6] - c.t[0]) * 1e-3);
   } else {
     CK(cudaEventElapsedTime(&ms, e->ev[0], e->ev[1]));
     st.hist_us = ms * 1000.f;
@@ -749,10 +767,12 @@ int mm_create(const mm_config* cfg, mm_engine** out) {
       !A((void**)&e->d_binlim, (e->Kp + 1) * 4) || !A((void**)&e->d_seg, e->n_segs * sizeof(SegInfo)) ||
       !A((void**)&e->d_members, cap * 8) || !A((void**)&e->d_src_idx, cap * 4) ||
       !A((void**)&e->d_hdr, (size_t)e->max_lobbies * sizeof(mm_lobby_hdr)) ||
-      !A((void**)&e->d_emit_seq, (size_t)e->max_lobbies * 4) || !A((void**)&e->d_ctr, sizeof(TickCtr)) ||
+      !A((void**)&e->d_emit_seq, (size_t)e->max_lobbies * 4) || !A((void**)&e->d_ctr2, 2 * sizeof(TickCtr)) ||
       !A((void**)&e->d_small, 64) ||
       !A((void**)&e->d_blockhist, (size_t)e->n_segs * (kEnqChunk / kIngestItems + 1) * 4))
     return bail(fail(e, cudaGetLastError(), "cudaMalloc"));
+  if (cudaMemset(e->d_ctr2, 0, 2 * sizeof(TickCtr)) != cudaSuccess) return bail(MM_E_CUDA);
+  e->d_ctr = e->d_ctr2;
   if (cudaMallocHost(&e->h_ctr, sizeof(TickCtr)) != cudaSuccess || cudaMallocHost(&e->h_small, 64) != cudaSuccess)
     return bail(MM_E_CUDA);
   if ((rc = alloc_tick_scratch(e))) return bail(rc);
@@ -783,7 +803,7 @@ int mm_destroy(mm_engine* e) {
   cudaFree(e->d_lut); cudaFree(e->d_grp_lut); cudaFree(e->d_mode_tsize); cudaFree(e->d_seg_bin_lo); cudaFree(e->d_seg_L);
   cudaFree(e->d_M); cudaFree(e->d_P); cudaFree(e->d_outbase); cudaFree(e->d_binlim); cudaFree(e->d_bin_seg);
   cudaFree(e->d_bin_key); cudaFree(e->d_seg); cudaFree(e->d_members); cudaFree(e->d_members32); cudaFree(e->d_src_idx);
-  cudaFree(e->d_hdr); cudaFree(e->d_emit_seq); cudaFree(e->d_rescnt); cudaFree(e->d_ctr); cudaFree(e->d_small);
+  cudaFree(e->d_hdr); cudaFree(e->d_emit_seq); cudaFree(e->d_rescnt); cudaFree(e->d_ctr2); cudaFree(e->d_small);
   cudaFree(e->d_in_id); cudaFree(e->d_hslot); cudaFree(e->d_in_rating); cudaFree(e->d_in_mode); cudaFree(e->d_code);
   cudaFree(e->d_in_ts); cudaFree(e->d_blocksum); cudaFree(e->d_blockhist); cudaFree(e->d_part); cudaFree(e->d_in_key);
   cudaFree(e->d_in_handle); cudaFree(e->d_rej_idx); cudaFree(e->d_rej_code);
@@ -952,8 +972,8 @@ int mm_remove(mm_engine* e, uint32_t n, const uint64_t* id, uint32_t* n_removed)
   const Pool& p = e->pool[e->cur];
   CK(cudaMemcpyAsync(e->d_in_id, id, (size_t)n * 8, cudaMemcpyHostToDevice, e->stream));
   CK(cudaMemsetAsync(e->d_small, 0, 16, e->stream));
-  k_remove<<<(n + 255) / 256, 256, 0, e->stream>>>(n, e->d_in_id, act_view(e), p.v, (uint32_t)pool_slots(e), e->gen, e->K,
-                                                   p.m.tot, e->d_small + 2);
+  k_remove<<<(n + 255) / 256, 256, 0, e->stream>>>(n, e->d_in_id, act_view(e), p.v, p.m, (uint32_t)pool_slots(e), e->gen, e->K,
+                                                   e->d_bin_seg, e->d_seg_bin_lo, e->d_small + 2);
   CK(cudaGetLastError());
   CK(cudaMemcpyAsync(e->h_small, e->d_small, 16, cudaMemcpyDeviceToHost, e->stream));
   CK(cudaStreamSynchronize(e->stream));
@@ -976,8 +996,8 @@ int mm_take(mm_engine* e, uint32_t n, const uint64_t* id, uint32_t* n_taken) {
   const Pool& p = e->pool[e->cur];
   CK(cudaMemcpyAsync(e->d_in_id, id, (size_t)n * 8, cudaMemcpyHostToDevice, e->stream));
   CK(cudaMemsetAsync(e->d_small, 0, 16, e->stream));
-  k_take<<<(n + 255) / 256, 256, 0, e->stream>>>(n, e->d_in_id, act_view(e), p.v, (uint32_t)pool_slots(e), e->gen, e->K,
-                                                 p.m.tot, e->d_small + 2);
+  k_take<<<(n + 255) / 256, 256, 0, e->stream>>>(n, e->d_in_id, act_view(e), p.v, p.m, (uint32_t)pool_slots(e), e->gen, e->K,
+                                                 e->d_bin_seg, e->d_seg_bin_lo, e->d_small + 2);
   CK(cudaGetLastError());
   CK(cudaMemcpyAsync(e->h_small, e->d_small, 16, cudaMemcpyDeviceToHost, e->stream));
   CK(cudaStreamSynchronize(e->stream));

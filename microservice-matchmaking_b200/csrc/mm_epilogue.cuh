@@ -28,6 +28,7 @@ struct EpiArgs {
   ActiveView act;
   const SegInfo* seg;
   const uint32_t* seg_L;
+  const uint32_t* seg_bin_lo;
   mm_lobby_hdr* hdr;
   const uint32_t* src_idx;
   uint32_t* emit_seq;
@@ -138,7 +139,10 @@ __device__ __forceinline__ void epilogue_body(uint32_t* scratch, const Geo& g, c
         const uint32_t t = (s_newch[p] + loc / kTile) * kTile + loc % kTile;
         const uint64_t pid = src.id[i];
         dst.id[t] = pid; dst.rating[t] = src.rating[i]; dst.mode[t] = src.mode[i];
-        dst.tsize[t] = src.tsize[i]; dst.ts[t] = src.ts[i]; dst.bin[t] = src.bin[i]; dst.seq[t] = src.seq[i];
+        dst.tsize[t] = src.tsize[i]; dst.ts[t] = src.ts[i]; dst.seq[t] = src.seq[i];
+        const uint32_t key = src.bin[i];
+        dst.bin[t] = (uint16_t)key;
+        if (a.dst_meta.chist) atomicAdd(&a.dst_meta.chist[(size_t)(t / kTile) * kChunkHist + (key - a.seg_bin_lo[p])], 1u);
         if (act.on()) {
           const uint64_t h = act_find(act, pid);
           if (h != ~0ull) *act.val(h) = ((unsigned long long)new_gen << 32) | t;

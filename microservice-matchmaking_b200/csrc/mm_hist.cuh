@@ -112,4 +112,53 @@ __device__ __forceinline__ void hist_body(unsigned char* smem_raw, const Geo& g,
     for (uint32_t s = 0; s < kHistStages; ++s) mbar_inval(&full[s]);
 }
 
+// ---------------------------------------------------------------------------------------
+// rowsum_body<BLOCK>: the same M[row][bin] WITHOUT streaming the pool — when every partition has <= 255 keys the
+// engine keeps a histogram per chunk current (PoolMeta::chist: +1 at ingest, -1 at remove / take, rebuilt for the
+// compacted pool), so a row only adds up the histograms of its <= tiles-per-row chunks: ~1 KB per tile instead of the
+// tile's 4 KB key column and no shared-memory atomics.  Thread k owns key k of the current partition.
+// Shared memory: the tile descriptor cache only.
+// ---------------------------------------------------------------------------------------
+template <int BLOCK>
+__device__ __forceinline__ void rowsum_body(unsigned char* smem_raw, const Geo& g, const PoolMeta meta, uint32_t Kp,
+                                            const uint32_t* __restrict__ seg_bin_lo, uint32_t* __restrict__ M) {
+  DescCache& dc = *reinterpret_cast<DescCache*>(smem_raw);
+  const uint32_t tid = threadIdx.x, row = blockIdx.x;
+  const uint32_t s0 = row * g.tpr < g.NT ? row * g.tpr : g.NT;
+  const uint32_t s1 = s0 + g.tpr < g.NT ? s0 + g.tpr : g.NT;
+  uint32_t* mrow = M + (size_t)row * Kp;
+  uint32_t cur_sg = 0xFFFFFFFFu, acc = 0;
+  for (uint32_t tb = s0; tb < s1; tb += kDescCap) {
+    __syncthreads();
+    desc_fill<BLOCK>(dc, g, meta, tb, s1);
+    __syncthreads();
+    const uint32_t nt = s1 - tb < kDescCap ? s1 - tb : kDescCap;
+    constexpr uint32_t U = 8;  // loads in flight per thread: the histograms are cold in DRAM, one at a time is 17 x 0.8 us
+    for (uint32_t t0 = 0; t0 < nt; t0 += U) {
+      uint32_t v[U];
+#pragma unroll
+      for (uint32_t u = 0; u < U; ++u)
+        v[u] = (t0 + u < nt && tid < kChunkHist) ? __ldcg(&meta.chist[(size_t)dc.phys[t0 + u] * kChunkHist + tid]) : 0u;
+#pragma unroll
+      for (uint32_t u = 0; u < U; ++u) {
+        if (t0 + u >= nt) break;
+        const uint32_t sg = dc.nvsg[t0 + u] >> 16;
+        if (sg != cur_sg) {  // (uniform) the row leaves a partition: its sums go to M
+          if (cur_sg != 0xFFFFFFFFu) {
+            const uint32_t b0 = seg_bin_lo[cur_sg], nb = seg_bin_lo[cur_sg + 1] - b0;
+            if (tid < nb) mrow[b0 + tid] = acc;
+          }
+          cur_sg = sg; acc = 0;
+        }
+        acc += v[u];
+      }
+    }
+  }
+  if (cur_sg != 0xFFFFFFFFu) {
+    const uint32_t b0 = seg_bin_lo[cur_sg], nb = seg_bin_lo[cur_sg + 1] - b0;
+    if (tid < nb) mrow[b0 + tid] = acc;
+  }
+  __syncthreads();
+}
+
 }  // namespace mm

@@ -12,7 +12,8 @@
 //   bin(player) = mode * stride + lut[clamp(rating)]          (K bins, K ~ 5k * modes; ~K / partitions per tile)
 // followed by the per-partition lobby cut.  One cooperative launch, k_tick<512>, runs the four phases
 // (each also exists as a stand-alone kernel):
-//   k_hist     row histograms M[row][bin] from the resident 16-bit bin column (2 B/player, TMA ring)
+//   k_hist     row histograms M[row][bin]: sums of the resident per-chunk histograms (kept current by ingest / remove /
+//              tick) when every partition has <= 255 keys, else from the 16-bit bin column (2 B/player, TMA ring)
 //   k_colscan  the tail: per bin, how many players are matched (a prefix of the bin) and the member slot of the first
 //              one — policy S0 (reference behaviour) or S1 (rating window, extension) — from the resident bin totals;
 //              layout and bin totals of the compacted pool; column prefix of M only when a partition spans many rows
@@ -39,7 +40,8 @@ __global__ void __launch_bounds__(BLOCK, 2)
   __shared__ Geo geo;
   __shared__ uint32_t s_gtmp[33];
   geo_build<BLOCK>(geo, meta.fill, n_segs, R, s_gtmp);
-  hist_body<BLOCK>(smem_raw, geo, bins16, meta, Kp, max_nb, seg_bin_lo, M);
+  if (meta.chist) rowsum_body<BLOCK>(smem_raw, geo, meta, Kp, seg_bin_lo, M);
+  else hist_body<BLOCK>(smem_raw, geo, bins16, meta, Kp, max_nb, seg_bin_lo, M);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -61,6 +63,7 @@ struct TickArgs {
   TailArgs tail;   // Kp, K, n_segs, src bin totals, segment tables, outbase / binlim, counters, src fill, dst meta
   PlaceArgs place;
   EpiArgs epi;
+  TickCtr* next_ctr;  // the OTHER counter block (ticks alternate): re-armed by the last CTA so no memset precedes a launch
 };
 
 template <int BLOCK>
@@ -84,16 +87,23 @@ __global__ void __launch_bounds__(BLOCK, 2) k_tick(const TickArgs a) {
     }
   };
   stamp(0);
-  geo_build<BLOCK>(geo, a.place.meta.fill, a.tail.n_segs, R, s_gtmp);
-  if (is_row) hist_body<BLOCK>(smem_raw, geo, a.src.bin, a.place.meta, Kp, a.place.max_nb, a.tail.seg_bin_lo, a.M);
-  if (blockIdx.x == G - 1) {  // the last CTA: helper 0's job when there are helpers, else after its own row
+  const bool tail_cta = blockIdx.x == G - 1;
+  auto run_tail = [&]() {
     colscan_tail_body(scratch, a.tail);
     if (threadIdx.x == 0) {
       unsigned long long t;
       asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
       ctr->t[5] = t;
     }
+  };
+  if (tail_cta && !is_row) run_tail();  // the tail needs no tile geometry: it starts at once, beside the rows' pass
+  geo_build<BLOCK>(geo, a.place.meta.fill, a.tail.n_segs, R, s_gtmp);
+  if (is_row) {
+    if (a.place.meta.chist) rowsum_body<BLOCK>(smem_raw, geo, a.place.meta, Kp, a.tail.seg_bin_lo, a.M);
+    else hist_body<BLOCK>(smem_raw, geo, a.src.bin, a.place.meta, Kp, a.place.max_nb, a.tail.seg_bin_lo, a.M);
   }
+  if (tail_cta && is_row) run_tail();   // a grid without helpers: after its own row
+  if (threadIdx.x == 0) { unsigned long long tm; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tm)); if (is_row) atomicMax(&ctr->t[8], tm); }
   grid_barrier(&ctr->gbar, (bar += G));
   stamp(1);
   if (geo_use_colscan(geo)) {  // (uniform over the grid)
@@ -102,7 +112,15 @@ __global__ void __launch_bounds__(BLOCK, 2) k_tick(const TickArgs a) {
   }
   stamp(2);
   if (is_row) place_body<BLOCK>(smem_raw, geo, a.place);
-  else if (!a.epi.write_headers) headers_only<BLOCK>(scratch, geo, a.epi, helper, n_helpers);
+  if (threadIdx.x == 0 && is_row) { unsigned long long tm; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tm)); atomicMax(&ctr->t[10], tm); }
+  if (a.epi.dst_meta.chist && (!is_row || n_helpers == 0)) {
+    // the compacted pool's chunks start with empty histograms (the epilogue fills them): helpers, or the rows when
+    // the grid has no helper
+    const uint32_t part = n_helpers ? helper : blockIdx.x, nparts = n_helpers ? n_helpers : G;
+    const size_t words = (size_t)__ldcg(a.epi.dst_meta.bump) * kChunkHist;
+    for (size_t i = (size_t)part * BLOCK + threadIdx.x; i < words; i += (size_t)nparts * BLOCK) a.epi.dst_meta.chist[i] = 0;
+  }
+  if (!is_row && !a.epi.write_headers) headers_only<BLOCK>(scratch, geo, a.epi, helper, n_helpers);
   grid_barrier(&ctr->gbar, (bar += G));
   stamp(3);
   epilogue_body<BLOCK>(scratch, geo, a.epi, &ctr->t[7]);
@@ -111,6 +129,12 @@ __global__ void __launch_bounds__(BLOCK, 2) k_tick(const TickArgs a) {
     unsigned long long tm;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tm));
     atomicMax(&ctr->t[6], tm);
+    __threadfence();
+    if (atomicAdd(&ctr->done, 1u) == G - 1) {  // ... and arms the other counter block for the next tick
+      TickCtr* nx = a.next_ctr;
+      nx->gbar = 0; nx->done = 0;
+      nx->t[6] = 0; nx->t[7] = 0; nx->t[8] = 0; nx->t[10] = 0;
+    }
   }
 }
 

@@ -160,7 +160,14 @@ __device__ __forceinline__ void place_body(unsigned char* smem_raw, const Geo& g
           // __ldcg: these arrays are produced earlier in the same (fused) launch by other SMs
           uint32_t pre = 0;
           if (scanned) pre = __ldcg(&a.P[(size_t)row * Kp + i]);
-          else for (uint32_t r = rlo; r < row; ++r) pre += __ldcg(&a.M[(size_t)r * Kp + i]);  // few rows per partition
+          else
+            for (uint32_t r = rlo; r < row; r += 8) {  // few rows per partition; 8 independent L2 loads in flight
+              uint32_t v[8];
+#pragma unroll
+              for (uint32_t u = 0; u < 8; ++u) v[u] = r + u < row ? __ldcg(&a.M[(size_t)(r + u) * Kp + i]) : 0u;
+#pragma unroll
+              for (uint32_t u = 0; u < 8; ++u) pre += v[u];
+            }
           const uint32_t c = __ldcg(&a.M[(size_t)row * Kp + i]);
           const uint32_t start = __ldcg(&a.outbase[i]) + pre;
           v = start | ((start + c > __ldcg(&a.binlim[i])) ? 0x80000000u : 0u);

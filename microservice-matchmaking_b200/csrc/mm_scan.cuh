@@ -17,7 +17,7 @@ namespace mm {
 // ---------------------------------------------------------------------------------------
 constexpr int kScanBlock = 512;
 constexpr uint32_t kColScratchWords = (kScanBlock / 32) * 33;      // column CTA scratch
-constexpr uint32_t kTailScratchWords = 64 + 4 + 5 * kMaxSegs + 8;  // tail CTA scratch, fixed part
+constexpr uint32_t kTailScratchWords = 64 + 4 + 6 * kMaxSegs + 8;  // tail CTA scratch, fixed part
 
 // One 32-bin column group: exclusive prefix down the rows of M (scratch: kColScratchWords).  Bin b belongs to one
 // partition, and only the rows holding that partition's tiles wrote M[.][b] (mm_hist.cuh): the scan of a column is
@@ -103,10 +103,12 @@ __device__ __forceinline__ void colscan_tail_body(uint32_t* scratch, const TailA
   uint32_t* s_mt = s_ns + kMaxSegs;     // [kMaxSegs] matched players of the segment
   uint32_t* s_lo = s_mt + kMaxSegs;     // [kMaxSegs + 1] first bin of the segment
   uint32_t* s_nch = s_lo + kMaxSegs + 1;   // [kMaxSegs + 1] first chunk of the segment in the compacted pool
+  uint32_t* s_L = s_nch + kMaxSegs + 1;    // [kMaxSegs] lobby size of the segment
   uint32_t* s_bb = scratch + kTailScratchWords;  // [Kp + 1] sorted position of the bin's first player
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, Kp = t.Kp, K = t.K, n_segs = t.n_segs;
   if (tid == 0) s_misc[0] = 0;
-  for (uint32_t sg = tid; sg <= n_segs; sg += kScanBlock) s_lo[sg] = t.seg_bin_lo[sg];
+  for (uint32_t sg = tid; sg <= n_segs; sg += kScanBlock) s_lo[sg] = t.seg_bin_lo[sg];  // all the cold loads at once
+  for (uint32_t sg = tid; sg < n_segs; sg += kScanBlock) s_L[sg] = t.seg_L[sg];
   for (uint32_t i = tid; i < Kp; i += kScanBlock) s_bb[i] = __ldcg(&t.tot[i]);  // coalesced, independent loads
   __syncthreads();
   // list-ranked partitions only: does some bin expect > 8 players per tile of its partition?
@@ -129,7 +131,7 @@ __device__ __forceinline__ void colscan_tail_body(uint32_t* scratch, const TailA
   if (!windowed) {
     // S0: lobbies_s = n_s / L; the partition's first lobbies_s * L sorted positions are matched.
     for (uint32_t sg = tid; sg < n_segs; sg += kScanBlock) {
-      const uint32_t ns = s_bb[s_lo[sg + 1]] - s_bb[s_lo[sg]], L = t.seg_L[sg];
+      const uint32_t ns = s_bb[s_lo[sg + 1]] - s_bb[s_lo[sg]], L = s_L[sg];
       s_ns[sg] = ns; s_mt[sg] = ns / L * L;
     }
   } else {
@@ -224,7 +226,7 @@ __device__ __forceinline__ void colscan_tail_body(uint32_t* scratch, const TailA
     for (uint32_t base = 0; base < n_segs; base += 32) {
       const uint32_t sg = base + lane;
       const bool on = sg < n_segs;
-      const uint32_t ns = on ? s_ns[sg] : 0u, mt = on ? s_mt[sg] : 0u, L = on ? t.seg_L[sg] : 1u;
+      const uint32_t ns = on ? s_ns[sg] : 0u, mt = on ? s_mt[sg] : 0u, L = on ? s_L[sg] : 1u;
       const uint32_t nl = mt / L, nleft = ns - mt, nch = (nleft + kTile - 1) / kTile;
       uint32_t i_mem = mt, i_lob = nl, i_left = nleft, i_ch = nch;
 #pragma unroll
