@@ -197,6 +197,7 @@ def main():
     ap.add_argument("--no-numa", action="store_true", help="do not bind the rank to its GPU's NUMA node")
     ap.add_argument("--boundary-w", type=int, default=2,
                     help="under torchrun: window of the boundary-pass extension leg (0 = skip)")
+    ap.add_argument("--boundary-players", type=int, default=12_000, help="pool size of the boundary-pass leg (sparse: windows fail, residuals sit near the boundaries)")
     ap.add_argument("--stream-seconds", type=float, default=1.0, help="length of the streaming leg (configs[4]); 0 = skip")
     ap.add_argument("--stream-rate", type=float, default=1e6)
     ap.add_argument("--stream-dt-ms", type=float, default=1.0)
@@ -320,12 +321,14 @@ def main():
         # -- EXTENSION leg (not reference behaviour): policy S1 (max_spread W) on the same sharded pool + the boundary
         #    pass: residual players within W of a group boundary owned by another rank travel over NCCL send/recv
         if args.boundary_w > 0:
-            Wb = args.boundary_w
-            cfg_b, _ = pkg.synth.workload_config(args.workload, abi.MM_ORDER_RATING, n_mine + 65536, device=local,
+            Wb, nb_pool = args.boundary_w, min(n, args.boundary_players)
+            # a SPARSE slice of the same pool: on the dense 10 M pool every window fills and nobody is left near a boundary
+            mine_b = mine[:nb_pool]
+            cfg_b, _ = pkg.synth.workload_config(args.workload, abi.MM_ORDER_RATING, int(mine_b.sum()) + 65536, device=local,
                                                  single_mode=not args.two_modes)
             eng = pkg.Engine(cfg_b)
             eng.set_option("max_spread", Wb)
-            assert eng.enqueue(g_ids[mine], g_rating[mine], g_mode[mine], g_ts[mine]).all()
+            assert eng.enqueue(g_ids[:nb_pool][mine_b], g_rating[:nb_pool][mine_b], g_mode[:nb_pool][mine_b]).all()
             stb = eng.tick_device()
             comm = shard.DistComm(device=torch.device("cuda", local))
             cache = {}
@@ -341,7 +344,8 @@ def main():
                               device="cuda", dtype=torch.int64)
             dist.all_reduce(tb)
             strong["boundary_pass"] = {
-                "policy": f"S1 extension, max lobby spread {Wb}", "players_left_queued_by_the_local_ticks": int(tb[5].item()),
+                "policy": f"S1 extension, max lobby spread {Wb}", "pool": f"first {nb_pool} players of the workload (sparse)",
+                "players_left_queued_by_the_local_ticks": int(tb[5].item()),
                 "players_sent_to_the_lower_neighbour": int(tb[0].item()), "players_received": int(tb[1].item()),
                 "players_matched_across_a_boundary": int(tb[2].item()), "lobbies": int(tb[3].item()),
                 "bytes_over_nccl": int(tb[4].item()), "wall_ms": bp_ms,
