@@ -165,17 +165,22 @@ __global__ void __launch_bounds__(512) k_enq_alloc(uint32_t n_segs, uint32_t nbl
     const uint32_t fill = meta.fill[p];
     uint32_t carry = fill;
     uint32_t* hrow = blockhist + (size_t)p * nblk;
-    for (uint32_t b0 = 0; b0 < nblk; b0 += 32) {
-      const uint32_t b = b0 + lane;
-      const uint32_t v = b < nblk ? hrow[b] : 0u;
-      uint32_t incl = v;
+    for (uint32_t b0 = 0; b0 < nblk; b0 += 128) {  // four independent loads in flight per lane
+      uint32_t v[4];
 #pragma unroll
-      for (int off = 1; off < 32; off <<= 1) {
-        const uint32_t u = __shfl_up_sync(0xFFFFFFFFu, incl, off);
-        if (lane >= (uint32_t)off) incl += u;
+      for (int k = 0; k < 4; ++k) { const uint32_t b = b0 + k * 32 + lane; v[k] = b < nblk ? hrow[b] : 0u; }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const uint32_t b = b0 + k * 32 + lane;
+        uint32_t incl = v[k];
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+          const uint32_t u = __shfl_up_sync(0xFFFFFFFFu, incl, off);
+          if (lane >= (uint32_t)off) incl += u;
+        }
+        if (b < nblk) hrow[b] = carry + incl - v[k];
+        carry += __shfl_sync(0xFFFFFFFFu, incl, 31);
       }
-      if (b < nblk) hrow[b] = carry + incl - v;
-      carry += __shfl_sync(0xFFFFFFFFu, incl, 31);
     }
     if (lane == 0) {
       s_old[p] = fill; s_new[p] = carry;
@@ -202,7 +207,10 @@ __global__ void __launch_bounds__(512) k_enq_alloc(uint32_t n_segs, uint32_t nbl
 
 // E4: append winners to their partition in batch order (= enqueue order) and commit their active-set entries.
 // Stable rank inside the block: peers of the same partition inside a warp by ballots over the partition index bits,
-// per-warp counters in shared memory, prefix over the block's 8 warps.
+// per-warp counters in shared memory, prefix over the block's 8 warps.  The block's winners are then laid out by
+// (partition, rank) in shared memory — only their batch-local index — and the write-back walks that order: consecutive
+// threads write consecutive pool slots (one run per partition), the inputs are gathered from the block's 1024-entry
+// window of the batch columns.
 __global__ void __launch_bounds__(256) k_enq_append(uint32_t base, uint32_t n, const uint64_t* __restrict__ id,
                                                     const int32_t* __restrict__ rating, const uint8_t* __restrict__ mode,
                                                     const uint32_t* __restrict__ ts, const uint8_t* __restrict__ mode_tsize,
@@ -211,22 +219,26 @@ __global__ void __launch_bounds__(256) k_enq_append(uint32_t base, uint32_t n, c
                                                     uint32_t n_segs, uint32_t nblk, const uint32_t* __restrict__ blockbase,
                                                     PoolView pool, PoolMeta meta, uint32_t gen, uint32_t seq_base, BinMap bm,
                                                     const uint32_t* __restrict__ seg_bin_lo) {
-  extern __shared__ __align__(16) uint32_t s_dyn[];  // wc[8][n_segs + 1] u16 | bbase[n_segs] u32
-  uint16_t* wc = reinterpret_cast<uint16_t*>(s_dyn);
+  extern __shared__ __align__(16) uint32_t s_dyn[];  // start[n_segs] | bbase[n_segs] | tmp[64] | wc[8][n_segs+1] u16 | src[1024] u16 | sp[1024] u16
   const uint32_t S1 = n_segs + 1;                     // digit n_segs = not a winner
-  uint32_t* bbase = s_dyn + (8 * S1 + 1) / 2;
+  uint32_t* start = s_dyn;
+  uint32_t* bbase = start + n_segs;
+  uint32_t* s_tmp = bbase + n_segs;
+  uint16_t* wc = reinterpret_cast<uint16_t*>(s_tmp + 64);
+  uint16_t* src = wc + ((8 * S1 + 1) & ~1u);
+  uint16_t* sp = src + kIngestItems;
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t lt_mask = (1u << lane) - 1u;
   for (uint32_t k = tid; k < 8 * S1; k += 256) wc[k] = 0;
   for (uint32_t p = tid; p < n_segs; p += 256) bbase[p] = blockbase[(size_t)p * nblk + blockIdx.x];
   __syncthreads();
   const uint32_t nbits = 32u - __clz(n_segs);
-  uint32_t dg[4], rk[4], idx[4];
+  const uint32_t blk0 = base + blockIdx.x * kIngestItems;
+  uint32_t dg[4], rk[4];
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
-    const uint32_t t = blockIdx.x * kIngestItems + warp * 128 + j * 32 + lane;
-    idx[j] = base + t;
-    dg[j] = (t < n && code[idx[j]] == 1) ? (uint32_t)part[idx[j]] : n_segs;
+    const uint32_t li = warp * 128 + j * 32 + lane, t = blockIdx.x * kIngestItems + li;
+    dg[j] = (t < n && code[blk0 + li] == 1) ? (uint32_t)part[blk0 + li] : n_segs;
     uint32_t peers = 0xFFFFFFFFu;
     for (uint32_t bit = 0; bit < nbits; ++bit) {
       const bool on = (dg[j] >> bit) & 1u;
@@ -242,25 +254,55 @@ __global__ void __launch_bounds__(256) k_enq_append(uint32_t base, uint32_t n, c
     rk[j] = old + __popc(peers & lt_mask);
   }
   __syncthreads();
-  for (uint32_t p = tid; p < n_segs; p += 256) {  // prefix over the 8 warps
+  for (uint32_t p = tid; p < n_segs; p += 256) {  // prefix over the 8 warps; the partition's winners in this block
     uint32_t run = 0;
 #pragma unroll
     for (int w = 0; w < 8; ++w) { const uint32_t v = wc[w * S1 + p]; wc[w * S1 + p] = (uint16_t)run; run += v; }
+    start[p] = run;
   }
   __syncthreads();
+  const uint32_t n_win = block_excl_scan<256>(start, n_segs, s_tmp);  // -> the partition's first sorted position
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
     if (dg[j] >= n_segs) continue;
-    const uint32_t p = dg[j], i = idx[j];
-    const uint32_t pos = bbase[p] + wc[warp * S1 + p] + rk[j];
-    const uint32_t slot = meta.chunk_tab[(size_t)p * meta.max_ch + pos / kTile] * kTile + pos % kTile;
-    pool.id[slot] = id[i]; pool.rating[slot] = rating[i]; pool.mode[slot] = mode[i];
-    pool.tsize[slot] = mode_tsize[mode[i]]; pool.ts[slot] = ts ? ts[i] : 0u;
-    pool.bin[slot] = (uint16_t)bin_of(bm, bm.lut, rating[i], mode[i]);  // the tick's sort key, derived once at ingest
-    pool.seq[slot] = seq_base + i;
-    atomicAdd(&meta.tot[pool.bin[slot]], 1u);  // bin totals stay current: the tick needs no counting pass for them
-    if (meta.chist) atomicAdd(&meta.chist[(size_t)(slot / kTile) * kChunkHist + (pool.bin[slot] - seg_bin_lo[p])], 1u);
-    if (act.on()) *act.val(hslot[i]) = ((unsigned long long)gen << 32) | slot;
+    const uint32_t q = start[dg[j]] + wc[warp * S1 + dg[j]] + rk[j];
+    src[q] = (uint16_t)(warp * 128 + j * 32 + lane);
+    sp[q] = (uint16_t)dg[j];
+  }
+  __syncthreads();
+  for (uint32_t q0 = 0; q0 < n_win; q0 += 1024) {
+    uint32_t slot[4], i[4], bin[4];
+    uint64_t pid[4];
+    int32_t rt[4];
+    uint8_t md[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const uint32_t q = q0 + j * 256 + tid;
+      slot[j] = ~0u;
+      if (q >= n_win) continue;
+      const uint32_t p = sp[q];
+      const uint32_t pos = bbase[p] + (q - start[p]);
+      i[j] = blk0 + src[q];
+      slot[j] = meta.chunk_tab[(size_t)p * meta.max_ch + pos / kTile] * kTile + pos % kTile;
+      pid[j] = id[i[j]]; rt[j] = rating[i[j]]; md[j] = mode[i[j]];
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (slot[j] == ~0u) continue;
+      bin[j] = bin_of(bm, bm.lut, rt[j], md[j]);  // the tick's sort key, derived once at ingest
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (slot[j] == ~0u) continue;
+      const uint32_t s = slot[j];
+      pool.id[s] = pid[j]; pool.rating[s] = rt[j]; pool.mode[s] = md[j];
+      pool.tsize[s] = mode_tsize[md[j]]; pool.ts[s] = ts ? ts[i[j]] : 0u;
+      pool.bin[s] = (uint16_t)bin[j];
+      pool.seq[s] = seq_base + i[j];
+      atomicAdd(&meta.tot[bin[j]], 1u);  // bin totals stay current: the tick needs no counting pass for them
+      if (meta.chist) atomicAdd(&meta.chist[(size_t)(s / kTile) * kChunkHist + (bin[j] - seg_bin_lo[sp[q0 + j * 256 + tid]])], 1u);
+      if (act.on()) *act.val(hslot[i[j]]) = ((unsigned long long)gen << 32) | s;
+    }
   }
 }
 

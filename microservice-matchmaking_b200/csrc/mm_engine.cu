@@ -417,7 +417,7 @@ int enq_chunk(mm_engine* e, uint32_t base, uint32_t cnt, const uint64_t* id, con
   }
   k_enq_route<<<nblk, 256, 0, e->stream>>>(base, cnt, av, e->d_hslot, e->d_code, e->d_part, e->n_segs, nblk, e->d_blockhist);
   k_enq_alloc<<<1, 512, 0, e->stream>>>(e->n_segs, nblk, e->d_blockhist, p.m, e->d_small);
-  const size_t smem = ((size_t)(8 * (e->n_segs + 1) + 1) / 2 + e->n_segs) * 4;
+  const size_t smem = (size_t)(2 * e->n_segs + 64) * 4 + (size_t)(((8 * (e->n_segs + 1) + 1) & ~1u) + 2 * kIngestItems) * 2;
   k_enq_append<<<nblk, 256, smem, e->stream>>>(base, cnt, id, rating, mode, ts, e->d_mode_tsize, av, e->d_hslot, e->d_code,
                                                e->d_part, e->n_segs, nblk, e->d_blockhist, p.v, p.m, e->gen, e->seq_next,
                                                bin_map(e), e->d_seg_bin_lo);
