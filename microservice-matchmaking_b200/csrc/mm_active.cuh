@@ -18,6 +18,8 @@ namespace mm {
 // fill[partition] + its stable rank among the batch's winners of that partition — enqueue order is kept inside
 // the partition, which is all the serialized reference defines (one queue per group, search/worker.ex:46-66).
 // =======================================================================================
+constexpr uint32_t kEnqChunk = 1u << 20;     // batch entries per ingest chunk when the columns arrive over PCIe (pipelined)
+constexpr uint32_t kEnqChunkDev = 1u << 22;  // ... when they are already in HBM: fewer, fuller launches
 constexpr uint32_t kIngestItems = 1024;  // batch entries per ingest block: 256 threads x 4, warp-striped
 constexpr uint16_t kNoPart = 0xFFFFu;
 
@@ -165,12 +167,13 @@ __global__ void __launch_bounds__(512) k_enq_alloc(uint32_t n_segs, uint32_t nbl
     const uint32_t fill = meta.fill[p];
     uint32_t carry = fill;
     uint32_t* hrow = blockhist + (size_t)p * nblk;
-    for (uint32_t b0 = 0; b0 < nblk; b0 += 128) {  // four independent loads in flight per lane
-      uint32_t v[4];
+    for (uint32_t b0 = 0; b0 < nblk; b0 += 1024) {  // 32 loads in flight per lane: one memory round trip per 1024 blocks
+      uint32_t v[32];
 #pragma unroll
-      for (int k = 0; k < 4; ++k) { const uint32_t b = b0 + k * 32 + lane; v[k] = b < nblk ? hrow[b] : 0u; }
+      for (int k = 0; k < 32; ++k) { const uint32_t b = b0 + k * 32 + lane; v[k] = b < nblk ? hrow[b] : 0u; }
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
+      for (int k = 0; k < 32; ++k) {
+        if (b0 + (uint32_t)k * 32 >= nblk) break;
         const uint32_t b = b0 + k * 32 + lane;
         uint32_t incl = v[k];
 #pragma unroll
@@ -301,7 +304,7 @@ __global__ void __launch_bounds__(256) k_enq_append(uint32_t base, uint32_t n, c
       pool.seq[s] = seq_base + i[j];
       atomicAdd(&meta.tot[bin[j]], 1u);  // bin totals stay current: the tick needs no counting pass for them
       if (meta.chist) atomicAdd(&meta.chist[(size_t)(s / kTile) * kChunkHist + (bin[j] - seg_bin_lo[sp[q0 + j * 256 + tid]])], 1u);
-      if (act.on()) *act.val(hslot[i[j]]) = ((unsigned long long)gen << 32) | s;
+      if (act.on()) *act.val(act.dcap ? pid[j] : hslot[i[j]]) = ((unsigned long long)gen << 32) | s;  // dense set: the handle is the slot
     }
   }
 }

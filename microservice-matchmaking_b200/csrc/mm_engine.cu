@@ -126,7 +126,6 @@ struct mm_engine {
 
 namespace {
 
-constexpr uint32_t kEnqChunk = 1u << 20;  // batch entries per pipelined ingest chunk
 
 int fail(mm_engine* e, cudaError_t err, const char* what) {
   if (e) std::snprintf(e->last_err, sizeof(e->last_err), "%s: %s", what, cudaGetErrorString(err));
@@ -365,7 +364,7 @@ int ensure_enq_scratch(mm_engine* e, uint32_t n) {
   CK(cudaMalloc(&e->d_in_key, c * 2));
   CK(cudaMalloc(&e->d_in_handle, c * 4));
   CK(cudaMalloc(&e->d_in_ts, c * 4));
-  CK(cudaMalloc(&e->d_blocksum, (std::min<size_t>(c, kEnqChunk) / 256 + 2) * 4));
+  CK(cudaMalloc(&e->d_blocksum, (std::min<size_t>(c, kEnqChunkDev) / 256 + 2) * 4));
   e->enq_cap = n;
   return MM_OK;
 }
@@ -445,12 +444,12 @@ int enq_finish(mm_engine* e, uint32_t n, uint8_t* accepted_dev, uint32_t* n_acce
 // behind the PCIe transfer except for the last chunk.
 template <class Upload>
 int enqueue_batch(mm_engine* e, uint32_t n, const uint64_t* id, const int32_t* rating, const uint8_t* mode,
-                  const uint32_t* ts, Upload upload) {
+                  const uint32_t* ts, uint32_t chunk, Upload upload) {
   int rc = enq_prepare(e, n);
   if (rc) return rc;
   const bool may_overflow = (uint64_t)e->pool[e->cur].n + n > e->capacity;
-  for (uint32_t base = 0; base < n; base += kEnqChunk) {
-    const uint32_t cnt = std::min(kEnqChunk, n - base);
+  for (uint32_t base = 0; base < n; base += chunk) {
+    const uint32_t cnt = std::min(chunk, n - base);
     if ((rc = upload(base, cnt))) return rc;
     if ((rc = enq_chunk(e, base, cnt, id, rating, mode, ts, may_overflow))) return rc;
   }
@@ -769,7 +768,7 @@ int mm_create(const mm_config* cfg, mm_engine** out) {
       !A((void**)&e->d_hdr, (size_t)e->max_lobbies * sizeof(mm_lobby_hdr)) ||
       !A((void**)&e->d_emit_seq, (size_t)e->max_lobbies * 4) || !A((void**)&e->d_ctr2, 2 * sizeof(TickCtr)) ||
       !A((void**)&e->d_small, 64) ||
-      !A((void**)&e->d_blockhist, (size_t)e->n_segs * (kEnqChunk / kIngestItems + 1) * 4))
+      !A((void**)&e->d_blockhist, (size_t)e->n_segs * (kEnqChunkDev / kIngestItems + 1) * 4))
     return bail(fail(e, cudaGetLastError(), "cudaMalloc"));
   if (cudaMemset(e->d_ctr2, 0, 2 * sizeof(TickCtr)) != cudaSuccess) return bail(MM_E_CUDA);
   e->d_ctr = e->d_ctr2;
@@ -865,7 +864,7 @@ int mm_enqueue_device(mm_engine* e, uint32_t n, const uint64_t* id, const int32_
   if (n == 0) return MM_OK;
   std::lock_guard<std::mutex> lk(e->mu);
   CK(cudaSetDevice(e->device));
-  int rc = enqueue_batch(e, n, id, rating, mode, enq_ts, [](uint32_t, uint32_t) { return (int)MM_OK; });
+  int rc = enqueue_batch(e, n, id, rating, mode, enq_ts, kEnqChunkDev, [](uint32_t, uint32_t) { return (int)MM_OK; });
   if (rc) return rc;
   return enq_finish(e, n, accepted, n_accepted);
 }
@@ -888,7 +887,7 @@ int mm_enqueue(mm_engine* e, uint32_t n, const uint64_t* id, const int32_t* rati
     CK(cudaStreamWaitEvent(e->stream, e->ev_copy, 0));
     return MM_OK;
   };
-  rc = enqueue_batch(e, n, e->d_in_id, e->d_in_rating, e->d_in_mode, enq_ts ? e->d_in_ts : nullptr, upload);
+  rc = enqueue_batch(e, n, e->d_in_id, e->d_in_rating, e->d_in_mode, enq_ts ? e->d_in_ts : nullptr, kEnqChunk, upload);
   if (rc) { cudaStreamSynchronize(e->copy_stream); return rc; }
   rc = enq_finish(e, n, nullptr, nullptr);
   if (rc) return rc;
@@ -919,7 +918,7 @@ int mm_enqueue_packed(mm_engine* e, uint32_t n, const uint32_t* handle, const ui
     CK(cudaGetLastError());
     return MM_OK;
   };
-  rc = enqueue_batch(e, n, e->d_in_id, e->d_in_rating, e->d_in_mode, enq_ts ? e->d_in_ts : nullptr, upload);
+  rc = enqueue_batch(e, n, e->d_in_id, e->d_in_rating, e->d_in_mode, enq_ts ? e->d_in_ts : nullptr, kEnqChunk, upload);
   if (rc) { cudaStreamSynchronize(e->copy_stream); return rc; }
   rc = enq_finish(e, n, nullptr, nullptr);
   if (rc) return rc;
