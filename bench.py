@@ -10,8 +10,10 @@ A step = one pass of the hot path (one search tick) over one synthetic player po
   e2e    same metric through the C ABI with HOST buffers, every step a NEW batch of players:
          mm_enqueue_packed (pinned host columns: u32 handle + u16 mode|rating = 6 B/player H2D
          inside) + mm_enqueue_rejects + mm_tick_packed (lobby headers + u32 member handles D2H
-         inside), wall clock.  `pipelined`: a tick's host copies finish under the next step's
-         ingest (mm_set_option "async_results"); `sequential`: fully blocking calls;
+         inside), wall clock.  `pipelined`: two batches in flight — step k+1's upload
+         (mm_enqueue_packed_begin) and step k-1's host copies (mm_set_option "async_results") run
+         under step k's ingest + tick; `pipelined_results_only`: only the result copies overlap;
+         `sequential`: fully blocking calls;
          `u64_api`: the 17 B/player mm_enqueue + 8 B/player mm_tick entry points, blocking.
   strong (N > 1 only) BASELINE configs[3]: ONE pool of the workload's size, its rating groups
          dealt to the ranks (generic/worker.ex:55-69), device-timed like `value`.
@@ -406,6 +408,27 @@ def main():
             if k:
                 lob_pipe += st3.n_lobbies
         eng.results_wait()
+        res_s = (time.perf_counter() - t0) / S
+        eng.close()
+        tot_res = lob_pipe / S
+        # -- two batches in flight: step k+1's upload (mm_enqueue_packed_begin) runs under step k's ingest, tick and
+        #    result copies; every step's host->device and device->host copies are still inside the timed region
+        eng = pkg.Engine(cfgp); options(eng)
+        eng.set_option("async_results", 1)
+        step_packed(eng, batches[0])  # warm-up
+        eng.results_wait()
+        barrier()
+        lob_pipe = 0
+        t0 = time.perf_counter()
+        eng.enqueue_packed_begin_raw(n, batches[1][0].data_ptr(), batches[1][1].data_ptr())
+        for k in range(1, S + 1):
+            if k < S:
+                eng.enqueue_packed_begin_raw(n, batches[k + 1][0].data_ptr(), batches[k + 1][1].data_ptr())
+            eng.enqueue_packed_end_raw()
+            rej_idx, _ = eng.enqueue_rejects()
+            assert len(rej_idx) == 0
+            lob_pipe += eng.tick_raw(h_lob.data_ptr(), lob_cap, h_mem32.data_ptr(), mem_cap, packed=True).n_lobbies
+        eng.results_wait()
         e2e_s = (time.perf_counter() - t0) / S
         eng.close()
         del batches
@@ -429,27 +452,32 @@ def main():
         u64_s = sum(u_times) / len(u_times)
 
         if world > 1:
-            t = torch.tensor([e2e_s, seq_s, u64_s], device="cuda", dtype=torch.float64)
+            t = torch.tensor([e2e_s, seq_s, u64_s, res_s], device="cuda", dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            e2e_s, seq_s, u64_s = (float(x) for x in t.tolist())
-            tl2 = torch.tensor([tot_pipe], device="cuda", dtype=torch.float64)
+            e2e_s, seq_s, u64_s, res_s = (float(x) for x in t.tolist())
+            tl2 = torch.tensor([tot_pipe, tot_res], device="cuda", dtype=torch.float64)
             dist.all_reduce(tl2)
-            tot_pipe = float(tl2.item())
+            tot_pipe, tot_res = (float(x) for x in tl2.tolist())
         pipelined = {"value": tot_pipe / e2e_s, "ms_per_step": 1e3 * e2e_s, "steps": S,
-                     "call": "per step: mm_enqueue_packed(pinned host handles + keys) + mm_enqueue_rejects + "
-                             "mm_tick_packed(host lobbies / member handles) with mm_set_option(async_results): a tick's "
-                             "device-to-host copies complete under the next step's ingest; mm_results_wait after the "
-                             "last step, inside the timed region"}
+                     "call": "per step: mm_enqueue_packed_begin(next step's pinned host handles + keys) + "
+                             "mm_enqueue_packed_end(this step's) + mm_enqueue_rejects + mm_tick_packed(host lobbies / "
+                             "member handles) with mm_set_option(async_results): two batches in flight — a step's "
+                             "upload runs under the previous step's ingest + tick, its device-to-host copies under "
+                             "the next step; the first upload and mm_results_wait after the last step are inside "
+                             "the timed region"}
+        results_only = {"value": tot_res / res_s, "ms_per_step": 1e3 * res_s, "steps": S,
+                        "call": "per step: blocking mm_enqueue_packed + mm_enqueue_rejects + mm_tick_packed with "
+                                "async_results (only the device-to-host copies overlap the next step)"}
         sequential = {"value": total_lobbies_per_step / seq_s, "ms_per_step": 1e3 * seq_s, "steps": len(times),
                       "enqueue_ms": 1e3 * seq_enq_s, "tick_and_d2h_ms": 1e3 * (seq_s - seq_enq_s),
                       "call": "blocking mm_enqueue_packed + mm_enqueue_rejects + blocking mm_tick_packed, one step at a time"}
-        best = pipelined if pipelined["value"] >= sequential["value"] else sequential  # both include every copy
+        best = pipelined if pipelined["value"] >= sequential["value"] else sequential  # all include every copy
         e2e = {"value": best["value"], "unit": "lobbies/s",
                "h2d_bytes_per_step": n * (4 + 2), "d2h_bytes_per_step": 8 + st2.n_matched * 4 + st2.n_lobbies * 8,
                "ms_per_step": best["ms_per_step"], "steps": best["steps"], "call": best["call"],
                "mode": "pipelined" if best is pipelined else "sequential",
                "ids": "dense 32-bit host handles (MM_F_DENSE_IDS; the host owns the UUID <-> handle table, SURVEY §7.3)",
-               "pipelined": pipelined, "sequential": sequential,
+               "pipelined": pipelined, "pipelined_results_only": results_only, "sequential": sequential,
                "u64_api": {"value": total_lobbies_per_step / u64_s, "ms_per_step": 1e3 * u64_s,
                            "h2d_bytes_per_step": n * (8 + 4 + 1 + 4), "d2h_bytes_per_step": n + st4.n_matched * 8 + st4.n_lobbies * 8,
                            "call": "blocking mm_enqueue(pinned u64 ids, i32 rating, u8 mode, u32 ts; accepted[] back) + "

@@ -151,6 +151,17 @@ int mm_enqueue_device(mm_engine* e, uint32_t n, const uint64_t* id, const int32_
 int mm_enqueue_packed(mm_engine* e, uint32_t n, const uint32_t* handle, const uint16_t* key,
                       const uint32_t* enq_ts, uint8_t* accepted);
 
+/* Split form of mm_enqueue_packed for a software-pipelined host loop (PCIe is full duplex and the copy engines run
+ * beside the kernels): _begin starts the host-to-device copy of a batch into one of two staging slots and returns at
+ * once; _end (oldest staged batch first) waits for that copy and runs the ingest.  Between the two the caller may run
+ * mm_tick* / mm_enqueue_rejects of the PREVIOUS batch, so a step's upload hides behind the previous step's tick and
+ * result copies.  The host arrays must stay valid until the matching _end returns.  MM_E_STATE: both slots staged
+ * (_begin) / nothing staged (_end).  Replaces nothing in the reference: AMQP prefetch (search/worker.ex:36) is the
+ * reference's own way of having the next deliveries in flight while one is consumed.                                */
+int mm_enqueue_packed_begin(mm_engine* e, uint32_t n, const uint32_t* handle, const uint16_t* key,
+                            const uint32_t* enq_ts);
+int mm_enqueue_packed_end(mm_engine* e, uint8_t* accepted, uint32_t* n_accepted);
+
 /* The ack / nack list of the LAST mm_enqueue* batch without a per-player transfer: the batch indices whose code is
  * not 1 (unordered) and their codes — pass accepted = NULL to mm_enqueue* and ack everything else
  * (search/worker.ex:323 acks per delivery).  MM_E_CAP if there are more than cap (n_rejects says how many).   */

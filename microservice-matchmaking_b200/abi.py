@@ -82,6 +82,8 @@ PROTOTYPES = {
     "mm_enqueue": (C.c_int, [_vp, C.c_uint32, _vp, _vp, _vp, _vp, _vp]),
     "mm_enqueue_device": (C.c_int, [_vp, C.c_uint32, _vp, _vp, _vp, _vp, _vp, _P(C.c_uint32)]),
     "mm_enqueue_packed": (C.c_int, [_vp, C.c_uint32, _vp, _vp, _vp, _vp]),
+    "mm_enqueue_packed_begin": (C.c_int, [_vp, C.c_uint32, _vp, _vp, _vp]),
+    "mm_enqueue_packed_end": (C.c_int, [_vp, _vp, _vp]),
     "mm_enqueue_rejects": (C.c_int, [_vp, C.c_uint32, _vp, _vp, _P(C.c_uint32)]),
     "mm_remove": (C.c_int, [_vp, C.c_uint32, _vp, _P(C.c_uint32)]),
     "mm_remove_packed": (C.c_int, [_vp, C.c_uint32, _vp, _P(C.c_uint32)]),

@@ -119,6 +119,16 @@ struct mm_engine {
   uint32_t last_batch_n = 0;    // entries of the last ingest batch (their codes are still in d_code)
   uint32_t* d_rej_idx = nullptr; uint8_t* d_rej_code = nullptr; uint32_t rej_cap = 0;
 
+  // mm_enqueue_packed_begin / _end: two staging slots for packed batches whose upload is in flight (FIFO)
+  struct Stage {
+    uint32_t *handle = nullptr, *ts = nullptr;
+    uint16_t* key = nullptr;
+    uint32_t cap = 0, n = 0;
+    bool has_ts = false;
+    cudaEvent_t ready = nullptr;  // recorded on the copy stream behind the slot's last copy
+  } stage[2];
+  int stage_head = 0, stage_count = 0;
+
   // last tick
   mm_tick_stats last{};
   bool last_fused = false;
@@ -811,6 +821,7 @@ int mm_destroy(mm_engine* e) {
   for (auto& ev : e->ev)
     if (ev) cudaEventDestroy(ev);
   if (e->stream && e->own_stream) cudaStreamDestroy(e->stream);
+  for (auto& st : e->stage) { cudaFree(st.handle); cudaFree(st.key); cudaFree(st.ts); if (st.ready) cudaEventDestroy(st.ready); }
   if (e->d2h_stream) cudaStreamDestroy(e->d2h_stream);
   if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
   if (e->ev_copy) cudaEventDestroy(e->ev_copy);
@@ -921,6 +932,64 @@ int mm_enqueue_packed(mm_engine* e, uint32_t n, const uint32_t* handle, const ui
   rc = enqueue_batch(e, n, e->d_in_id, e->d_in_rating, e->d_in_mode, enq_ts ? e->d_in_ts : nullptr, kEnqChunk, upload);
   if (rc) { cudaStreamSynchronize(e->copy_stream); return rc; }
   rc = enq_finish(e, n, nullptr, nullptr);
+  if (rc) return rc;
+  if (accepted) {
+    CK(cudaMemcpyAsync(accepted, e->d_code, n, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+  }
+  return MM_OK;
+}
+
+int mm_enqueue_packed_begin(mm_engine* e, uint32_t n, const uint32_t* handle, const uint16_t* key, const uint32_t* enq_ts) {
+  if (!e || !n || !handle || !key) return MM_E_ARG;
+  std::lock_guard<std::mutex> lk(e->mu);
+  CK(cudaSetDevice(e->device));
+  if (e->stage_count == 2) {
+    std::snprintf(e->last_err, sizeof(e->last_err), "both staging slots hold a batch: call mm_enqueue_packed_end first");
+    return MM_E_STATE;
+  }
+  mm_engine::Stage& st = e->stage[(e->stage_head + e->stage_count) & 1];
+  if (n > st.cap) {  // the slot's previous batch was consumed by an _end that synchronised the engine stream
+    cudaFree(st.handle); cudaFree(st.key); cudaFree(st.ts);
+    st.handle = nullptr; st.key = nullptr; st.ts = nullptr; st.cap = 0;
+    CK(cudaMalloc(&st.handle, ((size_t)n + 64) * 4));
+    CK(cudaMalloc(&st.key, ((size_t)n + 64) * 2));
+    CK(cudaMalloc(&st.ts, ((size_t)n + 64) * 4));
+    st.cap = n;
+  }
+  if (!st.ready) CK(cudaEventCreateWithFlags(&st.ready, cudaEventDisableTiming));
+  CK(cudaMemcpyAsync(st.handle, handle, (size_t)n * 4, cudaMemcpyHostToDevice, e->copy_stream));
+  CK(cudaMemcpyAsync(st.key, key, (size_t)n * 2, cudaMemcpyHostToDevice, e->copy_stream));
+  if (enq_ts) CK(cudaMemcpyAsync(st.ts, enq_ts, (size_t)n * 4, cudaMemcpyHostToDevice, e->copy_stream));
+  CK(cudaEventRecord(st.ready, e->copy_stream));
+  st.n = n; st.has_ts = enq_ts != nullptr;
+  ++e->stage_count;
+  return MM_OK;
+}
+
+int mm_enqueue_packed_end(mm_engine* e, uint8_t* accepted, uint32_t* n_accepted) {
+  if (!e) return MM_E_ARG;
+  std::lock_guard<std::mutex> lk(e->mu);
+  CK(cudaSetDevice(e->device));
+  if (e->stage_count == 0) {
+    std::snprintf(e->last_err, sizeof(e->last_err), "no staged batch: call mm_enqueue_packed_begin first");
+    return MM_E_STATE;
+  }
+  mm_engine::Stage& st = e->stage[e->stage_head];
+  e->stage_head ^= 1; --e->stage_count;  // the slot is released whatever happens below
+  const uint32_t n = st.n;
+  int rc = ensure_enq_scratch(e, n);
+  if (rc) return rc;
+  CK(cudaStreamWaitEvent(e->stream, st.ready, 0));
+  auto unpack = [&](uint32_t base, uint32_t cnt) -> int {
+    k_unpack<<<(cnt + 255) / 256, 256, 0, e->stream>>>(cnt, st.handle + base, st.key + base, e->d_in_id + base,
+                                                       e->d_in_rating + base, e->d_in_mode + base);
+    CK(cudaGetLastError());
+    return MM_OK;
+  };
+  rc = enqueue_batch(e, n, e->d_in_id, e->d_in_rating, e->d_in_mode, st.has_ts ? st.ts : nullptr, kEnqChunkDev, unpack);
+  if (rc) { cudaStreamSynchronize(e->stream); return rc; }
+  rc = enq_finish(e, n, nullptr, n_accepted);
   if (rc) return rc;
   if (accepted) {
     CK(cudaMemcpyAsync(accepted, e->d_code, n, cudaMemcpyDeviceToHost, e->stream));

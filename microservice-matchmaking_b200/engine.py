@@ -59,6 +59,7 @@ class Engine:
         if rc != abi.MM_OK:
             raise EngineError(rc, "mm_create", self.lib.mm_strerror(rc).decode())
         self.h = h
+        self._staged = []  # host arrays of staged packed batches (kept alive until their _end)
 
     # -- lifecycle ---------------------------------------------------------------
     def close(self):
@@ -131,6 +132,38 @@ class Engine:
     def enqueue_packed_raw(self, n, p_handles, p_keys, p_ts=0, p_accepted=0):
         self._check(self.lib.mm_enqueue_packed(self.h, n, p_handles, p_keys, p_ts or None, p_accepted or None),
                     "mm_enqueue_packed")
+
+    def enqueue_packed_begin(self, handles, keys, enq_ts=None):
+        """Start the upload of a packed batch (mm_enqueue_packed_begin); the arrays are kept alive until the matching
+        enqueue_packed_end()."""
+        handles = np.ascontiguousarray(handles, np.uint32)
+        keys = np.ascontiguousarray(keys, np.uint16)
+        assert len(keys) == len(handles)
+        if enq_ts is not None:
+            enq_ts = np.ascontiguousarray(enq_ts, np.uint32)
+        self._check(self.lib.mm_enqueue_packed_begin(self.h, len(handles), _p(handles), _p(keys), _p(enq_ts)),
+                    "mm_enqueue_packed_begin")
+        self._staged.append((handles, keys, enq_ts))
+
+    def enqueue_packed_end(self, want_codes=True):
+        """Ingest the oldest staged batch -> (accepted u8[n] or None, n_accepted)."""
+        acc = None
+        if want_codes and self._staged:
+            acc = np.empty(len(self._staged[0][0]), np.uint8)
+        n_acc = C.c_uint32(0)
+        rc = self.lib.mm_enqueue_packed_end(self.h, _p(acc), C.byref(n_acc))
+        if self._staged:
+            self._staged.pop(0)
+        self._check(rc, "mm_enqueue_packed_end")
+        return acc, n_acc.value
+
+    def enqueue_packed_begin_raw(self, n, p_handles, p_keys, p_ts=0):
+        self._check(self.lib.mm_enqueue_packed_begin(self.h, n, p_handles, p_keys, p_ts or None), "mm_enqueue_packed_begin")
+
+    def enqueue_packed_end_raw(self):
+        n_acc = C.c_uint32(0)
+        self._check(self.lib.mm_enqueue_packed_end(self.h, None, C.byref(n_acc)), "mm_enqueue_packed_end")
+        return n_acc.value
 
     def enqueue_rejects(self, cap=4096):
         """(batch index, code) of the entries of the last enqueue batch that were not queued (unordered)."""

@@ -547,6 +547,44 @@ def test_packed_rejects_list(pkg):
         assert eng.remove_packed(np.array([5, 5, 99], np.uint32)) == 1
 
 
+def test_staged_packed_ingest_equals_the_blocking_one(pkg, oracle):
+    """mm_enqueue_packed_begin / _end with two batches in flight and ticks in between == the same batches through the
+    blocking mm_enqueue_packed, tick by tick (codes, reject lists, lobbies, members, emission order, leftovers); the
+    blocking path itself is held to the oracle by the tests above."""
+    n, steps = 120_011, 4
+    cfg = pkg.synth.make_config(n_groups=32, order=RATING, capacity=2 * n, active_capacity=(steps + 1) * n)
+    cfg.flags |= pkg.abi.MM_F_DENSE_IDS
+    batches = []
+    for k in range(steps):
+        _, rating, mode, ts = make_pool(pkg, 500 + k, n, oor=0.0)
+        handles = (np.arange(n, dtype=np.uint32) + np.uint32(k * n))
+        if k:  # a few players of the previous batch offered again: "already in the queue"
+            handles[:50] = batches[-1][0][100:150]
+        batches.append((handles, rating, mode, ts))
+    with pkg.Engine(cfg) as a, pkg.Engine(cfg) as b:
+        with pytest.raises(pkg.EngineError):
+            a.enqueue_packed_end()  # nothing staged
+        a.enqueue_packed_begin(batches[0][0], pkg.Engine.pack_key(batches[0][1], batches[0][2]), batches[0][3])
+        for k in range(steps):
+            h, rating, mode, ts = batches[k]
+            if k + 1 < steps:
+                hn, rn, mn, tn = batches[k + 1]
+                a.enqueue_packed_begin(hn, pkg.Engine.pack_key(rn, mn), tn)  # next upload in flight
+                if k == 0:
+                    with pytest.raises(pkg.EngineError):
+                        a.enqueue_packed_begin(hn, pkg.Engine.pack_key(rn, mn), tn)  # both slots hold a batch
+            acc_a, n_acc = a.enqueue_packed_end()
+            acc_b = b.enqueue_packed(h, pkg.Engine.pack_key(rating, mode), ts)
+            assert np.array_equal(acc_a, acc_b) and n_acc == int((acc_b == 1).sum())
+            ia, ca = a.enqueue_rejects(); ib, cb = b.enqueue_rejects()
+            assert np.array_equal(np.sort(ia), np.sort(ib)) and len(ia) == (50 if k else 0)
+            la, ma, sa, _ = a.tick_packed()
+            lb, mb, sb, _ = b.tick_packed()
+            assert np.array_equal(la, lb) and np.array_equal(ma, mb) and np.array_equal(sa, sb)
+            assert len(la) > 0
+        assert np.array_equal(a.pool_read()["id"], b.pool_read()["id"])
+
+
 # ---- rating-group shards on real engines (SURVEY §8e): K engines, one per rank's group range, merged ----------------
 @pytest.mark.parametrize("K,workload", [(2, None), (4, None), (8, "config3_10m_g32_5v5")])
 @pytest.mark.parametrize("order", [RATING, ARRIVAL])
