@@ -57,6 +57,10 @@ typedef enum mm_order_mode { MM_ORDER_ARRIVAL = 0, MM_ORDER_RATING = 1 } mm_orde
 #define MM_F_DENSE_IDS 2u /* player ids are dense host handles 0 .. active_capacity-1 (the host owns the
                              UUID <-> handle table): the active set is a direct-mapped array instead of a hash
                              table, and the packed entry points (mm_enqueue_packed / mm_tick_packed) apply.        */
+#define MM_F_WIDE_PARTITIONS 4u /* keep every (mode, group) queue ONE pool partition however many ratings it spans
+                             (default: groups wider than 255 ratings are stored as several partitions of <= 255
+                             sort keys so that every tile takes the 8-bit ranking path).  Results are identical;
+                             this keeps the list-ranking path reachable for tests and comparisons.              */
 
 typedef struct mm_mode_desc {
   uint16_t teams;     /* T: number of teams ("1v1" -> 2, "5v5" -> 2)   */

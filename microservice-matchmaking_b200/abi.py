@@ -22,6 +22,7 @@ MM_ORDER_RATING = 1
 
 MM_F_NO_DEDUPE = 1
 MM_F_DENSE_IDS = 2
+MM_F_WIDE_PARTITIONS = 4
 
 
 class ModeDesc(C.Structure):

@@ -27,7 +27,7 @@ constexpr uint16_t kNoPart = 0xFFFFu;
 // is what a serialized in_queue?/add_user sequence (middleware/worker.ex:65-70) yields.
 __global__ void k_enq_claim(uint32_t base, uint32_t n, const uint64_t* __restrict__ id, const int32_t* __restrict__ rating,
                             const uint8_t* __restrict__ mode, const uint8_t* __restrict__ grp_lut, int32_t key_lo,
-                            uint32_t KR, uint32_t n_modes, uint32_t n_groups, ActiveView act,
+                            uint32_t KR, uint32_t n_modes, BinMap bm, const uint16_t* __restrict__ bin_seg, ActiveView act,
                             uint64_t* __restrict__ hslot, uint8_t* __restrict__ code, uint16_t* __restrict__ part) {
   const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;  // this launch covers batch indices [base, base + n)
   if (t >= n) return;
@@ -38,7 +38,7 @@ __global__ void k_enq_claim(uint32_t base, uint32_t n, const uint64_t* __restric
   const uint32_t grp = grp_lut[r - key_lo];
   const bool bad_id = act.dcap ? pid >= act.dcap : pid >= kTombKey;
   if (mode[i] >= n_modes || bad_id || grp == 0xFF) { code[i] = 2; hslot[i] = ~0ull; part[i] = kNoPart; return; }
-  part[i] = (uint16_t)(mode[i] * n_groups + grp);
+  part[i] = bin_seg[bin_of(bm, bm.lut, rating[i], mode[i])];  // the layout partition that holds the player's sort key
   if (!act.on()) { code[i] = 1; hslot[i] = ~0ull; return; }
   if (act.dcap) {
     const unsigned long long old = atomicMin(act.val(pid), kPending | i);

@@ -51,10 +51,10 @@ struct BinMap {
   uint32_t K;           // live bins; bin K = removed-while-queued players
 };
 
-struct SegInfo {        // one (mode, group) partition, written by the scan tail
+struct SegInfo {        // one layout partition, written by the scan tail
   uint32_t n;           // alive players
-  uint32_t n_lobbies;
-  uint32_t member_base; // first slot in member_ids
+  uint32_t n_lobbies;   // lobbies of the partition's cut segment that START in this partition
+  uint32_t member_base; // member_ids slot of the first of them
   uint32_t lobby_base;  // first lobby index
   uint32_t left_base;   // leftover players of earlier partitions (rank base of the compaction)
   uint32_t new_chunk;   // first chunk of the partition in the compacted pool

@@ -52,7 +52,11 @@ struct mm_engine {
 
   // key domain
   int32_t key_lo = 0;
-  uint32_t KR = 0, stride = 0, K = 0, Kp = 0, n_segs = 0;
+  uint32_t KR = 0, stride = 0, K = 0, Kp = 0;
+  uint32_t n_segs = 0;  // layout partitions (see build_tables)
+  uint32_t n_cut = 0;   // (mode, group) cut segments
+  uint16_t* d_part_cut = nullptr;   // [n_segs] partition -> cut segment
+  uint32_t* d_cut_lp_lo = nullptr;  // [n_cut + 1] first partition of the cut segment
   uint16_t* d_lut = nullptr;
   uint8_t* d_grp_lut = nullptr;
   uint8_t* d_mode_tsize = nullptr;
@@ -245,7 +249,7 @@ int check_config(const mm_config* c) {
   if (c->default_group >= (int32_t)c->n_groups || c->default_group < -1) return MM_E_ARG;
   if (c->order_mode > MM_ORDER_RATING) return MM_E_ARG;
   if (c->capacity == 0 || c->capacity > 0x7FFF0000u) return MM_E_ARG;
-  if (c->flags & ~(MM_F_NO_DEDUPE | MM_F_DENSE_IDS)) return MM_E_ARG;
+  if (c->flags & ~(MM_F_NO_DEDUPE | MM_F_DENSE_IDS | MM_F_WIDE_PARTITIONS)) return MM_E_ARG;
   for (uint32_t g = 0; g < c->n_groups; ++g) {
     if (c->group_lo[g] > c->group_hi[g]) return MM_E_ARG;
     if (c->group_lo[g] < -(1 << 30) || c->group_hi[g] > (1 << 30)) return MM_E_ARG;
@@ -304,22 +308,48 @@ int build_tables(mm_engine* e) {
   e->K = c.n_modes * e->stride;
   e->Kp = e->K + 1;
   if (e->Kp > 65535u) return MM_E_ARG;  // the resident sort key is 16 bits
-  e->n_segs = c.n_modes * G;
-  std::vector<uint32_t> seg_lo(e->n_segs + 1), seg_L(e->n_segs);
+  // Layout partitions: a (mode, group) CUT SEGMENT — the unit of the lobby cut — is stored as one or more PARTITIONS
+  // of at most kFastBins consecutive sort keys each, so that every tile ranks on the 8-bit path and carries a chunk
+  // histogram whatever the width of the rating group (the reference's default groups span 500 - 1 500 ratings,
+  // config/config.exs:27-36).  Narrow groups: one partition per segment.
+  e->n_cut = c.n_modes * G;
+  std::vector<uint32_t> seg_lo, seg_L, cut_lp_lo(e->n_cut + 1);
+  std::vector<uint16_t> part_cut;
   e->min_L = 0xFFFFFFFFu;
   std::vector<uint8_t> tsz(MM_MAX_MODES, 0);
-  for (uint32_t m = 0; m < c.n_modes; ++m) {
-    const uint32_t L = (uint32_t)c.modes[m].teams * c.modes[m].team_size;
-    e->min_L = std::min(e->min_L, L);
-    tsz[m] = (uint8_t)c.modes[m].team_size;
-    for (uint32_t g = 0; g < G; ++g) { seg_lo[m * G + g] = m * e->stride + first[g]; seg_L[m * G + g] = L; }
+  bool split = !(c.flags & MM_F_WIDE_PARTITIONS);
+  for (int attempt = 0; attempt < 2; ++attempt) {
+    seg_lo.clear(); seg_L.clear(); part_cut.clear();
+    for (uint32_t m = 0; m < c.n_modes; ++m) {
+      const uint32_t L = (uint32_t)c.modes[m].teams * c.modes[m].team_size;
+      e->min_L = std::min(e->min_L, L);
+      tsz[m] = (uint8_t)c.modes[m].team_size;
+      for (uint32_t g = 0; g < G; ++g) {
+        const uint32_t lo = m * e->stride + first[g], nk = first[g + 1] - first[g];
+        const uint32_t nsub = split ? std::max(1u, (nk + kFastBins - 1) / kFastBins) : 1u;
+        const uint32_t per = (nk + nsub - 1) / nsub;
+        cut_lp_lo[m * G + g] = (uint32_t)seg_lo.size();
+        for (uint32_t j = 0; j < nsub; ++j) {
+          seg_lo.push_back(lo + std::min(nk, j * per)); seg_L.push_back(L); part_cut.push_back((uint16_t)(m * G + g));
+        }
+      }
+    }
+    if (seg_lo.size() <= kMaxSegs) break;
+    split = false;  // too many partitions for the on-chip tables: whole segments, list ranking for the wide ones
   }
-  seg_lo[e->n_segs] = e->K;
+  e->n_segs = (uint32_t)seg_lo.size();
+  if (e->n_segs > kMaxSegs) return MM_E_ARG;
+  cut_lp_lo[e->n_cut] = e->n_segs;
+  seg_lo.push_back(e->K);
   e->max_nb = 1;
   for (uint32_t sgi = 0; sgi < e->n_segs; ++sgi) e->max_nb = std::max(e->max_nb, seg_lo[sgi + 1] - seg_lo[sgi]);
   std::vector<uint16_t> bin_seg(e->Kp, 0);
   for (uint32_t sgi = 0; sgi < e->n_segs; ++sgi)
     for (uint32_t b = seg_lo[sgi]; b < seg_lo[sgi + 1]; ++b) bin_seg[b] = (uint16_t)sgi;
+  CK(cudaMalloc(&e->d_part_cut, e->n_segs * 2));
+  CK(cudaMemcpy(e->d_part_cut, part_cut.data(), e->n_segs * 2, cudaMemcpyHostToDevice));
+  CK(cudaMalloc(&e->d_cut_lp_lo, (e->n_cut + 1) * 4));
+  CK(cudaMemcpy(e->d_cut_lp_lo, cut_lp_lo.data(), (e->n_cut + 1) * 4, cudaMemcpyHostToDevice));
   std::vector<uint16_t> bin_key(e->Kp, 0);
   if (!key_of.empty())
     for (uint32_t b = 0; b < e->K; ++b) bin_key[b] = key_of[b % e->stride];
@@ -417,7 +447,7 @@ int enq_chunk(mm_engine* e, uint32_t base, uint32_t cnt, const uint64_t* id, con
   ActiveView av = act_view(e);
   const uint32_t nb = (cnt + 255) / 256, nblk = (cnt + kIngestItems - 1) / kIngestItems;
   k_enq_claim<<<nb, 256, 0, e->stream>>>(base, cnt, id, rating, mode, e->d_grp_lut, e->key_lo, e->KR, e->cfg.n_modes,
-                                         e->cfg.n_groups, av, e->d_hslot, e->d_code, e->d_part);
+                                         bin_map(e), e->d_bin_seg, av, e->d_hslot, e->d_code, e->d_part);
   if (may_overflow) {  // the batch might not fit: the winners past the pool capacity are rolled back (code 3)
     const uint32_t room = e->capacity > p.n ? e->capacity - p.n : 0u;
     k_enq_count<<<nb, 256, 0, e->stream>>>(base, cnt, av, e->d_hslot, e->d_code, e->d_blocksum);
@@ -470,6 +500,7 @@ TailArgs tail_args(mm_engine* e) {
   TailArgs t{};
   t.Kp = e->Kp; t.K = e->K; t.n_segs = e->n_segs; t.max_spread = e->max_spread; t.layout = tail_layout(e);
   t.tot = e->pool[e->cur].m.tot; t.seg_bin_lo = e->d_seg_bin_lo; t.seg_L = e->d_seg_L; t.bin_seg = e->d_bin_seg;
+  t.n_cut = e->n_cut; t.part_cut = e->d_part_cut; t.cut_lp_lo = e->d_cut_lp_lo;
   t.bin_key = e->d_bin_key; t.outbase = e->d_outbase; t.binlim = e->d_binlim; t.seg = e->d_seg; t.ctr = e->d_ctr;
   t.fill = e->pool[e->cur].m.fill;
   t.dst = e->pool[e->cur ^ 1].m;
@@ -500,7 +531,7 @@ EpiArgs epi_args(mm_engine* e, bool want_seq, bool headers) {
   a.src_meta = e->pool[e->cur].m; a.dst_meta = e->pool[e->cur ^ 1].m;
   a.R = tick_rows(e); a.new_gen = next_gen(e); a.n_segs = e->n_segs; a.n_groups = e->cfg.n_groups; a.Kp = e->Kp;
   a.write_headers = headers ? 1u : 0u;
-  a.rescnt = e->d_rescnt; a.left_bits = e->d_left_bits; a.act = act_view(e); a.seg = e->d_seg; a.seg_L = e->d_seg_L;
+  a.rescnt = e->d_rescnt; a.left_bits = e->d_left_bits; a.act = act_view(e); a.seg = e->d_seg; a.seg_L = e->d_seg_L; a.part_cut = e->d_part_cut;
   a.seg_bin_lo = e->d_seg_bin_lo;
   a.hdr = e->d_hdr; a.src_idx = want_seq ? e->d_src_idx : nullptr; a.emit_seq = want_seq ? e->d_emit_seq : nullptr;
   a.ctr = e->d_ctr;
@@ -810,6 +841,7 @@ int mm_destroy(mm_engine* e) {
   free_pool(e->pool[0]); free_pool(e->pool[1]); free_pool(e->snap); cudaFree(e->d_left_bits);
   for (auto& t : e->tab) cudaFree(t.kv);
   cudaFree(e->d_lut); cudaFree(e->d_grp_lut); cudaFree(e->d_mode_tsize); cudaFree(e->d_seg_bin_lo); cudaFree(e->d_seg_L);
+  cudaFree(e->d_part_cut); cudaFree(e->d_cut_lp_lo);
   cudaFree(e->d_M); cudaFree(e->d_P); cudaFree(e->d_outbase); cudaFree(e->d_binlim); cudaFree(e->d_bin_seg);
   cudaFree(e->d_bin_key); cudaFree(e->d_seg); cudaFree(e->d_members); cudaFree(e->d_members32); cudaFree(e->d_src_idx);
   cudaFree(e->d_hdr); cudaFree(e->d_emit_seq); cudaFree(e->d_rescnt); cudaFree(e->d_ctr2); cudaFree(e->d_small);

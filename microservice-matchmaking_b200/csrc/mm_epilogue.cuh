@@ -28,6 +28,7 @@ struct EpiArgs {
   ActiveView act;
   const SegInfo* seg;
   const uint32_t* seg_L;
+  const uint16_t* part_cut;  // [n_segs] partition -> (mode, group) cut segment
   const uint32_t* seg_bin_lo;
   mm_lobby_hdr* hdr;
   const uint32_t* src_idx;
@@ -48,8 +49,9 @@ __device__ __forceinline__ void headers_body(const Geo& g, const EpiArgs& a, con
     const uint32_t L = s_L[sg], mb = s_mbase[sg];
     mm_lobby_hdr h;
     h.n_members = (uint16_t)L;
-    h.mode = (uint8_t)(sg / n_groups);
-    h.group = (uint8_t)(sg % n_groups);
+    const uint32_t cut = a.part_cut[sg];
+    h.mode = (uint8_t)(cut / n_groups);
+    h.group = (uint8_t)(cut % n_groups);
     for (uint32_t c = l0 + part * BLOCK + tid; c < l1; c += nparts * BLOCK) {
       h.first_member = mb + (c - l0) * L;
       a.hdr[c] = h;

@@ -17,7 +17,7 @@ namespace mm {
 // ---------------------------------------------------------------------------------------
 constexpr int kScanBlock = 512;
 constexpr uint32_t kColScratchWords = (kScanBlock / 32) * 33;      // column CTA scratch
-constexpr uint32_t kTailScratchWords = 64 + 4 + 6 * kMaxSegs + 8;  // tail CTA scratch, fixed part
+constexpr uint32_t kTailScratchWords = 64 + 4 + 9 * kMaxSegs + 12;  // tail CTA scratch, fixed part
 
 // One 32-bin column group: exclusive prefix down the rows of M (scratch: kColScratchWords).  Bin b belongs to one
 // partition, and only the rows holding that partition's tiles wrote M[.][b] (mm_hist.cuh): the scan of a column is
@@ -65,6 +65,9 @@ __device__ __forceinline__ void colscan_cols_body(uint32_t* scratch, const Geo& 
 // arguments of the tail (shared by k_colscan and the fused k_tick)
 struct TailArgs {
   uint32_t Kp, K, n_segs;
+  uint32_t n_cut;                     // (mode, group) cut segments; each is a run of partitions
+  const uint16_t* part_cut;           // [n_segs] partition -> cut segment
+  const uint32_t* cut_lp_lo;          // [n_cut + 1] first partition of the cut segment
   uint32_t layout;                    // bit 0: matched counts in shared memory; bit 1: bin keys too (tail_words)
   int32_t max_spread;                 // < 0: unlimited (policy S0); >= 0: policy S1, rating order only
   const uint32_t* tot;                // [Kp] bin totals of the pool being matched (kept up to date by ingest / remove / tick)
@@ -104,11 +107,15 @@ __device__ __forceinline__ void colscan_tail_body(uint32_t* scratch, const TailA
   uint32_t* s_lo = s_mt + kMaxSegs;     // [kMaxSegs + 1] first bin of the segment
   uint32_t* s_nch = s_lo + kMaxSegs + 1;   // [kMaxSegs + 1] first chunk of the segment in the compacted pool
   uint32_t* s_L = s_nch + kMaxSegs + 1;    // [kMaxSegs] lobby size of the segment
+  uint32_t* s_pc = s_L + kMaxSegs;         // [kMaxSegs] cut segment of the partition
+  uint32_t* s_clp = s_pc + kMaxSegs;       // [kMaxSegs + 1] first partition of the cut segment
+  uint32_t* s_ms = s_clp + kMaxSegs + 1;   // [kMaxSegs + 1] member slot of the partition's first matched player
   uint32_t* s_bb = scratch + kTailScratchWords;  // [Kp + 1] sorted position of the bin's first player
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, Kp = t.Kp, K = t.K, n_segs = t.n_segs;
   if (tid == 0) s_misc[0] = 0;
   for (uint32_t sg = tid; sg <= n_segs; sg += kScanBlock) s_lo[sg] = t.seg_bin_lo[sg];  // all the cold loads at once
-  for (uint32_t sg = tid; sg < n_segs; sg += kScanBlock) s_L[sg] = t.seg_L[sg];
+  for (uint32_t sg = tid; sg < n_segs; sg += kScanBlock) { s_L[sg] = t.seg_L[sg]; s_pc[sg] = t.part_cut[sg]; }
+  for (uint32_t c = tid; c <= t.n_cut; c += kScanBlock) s_clp[c] = t.cut_lp_lo[c];
   for (uint32_t i = tid; i < Kp; i += kScanBlock) s_bb[i] = __ldcg(&t.tot[i]);  // coalesced, independent loads
   __syncthreads();
   // list-ranked partitions only: does some bin expect > 8 players per tile of its partition?
@@ -129,10 +136,14 @@ __device__ __forceinline__ void colscan_tail_body(uint32_t* scratch, const TailA
   uint32_t* s_m = m_smem ? s_bb + Kp + 2 : t.binlim;  // S1: [Kp + 1] matched players of the bin
 
   if (!windowed) {
-    // S0: lobbies_s = n_s / L; the partition's first lobbies_s * L sorted positions are matched.
+    // S0: a cut segment of n players gives n / L lobbies: its first (n / L) * L sorted positions are matched; a
+    // partition holds the part of that prefix that falls into its own position range.
     for (uint32_t sg = tid; sg < n_segs; sg += kScanBlock) {
-      const uint32_t ns = s_bb[s_lo[sg + 1]] - s_bb[s_lo[sg]], L = s_L[sg];
-      s_ns[sg] = ns; s_mt[sg] = ns / L * L;
+      const uint32_t c = s_pc[sg], cs = s_bb[s_lo[s_clp[c]]], ce = s_bb[s_lo[s_clp[c + 1]]], L = s_L[sg];
+      const uint32_t mend = cs + (ce - cs) / L * L;
+      const uint32_t a = s_bb[s_lo[sg]], b = s_bb[s_lo[sg + 1]];
+      s_ns[sg] = b - a;
+      s_mt[sg] = (mend < a ? a : (mend > b ? b : mend)) - a;
     }
   } else {
     uint16_t* s_key = reinterpret_cast<uint16_t*>(s_bb + (m_smem ? 2 : 1) * (Kp + 2));
@@ -148,16 +159,17 @@ __device__ __forceinline__ void colscan_tail_body(uint32_t* scratch, const TailA
     //            a = rsel - cur the bin seeds a / L lobbies and p2 = rsel - a mod L is the next unconsumed position
     // and on the chain only: cur = max(pos, b0); a; a mod L by a reciprocal multiply; p2; select.  Empty bins
     // fall out of the same arithmetic (cur >= b1), so the 32 bins of a batch are visited by an unrolled loop.
-    for (uint32_t sg0 = warp; sg0 < n_segs; sg0 += 2 * NW) {
+    for (uint32_t sg = tid; sg < n_segs; sg += kScanBlock) s_ns[sg] = s_bb[s_lo[sg + 1]] - s_bb[s_lo[sg]];
+    // the walk runs over whole CUT segments (a window may span the partitions of a wide rating group)
+    for (uint32_t sg0 = warp; sg0 < t.n_cut; sg0 += 2 * NW) {
       uint32_t lo[2], hi[2], L[2], Mrec[2], pos[2];
 #pragma unroll
       for (int q = 0; q < 2; ++q) {
         const uint32_t sg = sg0 + q * NW;
-        const bool on = sg < n_segs;
-        lo[q] = on ? s_lo[sg] : 0u; hi[q] = on ? s_lo[sg + 1] : 0u; L[q] = on ? t.seg_L[sg] : 1u;
+        const bool on = sg < t.n_cut;
+        lo[q] = on ? s_lo[s_clp[sg]] : 0u; hi[q] = on ? s_lo[s_clp[sg + 1]] : 0u; L[q] = on ? s_L[s_clp[sg]] : 1u;
         Mrec[q] = 0xFFFFFFFFu / L[q];  // umulhi(a, Mrec) is a / L or a / L - 1 for every 32-bit a
         pos[q] = s_bb[lo[q]];
-        if (on && lane == 0) s_ns[sg] = s_bb[hi[q]] - s_bb[lo[q]];
       }
       const uint32_t span0 = hi[0] - lo[0], span1 = hi[1] - lo[1], span = span0 > span1 ? span0 : span1;
       for (uint32_t off = 0; off < span; off += 32) {
@@ -222,30 +234,54 @@ __device__ __forceinline__ void colscan_tail_body(uint32_t* scratch, const TailA
   // bases, and the layout of the compacted pool — partition sg keeps n_left players in ceil(n_left / kTile) fresh
   // chunks handed out in partition order from chunk 0 (the epilogue moves the players).
   if (warp == 0) {
-    uint32_t c_mem = 0, c_lob = 0, c_left = 0, c_ch = 0;
+    uint32_t c_mem = 0, c_left = 0, c_ch = 0;
     for (uint32_t base = 0; base < n_segs; base += 32) {
       const uint32_t sg = base + lane;
       const bool on = sg < n_segs;
-      const uint32_t ns = on ? s_ns[sg] : 0u, mt = on ? s_mt[sg] : 0u, L = on ? s_L[sg] : 1u;
-      const uint32_t nl = mt / L, nleft = ns - mt, nch = (nleft + kTile - 1) / kTile;
-      uint32_t i_mem = mt, i_lob = nl, i_left = nleft, i_ch = nch;
+      const uint32_t ns = on ? s_ns[sg] : 0u, mt = on ? s_mt[sg] : 0u;
+      const uint32_t nleft = ns - mt, nch = (nleft + kTile - 1) / kTile;
+      uint32_t i_mem = mt, i_left = nleft, i_ch = nch;
 #pragma unroll
       for (int off = 1; off < 32; off <<= 1) {
-        const uint32_t a = __shfl_up_sync(0xFFFFFFFFu, i_mem, off), b = __shfl_up_sync(0xFFFFFFFFu, i_lob, off);
+        const uint32_t a = __shfl_up_sync(0xFFFFFFFFu, i_mem, off);
         const uint32_t c = __shfl_up_sync(0xFFFFFFFFu, i_left, off), d = __shfl_up_sync(0xFFFFFFFFu, i_ch, off);
-        if (lane >= (uint32_t)off) { i_mem += a; i_lob += b; i_left += c; i_ch += d; }
+        if (lane >= (uint32_t)off) { i_mem += a; i_left += c; i_ch += d; }
+      }
+      if (on) {
+        s_ms[sg] = c_mem + i_mem - mt;
+        s_a[sg] = c_left + i_left - nleft;
+        s_nch[sg] = c_ch + i_ch - nch;
+        t.dst.fill[sg] = nleft;
+      }
+      c_mem += __shfl_sync(0xFFFFFFFFu, i_mem, 31);
+      c_left += __shfl_sync(0xFFFFFFFFu, i_left, 31); c_ch += __shfl_sync(0xFFFFFFFFu, i_ch, 31);
+    }
+    __syncwarp();
+    // Lobbies are cut per CUT segment: lobby k of segment c = member slots [mb_c + k L, + L).  A partition is
+    // credited with the lobbies that START inside its member-slot range, so the header writers can loop per partition.
+    uint32_t c_lob = 0;
+    for (uint32_t base = 0; base < n_segs; base += 32) {
+      const uint32_t sg = base + lane;
+      const bool on = sg < n_segs;
+      uint32_t nl = 0, hb = 0;
+      if (on) {
+        const uint32_t L = s_L[sg], mb = s_ms[s_clp[s_pc[sg]]], m0 = s_ms[sg] - mb, m1 = m0 + s_mt[sg];
+        const uint32_t k0 = (m0 + L - 1) / L, k1 = (m1 + L - 1) / L;
+        nl = k1 - k0; hb = mb + k0 * L;
+      }
+      uint32_t i_lob = nl;
+#pragma unroll
+      for (int off = 1; off < 32; off <<= 1) {
+        const uint32_t b = __shfl_up_sync(0xFFFFFFFFu, i_lob, off);
+        if (lane >= (uint32_t)off) i_lob += b;
       }
       if (on) {
         SegInfo si;
-        si.n = ns; si.n_lobbies = nl; si.member_base = c_mem + i_mem - mt; si.lobby_base = c_lob + i_lob - nl;
-        si.left_base = c_left + i_left - nleft; si.new_chunk = c_ch + i_ch - nch; si.n_left = nleft; si.reserved = 0;
+        si.n = s_ns[sg]; si.n_lobbies = nl; si.member_base = hb; si.lobby_base = c_lob + i_lob - nl;
+        si.left_base = s_a[sg]; si.new_chunk = s_nch[sg]; si.n_left = s_ns[sg] - s_mt[sg]; si.reserved = 0;
         t.seg[sg] = si;
-        t.dst.fill[sg] = nleft;
-        s_a[sg] = si.left_base;
-        s_nch[sg] = si.new_chunk;
       }
-      c_mem += __shfl_sync(0xFFFFFFFFu, i_mem, 31); c_lob += __shfl_sync(0xFFFFFFFFu, i_lob, 31);
-      c_left += __shfl_sync(0xFFFFFFFFu, i_left, 31); c_ch += __shfl_sync(0xFFFFFFFFu, i_ch, 31);
+      c_lob += __shfl_sync(0xFFFFFFFFu, i_lob, 31);
     }
     if (lane == 0) {
       s_nch[n_segs] = c_ch;

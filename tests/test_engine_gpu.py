@@ -37,11 +37,13 @@ def make_pool(pkg, seed, n, n_modes=2, bell=False, oor=0.01):
     return ids, rating, mode, ts
 
 
+@pytest.mark.parametrize("wide", [0, 1])  # 1: MM_F_WIDE_PARTITIONS — a 1 500-rating group stays ONE partition (list ranking)
 @pytest.mark.parametrize("impl", [3, 2])
 @pytest.mark.parametrize("order", [ARRIVAL, RATING])
 @pytest.mark.parametrize("n", [0, 1, 2, 9, 31, 33, 1000, 2047, 2048, 2049, 4097, 70001])
-def test_random_pool_matches_literal_oracle(pkg, oracle, n, order, impl):
-    cfg = pkg.synth.make_config(groups=pkg.synth.REFERENCE_GROUPS, order=order, capacity=max(n, 1))
+def test_random_pool_matches_literal_oracle(pkg, oracle, n, order, impl, wide):
+    cfg = pkg.synth.make_config(groups=pkg.synth.REFERENCE_GROUPS, order=order, capacity=max(n, 1),
+                                flags=pkg.abi.MM_F_WIDE_PARTITIONS * wide)
     ids, rating, mode, ts = make_pool(pkg, 11 + n, n)
     with pkg.Engine(cfg) as eng:
         eng.set_option("rank_impl", impl)
@@ -56,11 +58,12 @@ def test_random_pool_matches_literal_oracle(pkg, oracle, n, order, impl):
             assert np.array_equal(np.argsort(seq, kind="stable"), np.argsort(ref.emission_rank, kind="stable"))
 
 
+@pytest.mark.parametrize("wide", [0, 1])
 @pytest.mark.parametrize("order", [ARRIVAL, RATING])
 @pytest.mark.parametrize("bell", [False, True])
-def test_one_million_mixed(pkg, oracle, order, bell):
+def test_one_million_mixed(pkg, oracle, order, bell, wide):
     n = 1_000_003
-    cfg = pkg.synth.make_config(n_groups=8, order=order, capacity=n)
+    cfg = pkg.synth.make_config(n_groups=8, order=order, capacity=n, flags=pkg.abi.MM_F_WIDE_PARTITIONS * wide)
     ids, rating, mode, ts = make_pool(pkg, 5, n, bell=bell, oor=0.0)
     with pkg.Engine(cfg) as eng:
         assert eng.enqueue(ids, rating, mode, ts).all()

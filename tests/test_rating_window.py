@@ -112,11 +112,13 @@ def check(eng, ref, lob, mem, seq, st, seq_of=None):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("wide", [0, 1])  # 0: wide rating groups stored as several partitions — windows cross them
 @pytest.mark.parametrize("tick_impl", [1, 0])
 @pytest.mark.parametrize("W", [-1, 0, 2, 40, 100000])
 @pytest.mark.parametrize("n", [0, 3, 2049, 70001, 600_011])
-def test_window_parity_random_pools(pkg, oracle, n, W, tick_impl):
-    cfg = pkg.synth.make_config(groups=pkg.synth.REFERENCE_GROUPS, order=RATING, capacity=max(n, 1))
+def test_window_parity_random_pools(pkg, oracle, n, W, tick_impl, wide):
+    cfg = pkg.synth.make_config(groups=pkg.synth.REFERENCE_GROUPS, order=RATING, capacity=max(n, 1),
+                                flags=pkg.abi.MM_F_WIDE_PARTITIONS * wide)
     ids, rating, mode, ts = small_pool(pkg, 21 + n, n)
     alive = (np.random.default_rng(n + 1).random(n) > 0.05).astype(np.uint8)
     with pkg.Engine(cfg) as eng:
