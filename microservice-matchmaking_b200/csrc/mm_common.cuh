@@ -169,6 +169,22 @@ __device__ __forceinline__ void grid_barrier(unsigned int* bar, unsigned int tar
   }
   __syncthreads();
 }
+// The same barrier in two halves: work that needs nothing from the other CTAs can sit between arrive and wait.
+__device__ __forceinline__ void grid_arrive(unsigned int* bar) {
+  __syncthreads();
+  if (threadIdx.x == 0) { __threadfence(); atomicAdd(bar, 1u); }
+}
+__device__ __forceinline__ void grid_wait(unsigned int* bar, unsigned int target) {
+  if (threadIdx.x == 0) {
+    unsigned int v;
+    do {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(bar) : "memory");
+      if (v < target) __nanosleep(32);
+    } while (v < target);
+    __threadfence();
+  }
+  __syncthreads();
+}
 // global -> shared bulk copy (SASS: UBLKCP), completion counted on `bar`, with an L2 cache-policy hint
 __device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar, uint64_t pol) {
   asm volatile(

@@ -510,7 +510,11 @@ TailArgs tail_args(mm_engine* e) {
 // tiles per row at least; the tile count is bounded from the host-side player count.
 uint32_t tick_rows(const mm_engine* e) {
   const uint64_t tiles = (uint64_t)e->pool[e->cur].n / kTile + e->n_segs;
-  return (uint32_t)std::min<uint64_t>(e->R, std::max<uint64_t>(1, (tiles + 1) / 2));
+  // the lobby headers (one per L players, written by the helper CTAs while the rows place) are ~0.14 / L of the
+  // placement work: small lobbies get more helpers, at the rows' expense
+  const uint32_t total = e->R + e->helpers;
+  const uint32_t want = std::min(32u, std::max(e->helpers, (total * 14 / 100 + e->min_L - 1) / e->min_L));
+  return (uint32_t)std::min<uint64_t>(total - want, std::max<uint64_t>(1, (tiles + 1) / 2));
 }
 
 PlaceArgs place_args(mm_engine* e, bool want_seq) {
@@ -573,7 +577,9 @@ bool use_fused(const mm_engine* e) { return e->tick_impl == 1 && e->fused_ok; }
 int tick_fused(mm_engine* e, bool want_seq) {
   TickArgs a{};
   const uint32_t rows = tick_rows(e);
-  const uint32_t helpers = rows >= 64 ? e->helpers : (rows > 1 ? 1u : 0u);
+  // a grid that does not fill the GPU spends the spare CTA slots on helpers: at a few tiles per row the lobby headers
+  // (one per L players) are as much work as the placement
+  const uint32_t helpers = rows >= 64 ? std::min(32u, e->helpers + (e->R - rows)) : (rows > 1 ? 1u : 0u);
   a.src = e->pool[e->cur].v;
   a.R = rows;
   a.M = e->d_M;
@@ -767,8 +773,7 @@ int mm_create(const mm_config* cfg, mm_engine** out) {
     // overlap the other's work), else one.  Function attributes are process-global:
     // every kernel gets the device's opt-in maximum.
     const size_t static_smem = sizeof(Geo) + 512;
-    uint32_t st_max = 2;  // measured: 2 stages x 2 CTAs per SM beat 3 x 2 by ~1 us (MM_PLACE_STAGES=3 to compare)
-    if (const char* ev = std::getenv("MM_PLACE_STAGES")) st_max = (uint32_t)std::min(3, std::max(2, std::atoi(ev)));  // tuning override
+    const uint32_t st_max = 2;  // measured: 2 ring stages x 2 CTAs per SM beat 3 x 2 by ~1 us on config3
     for (uint32_t st = st_max; st >= 2 && !e->place_stages; --st)
       if (2 * (place_smem_bytes(e->max_nb, st) + static_smem + 1024) <= e->smem_sm) { e->place_stages = st; e->rows_per_sm = 2; }
     for (uint32_t st = kMaxStages; st >= 1 && !e->place_stages; --st)  // huge key domains: down to a single stage

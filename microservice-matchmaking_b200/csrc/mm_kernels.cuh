@@ -96,7 +96,11 @@ __global__ void __launch_bounds__(BLOCK, 2) k_tick(const TickArgs a) {
       ctr->t[5] = t;
     }
   };
-  if (tail_cta && !is_row) run_tail();  // the tail needs no tile geometry: it starts at once, beside the rows' pass
+  const bool tail_first = tail_cta && !is_row;
+  if (tail_first) {  // the tail needs no tile geometry: it starts at once, beside the rows' pass, and signals the
+    run_tail();      // barrier before it builds its own copy of the geometry (small ticks wait for the tail)
+    grid_arrive(&ctr->gbar);
+  }
   geo_build<BLOCK>(geo, a.place.meta.fill, a.tail.n_segs, R, s_gtmp);
   if (is_row) {
     if (a.place.meta.chist) rowsum_body<BLOCK>(smem_raw, geo, a.place.meta, Kp, a.tail.seg_bin_lo, a.M);
@@ -104,7 +108,8 @@ __global__ void __launch_bounds__(BLOCK, 2) k_tick(const TickArgs a) {
   }
   if (tail_cta && is_row) run_tail();   // a grid without helpers: after its own row
   if (threadIdx.x == 0) { unsigned long long tm; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tm)); if (is_row) atomicMax(&ctr->t[8], tm); }
-  grid_barrier(&ctr->gbar, (bar += G));
+  bar += G;
+  if (tail_first) grid_wait(&ctr->gbar, bar); else grid_barrier(&ctr->gbar, bar);
   stamp(1);
   if (geo_use_colscan(geo)) {  // (uniform over the grid)
     for (uint32_t grp = blockIdx.x; grp < (K + 31) / 32; grp += G) colscan_cols_body(scratch, geo, grp, Kp, K, a.tail.bin_seg, a.M, a.P);
