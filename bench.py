@@ -369,6 +369,8 @@ def main():
         cfgp.flags |= abi.MM_F_DENSE_IDS
         cfgp.active_capacity = (S + 3) * n  # handle range: every step brings new players, nobody has left yet
         h_mem32 = torch.empty(mem_cap, dtype=torch.int32).pin_memory()
+        h_lob2 = torch.empty(lob_cap, dtype=torch.int64).pin_memory()   # pipelined legs: results alternate between two
+        h_mem32b = torch.empty(mem_cap, dtype=torch.int32).pin_memory() # host buffer sets (tick k is read while k+1 runs)
         batches = []
         for k in range(S + 2):
             _, r_k, m_k, _ = pkg.synth.gen_pool(1, n, first=(rank + world * k) * n, mode=mode_idx)
@@ -427,7 +429,8 @@ def main():
             eng.enqueue_packed_end_raw()
             rej_idx, _ = eng.enqueue_rejects()
             assert len(rej_idx) == 0
-            lob_pipe += eng.tick_raw(h_lob.data_ptr(), lob_cap, h_mem32.data_ptr(), mem_cap, packed=True).n_lobbies
+            hl, hm = (h_lob, h_mem32) if k & 1 else (h_lob2, h_mem32b)
+            lob_pipe += eng.tick_raw(hl.data_ptr(), lob_cap, hm.data_ptr(), mem_cap, packed=True).n_lobbies
         eng.results_wait()
         e2e_s = (time.perf_counter() - t0) / S
         eng.close()

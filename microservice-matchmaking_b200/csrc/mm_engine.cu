@@ -47,6 +47,7 @@ struct mm_engine {
   cudaEvent_t ev_copy = nullptr;
   cudaStream_t d2h_stream = nullptr;   // async_results: a tick's host copies, overlapped with the next ingest
   bool async_results = false, results_pending = false;
+  bool last_packed = false;  // the pending host copies read only d_hdr / d_members32
   cudaEvent_t ev[5]{};  // tick start | after hist | after colscan | after place | after epilogue
   char last_err[512] = {0};
 
@@ -101,6 +102,10 @@ struct mm_engine {
   uint32_t* d_left_bits = nullptr;  // one bit per virtual pool position: stays queued after the tick
   uint64_t* d_members = nullptr;
   uint32_t* d_members32 = nullptr;  // mm_tick_packed: member handles narrowed for the host copy
+  // async_results + mm_tick_packed: headers and narrowed handles alternate between two buffer sets, so the next
+  // tick's kernels need not wait for this tick's host copies
+  uint32_t* d_members32_alt = nullptr;
+  mm_lobby_hdr* d_hdr_alt = nullptr;
   uint32_t* d_src_idx = nullptr;
   mm_lobby_hdr* d_hdr = nullptr;
   uint32_t* d_emit_seq = nullptr;
@@ -650,7 +655,16 @@ int tick_to_host(mm_engine* e, mm_lobby_hdr* lobbies, uint32_t lobby_cap, uint64
   const uint32_t n = e->pool[e->cur].n;
   const bool want_members = member_ids || member_handles;
   int rc;
-  if ((rc = wait_results(e))) return rc;
+  // The previous tick's host copies read d_hdr / d_members32 (packed) or d_members / d_emit_seq.  A packed tick
+  // switches to the other buffer set and lets its kernels run beside those copies; otherwise wait for them first.
+  const bool defer = e->async_results && e->results_pending && member_handles && !member_ids && !emit_seq &&
+                     e->last_packed && e->d_hdr_alt && e->d_members32_alt;
+  if (defer) {
+    std::swap(e->d_hdr, e->d_hdr_alt);
+    std::swap(e->d_members32, e->d_members32_alt);
+  } else if ((rc = wait_results(e))) {
+    return rc;
+  }
   // worst-case output sizes known up front -> the fused single launch is safe
   e->last_fused = use_fused(e) && (!lobbies || (uint64_t)lobby_cap >= n / e->min_L) && (!want_members || member_cap >= n);
   if (e->last_fused) {
@@ -675,6 +689,8 @@ int tick_to_host(mm_engine* e, mm_lobby_hdr* lobbies, uint32_t lobby_cap, uint64
     CK(cudaGetLastError());
     if (e->async_results) CK(cudaStreamSynchronize(e->stream));  // the copy stream must see the narrowed handles
   }
+  if ((rc = wait_results(e))) return rc;  // (deferred case) the caller's host arrays of the previous tick are complete
+  e->last_packed = member_handles && !member_ids && !emit_seq;
   // the tick is complete here (tick_commit synchronised the engine stream); with async_results the copies run on
   // their own stream and the call returns: the caller may ingest the next batch meanwhile (PCIe is full duplex)
   cudaStream_t cs = e->async_results ? e->d2h_stream : e->stream;
@@ -848,7 +864,7 @@ int mm_destroy(mm_engine* e) {
   cudaFree(e->d_lut); cudaFree(e->d_grp_lut); cudaFree(e->d_mode_tsize); cudaFree(e->d_seg_bin_lo); cudaFree(e->d_seg_L);
   cudaFree(e->d_part_cut); cudaFree(e->d_cut_lp_lo);
   cudaFree(e->d_M); cudaFree(e->d_P); cudaFree(e->d_outbase); cudaFree(e->d_binlim); cudaFree(e->d_bin_seg);
-  cudaFree(e->d_bin_key); cudaFree(e->d_seg); cudaFree(e->d_members); cudaFree(e->d_members32); cudaFree(e->d_src_idx);
+  cudaFree(e->d_bin_key); cudaFree(e->d_seg); cudaFree(e->d_members); cudaFree(e->d_members32); cudaFree(e->d_members32_alt); cudaFree(e->d_hdr_alt); cudaFree(e->d_src_idx);
   cudaFree(e->d_hdr); cudaFree(e->d_emit_seq); cudaFree(e->d_rescnt); cudaFree(e->d_ctr2); cudaFree(e->d_small);
   cudaFree(e->d_in_id); cudaFree(e->d_hslot); cudaFree(e->d_in_rating); cudaFree(e->d_in_mode); cudaFree(e->d_code);
   cudaFree(e->d_in_ts); cudaFree(e->d_blocksum); cudaFree(e->d_blockhist); cudaFree(e->d_part); cudaFree(e->d_in_key);
@@ -891,6 +907,12 @@ int mm_set_option(mm_engine* e, const char* name, int64_t value) {
     int rcw = wait_results(e);
     if (rcw) return rcw;
     e->async_results = value != 0;
+    if (e->async_results) {  // second set of the packed result buffers, allocated here rather than inside a tick
+      CK(cudaSetDevice(e->device));
+      if (!e->d_hdr_alt) CK(cudaMalloc(&e->d_hdr_alt, (size_t)e->max_lobbies * sizeof(mm_lobby_hdr)));
+      if (!e->d_members32) CK(cudaMalloc(&e->d_members32, ((size_t)e->capacity + 64) * 4));
+      if (!e->d_members32_alt) CK(cudaMalloc(&e->d_members32_alt, ((size_t)e->capacity + 64) * 4));
+    }
     return MM_OK;
   }
   if (!std::strcmp(name, "max_spread")) {

@@ -588,6 +588,38 @@ def test_staged_packed_ingest_equals_the_blocking_one(pkg, oracle):
         assert np.array_equal(a.pool_read()["id"], b.pool_read()["id"])
 
 
+def test_packed_async_results_do_not_block_the_next_tick(pkg):
+    """async_results + mm_tick_packed: a tick's kernels run while the previous tick's host copies are still in flight
+    (two device buffer sets); the previous tick's host arrays are complete once the next mm_tick_packed returns.
+    Host arrays alternate, as a consumer that reads tick k while tick k+1 runs would."""
+    import torch
+    n, steps = 250_007, 5
+    cfg = pkg.synth.make_config(n_groups=32, order=RATING, capacity=2 * n, active_capacity=(steps + 1) * n)
+    cfg.flags |= pkg.abi.MM_F_DENSE_IDS
+    lob_h = [torch.empty(n, dtype=torch.int64).pin_memory() for _ in range(2)]
+    mem_h = [torch.empty(2 * n, dtype=torch.int32).pin_memory() for _ in range(2)]
+    with pkg.Engine(cfg) as a, pkg.Engine(cfg) as b:
+        a.set_option("async_results", 1)
+        prev = None
+        for k in range(steps):
+            _, rating, mode, ts = make_pool(pkg, 900 + k, n, oor=0.0)
+            handles = np.arange(n, dtype=np.uint32) + np.uint32(k * n)
+            key = pkg.Engine.pack_key(rating, mode)
+            assert (a.enqueue_packed(handles, key, ts) == 1).all() and (b.enqueue_packed(handles, key, ts) == 1).all()
+            st = a.tick_raw(lob_h[k & 1].data_ptr(), n, mem_h[k & 1].data_ptr(), 2 * n, packed=True)
+            if prev is not None:  # tick k has returned: the host arrays of tick k-1 are complete
+                pst, plob, pmem = prev
+                assert np.array_equal(lob_h[(k - 1) & 1].numpy()[:pst.n_lobbies].view(plob.dtype), plob)
+                assert np.array_equal(mem_h[(k - 1) & 1].numpy()[:pst.n_matched].view(np.uint32), pmem)
+            lob, mem, _, stb = b.tick_packed(want_emit_seq=False)
+            assert (st.n_lobbies, st.n_matched) == (stb.n_lobbies, stb.n_matched) and st.n_lobbies > 0
+            prev = (st, lob, mem)
+        a.results_wait()
+        pst, plob, pmem = prev
+        assert np.array_equal(lob_h[(steps - 1) & 1].numpy()[:pst.n_lobbies].view(plob.dtype), plob)
+        assert np.array_equal(mem_h[(steps - 1) & 1].numpy()[:pst.n_matched].view(np.uint32), pmem)
+
+
 # ---- rating-group shards on real engines (SURVEY §8e): K engines, one per rank's group range, merged ----------------
 @pytest.mark.parametrize("K,workload", [(2, None), (4, None), (8, "config3_10m_g32_5v5")])
 @pytest.mark.parametrize("order", [RATING, ARRIVAL])

@@ -13,6 +13,8 @@ timeout 300 python bench.py --steps 10 --warmup 3 --tick-impl 0 --no-cpu-baselin
 for W in 0 20; do
 timeout 300 python bench.py --steps 10 --warmup 3 --max-spread $W --no-cpu-baseline --no-e2e > gpurun_out/bench_s1_w$W.log 2>&1; tail -1 gpurun_out/bench_s1_w$W.log | cut -c1-200
 done
+timeout 300 python tools/exp_ingest.py > gpurun_out/ingest.txt 2>&1; tail -2 gpurun_out/ingest.txt
+timeout 300 python tools/exp_small_tick.py > gpurun_out/small_tick.txt 2>&1; grep impl=1 gpurun_out/small_tick.txt
 # launch list of the fused tick with the clocks the profiler saw (reconciles ncu durations with the CUDA-event clock)
 timeout 600 ncu --metrics gpu__time_duration.sum,sm__cycles_elapsed.max,gpc__cycles_elapsed.avg.per_second,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -c 80 --csv --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/ncu_b.log 2>&1; echo "ncu list rc=$?"
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:"k_tick" -s 3 -c 1 -o gpurun_out/prof_tick -f python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/ncu_full.log 2>&1; echo "ncu full rc=$?"
