@@ -367,12 +367,12 @@ def main():
         # -- packed API on a dense-handle engine: 6 B/player up, 4 B/player down
         cfgp, _ = pkg.synth.workload_config(args.workload, order, cap, device=local, single_mode=not args.two_modes)
         cfgp.flags |= abi.MM_F_DENSE_IDS
-        cfgp.active_capacity = (S + 3) * n  # handle range: every step brings new players, nobody has left yet
+        cfgp.active_capacity = (S + 4) * n  # handle range: every step brings new players, nobody has left yet
         h_mem32 = torch.empty(mem_cap, dtype=torch.int32).pin_memory()
         h_lob2 = torch.empty(lob_cap, dtype=torch.int64).pin_memory()   # pipelined legs: results alternate between two
         h_mem32b = torch.empty(mem_cap, dtype=torch.int32).pin_memory() # host buffer sets (tick k is read while k+1 runs)
         batches = []
-        for k in range(S + 2):
+        for k in range(S + 3):
             _, r_k, m_k, _ = pkg.synth.gen_pool(1, n, first=(rank + world * k) * n, mode=mode_idx)
             handles = (np.arange(n, dtype=np.uint64) + np.uint64(k * n)).astype(np.uint32)
             batches.append((pin(handles), pin(pkg.Engine.pack_key(r_k, m_k))))
@@ -417,20 +417,27 @@ def main():
         #    result copies; every step's host->device and device->host copies are still inside the timed region
         eng = pkg.Engine(cfgp); options(eng)
         eng.set_option("async_results", 1)
-        step_packed(eng, batches[0])  # warm-up
-        eng.results_wait()
-        barrier()
-        lob_pipe = 0
-        t0 = time.perf_counter()
-        eng.enqueue_packed_begin_raw(n, batches[1][0].data_ptr(), batches[1][1].data_ptr())
-        for k in range(1, S + 1):
-            if k < S:
+
+        def staged_step(k, last):
+            if not last:
                 eng.enqueue_packed_begin_raw(n, batches[k + 1][0].data_ptr(), batches[k + 1][1].data_ptr())
             eng.enqueue_packed_end_raw()
             rej_idx, _ = eng.enqueue_rejects()
             assert len(rej_idx) == 0
             hl, hm = (h_lob, h_mem32) if k & 1 else (h_lob2, h_mem32b)
-            lob_pipe += eng.tick_raw(hl.data_ptr(), lob_cap, hm.data_ptr(), mem_cap, packed=True).n_lobbies
+            return eng.tick_raw(hl.data_ptr(), lob_cap, hm.data_ptr(), mem_cap, packed=True).n_lobbies
+
+        # warm-up: two staged steps, so that both staging slots and both result buffer sets exist before the clock starts
+        eng.enqueue_packed_begin_raw(n, batches[0][0].data_ptr(), batches[0][1].data_ptr())
+        staged_step(0, False)
+        staged_step(1, True)
+        eng.results_wait()
+        barrier()
+        lob_pipe = 0
+        t0 = time.perf_counter()
+        eng.enqueue_packed_begin_raw(n, batches[2][0].data_ptr(), batches[2][1].data_ptr())
+        for k in range(2, S + 2):
+            lob_pipe += staged_step(k, k == S + 1)
         eng.results_wait()
         e2e_s = (time.perf_counter() - t0) / S
         eng.close()
