@@ -216,8 +216,10 @@ int mm_tick_packed(mm_engine* e, uint64_t now, mm_lobby_hdr* lobbies, uint32_t l
                    mm_tick_stats* stats);
 
 /* With mm_set_option("async_results", 1) mm_tick returns as soon as the tick is done and its host copies are
- * queued: the caller's buffers are valid only after mm_results_wait (or the next mm_tick / mm_tick_device, which wait
- * first).  mm_enqueue / mm_remove / mm_in_queue may run meanwhile — the next batch's host-to-device transfer overlaps
+ * queued: the caller's buffers are valid only after mm_results_wait, or once the next mm_tick* call has returned (it
+ * waits for them — a packed tick after its own kernels, which write a second set of device result buffers; the other
+ * entry points before they start).  Give consecutive ticks different host arrays if tick k is read while tick k+1
+ * runs.  mm_enqueue* / mm_remove / mm_in_queue may run meanwhile — the next batch's host-to-device transfer overlaps
  * the previous tick's device-to-host transfer.  What replaces it: nothing (the reference publishes lobby by lobby,
  * search/worker.ex:250-261); it is the batched hand-off of SURVEY §8f-1.  No-op when nothing is pending.            */
 int mm_results_wait(mm_engine* e);
